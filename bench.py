@@ -1,0 +1,288 @@
+#!/usr/bin/env python
+"""
+Benchmark of the hot path on BASELINE.json's headline configuration.
+
+Workload (configs[4], the one the metric is quoted on): ensemble of 1024 random fabric profiles x 181 azimuths x
+5000 layers, f = 179 MHz, oblique incidence alpha = 10 deg (general anisotropic eigen path), synthetic profiles
+(tamm_b200/profiles.py: ensemble).  A "step" is one pass of the hot path over the whole ensemble:
+stack kernel (+ chunk scan) -> returns kernel -> power kernel, inputs resident in HBM.  The ensemble is split by
+profile over the ranks (strong scaling, no data-path collective: profiles are independent and the azimuth mean is
+local to a profile).  Metric: layer*freq*azimuth evaluations per second, whole job.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--profiles P --layers N --frames F]
+
+Under torchrun every rank runs its shard; rank 0 prints ONE JSON line.
+`--impl reference` times the CPU restatement of the reference's algorithm (oracle/, all host cores) on a bounded
+sample of the same workload; the Python reference itself cannot travel to the GPU box.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+F_ALG = 4000.0            # algorithmic FP64 flop per (layer, frequency, azimuth) evaluation, SURVEY.md 8(d)
+F_ALG_STACK = 3960.0      # of which stages A-G run in the stack kernel (H = 40 flop runs in the returns kernels)
+FP64_PEAK_FALLBACK = 34.2  # TFLOP/s, tools/dfma_peak.cu measured on this pool's B200 (profiles/r01_dfma_peak.log)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='tamm_b200', choices=['tamm_b200', 'reference'])
+    ap.add_argument('--profiles', type=int, default=1024)
+    ap.add_argument('--layers', type=int, default=5000)
+    ap.add_argument('--frames', type=int, default=181)
+    ap.add_argument('--alpha-deg', type=float, default=10.0)
+    ap.add_argument('--freq', type=float, default=179e6)
+    ap.add_argument('--batch', type=int, default=64, help='profiles per kernel launch')
+    ap.add_argument('--e2e-steps', type=int, default=2)
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--cpu-seconds', type=float, default=15.0)
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on the host cores (the one place bench.py may execute oracle/)
+# ---------------------------------------------------------------------------------------------------------
+def _cpu_worker(job):
+    seed_first, n_layers, n_frames, alpha, f = job
+    os.environ.setdefault('OMP_NUM_THREADS', '1')
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import tamm_oracle as orc
+    from tamm_b200 import profiles
+    nlm, z = profiles.ensemble(1, n_layers, first=seed_first)
+    t = time.perf_counter()
+    st = orc.OracleStack(nlm[0], z, N_frames=181)
+    idx = np.linspace(0, 180, n_frames).round().astype(int)
+    urd = st.get_URD(f, alpha, beta=st.beta[idx])
+    r = orc.returns_from_URD(urd, 1e3)
+    return time.perf_counter() - t, n_layers * n_frames, float(np.abs(r[5]).sum())
+
+
+def cpu_baseline(args, seconds):
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    alpha = np.deg2rad(args.alpha_deg)
+    # calibrate one small job, then size the sample for ~`seconds` of wall time on all cores
+    t0, ev0, _ = _cpu_worker((0, min(args.layers, 500), 8, alpha, args.freq))
+    rate = ev0 / t0
+    frames = int(max(4, min(args.frames, rate * seconds / args.layers)))
+    jobs = [(i, args.layers, frames, alpha, args.freq) for i in range(cores)]
+    ctx = mp.get_context('fork')
+    t = time.perf_counter()
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_cpu_worker, jobs)
+    wall = time.perf_counter() - t
+    evals = sum(r[1] for r in res)
+    return dict(value=evals / wall, unit='layer*freq*azimuth evals/s', cores=cores, kind='port',
+                sample='%d profiles x %d layers x %d of %d azimuths (%.3g evals, %.1f s wall), vectorised NumPy+LAPACK '
+                       'restatement of the reference (oracle/tamm_oracle.py), one process per core; the unmodified '
+                       'Python reference measured 1.15e3 evals/s/core in the build container (BASELINE.md)' % (
+                           cores, args.layers, frames, args.frames, evals, wall)), wall
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    t = time.perf_counter()
+    vals = []
+    base = None
+    for _ in range(max(1, min(args.steps, 3)) + (1 if args.warmup > 0 else 0)):
+        base, wall = cpu_baseline(args, args.cpu_seconds)
+        vals.append(base['value'])
+    vals = vals[1:] if args.warmup > 0 and len(vals) > 1 else vals
+    v = float(np.mean(vals))
+    base['value'] = v
+    evals_job = float(args.profiles) * args.layers * args.frames
+    line = dict(metric='layer*freq*azimuth evals/s (FP64)', value=v, unit='layer*freq*azimuth evals/s', impl='reference',
+                n_gpus=args.gpus, steps=len(vals), warmup=1 if args.warmup > 0 else 0, ms_per_step=1e3 * evals_job / v,
+                higher_is_better=True, scaling='strong', vs_baseline=None, dtype='f64', data='synthetic',
+                config=workload_config(args), cpu_baseline=base,
+                e2e=dict(value=v, unit='layer*freq*azimuth evals/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                gpu_launches=0, note='CPU arm: ms_per_step is the whole workload extrapolated from the bounded sample rate')
+    print(json.dumps(line))
+
+
+def workload_config(args):
+    return dict(workload='configs[4] ensemble: %d profiles x %d azimuths x %d layers, f=%.0f MHz, alpha=%g deg, GTM' % (
+        args.profiles, args.frames, args.layers, args.freq / 1e6, args.alpha_deg),
+        profiles=args.profiles, layers=args.layers, azimuths=args.frames, frequencies=1, alpha_deg=args.alpha_deg,
+        partition='profiles over ranks, no data-path collective', l2='inputs+outputs >> L2 (no flush needed)')
+
+
+# ---------------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+            'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+        while not self.stop_flag:
+            try:
+                o = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q, '--format=csv,noheader,nounits'],
+                                   capture_output=True, text=True, timeout=5).stdout.strip().split(',')
+                self.samples.append([x.strip() for x in o])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        s = [x for x in self.samples if len(x) >= 7 and x[0].isdigit()]
+        if not s:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['unavailable'])
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names) if any(x[3 + i].lower().startswith('active') for x in s)]
+        return dict(sm_mhz=float(np.median([float(x[0]) for x in s])), sm_max_mhz=float(s[0][1]), samples=len(s),
+                    power_w_max=max(float(x[2]) for x in s), reasons=reasons)
+
+
+def main():
+    args = parse()
+    if args.impl == 'reference':
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    import __graft_entry__ as g
+    if rank == 0:
+        g.build()
+    if world > 1:
+        dist.barrier()
+    from tamm_b200 import EnsembleStack, packing, profiles, shard_range
+    from tamm_b200.engine import MODE_URD, get_engine
+    eng = get_engine()
+    dev = eng.device
+
+    P, N, F = args.profiles, args.layers, args.frames
+    NI = N - 1
+    lo, hi = shard_range(P, rank, world)
+    Pl = hi - lo
+    alpha = np.deg2rad(args.alpha_deg)
+    nlm, z = profiles.ensemble(Pl, N, first=lo)
+    ens = EnsembleStack(nlm, z, N_frames=F)
+    zeta = ens.zeta(alpha)
+    layers_d = eng.to_device(ens.packed_layers())                       # (Pl, N, 10) resident in HBM
+    lanes_d = eng.to_device(packing.pack_lanes(ens.beta, args.freq))
+    etx = np.array([1e3, 0.0], dtype=np.complex128)
+    B = max(1, min(args.batch, Pl))
+    c, r = torch.complex128, torch.float64
+    out = dict(E_HH=eng.empty((Pl, 1, NI, F), c), E_HV=eng.empty((Pl, 1, NI, F), c), c_HHVV=eng.empty((Pl, 1, NI, F), c),
+               dP_HH=eng.empty((Pl, 1, NI, F), r), dP_HV=eng.empty((Pl, 1, NI, F), r), Pm_HH=eng.empty((Pl, 1, NI), r),
+               Pm_HV=eng.empty((Pl, 1, NI), r))
+    planes = eng.empty((B, NI, 4, F), c)
+    stack_events = []
+
+    def step(record=False):
+        for b0 in range(0, Pl, B):
+            b1 = min(Pl, b0 + B)
+            pl = planes[: b1 - b0]
+            if record:
+                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                e0.record()
+            res = eng.stack(layers_d[b0:b1], lanes_d, b1 - b0, N, 1, F, zeta, 1.0, MODE_URD, planes=pl)
+            if record:
+                e1.record()
+                stack_events.append((e0, e1, (b1 - b0)))
+            eng.returns(res, etx, True, out={k: v[b0:b1] for k, v in out.items()})
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    sync_all()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = eng.launches
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        step(record=True)
+    t1.record()
+    sync_all()
+    ms = t0.elapsed_time(t1)
+    launches = eng.launches - launches0
+    sampler.stop_flag = True
+    tm = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    ms = float(tm.item())
+    ms_per_step = ms / args.steps
+    evals_job = float(P) * N * F
+    value = evals_job / (ms_per_step * 1e-3)
+
+    # roofline of the dominant kernel (stack_kernel incl. the tiny chunk scan when chunked): CUDA events around its launches
+    stack_ms = sum(a.elapsed_time(b) for a, b, _ in stack_events)
+    stack_evals = sum(n for _, _, n in stack_events) * float(N) * F
+    stack_evals_per_s = stack_evals / (stack_ms * 1e-3)
+    try:
+        peak, peak_src = eng.fp64_peak_tflops(), 'DFMA probe kernel (tamm_fp64_probe) timed with CUDA events in this run; MEASURED_PEAKS.json has no FP64 entry'
+    except Exception:
+        peak, peak_src = FP64_PEAK_FALLBACK, 'fallback: tools/dfma_peak.cu on this pool (profiles/r01_dfma_peak.log)'
+    achieved = stack_evals_per_s * F_ALG_STACK / 1e12
+    roofline = dict(bound='fp64', kernel='stack_kernel<URD>', achieved=achieved, peak=peak, unit='TFLOP/s', frac=achieved / peak,
+                    traffic=None, peak_source=peak_src, flop_per_eval=F_ALG_STACK, evals_per_launch=float(B) * N * F,
+                    avg_launch_ms=stack_ms / max(1, len(stack_events)), share_of_step=stack_ms / ms if world == 1 else None,
+                    hbm_alg_bytes_per_eval=64.5, hbm_achieved_gbs=stack_evals_per_s * 64.5 / 1e9)
+
+    line = dict(metric='layer*freq*azimuth evals/s (FP64)', value=value, unit='layer*freq*azimuth evals/s', n_gpus=world,
+                steps=args.steps, warmup=max(3, args.warmup), ms_per_step=ms_per_step, higher_is_better=True, scaling='strong',
+                vs_baseline=None, dtype='f64', data='synthetic', config=workload_config(args), roofline=roofline,
+                gpu_launches=launches, fp64_tflops_alg=value * F_ALG / 1e12)
+
+    # end-to-end through the public API: host arrays in, host arrays out (all 7 returns of get_returns)
+    if not args.no_e2e:
+        try:
+            res = ens.get_returns(1e3, f=args.freq, alpha=alpha, batch=B)          # warm-up, allocates pinned outputs
+            pinned = ens._pinned
+            sync_all()
+            te = time.perf_counter()
+            for _ in range(args.e2e_steps):
+                res = ens.get_returns(1e3, f=args.freq, alpha=alpha, batch=B, out=pinned)
+            torch.cuda.synchronize()
+            dt = torch.tensor([(time.perf_counter() - te) / args.e2e_steps], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            d2h = sum(v.numel() * v.element_size() for v in pinned.values())
+            h2d = Pl * N * packing.LAYER_STRIDE * 8 + F * packing.LANE_STRIDE * 8
+            line['e2e'] = dict(value=evals_job / float(dt.item()), unit='layer*freq*azimuth evals/s', h2d_bytes_per_step=h2d,
+                               d2h_bytes_per_step=d2h, api='tamm_b200.EnsembleStack.get_returns (all 7 returns to pinned host arrays)',
+                               result_check=float(np.nanmax(res['Pm_HH'])))
+        except Exception as e:  # e.g. not enough pinned host memory
+            line['e2e'] = dict(value=None, error=repr(e)[:200])
+
+    if rank == 0:
+        line['clocks'] = sampler.summary()
+        if world == 1 and not args.no_cpu:
+            line['cpu_baseline'], _ = cpu_baseline(args, args.cpu_seconds)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,253 @@
+"""
+Drop-in for nicholasmr/tamm `lib/layerstack.py`: a vertical stack of horizontally homogeneous layers of anisotropic
+polycrystalline ice, with the transfer-matrix solve running as CUDA kernels on a B200 (tamm_b200 C ABI).
+
+Same constructor, attributes, methods, return shapes and error messages as the reference class (file:line cited
+per method).  Differences, all additive:
+  * `get_returns(..., f=)` also accepts a 1-D array of frequencies; the outputs then gain a leading frequency axis;
+  * `frm_layers` is a lazy view: `frm_layers[ff][nn]` materialises a `Layer` (attributes fetched from the device) on
+    demand instead of holding N_frames x N_layers Python objects;
+  * `modeltype='FP'` is accepted by the constructor but not yet solvable on the device.
+"""
+import numpy as np
+
+from layer import *        # noqa: F401,F403  (reference: layerstack.py:9)
+from layer_PPJ import *    # noqa: F401,F403  (reference: layerstack.py:10)
+from layer import Layer, nlm_to_c2, eigenbasis, _packing, _get_engine
+from layer_PPJ import exact_inv, c_const
+
+from tamm_b200.engine import MODE_URD, MODE_U
+
+
+class _FrameLayers:
+    """What `LayerStack.get_layerstack(beta, f, zeta)` returns: list-like over layers for one azimuth."""
+
+    def __init__(self, stack, beta, f, zeta):
+        self.stack, self.beta, self.f, self.zeta = stack, beta, f, zeta
+        self._dev = None
+
+    def __len__(self):
+        return self.stack.N_layers
+
+    def _fetch(self):
+        if self._dev is None:
+            st = self.stack
+            eng = _get_engine()
+            layers = st._packed_layers()
+            lanes = _packing.pack_lanes([self.beta], self.f)
+            o = eng.layer_matrices(eng.to_device(layers), eng.to_device(lanes), st.N_layers, 1, self.zeta, st.mu)
+            self._dev = {k: v.cpu().numpy()[0] for k, v in o.items()}
+        return self._dev
+
+    def __getitem__(self, nn):
+        if isinstance(nn, slice):
+            return [self[i] for i in range(*nn.indices(len(self)))]
+        st = self.stack
+        nn = int(nn)
+        if nn < 0:
+            nn += st.N_layers
+        d = self._fetch()
+        one = {k: v[nn] for k, v in d.items()}
+        return Layer(st.nlm[nn], self.beta, st.dz[nn], self.f, self.zeta, st.epsa[nn], st.epsc[nn], st.sigma[nn], st.mu,
+                     modeltype=st.modeltype, _device_result=one)
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+
+class _LazyFrames:
+    """`LayerStack.frm_layers`: list-like over azimuth frames of `_FrameLayers`."""
+
+    def __init__(self, stack, f, zeta, betas=None):
+        self.stack, self.f, self.zeta = stack, f, zeta
+        self.betas = stack.beta if betas is None else np.asarray(betas)
+        self._frames = {}
+
+    def __len__(self):
+        return len(self.betas)
+
+    def __getitem__(self, ff):
+        ff = int(ff)
+        if ff < 0:
+            ff += len(self)
+        if ff not in self._frames:
+            self._frames[ff] = _FrameLayers(self.stack, self.betas[ff], self.f, self.zeta)
+        return self._frames[ff]
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+
+class LayerStack:
+
+    def __init__(self, nlm, z, N_frames=100, epsa=[3.17 - 0.034], epsc=[3.17], sigma=[1e-5], mu=1, modeltype='GTM', VERBOSE=1):
+        """layerstack.py:14-47."""
+        self.modeltype = modeltype
+        if self.modeltype not in ['GTM', 'FP']:
+            raise ValueError('Argument "modeltype" must be either "GTM" or "FP"')
+
+        self.N_layers, _ = nlm.shape
+        self.N_frames = N_frames
+        self.layerlist = np.arange(self.N_layers)
+        self.framelist = np.arange(self.N_frames)
+        self.beta = np.linspace(0, np.pi, self.N_frames)
+
+        self.z = np.hstack(([np.abs(z[1] - z[0])], z))
+        self.dz = np.abs(np.diff(self.z))
+
+        self.mu = mu
+        self.epsa = np.full((self.N_layers), epsa[0]) if len(epsa) == 1 else epsa
+        self.epsc = np.full((self.N_layers), epsc[0]) if len(epsc) == 1 else epsc
+        self.sigma = np.full((self.N_layers), sigma[0]) if len(sigma) == 1 else sigma
+
+        self.nlm = nlm[:, :6]
+        self.lm = np.array([(0, 0), (2, -2), (2, -1), (2, 0), (2, 1), (2, 2)]).T
+
+        if len(self.z) != 1 + len(self.nlm):
+            raise ValueError('len(z) (=%i) != 1+len(nlm) (=%i)' % (len(self.z), 1 + len(self.nlm)))
+        if np.any(nlm[0, 1:]):
+            raise ValueError('n_2^m of top layer must vanish (surface layer must be isotropic)')
+
+        self.VERBOSE = VERBOSE
+        if self.VERBOSE:
+            print('Initialized "%s" layer stack: frames x layers = %i x %i' % (self.modeltype, self.N_frames, self.N_layers))
+
+    # ------------------------------------------------------------------------------------------
+    def _packed_layers(self):
+        return _packing.pack_layers(self.nlm, self.dz, self.epsa, self.epsc, self.sigma)
+
+    def _require_gtm(self):
+        if self.modeltype != 'GTM':
+            raise NotImplementedError('modeltype="FP" (Fujita-Paren) is not implemented on the device yet')
+
+    def _run(self, betas, f, zeta, mode):
+        """Hot path on the device for this stack: returns (engine, StackResult)."""
+        self._require_gtm()
+        if self.N_layers < 2:
+            raise ValueError('need at least two layers to form an interface')
+        eng = _get_engine()
+        fa = np.atleast_1d(np.asarray(f, dtype=np.float64))
+        layers = eng.to_device(self._packed_layers()[None])
+        lanes = eng.to_device(_packing.pack_lanes(betas, fa))
+        res = eng.stack(layers, lanes, 1, self.N_layers, fa.size, len(betas), zeta, self.mu, mode)
+        return eng, res
+
+    # ------------------------------------------------------------------------------------------
+    def get_eigenbasis(self):
+        """layerstack.py:50-62 (host side, O(N_layers))."""
+        shp = (self.N_layers, 3)
+        eigvals, e1, e2, e3 = np.zeros(shp), np.zeros(shp), np.zeros(shp), np.zeros(shp)
+        c2 = np.zeros((self.N_layers, 3, 3))
+        for nn in self.layerlist:
+            c2[nn, :, :] = nlm_to_c2(self.nlm[nn, :])
+            (eigvals[nn, :], e1[nn, :], e2[nn, :], e3[nn, :]) = eigenbasis(c2[nn, :, :])
+        return (eigvals, e1, e2, e3, c2)
+
+    def get_layerstack(self, beta, f, zeta):
+        """layerstack.py:65-66: the layers of this stack seen from azimuth `beta` (lazy list of `Layer`)."""
+        return _FrameLayers(self, beta, f, zeta)
+
+    def get_propconst(self):
+        """layerstack.py:69-71: k_s = omega/c q_s of frame 0, shape (N_layers, 4)."""
+        fr = self.frm_layers[0]
+        d = fr._fetch()
+        q2k = (2 * np.pi * fr.f) / c_const
+        return np.array(q2k * d['qs'], dtype=np.complex128)
+
+    # ------------------------------------------------------------------------------------------
+    def get_T_R(self, Aprev, Aprev_inv, Anext, Anext_inv):
+        """layerstack.py:76-132 for caller-supplied dynamical matrices (F, N-1, 4, 4).  The hot path forms these
+        interface matrices inside the CUDA kernel (tamm_core.cuh: interface_mats); this host utility exists for
+        API compatibility only."""
+        G = np.einsum('fnij,fnjk->fnik', Aprev_inv, Anext)
+        Gr = np.einsum('fnij,fnjk->fnik', Anext_inv, Aprev)
+        with np.errstate(all='ignore'):
+            den = G[:, :, 0, 0] * G[:, :, 1, 1] - G[:, :, 0, 1] * G[:, :, 1, 0]
+            T = np.nan_to_num(np.array([[G[:, :, 1, 1], -G[:, :, 0, 1]], [-G[:, :, 1, 0], G[:, :, 0, 0]]]) / den)
+            R = np.nan_to_num(np.array([
+                [G[:, :, 2, 0] * G[:, :, 1, 1] - G[:, :, 2, 1] * G[:, :, 1, 0], G[:, :, 0, 0] * G[:, :, 2, 1] - G[:, :, 2, 0] * G[:, :, 0, 1]],
+                [G[:, :, 3, 0] * G[:, :, 1, 1] - G[:, :, 3, 1] * G[:, :, 1, 0], G[:, :, 0, 0] * G[:, :, 3, 1] - G[:, :, 3, 0] * G[:, :, 0, 1]]]) / den)
+            denr = Gr[:, :, 2, 2] * Gr[:, :, 3, 3] - Gr[:, :, 2, 3] * Gr[:, :, 3, 2]
+            Trev = np.nan_to_num(np.array([[Gr[:, :, 3, 3], -Gr[:, :, 2, 3]], [-Gr[:, :, 3, 2], Gr[:, :, 2, 2]]]) / denr)
+        mv = lambda X: np.moveaxis(X.astype(np.complex128), (0, 1), (2, 3))
+        return mv(R), mv(T), mv(Trev)
+
+    def _frames_args(self, frm_layers):
+        if isinstance(frm_layers, _LazyFrames):
+            return frm_layers.betas, frm_layers.f, frm_layers.zeta
+        frames = list(frm_layers)
+        if not frames or not all(isinstance(fr, _FrameLayers) for fr in frames):
+            raise TypeError('frm_layers must come from get_layerstack()/get_returns() of this LayerStack')
+        f, zeta = frames[0].f, frames[0].zeta
+        if any(fr.f != f or fr.zeta != zeta for fr in frames):
+            raise ValueError('all frames must share f and zeta')
+        return np.array([fr.beta for fr in frames]), f, zeta
+
+    def get_URD(self, frm_layers):
+        """layerstack.py:135-196: total downward-reflected-upward 2x2 transformation, shape (N_frames, N_layers-1, 2, 2)."""
+        betas, f, zeta = self._frames_args(frm_layers)
+        eng, res = self._run(betas, f, zeta, MODE_URD)
+        return eng.export_jones(res).cpu().numpy()[0, 0]
+
+    def get_U(self, frm_layers):
+        """layerstack.py:198-225: upward product only, shape (N_frames, N_layers-1, 2, 2)."""
+        if self.modeltype != 'GTM':
+            raise ValueError('Only GTM model type supported')
+        betas, f, zeta = self._frames_args(frm_layers)
+        eng, res = self._run(betas, f, zeta, MODE_U)
+        return eng.export_jones(res).cpu().numpy()[0, 0]
+
+    # ------------------------------------------------------------------------------------------
+    def dB(self, amp):
+        """layerstack.py:229."""
+        return 20 * np.log10(amp)
+
+    def get_returns(self, E0, f=179.0e6, alpha=0, Tx_pol=([1, 0],), URD='URD', nn=None):
+        """layerstack.py:232-288 -> (Pm_HH, Pm_HV, dP_HH, dP_HV, c_HHVV, E_HH, E_HV), depth-major and squeezed
+        exactly like the reference.  `f` may be an array (extension): a leading frequency axis is added."""
+        self.epsiso = (2 * self.epsa[0] + self.epsc[0]) / 3
+        zeta = np.sqrt(self.epsiso) * np.sin(alpha)
+
+        if URD == 'URD':
+            mode = MODE_URD
+        elif URD == 'U':
+            if self.modeltype != 'GTM':
+                raise ValueError('Only GTM model type supported')
+            mode = MODE_U
+        else:
+            raise ValueError('get_returns(): argument URD="%s" not understood' % (URD))
+
+        eng, res = self._run(self.beta, f, zeta, mode)
+        p = Tx_pol[0]
+        E_Tx = np.array([E0 * p[0], E0 * p[1]], dtype=np.complex128)            # layerstack.py:249
+        out = eng.returns(res, E_Tx, gtm_phase=(self.modeltype == 'GTM'))
+        host = {k: v.cpu().numpy()[0] for k, v in out.items()}                   # (Q, N-1, F) / (Q, N-1)
+
+        scalar_f = (np.ndim(f) == 0)
+        I = slice(None) if nn is None else slice(nn, nn + 1) if nn != -1 else slice(nn, None)
+
+        def fmt(name, kind):
+            a = host[name][:, I]
+            if kind == 'Pm':
+                a = a[:, None, :]            # reference shape before squeeze: (1, Nl)
+            if scalar_f:
+                a = a[0]
+            return np.squeeze(a)
+
+        returns = (fmt('Pm_HH', 'Pm'), fmt('Pm_HV', 'Pm'), fmt('dP_HH', 'x'), fmt('dP_HV', 'x'),
+                   fmt('c_HHVV', 'x'), fmt('E_HH', 'x'), fmt('E_HV', 'x'))
+
+        self.frm_layers = _LazyFrames(self, f if scalar_f else np.atleast_1d(f)[0], zeta)   # layerstack.py:286
+        return returns
+
+    def get_Rx_all(self, E_Tx_list, URD, nn=None):
+        """layerstack.py:291-301: received fields for each transmitted polarisation from caller-supplied URD."""
+        Nl = self.N_layers - 1 if nn is None else 1
+        E_Rx = np.zeros((self.N_frames, Nl, 2 * len(E_Tx_list)), np.complex128)
+        for jj, E_Tx in enumerate(E_Tx_list):
+            cols = [2 * jj, 2 * jj + 1]
+            if nn is None:
+                E_Rx[:, :, cols] = np.einsum('fnij,j->fni', URD[:, :, :, :], E_Tx)
+            else:
+                E_Rx[:, 0, cols] = np.einsum('fij,j->fi', URD[:, nn, :, :], E_Tx)
+        return E_Rx

@@ -103,12 +103,21 @@ def c2_to_nlm(c2, n00=1 / np.sqrt(4 * np.pi)):
     return nlm.astype(np.complex128)
 
 
-def rotate_nlm(nlm, beta, precision='double'):
-    """layer.py:48-49: nlm' = diag(exp(+i m beta)) nlm.  nlm (N,6), beta (F,) -> (F,N,6)."""
+def rotate_nlm(nlm, beta, precision='double', faithful=False):
+    """layer.py:48-49: nlm' = diag(exp(+i m beta)) nlm.  nlm (N,6), beta (F,) -> (F,N,6).
+    faithful=True replays the reference's 6x6 `np.matmul` per (beta, layer) (BLAS zgemv rounding)."""
     fdt, cdt = _types(precision)
     beta = np.asarray(beta, dtype=fdt)
+    nlm = np.asarray(nlm, dtype=cdt)[:, :6]
+    if faithful and precision == 'double':
+        out = np.empty((beta.size, nlm.shape[0], 6), dtype=cdt)
+        for ff, b in enumerate(beta):
+            Qz = np.diag([np.exp(+1j * m * b) for m in [0, -2, -1, 0, +1, +2]])
+            for nn in range(nlm.shape[0]):
+                out[ff, nn] = np.matmul(Qz, nlm[nn])
+        return out
     Q = np.exp((1j * _M_ORDER[None, :]).astype(cdt) * beta[:, None])
-    return Q[:, None, :] * np.asarray(nlm, dtype=cdt)[None, :, :6]
+    return Q[:, None, :] * nlm[None, :, :]
 
 
 # ---------------------------------------------------------------------------------------------
@@ -523,7 +532,7 @@ def layer_matrices(nlm, beta, dz, f, zeta, epsa, epsc, sigma, mu=1, eig='lapack'
     """nlm (N,>=6), beta (F,), dz/epsa/epsc/sigma (N,) -> dict of arrays with batch shape (F,N)."""
     fdt, cdt = _types(precision)
     nlm = np.asarray(nlm)[:, :6]
-    nlm_rot = rotate_nlm(nlm, beta, precision)                          # layer.py:48-49
+    nlm_rot = rotate_nlm(nlm, beta, precision, faithful)                # layer.py:48-49
     ccavg = nlm_to_c2(nlm_rot)                                          # layer.py:50
     epsilon = get_epsavg(ccavg, np.asarray(epsa)[None, :], np.asarray(epsc)[None, :],
                          np.asarray(sigma)[None, :], f, precision)      # layer.py:53

@@ -1,0 +1,617 @@
+// tamm_b200 -- per-(layer, frequency, azimuth) physics of the layer-stack transfer-matrix solver.
+//
+// Everything here is `__host__ __device__` inline code over plain doubles so that the CUDA kernels
+// (tamm_kernels.cu) and the test-only host simulator (tests/hostsim) compile the SAME source.  The
+// product never runs this on the CPU: the shared library only exports entry points that launch kernels.
+//
+// Reference behaviour restated (nicholasmr/tamm, file:line):
+//   rotation + <c^2>            lib/layer.py:48-50, 135-159
+//   permittivity                lib/layer.py:57-68
+//   Berreman a-entries / Delta  lib/layer_PPJ.py:99-173
+//   eigenvalues, clean-up, transmitted/reflected partition, Poynting / E-field p-s sort
+//                               lib/layer_PPJ.py:175-293   (LAPACK eig replaced, see eig4_factored)
+//   Xu / Passler-Paarmann gamma lib/layer_PPJ.py:295-402   (useBerreman is dead code upstream)
+//   A, K                        lib/layer_PPJ.py:413-437
+//   A^-1                        lib/layer_PPJ.py:20-79     (adjugate / determinant)
+//   Mfwd, Mrev                  lib/layer.py:94-97
+//   interface R, T, Trev        lib/layerstack.py:76-132
+//   D_mul, U_mul, accumulation  lib/layerstack.py:185-194
+#pragma once
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define TAMM_HD __host__ __device__ __forceinline__
+#else
+#define TAMM_HD inline
+#endif
+
+namespace tamm {
+
+// layer_PPJ.py:14-18 -- must be bit-identical
+constexpr double C_CONST = 299792458.0;
+constexpr double EPS0 = 8.8541878128e-12;
+constexpr double QSD_THR = 1e-10;
+constexpr double ZERO_THR = 1e-10;
+
+struct cd {
+    double re, im;
+};
+
+TAMM_HD cd mk(double re, double im = 0.0) { return cd{re, im}; }
+TAMM_HD cd operator+(cd a, cd b) { return cd{a.re + b.re, a.im + b.im}; }
+TAMM_HD cd operator-(cd a, cd b) { return cd{a.re - b.re, a.im - b.im}; }
+TAMM_HD cd operator-(cd a) { return cd{-a.re, -a.im}; }
+TAMM_HD cd operator*(cd a, cd b) { return cd{a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
+TAMM_HD cd operator*(double s, cd a) { return cd{s * a.re, s * a.im}; }
+TAMM_HD cd operator*(cd a, double s) { return cd{s * a.re, s * a.im}; }
+TAMM_HD cd operator+(cd a, double s) { return cd{a.re + s, a.im}; }
+TAMM_HD cd operator-(cd a, double s) { return cd{a.re - s, a.im}; }
+TAMM_HD cd conj(cd a) { return cd{a.re, -a.im}; }
+TAMM_HD double abs2(cd a) { return a.re * a.re + a.im * a.im; }
+TAMM_HD double cabs_(cd a) { return hypot(a.re, a.im); }
+TAMM_HD cd csq(cd a) { return cd{(a.re - a.im) * (a.re + a.im), 2.0 * a.re * a.im}; }
+TAMM_HD cd crecip(cd b) {
+    double inv = 1.0 / (b.re * b.re + b.im * b.im);
+    return cd{b.re * inv, -b.im * inv};
+}
+TAMM_HD cd operator/(cd a, cd b) { return a * crecip(b); }
+TAMM_HD bool cisnan(cd a) { return isnan(a.re) || isnan(a.im); }
+TAMM_HD cd csel(bool c, cd a, cd b) { return cd{c ? a.re : b.re, c ? a.im : b.im}; }
+
+// principal square root
+TAMM_HD cd csqrt_(cd z) {
+    double m = hypot(z.re, z.im);
+    if (m == 0.0) return cd{0.0, 0.0};
+    if (z.re >= 0.0) {
+        double t = sqrt(0.5 * (m + z.re));
+        return cd{t, 0.5 * z.im / t};
+    }
+    double t = sqrt(0.5 * (m - z.re));
+    return cd{0.5 * fabs(z.im) / t, copysign(t, z.im)};
+}
+
+// numpy.nan_to_num semantics on a complex number (layerstack.py:101-112)
+TAMM_HD double n2n(double x) {
+    if (isnan(x)) return 0.0;
+    if (isinf(x)) return x > 0 ? 1.7976931348623157e308 : -1.7976931348623157e308;
+    return x;
+}
+TAMM_HD cd n2n(cd a) { return cd{n2n(a.re), n2n(a.im)}; }
+
+// -------------------------------------------------------------------------------------------------
+// Inputs.  One LayerParams per (profile, layer); one LaneParams per (frequency, azimuth) lane.
+// -------------------------------------------------------------------------------------------------
+struct LayerParams {  // 10 doubles = 80 B (multiple of 16 B for cp.async.bulk)
+    double t20;       // sqrt(2/3) * Re(n20/n00)                 layer.py:137,143
+    double n21r, n21i;  // n21p/n00
+    double n22r, n22i;  // n22p/n00
+    double mono;      // Re((2 epsa + epsc)/3)                   layer.py:61
+    double deps;      // Re(epsc - epsa)                         layer.py:62
+    double sigma;     // conductivity                            layer.py:65
+    double dz;        // thickness                               layerstack.py:27-28
+    double pad;
+};
+constexpr int LAYER_STRIDE = 10;
+
+struct LaneParams {  // 8 doubles = 64 B
+    double c1, s1;   // exp(+i beta)    (host: numpy.exp(1j*beta), layer.py:48)
+    double c2, s2;   // exp(+2i beta)
+    double twopif;   // 2*pi*f          layer.py:31, layer_PPJ.py:437
+    double w_eps0;   // 2*pi*f*eps0     layer.py:65
+    double pad0, pad1;
+};
+constexpr int LANE_STRIDE = 8;
+
+struct Sym3 {  // complex-symmetric permittivity: real symmetric part + isotropic imaginary part
+    double xx, xy, xz, yy, yz, zz;  // real parts
+    double im;                      // imaginary part of the diagonal (= -sigma/(2 pi f eps0))
+};
+
+// no-contraction helpers: stage A mirrors numpy's separately-rounded real arithmetic so eps is bit-faithful
+#if defined(__CUDA_ARCH__)
+#define TAMM_MUL(a, b) __dmul_rn((a), (b))
+#define TAMM_ADD(a, b) __dadd_rn((a), (b))
+#define TAMM_SUB(a, b) __dadd_rn((a), -(b))
+#else
+TAMM_HD double tamm_mul_(double a, double b) { volatile double r = a * b; return r; }
+TAMM_HD double tamm_add_(double a, double b) { volatile double r = a + b; return r; }
+#define TAMM_MUL(a, b) tamm_mul_((a), (b))
+#define TAMM_ADD(a, b) tamm_add_((a), (b))
+#define TAMM_SUB(a, b) tamm_add_((a), -(b))
+#endif
+
+// layer.py:48-50,135-159 (rotation about z, <c^2>) and layer.py:57-68 (permittivity)
+TAMM_HD Sym3 permittivity(const LayerParams& lp, const LaneParams& ln) {
+    const double s23h = 0.5;                       // 1/2*n20term
+    const double s215 = 0.36514837167011072;       // sqrt(2/15)
+    const double third = 0.33333333333333331;      // np.eye(3)/3
+    // n22' = exp(2i beta) * n22p ; n21' = exp(i beta) * n21p  (complex products, separately rounded)
+    double n22re = TAMM_SUB(TAMM_MUL(ln.c2, lp.n22r), TAMM_MUL(ln.s2, lp.n22i));
+    double n22im = TAMM_ADD(TAMM_MUL(ln.c2, lp.n22i), TAMM_MUL(ln.s2, lp.n22r));
+    double n21re = TAMM_SUB(TAMM_MUL(ln.c1, lp.n21r), TAMM_MUL(ln.s1, lp.n21i));
+    double n21im = TAMM_ADD(TAMM_MUL(ln.c1, lp.n21i), TAMM_MUL(ln.s1, lp.n21r));
+    double half = TAMM_MUL(s23h, lp.t20);
+    double cxx = TAMM_ADD(third, TAMM_MUL(s215, TAMM_SUB(n22re, half)));
+    double cyy = TAMM_ADD(third, TAMM_MUL(s215, TAMM_SUB(-n22re, half)));
+    double czz = TAMM_ADD(third, TAMM_MUL(s215, lp.t20));
+    double cxy = TAMM_ADD(0.0, TAMM_MUL(s215, -n22im));
+    double cxz = TAMM_ADD(0.0, TAMM_MUL(s215, -n21re));
+    double cyz = TAMM_ADD(0.0, TAMM_MUL(s215, n21im));
+    Sym3 e;
+    e.xx = TAMM_ADD(lp.mono, TAMM_MUL(lp.deps, TAMM_SUB(cxx, third)));
+    e.yy = TAMM_ADD(lp.mono, TAMM_MUL(lp.deps, TAMM_SUB(cyy, third)));
+    e.zz = TAMM_ADD(lp.mono, TAMM_MUL(lp.deps, TAMM_SUB(czz, third)));
+    e.xy = TAMM_ADD(0.0, TAMM_MUL(lp.deps, cxy));
+    e.xz = TAMM_ADD(0.0, TAMM_MUL(lp.deps, cxz));
+    e.yz = TAMM_ADD(0.0, TAMM_MUL(lp.deps, cyz));
+    e.im = -(lp.sigma / ln.w_eps0);
+    return e;
+}
+
+// -------------------------------------------------------------------------------------------------
+// Eigenvalues of the Berreman matrix without forming it.
+//
+// Eliminating Ez from [mu*eps + k k^T - |k|^2 I] E = 0, k = (zeta, 0, q), leaves a complex-symmetric 2x2
+// wave matrix N(q) on (Ex, Ey); det N(q) = 0 is the characteristic quartic of Delta (layer_PPJ.py:197).
+// N is always evaluated entry-wise (never via expanded quartic coefficients): the entries are O(|q_p-q_s|)
+// near a root with absolute error O(eps*|eps_ij|), so roots keep ~1 ulp accuracy even for |q_p-q_s| -> 0,
+// where coefficient-form root finding loses half the digits.
+// -------------------------------------------------------------------------------------------------
+struct WaveCoef {
+    cd e00, e01, e02;  // mu*eps entries used by N
+    cd k;              // 1/(mu*eps_zz - zeta^2)
+    cd w1;             // mu*eps_yz * k
+    cd d0;             // mu*eps_yy - zeta^2 - mu*eps_yz*w1
+    cd db;             // dN01/dq = -zeta*w1   (constant)
+    double zeta;
+};
+
+TAMM_HD WaveCoef wave_coef(const Sym3& e, double mu, double zeta) {
+    WaveCoef w;
+    w.zeta = zeta;
+    w.e00 = mk(mu * e.xx, mu * e.im);
+    w.e01 = mk(mu * e.xy, 0.0);
+    w.e02 = mk(mu * e.xz, 0.0);
+    cd e33 = mk(mu * e.zz - zeta * zeta, mu * e.im);
+    w.k = crecip(e33);
+    double e12 = mu * e.yz;
+    w.w1 = e12 * w.k;
+    w.d0 = mk(mu * e.yy - zeta * zeta, mu * e.im) - e12 * w.w1;
+    w.db = (-zeta) * w.w1;
+    return w;
+}
+
+struct WaveMat {
+    cd a, b, d;    // N = [[a, b], [b, d]]
+    cd da, dd;     // dN/dq diagonal entries (off-diagonal is WaveCoef::db)
+};
+
+TAMM_HD WaveMat wave_matrix(const WaveCoef& w, cd q) {
+    WaveMat m;
+    cd u = w.e02 + w.zeta * q;
+    cd uk = u * w.k;
+    cd q2 = csq(q);
+    m.a = w.e00 - q2 - u * uk;
+    m.b = w.e01 - u * w.w1;
+    m.d = w.d0 - q2;
+    m.dd = (-2.0) * q;
+    m.da = m.dd - (2.0 * w.zeta) * uk;
+    return m;
+}
+
+// One successive-linear-problem step: eigenvalues of G = -N'(q)^-1 N(q).  Returns both eigenvalues
+// (h_big, h_small); h_small (closest to zero) is the Newton-like correction for a root near q,
+// h_big is the distance to the partner root of a near-degenerate pair.
+TAMM_HD void mslp_eigs(const WaveMat& m, cd db, cd& h_big, cd& h_small) {
+    // adj(N') N  with N' = [[da, db],[db, dd]]
+    cd g00 = m.dd * m.a - db * m.b;
+    cd g01 = m.dd * m.b - db * m.d;
+    cd g10 = m.da * m.b - db * m.a;
+    cd g11 = m.da * m.d - db * m.b;
+    cd det1 = m.da * m.dd - db * db;
+    cd hm = 0.5 * (g00 + g11);
+    cd hd = 0.5 * (g00 - g11);
+    cd s = csqrt_(csq(hd) + g01 * g10);
+    bool flip = (hm.re * s.re + hm.im * s.im) < 0.0;
+    s = csel(flip, -s, s);
+    cd big = hm + s;
+    cd detg = g00 * g11 - g01 * g10;
+    cd ninv = -crecip(det1);  // G = -(adj(N') N)/det N'
+    cd small = (abs2(big) > 0.0) ? detg / big : mk(0.0);
+    h_big = big * ninv;
+    h_small = small * ninv;
+}
+
+// Four roots.  q0,q1: pair seeded at -sqrt(.), q2,q3: pair seeded at +sqrt(.).
+TAMM_HD void eig4_factored(const WaveCoef& w, cd& q0, cd& q1, cd& q2, cd& q3) {
+    cd c00 = w.e00 - w.e02 * (w.e02 * w.k);   // N(0) entries (Schur complement of eps_zz - zeta^2/mu)
+    cd c01 = w.e01 - w.e02 * w.w1;
+    cd c11 = w.d0;
+    if (w.zeta == 0.0) {
+        // zeta = 0 -> N(q) = C0 - q^2 I: closed form (biquadratic), no iteration
+        cd hm = 0.5 * (c00 + c11), hd = 0.5 * (c00 - c11);
+        cd s = csqrt_(csq(hd) + csq(c01));
+        bool flip = (hm.re * s.re + hm.im * s.im) < 0.0;
+        s = csel(flip, -s, s);
+        cd lbig = hm + s;
+        cd lsmall = (c00 * c11 - csq(c01)) / lbig;      // cancellation-free smaller eigenvalue
+        cd r0 = csqrt_(lbig), r1 = csqrt_(lsmall);
+        q0 = -r0; q1 = -r1; q2 = r0; q3 = r1;
+        return;
+    }
+    // seed: centre of each pair.  The p-like root of a(q) is scaled by 1/(1 + zeta^2 k).
+    cd kap = mk(1.0) + (w.zeta * w.zeta) * w.k;
+    cd qc = csqrt_(0.5 * (c00 / kap + c11));
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int idx = 0; idx < 4; ++idx) {
+        cd centre = idx < 2 ? -qc : qc;
+        WaveMat m = wave_matrix(w, centre);
+        cd hb, hs;
+        mslp_eigs(m, w.db, hb, hs);
+        cd x = centre + ((idx & 1) ? hs : hb);
+        // Newton-like MSLP steps; quadratic convergence => stop after a step below 1e-8 |q|
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        for (int it = 0; it < 24; ++it) {
+            WaveMat mm = wave_matrix(w, x);
+            cd b2, h;
+            mslp_eigs(mm, w.db, b2, h);
+            x = x + h;
+            if (!(abs2(h) > 1e-16 * abs2(x))) break;
+        }
+        if (idx == 0) q0 = x; else if (idx == 1) q1 = x; else if (idx == 2) q2 = x; else q3 = x;
+    }
+}
+
+TAMM_HD double sel4(int i, double a, double b, double c, double d) { return i == 0 ? a : (i == 1 ? b : (i == 2 ? c : d)); }
+TAMM_HD cd sel4(int i, cd a, cd b, cd c, cd d) { return cd{sel4(i, a.re, b.re, c.re, d.re), sel4(i, a.im, b.im, c.im, d.im)}; }
+
+// -------------------------------------------------------------------------------------------------
+// Per-layer state handed to the interface stage
+// -------------------------------------------------------------------------------------------------
+struct LayerMats {
+    cd A[4][4];      // dynamical matrix                (layer_PPJ.py:429-433)
+    cd Ai[4][4];     // its inverse                     (layer.py:94)
+    cd Mfwd[2];      // diag of K^-1[0:2,0:2]           (layer.py:96)
+    cd Mrev[2];      // diag of K[2:,2:]                (layer.py:97)
+};
+
+struct LayerDiag {   // optional diagnostics backing the `Layer` attributes of the Python API
+    cd eps[3][3];
+    cd Delta[4][4];
+    cd a_used[8];    // a[2,0], a[2,1], a[2,3], a[2,4], a[5,0], a[5,1], a[5,3], a[5,4]
+    cd qs[4];
+    cd gamma[4][3];
+    cd Py[3][4];
+    cd Kd[4];
+    int status;      // bit0: transmitted/reflected partition was not 2+2
+};
+
+TAMM_HD cd clean_q(cd q) {  // layer_PPJ.py:199-203
+    if (fabs(q.im) > 0.0 && fabs(q.im) < ZERO_THR) q.im = 0.0;
+    if (fabs(q.re) > 0.0 && fabs(q.re) < ZERO_THR) q.re = 0.0;
+    return q;
+}
+
+// 4x4 complex inverse via 2x2 minors (Laplace expansion); same adjugate/determinant as layer_PPJ.py:20-79
+TAMM_HD void inv4(const cd a[4][4], cd o[4][4]) {
+    cd s0 = a[0][0] * a[1][1] - a[1][0] * a[0][1];
+    cd s1 = a[0][0] * a[1][2] - a[1][0] * a[0][2];
+    cd s2 = a[0][0] * a[1][3] - a[1][0] * a[0][3];
+    cd s3 = a[0][1] * a[1][2] - a[1][1] * a[0][2];
+    cd s4 = a[0][1] * a[1][3] - a[1][1] * a[0][3];
+    cd s5 = a[0][2] * a[1][3] - a[1][2] * a[0][3];
+    cd c5 = a[2][2] * a[3][3] - a[3][2] * a[2][3];
+    cd c4 = a[2][1] * a[3][3] - a[3][1] * a[2][3];
+    cd c3 = a[2][1] * a[3][2] - a[3][1] * a[2][2];
+    cd c2 = a[2][0] * a[3][3] - a[3][0] * a[2][3];
+    cd c1 = a[2][0] * a[3][2] - a[3][0] * a[2][2];
+    cd c0 = a[2][0] * a[3][1] - a[3][0] * a[2][1];
+    cd det = s0 * c5 - s1 * c4 + s2 * c3 + s3 * c2 - s4 * c1 + s5 * c0;
+    cd id = crecip(det);
+    o[0][0] = (a[1][1] * c5 - a[1][2] * c4 + a[1][3] * c3) * id;
+    o[0][1] = (a[0][2] * c4 - a[0][1] * c5 - a[0][3] * c3) * id;
+    o[0][2] = (a[3][1] * s5 - a[3][2] * s4 + a[3][3] * s3) * id;
+    o[0][3] = (a[2][2] * s4 - a[2][1] * s5 - a[2][3] * s3) * id;
+    o[1][0] = (a[1][2] * c2 - a[1][0] * c5 - a[1][3] * c1) * id;
+    o[1][1] = (a[0][0] * c5 - a[0][2] * c2 + a[0][3] * c1) * id;
+    o[1][2] = (a[3][2] * s2 - a[3][0] * s5 - a[3][3] * s1) * id;
+    o[1][3] = (a[2][0] * s5 - a[2][2] * s2 + a[2][3] * s1) * id;
+    o[2][0] = (a[1][0] * c4 - a[1][1] * c2 + a[1][3] * c0) * id;
+    o[2][1] = (a[0][1] * c2 - a[0][0] * c4 - a[0][3] * c0) * id;
+    o[2][2] = (a[3][0] * s4 - a[3][1] * s2 + a[3][3] * s0) * id;
+    o[2][3] = (a[2][1] * s2 - a[2][0] * s4 - a[2][3] * s0) * id;
+    o[3][0] = (a[1][1] * c1 - a[1][0] * c3 - a[1][2] * c0) * id;
+    o[3][1] = (a[0][0] * c3 - a[0][1] * c1 + a[0][2] * c0) * id;
+    o[3][2] = (a[3][1] * s1 - a[3][0] * s3 - a[3][2] * s0) * id;
+    o[3][3] = (a[2][0] * s3 - a[2][1] * s1 + a[2][2] * s0) * id;
+}
+
+// exp(-i * (2 pi f q d)/c) with the reference's operation order (layer_PPJ.py:437); sign=+1 gives the inverse
+TAMM_HD cd phase(cd q, double twopif, double d, double sign) {
+    const double rc = 1.0 / C_CONST;
+    cd z = (twopif * q) * d;                    // 2 pi f q d
+    double ar = sign * (z.im * rc);             // Re(-i z / c) =  z.im / c
+    double ai = sign * (-(z.re * rc));          // Im(-i z / c) = -z.re / c
+    double m = exp(ar);
+    double sn, cs;
+    sincos(ai, &sn, &cs);
+    return cd{m * cs, m * sn};
+}
+
+struct ModeVec {  // what the p/s sort needs from the Berreman state of one mode
+    cd Px, Py, Pz;
+    double Cp, Ce;
+};
+
+// Full per-layer solve.  DIAG != nullptr additionally records the Layer attributes.
+TAMM_HD int layer_solve(const LayerParams& lp, const LaneParams& ln, double zeta, double mu, LayerMats& L,
+                        LayerDiag* diag) {
+    int status = 0;
+    const Sym3 e = permittivity(lp, ln);
+    const WaveCoef w = wave_coef(e, mu, zeta);
+
+    // ---- eigenvalues (layer_PPJ.py:197) + clean-up (199-203)
+    cd qu[4];
+    eig4_factored(w, qu[0], qu[1], qu[2], qu[3]);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < 4; ++k) qu[k] = clean_q(qu[k]);
+
+    // ---- Berreman a-entries (layer_PPJ.py:125-135 with M = blockdiag(eps, mu I)):
+    //      b = eps_zz*mu ; a20 = -eps_zx*mu/b ; a21 = -eps_zy*mu/b ; a24 = -zeta*mu/b ; a51 = zeta ; others 0
+    const cd ezz = mk(e.zz, e.im);
+    const cd ib = crecip(mu * ezz);
+    const cd a20 = (-(e.xz * mu)) * ib;
+    const cd a21 = (-(e.yz * mu)) * ib;
+    const cd a24 = (-(zeta * mu)) * ib;
+    const double a51 = zeta / mu;                  // (M52*M21 - M22*(M51 - zeta))/b = eps_zz*zeta/(eps_zz*mu)
+    // Delta row 0 (layer_PPJ.py:158-161): [ -zeta*eps_zx/eps_zz , mu - zeta^2/eps_zz , -zeta*eps_zy/eps_zz , 0 ]
+    const cd D00 = zeta * a20, D01 = mk(mu) + zeta * a24, D02 = zeta * a21;
+
+    // ---- eigenvectors for the sort only (layer_PPJ.py:233-249)
+    ModeVec mv[4];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < 4; ++k) {
+        const cd q = qu[k];
+        WaveMat m = wave_matrix(w, q);
+        bool use0 = abs2(m.a) >= abs2(m.d);
+        cd Ex = csel(use0, -m.b, m.d);
+        cd Ey = csel(use0, m.a, -m.b);
+        if (abs2(Ex) + abs2(Ey) == 0.0) { Ex = mk(1.0); Ey = mk(0.0); }
+        cd Hy = ((q - D00) * Ex - D02 * Ey) / D01;     // row 0 of Delta psi = q psi
+        cd Hx = -((1.0 / mu) * (q * Ey));               // row 2: mu psi3 = q psi2, Hx = -psi3
+        cd Ez = a20 * Ex + a21 * Ey + a24 * Hy;         // layer_PPJ.py:239
+        cd Hz = a51 * Ey;                               // layer_PPJ.py:241 (only the a[5,1] term survives)
+        mv[k].Px = Ey * Hz - Ez * Hy;                   // 243
+        mv[k].Py = Ez * Hx - Ex * Hz;                   // 244
+        mv[k].Pz = Ex * Hy - Ey * Hx;                   // 245
+        double px = abs2(mv[k].Px), py = abs2(mv[k].Py);
+        mv[k].Cp = px / (px + py);                      // 255-256 (NaN when both vanish)
+        double ex = abs2(Ex), ey = abs2(Ey);
+        mv[k].Ce = ex / (ex + ey);                      // 269-270
+    }
+
+    // ---- partition into transmitted / reflected in index order (layer_PPJ.py:216-231)
+    bool has_im = (qu[0].im != 0.0) || (qu[1].im != 0.0) || (qu[2].im != 0.0) || (qu[3].im != 0.0);
+    int tmask = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < 4; ++k) {
+        bool t = has_im ? (qu[k].im >= 0.0) : (qu[k].re > 0.0);
+        tmask |= (t ? 1 : 0) << k;
+    }
+    int t0, t1, r0, r1;
+    switch (tmask) {
+        case 0x3: t0 = 0; t1 = 1; r0 = 2; r1 = 3; break;
+        case 0xC: t0 = 2; t1 = 3; r0 = 0; r1 = 1; break;
+        case 0x5: t0 = 0; t1 = 2; r0 = 1; r1 = 3; break;
+        case 0xA: t0 = 1; t1 = 3; r0 = 0; r1 = 2; break;
+        case 0x6: t0 = 1; t1 = 2; r0 = 0; r1 = 3; break;
+        case 0x9: t0 = 0; t1 = 3; r0 = 1; r1 = 2; break;
+        default:  t0 = 0; t1 = 1; r0 = 2; r1 = 3; status |= 1; break;  // reference would raise / mis-index
+    }
+    // ---- p/s sort (layer_PPJ.py:254-276)
+    auto Cp = [&](int i) { return sel4(i, mv[0].Cp, mv[1].Cp, mv[2].Cp, mv[3].Cp); };
+    auto Ce = [&](int i) { return sel4(i, mv[0].Ce, mv[1].Ce, mv[2].Ce, mv[3].Ce); };
+    double Cp_t0 = Cp(t0), Cp_t1 = Cp(t1);
+    bool biref = fabs(Cp_t0 - Cp_t1) > QSD_THR;   // false for NaN
+    bool flip_t, flip_r;
+    if (biref) {
+        flip_t = Cp_t1 > Cp_t0;
+        flip_r = Cp(r1) > Cp(r0);
+    } else {
+        flip_t = Ce(t1) > Ce(t0);
+        flip_r = Ce(r1) > Ce(r0);
+    }
+    int ord[4];
+    ord[0] = flip_t ? t1 : t0; ord[1] = flip_t ? t0 : t1;
+    ord[2] = flip_r ? r1 : r0; ord[3] = flip_r ? r0 : r1;
+    cd qs[4];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < 4; ++k) {
+        int o = ord[k];
+        qs[k] = sel4(o, qu[0], qu[1], qu[2], qu[3]);
+    }
+
+    // ---- gamma (layer_PPJ.py:309-402), eps symmetric
+    const cd e00 = mk(e.xx, e.im), e11 = mk(e.yy, e.im);
+    const double e01 = e.xy, e02 = e.xz, e12 = e.yz;
+    const cd mez = mu * ezz - zeta * zeta;                                  // 315
+    const cd imez = crecip(mez);
+    cd g[4][3];
+    {
+        // transmitted pair
+        cd u0 = mk(mu * e02) + zeta * qs[0];                                // mu*eps20 + zeta*q0
+        cd u1 = mk(mu * e02) + zeta * qs[1];
+        bool deg = cabs_(qs[0] - qs[1]) < QSD_THR;                          // 317
+        cd g12, g13, g21, g23;
+        cd g13_plain = (-u0) * imez;                                        // 320 / 340
+        cd g23_plain = mk(-(mu * e12)) * imez;                              // 324 / 354
+        {
+            cd num = (mu * e12) * u0 - (mu * e01) * mez;                    // 327-328
+            cd den = mez * (mu * e11 - zeta * zeta - csq(qs[0])) - mk(mu * mu * e12 * e12);   // 329-330
+            g12 = num / den;                                                // 331
+            if (cisnan(g12)) g12 = mk(0.0);                                 // 332
+            g13 = ((-u0) - (mu * e12) * g12) * imez;                        // 335-337
+            if (cisnan(g13)) g13 = g13_plain;                               // 339
+            cd num2 = (mu * e12) * u1 - (mu * e01) * mez;                   // 343-344
+            cd den2 = mez * (mu * e00 - csq(qs[1])) - u1 * u1;              // 345-346
+            g21 = num2 / den2;                                              // 347
+            if (cisnan(g21)) g21 = mk(0.0);
+            g23 = ((-u1) * g21 - mk(mu * e12)) * imez;                      // 351-352
+            if (cisnan(g23)) g23 = g23_plain;
+        }
+        if (deg) { g12 = mk(0.0); g13 = g13_plain; g21 = mk(0.0); g23 = g23_plain; }   // 317-324
+        g[0][0] = mk(1.0); g[0][1] = g12; g[0][2] = g13;
+        g[1][0] = g21; g[1][1] = mk(1.0); g[1][2] = g23;
+        // reflected pair
+        cd u2 = mk(mu * e02) + zeta * qs[2];
+        cd u3 = mk(mu * e02) + zeta * qs[3];
+        bool degr = cabs_(qs[2] - qs[3]) < QSD_THR;                         // 356
+        cd g32, g33, g41, g43;
+        cd g33_plain = u2 * imez;                                           // 358 / 375
+        cd g43_plain = g23_plain;                                           // 360 / 389
+        {
+            cd num = (mu * e01) * mez - (mu * e12) * u2;                    // 363-364
+            cd den = mez * (mu * e11 - zeta * zeta - csq(qs[2])) - mk(mu * mu * e12 * e12);   // 365-366
+            g32 = num / den;
+            if (cisnan(g32)) g32 = mk(0.0);
+            g33 = (u2 + (mu * e12) * g32) * imez;                           // 371-373
+            if (cisnan(g33)) g33 = g33_plain;
+            cd num2 = (mu * e12) * u3 - (mu * e01) * mez;                   // 377-378
+            cd den2 = mez * (mu * e00 - csq(qs[3])) - u3 * u3;              // 379-380
+            g41 = num2 / den2;
+            if (cisnan(g41)) g41 = mk(0.0);
+            g43 = ((-u3) * g41 - mk(mu * e12)) * imez;                      // 385-387
+            if (cisnan(g43)) g43 = g43_plain;
+        }
+        if (degr) { g32 = mk(0.0); g33 = g33_plain; g41 = mk(0.0); g43 = g43_plain; }
+        g[2][0] = mk(-1.0); g[2][1] = g32; g[2][2] = g33;
+        g[3][0] = g41; g[3][1] = mk(1.0); g[3][2] = g43;
+    }
+    // normalise rows (399-402)
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < 4; ++k) {
+        double n2 = (g[k][0].re * g[k][0].re + g[k][1].re * g[k][1].re + g[k][2].re * g[k][2].re) +
+                    (g[k][0].im * g[k][0].im + g[k][1].im * g[k][1].im + g[k][2].im * g[k][2].im);
+        double inv = 1.0 / sqrt(n2);
+        g[k][0] = g[k][0] * inv; g[k][1] = g[k][1] * inv; g[k][2] = g[k][2] * inv;
+    }
+
+    // ---- A (layer_PPJ.py:429-433) and phases (437), Mfwd/Mrev (layer.py:96-97)
+    const double imu = 1.0 / mu;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < 4; ++k) {
+        L.A[0][k] = g[k][0];
+        L.A[1][k] = g[k][1];
+        L.A[2][k] = (qs[k] * g[k][0] - zeta * g[k][2]) * imu;
+        L.A[3][k] = (qs[k] * g[k][1]) * imu;
+    }
+    inv4(L.A, L.Ai);
+    L.Mfwd[0] = phase(qs[0], ln.twopif, lp.dz, -1.0);   // 1/K00 = exp(+i k0 q0 d)
+    L.Mfwd[1] = phase(qs[1], ln.twopif, lp.dz, -1.0);
+    L.Mrev[0] = phase(qs[2], ln.twopif, lp.dz, +1.0);   // K22
+    L.Mrev[1] = phase(qs[3], ln.twopif, lp.dz, +1.0);
+
+    if (diag) {
+        const cd E3[3][3] = {{e00, mk(e01), mk(e02)}, {mk(e01), e11, mk(e12)}, {mk(e02), mk(e12), ezz}};
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) diag->eps[i][j] = E3[i][j];
+        // Delta (layer_PPJ.py:158-173) in closed form
+        cd Dl[4][4];
+        for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) Dl[i][j] = mk(0.0);
+        Dl[0][0] = D00; Dl[0][1] = D01; Dl[0][2] = D02;
+        Dl[1][0] = e00 + e02 * a20; Dl[1][1] = e02 * a24; Dl[1][2] = mk(e01) + e02 * a21;
+        Dl[2][3] = mk(mu);
+        Dl[3][0] = mk(e01) + e12 * a20; Dl[3][1] = e12 * a24; Dl[3][2] = e11 + e12 * a21 - mk(zeta * zeta / mu);
+        for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) diag->Delta[i][j] = Dl[i][j];
+        diag->a_used[0] = a20; diag->a_used[1] = a21; diag->a_used[2] = mk(0.0); diag->a_used[3] = a24;
+        diag->a_used[4] = mk(0.0); diag->a_used[5] = mk(a51); diag->a_used[6] = mk(0.0); diag->a_used[7] = mk(0.0);
+        for (int k = 0; k < 4; ++k) {
+            diag->qs[k] = qs[k];
+            for (int j = 0; j < 3; ++j) diag->gamma[k][j] = g[k][j];
+            diag->Py[0][k] = sel4(ord[k], mv[0].Px, mv[1].Px, mv[2].Px, mv[3].Px);
+            diag->Py[1][k] = sel4(ord[k], mv[0].Py, mv[1].Py, mv[2].Py, mv[3].Py);
+            diag->Py[2][k] = sel4(ord[k], mv[0].Pz, mv[1].Pz, mv[2].Pz, mv[3].Pz);
+            diag->Kd[k] = phase(qs[k], ln.twopif, lp.dz, +1.0);
+        }
+        diag->status = status;
+    }
+    return status;
+}
+
+// -------------------------------------------------------------------------------------------------
+// Interface between layer n (prev) and n+1 (next): R_n, D_mul_n = Mfwd_{n+1} T_n, U_mul_n = Trev_n Mrev_{n+1}
+// (layerstack.py:82-132, 185-186).  Needs prev.Ai (all rows), prev.A[:,2:4], next.A[:,0:2], next.Ai[2:4,:].
+// 2x2 matrices are stored row-major as m[0]=m00, m[1]=m01, m[2]=m10, m[3]=m11.
+// -------------------------------------------------------------------------------------------------
+TAMM_HD void interface_mats(const cd prevAi[4][4], const cd prevAr[4][2], const LayerMats& next, cd R[4], cd Dm[4],
+                            cd Um[4]) {
+    cd G[4][2];   // Gamma[:, 0:2] = prev.Ai @ next.A[:, 0:2]            (layerstack.py:89)
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < 4; ++i) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int j = 0; j < 2; ++j)
+            G[i][j] = prevAi[i][0] * next.A[0][j] + prevAi[i][1] * next.A[1][j] + prevAi[i][2] * next.A[2][j] +
+                      prevAi[i][3] * next.A[3][j];
+    }
+    cd den = G[0][0] * G[1][1] - G[0][1] * G[1][0];                        // 93 (after the 1<->2 permutation)
+    cd iden = crecip(den);
+    cd rpp = n2n((G[2][0] * G[1][1] - G[2][1] * G[1][0]) * iden);          // 96,101
+    cd rss = n2n((G[0][0] * G[3][1] - G[3][0] * G[0][1]) * iden);          // 97,102
+    cd rps = n2n((G[3][0] * G[1][1] - G[3][1] * G[1][0]) * iden);          // 98,103
+    cd rsp = n2n((G[0][0] * G[2][1] - G[2][0] * G[0][1]) * iden);          // 99,104
+    R[0] = rpp; R[1] = rsp; R[2] = rps; R[3] = rss;                        // 106
+    cd tpp = n2n(G[1][1] * iden), tss = n2n(G[0][0] * iden);               // 109-110
+    cd tps = n2n(-(G[1][0] * iden)), tsp = n2n(-(G[0][1] * iden));         // 111-112
+    // D_mul = diag(Mfwd_{n+1}) @ [[tpp, tsp],[tps, tss]]                   (185)
+    Dm[0] = next.Mfwd[0] * tpp; Dm[1] = next.Mfwd[0] * tsp;
+    Dm[2] = next.Mfwd[1] * tps; Dm[3] = next.Mfwd[1] * tss;
+    // Gamma_rev[2:4, 2:4] = next.Ai[2:4, :] @ prev.A[:, 2:4]               (118)
+    cd H[2][2];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < 2; ++i) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int j = 0; j < 2; ++j)
+            H[i][j] = next.Ai[2 + i][0] * prevAr[0][j] + next.Ai[2 + i][1] * prevAr[1][j] +
+                      next.Ai[2 + i][2] * prevAr[2][j] + next.Ai[2 + i][3] * prevAr[3][j];
+    }
+    cd dr = H[0][0] * H[1][1] - H[0][1] * H[1][0];                          // 121
+    cd idr = crecip(dr);
+    cd tppr = n2n(H[1][1] * idr), tssr = n2n(H[0][0] * idr);               // 124-125
+    cd tpsr = n2n(-(H[1][0] * idr)), tspr = n2n(-(H[0][1] * idr));         // 126-127
+    // U_mul = [[tppr, tspr],[tpsr, tssr]] @ diag(Mrev_{n+1})               (186)
+    Um[0] = tppr * next.Mrev[0]; Um[1] = tspr * next.Mrev[1];
+    Um[2] = tpsr * next.Mrev[0]; Um[3] = tssr * next.Mrev[1];
+}
+
+TAMM_HD void mul22(const cd a[4], const cd b[4], cd o[4]) {
+    cd o0 = a[0] * b[0] + a[1] * b[2];
+    cd o1 = a[0] * b[1] + a[1] * b[3];
+    cd o2 = a[2] * b[0] + a[3] * b[2];
+    cd o3 = a[2] * b[1] + a[3] * b[3];
+    o[0] = o0; o[1] = o1; o[2] = o2; o[3] = o3;
+}
+
+}  // namespace tamm

@@ -1,0 +1,566 @@
+// tamm_b200 -- CUDA kernels (sm_100a) and the C ABI declared in include/tamm_b200.h.
+//
+// Kernels
+//   stack_kernel        FP64-pipe bound.  One thread = one (profile, lane, depth-chunk): it walks the chunk's
+//                       layers sequentially, solving each layer (tamm_core.cuh: rotation -> eps -> Berreman
+//                       eigenmodes -> sort -> gamma -> A, A^-1, phases), forming the interface matrices with
+//                       the previous layer carried in registers, and accumulating the chunk-local 2x2 products.
+//                       A and A^-1 never touch HBM.  A warp = 32 consecutive lanes of the same profile and
+//                       chunk, so the per-layer parameters are warp-uniform; they are streamed global->shared
+//                       by the TMA engine (cp.async.bulk + mbarrier, double buffered) and read as broadcasts.
+//   chunk_scan_kernel   warp-shuffle (Kogge-Stone) scan over the chunk aggregates (D, U): exclusive prefixes.
+//   returns_kernel      HBM bound.  Applies the prefixes, Tx polarisation, |E|, HH-VV coherence.
+//   power_kernel        HBM bound.  Azimuth mean (warp reduction), dB, anomalies.
+//   export_kernel       HBM bound.  Prefix fix-up + transpose into the reference's (F, N-1, 2, 2) layout.
+//   layer_diag_kernel   per-(lane, layer) matrices for the `Layer` attribute API and the parity tests.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/tamm_b200.h"
+#include "tamm_core.cuh"
+
+using namespace tamm;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(const char* fmt, const char* a = "", long b = 0) {
+    snprintf(g_err, sizeof(g_err), fmt, a, b);
+    return 1;
+}
+#define CUDA_OK(call)                                                              \
+    do {                                                                           \
+        cudaError_t e_ = (call);                                                   \
+        if (e_ != cudaSuccess) return fail("%s (CUDA error %ld)", cudaGetErrorString(e_), (long)e_); \
+    } while (0)
+
+constexpr int TL = 32;  // layers per TMA sub-tile (32 * 80 B = 2560 B)
+
+// ---- mbarrier / bulk-copy (TMA) primitives -----------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ void st_cd(cd* p, cd v) { *reinterpret_cast<double2*>(p) = make_double2(v.re, v.im); }
+__device__ __forceinline__ cd ld_cd(const cd* p) {
+    double2 v = *reinterpret_cast<const double2*>(p);
+    return cd{v.x, v.y};
+}
+
+// ---- the hot kernel ------------------------------------------------------------------------------
+// grid = (lane tiles, chunks, profiles); block = TB threads (multiple of 32).
+template <int MODE>
+__global__ void __launch_bounds__(256, 1)
+stack_kernel(const double* __restrict__ layers, const double* __restrict__ lanes, int N, int QF, double zeta, double mu,
+             int chunk, int nchunks, cd* __restrict__ planes, cd* __restrict__ agg, int* __restrict__ status) {
+    __shared__ alignas(128) double sbuf[2][TL * LAYER_STRIDE];
+    __shared__ alignas(8) uint64_t bar[2];
+
+    const int NI = N - 1;
+    const int p = blockIdx.z;
+    const int c = blockIdx.y;
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = l < QF;
+    const int lc = live ? l : QF - 1;
+    const int n0 = c * chunk;
+    const int n1 = min(NI, n0 + chunk);
+    const int cnt = n1 - n0 + 1;  // layers n0..n1
+    const int ntile = (cnt + TL - 1) / TL;
+    const double* src = layers + ((size_t)p * N + n0) * LAYER_STRIDE;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t bytes = (uint32_t)(min(TL, cnt) * LAYER_STRIDE * sizeof(double));
+        mbar_expect_tx(&bar[0], bytes);
+        tma_bulk_g2s(&sbuf[0][0], src, bytes, &bar[0]);
+    }
+
+    LaneParams ln;
+    {
+        const double2* lp2 = reinterpret_cast<const double2*>(lanes + (size_t)lc * LANE_STRIDE);
+        double2 a = __ldg(lp2), b = __ldg(lp2 + 1), c2 = __ldg(lp2 + 2);
+        ln.c1 = a.x; ln.s1 = a.y; ln.c2 = b.x; ln.s2 = b.y;
+        ln.twopif = c2.x; ln.w_eps0 = c2.y; ln.pad0 = 0; ln.pad1 = 0;
+    }
+
+    cd prevAi[4][4], prevAr[4][2];
+    cd D[4] = {mk(1.0), mk(0.0), mk(0.0), mk(1.0)};
+    cd U[4] = {mk(1.0), mk(0.0), mk(0.0), mk(1.0)};
+    int st = 0;
+    cd* out = planes + ((size_t)p * NI * 4) * QF + lc;
+
+#pragma unroll 1
+    for (int t = 0; t < ntile; ++t) {
+        // all threads are done with tile t-1 (buffer (t+1)&1) -> refill it with tile t+1
+        __syncthreads();
+        if (threadIdx.x == 0 && t + 1 < ntile) {
+            int rem = cnt - (t + 1) * TL;
+            uint32_t bytes = (uint32_t)(min(TL, rem) * LAYER_STRIDE * sizeof(double));
+            mbar_expect_tx(&bar[(t + 1) & 1], bytes);
+            tma_bulk_g2s(&sbuf[(t + 1) & 1][0], src + (size_t)(t + 1) * TL * LAYER_STRIDE, bytes, &bar[(t + 1) & 1]);
+        }
+        mbar_wait(&bar[t & 1], (uint32_t)((t >> 1) & 1));
+        const double* tile = &sbuf[t & 1][0];
+        const int jn = min(TL, cnt - t * TL);
+#pragma unroll 1
+        for (int jj = 0; jj < jn; ++jj) {
+            const int j = t * TL + jj;
+            LayerParams lp;
+            {
+                const double2* s2 = reinterpret_cast<const double2*>(tile + jj * LAYER_STRIDE);
+                double2 v0 = s2[0], v1 = s2[1], v2 = s2[2], v3 = s2[3], v4 = s2[4];
+                lp.t20 = v0.x; lp.n21r = v0.y; lp.n21i = v1.x; lp.n22r = v1.y; lp.n22i = v2.x;
+                lp.mono = v2.y; lp.deps = v3.x; lp.sigma = v3.y; lp.dz = v4.x; lp.pad = 0;
+            }
+            LayerMats cur;
+            st |= layer_solve(lp, ln, zeta, mu, cur, nullptr);
+            if (j > 0) {
+                const int n = n0 + j - 1;  // interface between layers n and n+1
+                cd R[4], Dm[4], Um[4];
+                interface_mats(prevAi, prevAr, cur, R, Dm, Um);
+                cd o[4];
+                if (MODE == TAMM_MODE_URD) {
+                    cd RD[4];
+                    mul22(R, D, RD);
+                    mul22(U, RD, o);
+                } else {
+                    o[0] = U[0]; o[1] = U[1]; o[2] = U[2]; o[3] = U[3];
+                }
+                if (live) {
+                    cd* op = out + (size_t)n * 4 * QF;
+                    st_cd(op, o[0]);
+                    st_cd(op + QF, o[1]);
+                    st_cd(op + 2 * (size_t)QF, o[2]);
+                    st_cd(op + 3 * (size_t)QF, o[3]);
+                }
+                if (MODE == TAMM_MODE_URD) mul22(Dm, D, D);   // layerstack.py:189
+                mul22(U, Um, U);                              // layerstack.py:190
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) prevAi[r][k] = cur.Ai[r][k];
+                prevAr[r][0] = cur.A[r][2];
+                prevAr[r][1] = cur.A[r][3];
+            }
+        }
+    }
+    if (live) {
+        if (nchunks > 1) {
+            cd* a = agg + (((size_t)p * QF + l) * nchunks + c) * 8;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { st_cd(a + k, D[k]); st_cd(a + 4 + k, U[k]); }
+        }
+        if (st && status) atomicOr(status + p, st);
+    }
+}
+
+// ---- chunk prefix scan: one warp per (profile, lane) ---------------------------------------------
+struct DU {
+    cd D[4], U[4];
+};
+__device__ __forceinline__ DU du_identity() {
+    DU x;
+    x.D[0] = mk(1.0); x.D[1] = mk(0.0); x.D[2] = mk(0.0); x.D[3] = mk(1.0);
+    x.U[0] = mk(1.0); x.U[1] = mk(0.0); x.U[2] = mk(0.0); x.U[3] = mk(1.0);
+    return x;
+}
+// earlier (shallower) segment a followed by deeper segment b:  D = D_b D_a ,  U = U_a U_b
+__device__ __forceinline__ DU du_combine(const DU& a, const DU& b) {
+    DU r;
+    mul22(b.D, a.D, r.D);
+    mul22(a.U, b.U, r.U);
+    return r;
+}
+__device__ __forceinline__ DU du_shfl_up(const DU& x, int off) {
+    DU r;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        r.D[k].re = __shfl_up_sync(0xffffffffu, x.D[k].re, off);
+        r.D[k].im = __shfl_up_sync(0xffffffffu, x.D[k].im, off);
+        r.U[k].re = __shfl_up_sync(0xffffffffu, x.U[k].re, off);
+        r.U[k].im = __shfl_up_sync(0xffffffffu, x.U[k].im, off);
+    }
+    return r;
+}
+__device__ __forceinline__ DU du_shfl(const DU& x, int srcl) {
+    DU r;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        r.D[k].re = __shfl_sync(0xffffffffu, x.D[k].re, srcl);
+        r.D[k].im = __shfl_sync(0xffffffffu, x.D[k].im, srcl);
+        r.U[k].re = __shfl_sync(0xffffffffu, x.U[k].re, srcl);
+        r.U[k].im = __shfl_sync(0xffffffffu, x.U[k].im, srcl);
+    }
+    return r;
+}
+
+__global__ void __launch_bounds__(128) chunk_scan_kernel(const cd* __restrict__ agg, cd* __restrict__ pre, long nseq,
+                                                         int nchunks) {
+    const int lane = threadIdx.x & 31;
+    const long seq = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (seq >= nseq) return;
+    const cd* a = agg + (size_t)seq * nchunks * 8;
+    cd* o = pre + (size_t)seq * nchunks * 8;
+    DU carry = du_identity();
+    for (int g = 0; g < nchunks; g += 32) {
+        const int j = g + lane;
+        DU x = du_identity();
+        if (j < nchunks) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { x.D[k] = ld_cd(a + (size_t)j * 8 + k); x.U[k] = ld_cd(a + (size_t)j * 8 + 4 + k); }
+        }
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            DU y = du_shfl_up(x, off);
+            if (lane >= off) x = du_combine(y, x);
+        }
+        DU ex = du_shfl_up(x, 1);  // inclusive of lanes < this one
+        if (lane == 0) ex = du_identity();
+        ex = du_combine(carry, ex);
+        if (j < nchunks) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { st_cd(o + (size_t)j * 8 + k, ex.D[k]); st_cd(o + (size_t)j * 8 + 4 + k, ex.U[k]); }
+        }
+        DU tot = du_shfl(x, 31);
+        carry = du_combine(carry, tot);
+    }
+}
+
+// ---- fix-up helper: URD_n = Upre * loc * Dpre (MODE_URD) or U_n = Upre * loc (MODE_U) -------------
+__device__ __forceinline__ void load_prefix(const cd* __restrict__ pre, size_t seq, int nchunks, int c, cd Dp[4], cd Up[4]) {
+    const cd* q = pre + (seq * nchunks + c) * 8;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { Dp[k] = ld_cd(q + k); Up[k] = ld_cd(q + 4 + k); }
+}
+__device__ __forceinline__ void apply_prefix(int mode, const cd Dp[4], const cd Up[4], cd m[4]) {
+    cd t[4];
+    if (mode == TAMM_MODE_URD) { mul22(m, Dp, t); mul22(Up, t, m); }
+    else { mul22(Up, m, t); m[0] = t[0]; m[1] = t[1]; m[2] = t[2]; m[3] = t[3]; }
+}
+
+constexpr int TN = 16;  // depths per thread in the streaming kernels
+
+// grid = (lane tiles, depth tiles, P); block = 128 lanes.  Thread walks TN consecutive depths of one lane.
+__global__ void __launch_bounds__(128)
+returns_kernel(const cd* __restrict__ planes, const cd* __restrict__ pre, int N, int Q, int F, int mode, int chunk,
+               int nchunks, cd e0, cd e1, int gtm_phase, cd* __restrict__ E_HH, cd* __restrict__ E_HV,
+               cd* __restrict__ c_HHVV, double* __restrict__ aHH, double* __restrict__ aHV) {
+    const int NI = N - 1, QF = Q * F;
+    const int p = blockIdx.z;
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= QF) return;
+    const int iq = l / F, ifr = l - iq * F;
+    const int nb = blockIdx.y * TN, ne = min(NI, nb + TN);
+    const cd* in = planes + ((size_t)p * NI * 4) * QF + l;
+    const size_t obase = (((size_t)p * Q + iq) * NI) * F + ifr;
+    cd Dp[4], Up[4];
+    int cc = -1;
+    for (int n = nb; n < ne; ++n) {
+        const cd* ip = in + (size_t)n * 4 * QF;
+        cd m[4] = {ld_cd(ip), ld_cd(ip + QF), ld_cd(ip + 2 * (size_t)QF), ld_cd(ip + 3 * (size_t)QF)};
+        if (nchunks > 1) {
+            int c = n / chunk;
+            if (c != cc) { load_prefix(pre, (size_t)p * QF + l, nchunks, c, Dp, Up); cc = c; }
+            if (c > 0) apply_prefix(mode, Dp, Up, m);
+        }
+        // get_Rx_all (layerstack.py:298): E_Rx = URD @ E_Tx
+        cd hh = m[0] * e0 + m[1] * e1;
+        cd hv = m[2] * e0 + m[3] * e1;
+        // c_HHVV (layerstack.py:271-278)
+        cd num = m[0] * conj(m[3]);
+        double den = cabs_(m[0]) * cabs_(m[3]);
+        cd c = cd{num.re / den, num.im / den};
+        if (gtm_phase) c = cd{-c.re, c.im};   // -|c| exp(-i angle c) = -conj(c)
+        const size_t o = obase + (size_t)n * F;
+        st_cd(E_HH + o, hh);
+        st_cd(E_HV + o, hv);
+        st_cd(c_HHVV + o, c);
+        aHH[o] = cabs_(hh);
+        aHV[o] = cabs_(hv);
+    }
+}
+
+// one warp per (p, iq, n): azimuth mean of |E|, dB, anomaly (layerstack.py:257-267).  a* hold |E| on entry, dP on exit.
+__global__ void __launch_bounds__(256)
+power_kernel(double* __restrict__ aHH, double* __restrict__ aHV, double* __restrict__ Pm_HH, double* __restrict__ Pm_HV,
+             long nrows, int F) {
+    const int lane = threadIdx.x & 31;
+    const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= nrows) return;
+    double* h = aHH + (size_t)row * F;
+    double* v = aHV + (size_t)row * F;
+    double sh = 0.0, sv = 0.0;
+    for (int f = lane; f < F; f += 32) { sh += h[f]; sv += v[f]; }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        sh += __shfl_xor_sync(0xffffffffu, sh, off);
+        sv += __shfl_xor_sync(0xffffffffu, sv, off);
+    }
+    const double pmh = 20.0 * log10(sh / (double)F);
+    const double pmv = 20.0 * log10(sv / (double)F);
+    if (lane == 0) { Pm_HH[row] = pmh; Pm_HV[row] = pmv; }
+    for (int f = lane; f < F; f += 32) {
+        h[f] = 20.0 * log10(h[f]) - pmh;
+        v[f] = 20.0 * log10(v[f]) - pmv;
+    }
+}
+
+// planes (+prefix) -> reference layout [P][Q][F][N-1][2][2]
+__global__ void __launch_bounds__(128)
+export_kernel(const cd* __restrict__ planes, const cd* __restrict__ pre, int N, int QF, int mode, int chunk, int nchunks,
+              cd* __restrict__ out) {
+    const int NI = N - 1;
+    const int p = blockIdx.z;
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= QF) return;
+    const int nb = blockIdx.y * TN, ne = min(NI, nb + TN);
+    const cd* in = planes + ((size_t)p * NI * 4) * QF + l;
+    cd* o = out + (((size_t)p * QF + l) * NI) * 4;
+    cd Dp[4], Up[4];
+    int cc = -1;
+    for (int n = nb; n < ne; ++n) {
+        const cd* ip = in + (size_t)n * 4 * QF;
+        cd m[4] = {ld_cd(ip), ld_cd(ip + QF), ld_cd(ip + 2 * (size_t)QF), ld_cd(ip + 3 * (size_t)QF)};
+        if (nchunks > 1) {
+            int c = n / chunk;
+            if (c != cc) { load_prefix(pre, (size_t)p * QF + l, nchunks, c, Dp, Up); cc = c; }
+            if (c > 0) apply_prefix(mode, Dp, Up, m);
+        }
+        cd* op = o + (size_t)n * 4;
+        st_cd(op, m[0]); st_cd(op + 1, m[1]); st_cd(op + 2, m[2]); st_cd(op + 3, m[3]);
+    }
+}
+
+__global__ void __launch_bounds__(128)
+layer_diag_kernel(const double* __restrict__ layers, const double* __restrict__ lanes, int N, int QF, double zeta, double mu,
+                  cd* A, cd* Ainv, cd* Mfwd, cd* Mrev, cd* qs, cd* gamma, cd* eps, cd* Delta, cd* Py, cd* Kd, int* status) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;  // i = l*N + n
+    if (i >= (long)QF * N) return;
+    const int l = (int)(i / N), n = (int)(i - (long)l * N);
+    LayerParams lp;
+    LaneParams ln;
+    const double* a = layers + (size_t)n * LAYER_STRIDE;
+    lp.t20 = a[0]; lp.n21r = a[1]; lp.n21i = a[2]; lp.n22r = a[3]; lp.n22i = a[4];
+    lp.mono = a[5]; lp.deps = a[6]; lp.sigma = a[7]; lp.dz = a[8]; lp.pad = 0;
+    const double* b = lanes + (size_t)l * LANE_STRIDE;
+    ln.c1 = b[0]; ln.s1 = b[1]; ln.c2 = b[2]; ln.s2 = b[3]; ln.twopif = b[4]; ln.w_eps0 = b[5]; ln.pad0 = 0; ln.pad1 = 0;
+    LayerMats L;
+    LayerDiag d;
+    int st = layer_solve(lp, ln, zeta, mu, L, &d);
+    if (status) status[i] = st;
+    for (int r = 0; r < 4; ++r)
+        for (int c = 0; c < 4; ++c) {
+            if (A) A[i * 16 + r * 4 + c] = L.A[r][c];
+            if (Ainv) Ainv[i * 16 + r * 4 + c] = L.Ai[r][c];
+            if (Delta) Delta[i * 16 + r * 4 + c] = d.Delta[r][c];
+        }
+    for (int k = 0; k < 2; ++k) {
+        if (Mfwd) Mfwd[i * 2 + k] = L.Mfwd[k];
+        if (Mrev) Mrev[i * 2 + k] = L.Mrev[k];
+    }
+    for (int k = 0; k < 4; ++k) {
+        if (qs) qs[i * 4 + k] = d.qs[k];
+        if (Kd) Kd[i * 4 + k] = d.Kd[k];
+        for (int j = 0; j < 3; ++j) {
+            if (gamma) gamma[i * 12 + k * 3 + j] = d.gamma[k][j];
+            if (Py) Py[i * 12 + j * 4 + k] = d.Py[j][k];
+        }
+    }
+    if (eps)
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) eps[i * 9 + r * 3 + c] = d.eps[r][c];
+}
+
+__global__ void __launch_bounds__(256) fp64_probe_kernel(double* out, int iters, double a, double b) {
+    double x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = threadIdx.x * 1e-3 + i;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = fma(x[i], a, b);
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += x[i];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+int nchunks_of(int N, int chunk) { return (N - 1 + chunk - 1) / chunk; }
+
+int pick_block(int QF) {
+    // smallest padding waste among multiples of 32 up to 256 (ties -> larger block)
+    int best = 32;
+    double bestw = 1e9;
+    for (int tb = 32; tb <= 256; tb += 32) {
+        int tiles = (QF + tb - 1) / tb;
+        double waste = (double)tiles * tb / QF;
+        if (waste <= bestw + 1e-12) { bestw = waste; best = tb; }
+    }
+    return best;
+}
+
+bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+}  // namespace
+
+extern "C" {
+
+int tamm_version(void) { return 100; }
+const char* tamm_last_error(void) { return g_err; }
+
+int tamm_check_device(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) return fail("no CUDA device available: %s", cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail("device index out of range%s (%ld)", "", device);
+    cudaDeviceProp pr;
+    CUDA_OK(cudaGetDeviceProperties(&pr, device));
+    if (pr.major != 10) return fail("tamm_b200 is built for sm_100a only; device is %s (cc major %ld)", pr.name, pr.major);
+    return 0;
+}
+
+int tamm_fp64_probe(double* out, int blocks, int iters, void* stream) {
+    if (!out || blocks < 1 || iters < 1) return fail("tamm_fp64_probe: bad arguments%s", "");
+    fp64_probe_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(out, iters, 0.999999, 1e-9);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int tamm_layer_matrices(const double* layers, const double* lanes, int N, int QF, double zeta, double mu, void* A,
+                        void* Ainv, void* Mfwd, void* Mrev, void* qs, void* gamma, void* eps, void* Delta, void* Py,
+                        void* Kd, int* status, void* stream) {
+    if (!layers || !lanes) return fail("tamm_layer_matrices: null input%s", "");
+    if (N < 1 || QF < 1) return fail("tamm_layer_matrices: empty problem%s", "");
+    long tot = (long)N * QF;
+    int grid = (int)((tot + 127) / 128);
+    layer_diag_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(layers, lanes, N, QF, zeta, mu, (cd*)A, (cd*)Ainv, (cd*)Mfwd,
+                                                               (cd*)Mrev, (cd*)qs, (cd*)gamma, (cd*)eps, (cd*)Delta,
+                                                               (cd*)Py, (cd*)Kd, status);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+size_t tamm_stack_workspace_bytes(int P, int N, int QF, int chunk) {
+    if (P < 1 || N < 2 || QF < 1 || chunk < 1) return 0;
+    int nch = nchunks_of(N, chunk);
+    if (nch <= 1) return 16;
+    return (size_t)2 * P * QF * nch * 8 * sizeof(cd);
+}
+
+int tamm_suggest_chunk(int P, int N, int QF, int sm_count) {
+    if (N < 2) return 1;
+    const int NI = N - 1;
+    int tb = pick_block(QF);
+    long blocks_per_chunk = (long)P * ((QF + tb - 1) / tb);
+    // aim for >= 4 resident-CTA waves worth of blocks (1 CTA of <=256 threads per SM at 255 regs)
+    long want_blocks = 4L * (sm_count > 0 ? sm_count : 148);
+    long nch = (want_blocks + blocks_per_chunk - 1) / blocks_per_chunk;
+    if (nch < 1) nch = 1;
+    long chunk = (NI + nch - 1) / nch;
+    if (chunk < 8) chunk = 8;       // bound the 1-layer halo overhead at 12.5 %
+    if (chunk > NI) chunk = NI;
+    return (int)chunk;
+}
+
+int tamm_stack_urd(const double* layers, const double* lanes, int P, int N, int Q, int F, double zeta, double mu, int mode,
+                   int chunk, void* planes, void* workspace, int* status, void* stream) {
+    if (!layers || !lanes || !planes) return fail("tamm_stack_urd: null pointer%s", "");
+    if (P < 1 || Q < 1 || F < 1) return fail("tamm_stack_urd: empty batch%s", "");
+    if (N < 2) return fail("tamm_stack_urd: need at least 2 layers (N=%s%ld)", "", N);
+    if (chunk < 1) return fail("tamm_stack_urd: chunk must be >= 1%s", "");
+    if (mode != TAMM_MODE_URD && mode != TAMM_MODE_U) return fail("tamm_stack_urd: unknown mode%s (%ld)", "", mode);
+    if (!aligned16(layers) || !aligned16(lanes) || !aligned16(planes) || !aligned16(workspace))
+        return fail("tamm_stack_urd: buffers must be 16-byte aligned%s", "");
+    if (!(mu != 0.0)) return fail("tamm_stack_urd: mu must be non-zero%s", "");
+    const int QF = Q * F;
+    const int nch = nchunks_of(N, chunk);
+    if (nch > 65535 || P > 65535) return fail("tamm_stack_urd: grid too large (chunks/profiles > 65535)%s", "");
+    if (nch > 1 && !workspace) return fail("tamm_stack_urd: workspace required%s", "");
+    const int tb = pick_block(QF);
+    dim3 grid((QF + tb - 1) / tb, nch, P);
+    cd* agg = (cd*)workspace;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (mode == TAMM_MODE_URD)
+        stack_kernel<TAMM_MODE_URD><<<grid, tb, 0, s>>>(layers, lanes, N, QF, zeta, mu, chunk, nch, (cd*)planes, agg, status);
+    else
+        stack_kernel<TAMM_MODE_U><<<grid, tb, 0, s>>>(layers, lanes, N, QF, zeta, mu, chunk, nch, (cd*)planes, agg, status);
+    CUDA_OK(cudaGetLastError());
+    if (nch > 1) {
+        long nseq = (long)P * QF;
+        cd* pre = agg + (size_t)nseq * nch * 8;
+        int grid2 = (int)((nseq + 3) / 4);
+        chunk_scan_kernel<<<grid2, 128, 0, s>>>(agg, pre, nseq, nch);
+        CUDA_OK(cudaGetLastError());
+    }
+    return 0;
+}
+
+int tamm_export_jones(const void* planes, const void* workspace, int P, int N, int Q, int F, int mode, int chunk, void* out,
+                      void* stream) {
+    if (!planes || !out) return fail("tamm_export_jones: null pointer%s", "");
+    if (P < 1 || N < 2 || Q < 1 || F < 1 || chunk < 1) return fail("tamm_export_jones: bad sizes%s", "");
+    const int QF = Q * F, NI = N - 1, nch = nchunks_of(N, chunk);
+    const cd* pre = nch > 1 ? (const cd*)workspace + (size_t)P * QF * nch * 8 : nullptr;
+    dim3 grid((QF + 127) / 128, (NI + TN - 1) / TN, P);
+    export_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>((const cd*)planes, pre, N, QF, mode, chunk, nch, (cd*)out);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int tamm_returns(const void* planes, const void* workspace, int P, int N, int Q, int F, int mode, int chunk, const double* etx,
+                 int gtm_phase, void* E_HH, void* E_HV, void* c_HHVV, double* dP_HH, double* dP_HV, double* Pm_HH,
+                 double* Pm_HV, void* stream) {
+    if (!planes || !etx || !E_HH || !E_HV || !c_HHVV || !dP_HH || !dP_HV || !Pm_HH || !Pm_HV)
+        return fail("tamm_returns: null pointer%s", "");
+    if (P < 1 || N < 2 || Q < 1 || F < 1 || chunk < 1) return fail("tamm_returns: bad sizes%s", "");
+    const int QF = Q * F, NI = N - 1, nch = nchunks_of(N, chunk);
+    const cd* pre = nch > 1 ? (const cd*)workspace + (size_t)P * QF * nch * 8 : nullptr;
+    cudaStream_t s = (cudaStream_t)stream;
+    dim3 grid((QF + 127) / 128, (NI + TN - 1) / TN, P);
+    returns_kernel<<<grid, 128, 0, s>>>((const cd*)planes, pre, N, Q, F, mode, chunk, nch, cd{etx[0], etx[1]},
+                                        cd{etx[2], etx[3]}, gtm_phase, (cd*)E_HH, (cd*)E_HV, (cd*)c_HHVV, dP_HH, dP_HV);
+    CUDA_OK(cudaGetLastError());
+    long nrows = (long)P * Q * NI;
+    int grid2 = (int)((nrows + 7) / 8);
+    power_kernel<<<grid2, 256, 0, s>>>(dP_HH, dP_HV, Pm_HH, Pm_HV, nrows, F);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,153 @@
+"""
+Device-side driver of the hot path: owns the device buffers (torch tensors) and calls the C ABI.
+
+Batch axes: P profiles x Q frequencies x F azimuths ("lane" = iq*F + ifr) x N layers.
+Reference entry points covered: LayerStack.get_layerstack + get_T_R + get_URD / get_U + get_Rx_all + the tail of
+get_returns (lib/layerstack.py:65-66, 76-132, 135-225, 232-301).
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib, packing
+
+MODE_URD = 0
+MODE_U = 1
+
+
+def _torch():
+    import torch
+    return torch
+
+
+class StackResult:
+    """Chunk-local Jones planes + chunk prefixes left on the device by tamm_stack_urd."""
+
+    def __init__(self, planes, workspace, P, N, Q, F, mode, chunk, status):
+        self.planes, self.workspace = planes, workspace
+        self.P, self.N, self.Q, self.F, self.mode, self.chunk = P, N, Q, F, mode, chunk
+        self.status = status
+
+
+class Engine:
+    def __init__(self, device=None):
+        torch = _torch()
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.TammLibraryError('tamm_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback')
+        self.device = torch.device('cuda', torch.cuda.current_device() if device is None else device)
+        _lib.check(self.lib.tamm_check_device(self.device.index), self.lib)
+        self.sm_count = torch.cuda.get_device_properties(self.device).multi_processor_count
+        self.launches = 0  # kernels launched through this engine (bench.py reports it)
+
+    # -- helpers -------------------------------------------------------------------------------
+    def _stream(self):
+        return ctypes.c_void_p(_torch().cuda.current_stream(self.device).cuda_stream)
+
+    def to_device(self, arr):
+        torch = _torch()
+        t = torch.from_numpy(np.ascontiguousarray(arr))
+        return t.to(self.device, non_blocking=False)
+
+    def empty(self, shape, dtype):
+        return _torch().empty(shape, dtype=dtype, device=self.device)
+
+    def suggest_chunk(self, P, N, QF):
+        return int(self.lib.tamm_suggest_chunk(P, N, QF, self.sm_count))
+
+    def fp64_peak_tflops(self, reps=5):
+        """FP64 CUDA-core (DFMA) peak of this device, measured with the library's probe kernel and CUDA events."""
+        torch = _torch()
+        blocks, iters = self.sm_count * 8, 4000
+        out = self.empty((blocks * 256,), torch.float64)
+        best = 0.0
+        for i in range(reps + 1):
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _lib.check(self.lib.tamm_fp64_probe(out.data_ptr(), blocks, iters, self._stream()), self.lib)
+            e1.record()
+            e1.synchronize()
+            if i:   # first launch is the warm-up
+                best = max(best, 2.0 * blocks * 256 * iters * 128 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+        return best
+
+    # -- hot path ------------------------------------------------------------------------------
+    def stack(self, layers, lanes, P, N, Q, F, zeta, mu=1.0, mode=MODE_URD, chunk=None, planes=None, workspace=None):
+        """layers: float64 device tensor (P, N, 10); lanes: float64 device tensor (Q*F, 8)."""
+        torch = _torch()
+        if np.iscomplexobj(zeta) and np.imag(zeta) != 0:
+            raise NotImplementedError('complex zeta is not supported')
+        zeta = float(np.real(zeta)); mu = float(mu)
+        QF = Q * F
+        assert layers.dtype == torch.float64 and layers.is_contiguous() and layers.numel() == P * N * packing.LAYER_STRIDE
+        assert lanes.dtype == torch.float64 and lanes.is_contiguous() and lanes.numel() == QF * packing.LANE_STRIDE
+        if chunk is None:
+            chunk = self.suggest_chunk(P, N, QF)
+        chunk = max(1, min(int(chunk), N - 1))
+        if planes is None:
+            planes = self.empty((P, N - 1, 4, QF), torch.complex128)
+        wsb = int(self.lib.tamm_stack_workspace_bytes(P, N, QF, chunk))
+        if workspace is None or workspace.numel() * 8 < wsb:
+            workspace = self.empty(((wsb + 7) // 8,), torch.float64)
+        status = torch.zeros((P,), dtype=torch.int32, device=self.device)
+        rc = self.lib.tamm_stack_urd(layers.data_ptr(), lanes.data_ptr(), P, N, Q, F, zeta, mu, mode, chunk,
+                                     planes.data_ptr(), workspace.data_ptr(), status.data_ptr(), self._stream())
+        _lib.check(rc, self.lib)
+        self.launches += 1 if (N - 1 + chunk - 1) // chunk <= 1 else 2
+        return StackResult(planes, workspace, P, N, Q, F, mode, chunk, status)
+
+    def export_jones(self, res, out=None):
+        """-> complex128 device tensor (P, Q, F, N-1, 2, 2)  (layerstack.py:194/225 layout per profile/frequency)."""
+        torch = _torch()
+        if out is None:
+            out = self.empty((res.P, res.Q, res.F, res.N - 1, 2, 2), torch.complex128)
+        rc = self.lib.tamm_export_jones(res.planes.data_ptr(), res.workspace.data_ptr(), res.P, res.N, res.Q, res.F,
+                                        res.mode, res.chunk, out.data_ptr(), self._stream())
+        _lib.check(rc, self.lib)
+        self.launches += 1
+        return out
+
+    def returns(self, res, etx, gtm_phase=True, out=None):
+        """etx = (E0*p0, E0*p1) complex.  -> dict of device tensors, depth-major (P, Q, N-1, F)."""
+        torch = _torch()
+        P, Q, F, NI = res.P, res.Q, res.F, res.N - 1
+        if out is None:
+            out = dict(E_HH=self.empty((P, Q, NI, F), torch.complex128), E_HV=self.empty((P, Q, NI, F), torch.complex128),
+                       c_HHVV=self.empty((P, Q, NI, F), torch.complex128), dP_HH=self.empty((P, Q, NI, F), torch.float64),
+                       dP_HV=self.empty((P, Q, NI, F), torch.float64), Pm_HH=self.empty((P, Q, NI), torch.float64),
+                       Pm_HV=self.empty((P, Q, NI), torch.float64))
+        e = (ctypes.c_double * 4)(float(np.real(etx[0])), float(np.imag(etx[0])), float(np.real(etx[1])), float(np.imag(etx[1])))
+        rc = self.lib.tamm_returns(res.planes.data_ptr(), res.workspace.data_ptr(), P, res.N, Q, F, res.mode, res.chunk, e,
+                                   1 if gtm_phase else 0, out['E_HH'].data_ptr(), out['E_HV'].data_ptr(),
+                                   out['c_HHVV'].data_ptr(), out['dP_HH'].data_ptr(), out['dP_HV'].data_ptr(),
+                                   out['Pm_HH'].data_ptr(), out['Pm_HV'].data_ptr(), self._stream())
+        _lib.check(rc, self.lib)
+        self.launches += 2
+        return out
+
+    def layer_matrices(self, layers, lanes, N, QF, zeta, mu=1.0):
+        """Per-(lane, layer) matrices of one profile -> dict of device tensors (QF, N, ...)."""
+        torch = _torch()
+        c = torch.complex128
+        o = dict(Ai=self.empty((QF, N, 4, 4), c), Ai_inv=self.empty((QF, N, 4, 4), c), Mfwd=self.empty((QF, N, 2), c),
+                 Mrev=self.empty((QF, N, 2), c), qs=self.empty((QF, N, 4), c), gamma=self.empty((QF, N, 4, 3), c),
+                 epsilon=self.empty((QF, N, 3, 3), c), Delta=self.empty((QF, N, 4, 4), c), Py=self.empty((QF, N, 3, 4), c),
+                 Kdiag=self.empty((QF, N, 4), c), status=self.empty((QF, N), torch.int32))
+        rc = self.lib.tamm_layer_matrices(layers.data_ptr(), lanes.data_ptr(), N, QF, float(np.real(zeta)), float(mu),
+                                          o['Ai'].data_ptr(), o['Ai_inv'].data_ptr(), o['Mfwd'].data_ptr(), o['Mrev'].data_ptr(),
+                                          o['qs'].data_ptr(), o['gamma'].data_ptr(), o['epsilon'].data_ptr(),
+                                          o['Delta'].data_ptr(), o['Py'].data_ptr(), o['Kdiag'].data_ptr(),
+                                          o['status'].data_ptr(), self._stream())
+        _lib.check(rc, self.lib)
+        self.launches += 1
+        return o
+
+
+_engine = None
+
+
+def get_engine():
+    global _engine
+    if _engine is None:
+        _engine = Engine()
+    return _engine

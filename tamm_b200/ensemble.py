@@ -1,0 +1,131 @@
+"""
+Batched public API: many fabric profiles (and/or frequencies) through one solver call.
+
+`EnsembleStack` is the extension of `LayerStack` (lib/layerstack.py:12-47) to a leading profile axis: one
+`get_returns` gives what P separate `LayerStack(nlm[p], z, ...).get_returns(...)` calls give, stacked.  Profiles are
+independent, so they are also the unit that is sharded over the GPUs of a box (`shard=(rank, world)`).
+
+Host <-> device traffic is explicit: inputs are packed on the host, copied from pinned memory, results are copied
+into pinned host arrays; profile batches are double-buffered so the D2H copy of batch b overlaps the kernels of b+1.
+"""
+import numpy as np
+
+from . import packing
+from .engine import MODE_U, MODE_URD, get_engine
+
+RETURN_NAMES = ('Pm_HH', 'Pm_HV', 'dP_HH', 'dP_HV', 'c_HHVV', 'E_HH', 'E_HV')
+
+
+def shard_range(P, rank, world):
+    """Contiguous, balanced split of P profiles over `world` ranks: [lo, hi) of `rank`."""
+    base, rem = divmod(P, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class EnsembleStack:
+
+    def __init__(self, nlm, z, N_frames=100, epsa=(3.17 - 0.034,), epsc=(3.17,), sigma=(1e-5,), mu=1, modeltype='GTM',
+                 shard=(0, 1), VERBOSE=0):
+        """nlm: (P, N, >=6) complex; z: (N,) shared interface depths; epsa/epsc/sigma: length 1, (N,) or (P, N)."""
+        if modeltype not in ('GTM', 'FP'):
+            raise ValueError('Argument "modeltype" must be either "GTM" or "FP"')
+        nlm = np.asarray(nlm)
+        if nlm.ndim != 3:
+            raise ValueError('nlm must have shape (P, N, >=6)')
+        self.modeltype = modeltype
+        self.P_total, self.N_layers = nlm.shape[:2]
+        self.rank, self.world = shard
+        self.lo, self.hi = shard_range(self.P_total, self.rank, self.world)
+        self.N_frames = N_frames
+        self.beta = np.linspace(0, np.pi, N_frames)                       # layerstack.py:25
+        z = np.asarray(z)
+        self.z = np.hstack(([np.abs(z[1] - z[0])], z))                    # layerstack.py:27
+        self.dz = np.abs(np.diff(self.z))
+        if len(self.z) != 1 + self.N_layers:
+            raise ValueError('len(z) (=%i) != 1+len(nlm) (=%i)' % (len(self.z), 1 + self.N_layers))
+        if np.any(nlm[:, 0, 1:]):
+            raise ValueError('n_2^m of top layer must vanish (surface layer must be isotropic)')
+        self.mu = mu
+
+        def expand(v):
+            v = np.asarray(v)
+            if v.ndim == 1 and v.size == 1:
+                return np.full((self.P_total, self.N_layers), v[0])
+            return np.broadcast_to(v, (self.P_total, self.N_layers))
+        self.epsa, self.epsc, self.sigma = expand(epsa), expand(epsc), expand(sigma)
+        self.nlm = nlm[:, :, :6]
+        if VERBOSE:
+            print('Initialized "%s" ensemble: profiles x frames x layers = %i x %i x %i (rank %i/%i holds %i)' % (
+                modeltype, self.P_total, N_frames, self.N_layers, self.rank, self.world, self.hi - self.lo))
+
+    @property
+    def P_local(self):
+        return self.hi - self.lo
+
+    def zeta(self, alpha):
+        epsiso = (2 * self.epsa[0, 0] + self.epsc[0, 0]) / 3              # layerstack.py:236
+        return np.sqrt(epsiso) * np.sin(alpha)
+
+    def packed_layers(self, lo=None, hi=None):
+        lo = self.lo if lo is None else lo
+        hi = self.hi if hi is None else hi
+        sl = slice(lo, hi)
+        dz = np.broadcast_to(self.dz, (hi - lo, self.N_layers))
+        return packing.pack_layers(self.nlm[sl], dz, self.epsa[sl], self.epsc[sl], self.sigma[sl])
+
+    def get_returns(self, E0, f=179.0e6, alpha=0, Tx_pol=([1, 0],), URD='URD', batch=None, out=None, outputs=RETURN_NAMES):
+        """-> dict name -> host array for the local shard, shapes (P_local, [Q,] N-1, F) / (P_local, [Q,] N-1).
+        Same numbers as LayerStack.get_returns per profile (layerstack.py:232-288)."""
+        import torch
+        if self.modeltype != 'GTM':
+            raise NotImplementedError('modeltype="FP" (Fujita-Paren) is not implemented on the device yet')
+        if URD not in ('URD', 'U'):
+            raise ValueError('get_returns(): argument URD="%s" not understood' % (URD))
+        mode = MODE_URD if URD == 'URD' else MODE_U
+        eng = get_engine()
+        fa = np.atleast_1d(np.asarray(f, dtype=np.float64))
+        Q, F, N, NI, Pl = fa.size, self.N_frames, self.N_layers, self.N_layers - 1, self.P_local
+        zeta = self.zeta(alpha)
+        p = Tx_pol[0]
+        etx = np.array([E0 * p[0], E0 * p[1]], dtype=np.complex128)
+        if batch is None:   # keep device buffers around 2 x 4 GiB
+            batch = max(1, min(Pl, int(4 * 2 ** 30 // max(1, 64 * NI * Q * F))))
+        shapes = {n: ((Pl, Q, NI) if n.startswith('Pm') else (Pl, Q, NI, F)) for n in RETURN_NAMES}
+        dtypes = {n: (torch.complex128 if n in ('c_HHVV', 'E_HH', 'E_HV') else torch.float64) for n in RETURN_NAMES}
+        if out is None:
+            out = {n: torch.empty(shapes[n], dtype=dtypes[n], pin_memory=True) for n in outputs}
+        lanes = eng.to_device(packing.pack_lanes(self.beta, fa))
+        compute, copy = torch.cuda.current_stream(eng.device), torch.cuda.Stream(eng.device)
+        dev = [None, None]
+        done = [None, None]
+        planes = [None, None]
+        for bi, b0 in enumerate(range(0, Pl, batch)):
+            b1 = min(Pl, b0 + batch)
+            k = bi & 1
+            if done[k] is not None:
+                compute.wait_event(done[k])       # the previous D2H from this buffer set must have finished
+            lay_h = torch.from_numpy(self.packed_layers(self.lo + b0, self.lo + b1)).pin_memory()
+            lay = lay_h.to(eng.device, non_blocking=True)
+            if planes[k] is None or planes[k].shape[0] != b1 - b0:
+                planes[k] = eng.empty((b1 - b0, NI, 4, Q * F), torch.complex128)
+                dev[k] = None
+            res = eng.stack(lay, lanes, b1 - b0, N, Q, F, zeta, self.mu, mode, planes=planes[k])
+            dev[k] = eng.returns(res, etx, gtm_phase=True, out=dev[k])
+            ready = torch.cuda.Event()
+            ready.record(compute)
+            with torch.cuda.stream(copy):
+                copy.wait_event(ready)
+                for n in outputs:
+                    out[n][b0:b1].copy_(dev[k][n], non_blocking=True)
+                done[k] = torch.cuda.Event()
+                done[k].record(copy)
+        copy.synchronize()
+        compute.synchronize()
+        squeeze_q = (np.ndim(f) == 0)
+        res = {}
+        for n in outputs:
+            a = out[n].numpy()
+            res[n] = a[:, 0] if squeeze_q else a
+        self._pinned = out
+        return res

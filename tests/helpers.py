@@ -1,0 +1,121 @@
+"""Shared helpers of the test-suite: golden fixtures, oracle drivers, error metrics and the parity tolerances."""
+import glob
+import os
+
+import numpy as np
+
+import tamm_oracle as orc
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+RET_NAMES = ['Pm_HH', 'Pm_HV', 'dP_HH', 'dP_HV', 'c_HHVV', 'E_HH', 'E_HV']
+
+# north_star tolerances
+RTOL_COMPLEX = 1e-9   # complex reflection coefficients (URD, E_HH, E_HV), relative to the per-azimuth peak over depth
+ATOL_DB = 1e-6        # return power in dB
+
+
+def golden_names():
+    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, '*.npz')))
+
+
+def load_golden(name):
+    return dict(np.load(os.path.join(GOLDEN_DIR, name + '.npz'), allow_pickle=False))
+
+
+def stack_kwargs(g):
+    kw = {}
+    for k in ('epsa', 'epsc', 'sigma'):
+        if 'kw_' + k in g:
+            kw[k] = g['kw_' + k]
+    return kw
+
+
+def returns_kwargs(g):
+    kw = {}
+    if 'kw_Tx_pol' in g:
+        kw['Tx_pol'] = tuple(list(p) for p in g['kw_Tx_pol'])
+    if 'kw_URD' in g:
+        kw['URD'] = str(g['kw_URD'])
+    if 'kw_nn' in g:
+        kw['nn'] = int(g['kw_nn'])
+    return kw
+
+
+def oracle_stack(g):
+    return orc.OracleStack(g['nlm'], g['z'], N_frames=int(g['F']), **stack_kwargs(g))
+
+
+def peak_rel_err(got, want, axis):
+    """max |got - want| / (max over `axis` of |want|): error relative to the per-lane peak over depth."""
+    scale = np.abs(want).max(axis=axis, keepdims=True)
+    scale = np.where(scale == 0, 1.0, scale)
+    return float((np.abs(got - want) / scale).max())
+
+
+def elem_rel_err(got, want, floor=0.0):
+    with np.errstate(all='ignore'):
+        m = np.abs(want) > floor
+        return float((np.abs(got - want)[m] / np.abs(want)[m]).max()) if m.any() else 0.0
+
+
+def db_err(got, want):
+    """max |dB difference| where both are finite (exactly-zero cross-pol returns give -inf / nan in both)."""
+    fin = np.isfinite(want) & np.isfinite(got)
+    same_nonfinite = np.array_equal(np.isfinite(want), np.isfinite(got))
+    return (float(np.abs(got - want)[fin].max()) if fin.any() else 0.0), same_nonfinite
+
+
+def field_scale(ret):
+    """Per-azimuth scale of the received field: peak over depth of |(E_HH, E_HV)|.  Errors of a Jones matrix are
+    uniform over its components (and the cross-polar return vanishes identically at beta = 0, pi), so single
+    components are compared relative to this, not to their own magnitude."""
+    f = np.sqrt(np.abs(ret['E_HH']) ** 2 + np.abs(ret['E_HV']) ** 2)
+    s = f.max(axis=0, keepdims=True) if f.ndim == 2 else np.asarray(f.max())
+    return np.where(s == 0, 1.0, s)
+
+
+def assert_parity(got, want, arbiter=None, c_atol=1e-7, names=RET_NAMES):
+    """The parity criterion of this repository for the 7-tuple of get_returns (layerstack.py:280-283).
+
+    got     : CUDA path;  want : reference fixture / double-precision oracle;
+    arbiter : the same outputs from the extended-precision oracle (optional).
+      complex fields  |got - want| <= 1e-9 * field_scale                       (north_star: 1e-9 relative)
+      powers in dB    |got - want| <= 1e-6, anomalies dP only outside nulls    (north_star: 1e-6 dB)
+      coherence       |got - want| <= c_atol
+    The reference's own LAPACK eigenvalues are ~25 ulp from the true roots, which on smooth deep profiles puts the
+    reference itself ~1e-9 (of peak) away from the exact result.  When an arbiter is given the bound against `want`
+    is therefore widened by twice the reference's own deviation from the arbiter, element by element, and `got`
+    must additionally meet the plain tolerance against the arbiter."""
+    got = {n: np.asarray(a) for n, a in zip(names, got)}
+    want = {n: np.asarray(a) for n, a in zip(names, want)}
+    arb = None if arbiter is None else {n: np.asarray(a).astype(want[n].dtype) for n, a in zip(names, arbiter)}
+    scale = field_scale(want)
+    report = {}
+    with np.errstate(all='ignore'):
+        for n in names:
+            a, b = got[n], want[n]
+            assert a.shape == b.shape, (n, a.shape, b.shape)
+            assert a.dtype == b.dtype, (n, a.dtype, b.dtype)
+            ok = np.isfinite(a) & np.isfinite(b)
+            if n in ('E_HH', 'E_HV'):
+                tol = RTOL_COMPLEX * scale * np.ones(b.shape)
+            elif n == 'c_HHVV':
+                tol = np.full(b.shape, c_atol)
+            else:
+                tol = np.full(b.shape, ATOL_DB)
+                if n.startswith('dP'):     # dB of a null is unbounded in any finite precision
+                    amp = np.abs(want['E_HH'] if n.endswith('HH') else want['E_HV'])
+                    mean = amp.mean(axis=-1, keepdims=True) if amp.ndim == 2 else amp
+                    ok &= amp >= 1e-3 * mean
+            slack = 0.0
+            if arb is not None:
+                x = arb[n]
+                ok &= np.isfinite(x)
+                slack = 2 * np.abs(b - x)
+                bad = ok & (np.abs(a - x) > tol)
+                assert not bad.any(), (n, 'vs arbiter', float((np.abs(a - x) / tol)[ok].max()))
+            err = np.abs(a - b)
+            bad = ok & (err > tol + slack)
+            assert not bad.any(), (n, 'vs reference', float((err / (tol + slack))[ok].max()))
+            report[n] = float((err / tol)[ok].max()) if ok.any() else 0.0
+    return report

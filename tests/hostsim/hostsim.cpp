@@ -1,0 +1,90 @@
+// TEST INFRASTRUCTURE ONLY -- compiles tamm_b200/csrc/tamm_core.cuh with the host compiler so the exact
+// per-layer arithmetic of the CUDA kernels can be checked against the oracle on a machine without a GPU.
+// Nothing in the product (tamm_b200/, lib/) loads this library.
+#include "../../tamm_b200/csrc/tamm_core.cuh"
+#include <cstring>
+#include <vector>
+using namespace tamm;
+
+static inline void put(double* dst, cd v) { dst[0] = v.re; dst[1] = v.im; }
+
+extern "C" {
+
+// Per-(lane, layer) matrices.  All outputs are complex128 laid out (F, N, ...).
+int hostsim_layers(const double* layers, const double* lanes, int N, int F, double zeta, double mu, double* A,
+                   double* Ai, double* Mfwd, double* Mrev, double* qs, double* gamma, double* eps, double* Delta,
+                   double* Py, int* status) {
+    for (int f = 0; f < F; ++f) {
+        LaneParams ln; std::memcpy(&ln, lanes + (size_t)f * LANE_STRIDE, sizeof(ln));
+        for (int n = 0; n < N; ++n) {
+            LayerParams lp; std::memcpy(&lp, layers + (size_t)n * LAYER_STRIDE, sizeof(lp));
+            LayerMats L; LayerDiag d;
+            int st = layer_solve(lp, ln, zeta, mu, L, &d);
+            size_t i = (size_t)f * N + n;
+            status[i] = st;
+            for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) {
+                put(A + (i * 16 + r * 4 + c) * 2, L.A[r][c]);
+                put(Ai + (i * 16 + r * 4 + c) * 2, L.Ai[r][c]);
+                put(Delta + (i * 16 + r * 4 + c) * 2, d.Delta[r][c]);
+            }
+            for (int k = 0; k < 2; ++k) { put(Mfwd + (i * 2 + k) * 2, L.Mfwd[k]); put(Mrev + (i * 2 + k) * 2, L.Mrev[k]); }
+            for (int k = 0; k < 4; ++k) {
+                put(qs + (i * 4 + k) * 2, d.qs[k]);
+                for (int j = 0; j < 3; ++j) put(gamma + (i * 12 + k * 3 + j) * 2, d.gamma[k][j]);
+                for (int j = 0; j < 3; ++j) put(Py + (i * 12 + j * 4 + k) * 2, d.Py[j][k]);
+            }
+            for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) put(eps + (i * 9 + r * 3 + c) * 2, d.eps[r][c]);
+        }
+    }
+    return 0;
+}
+
+// URD (mode 0) or U (mode 1) with the kernels' chunked accumulation: local products per chunk, exclusive
+// prefix over chunk aggregates, fix-up  URD_n = Upre_c * URDloc_n * Dpre_c.  Output (F, N-1, 2, 2) complex128.
+int hostsim_urd(const double* layers, const double* lanes, int N, int F, double zeta, double mu, int chunk, int mode,
+                double* out) {
+    if (N < 2 || chunk < 1) return 1;
+    const int NI = N - 1;
+    const int nchunks = (NI + chunk - 1) / chunk;
+    std::vector<cd> Dagg((size_t)nchunks * 4), Uagg((size_t)nchunks * 4);
+    for (int f = 0; f < F; ++f) {
+        LaneParams ln; std::memcpy(&ln, lanes + (size_t)f * LANE_STRIDE, sizeof(ln));
+        cd* o = reinterpret_cast<cd*>(out) + (size_t)f * NI * 4;
+        for (int c = 0; c < nchunks; ++c) {
+            int n0 = c * chunk, n1 = std::min(NI, n0 + chunk);
+            LayerParams lp; std::memcpy(&lp, layers + (size_t)n0 * LAYER_STRIDE, sizeof(lp));
+            LayerMats prev; layer_solve(lp, ln, zeta, mu, prev, nullptr);
+            cd D[4] = {mk(1), mk(0), mk(0), mk(1)}, U[4] = {mk(1), mk(0), mk(0), mk(1)};
+            for (int n = n0; n < n1; ++n) {
+                std::memcpy(&lp, layers + (size_t)(n + 1) * LAYER_STRIDE, sizeof(lp));
+                LayerMats next; layer_solve(lp, ln, zeta, mu, next, nullptr);
+                cd prevAr[4][2];
+                for (int r = 0; r < 4; ++r) { prevAr[r][0] = prev.A[r][2]; prevAr[r][1] = prev.A[r][3]; }
+                cd R[4], Dm[4], Um[4];
+                interface_mats(prev.Ai, prevAr, next, R, Dm, Um);
+                if (mode == 0) { cd RD[4]; mul22(R, D, RD); mul22(U, RD, o + (size_t)n * 4); }
+                else { for (int k = 0; k < 4; ++k) o[(size_t)n * 4 + k] = U[k]; }
+                mul22(Dm, D, D);     // D_{n+1} = D_mul_n D_n       layerstack.py:189
+                mul22(U, Um, U);     // U_{n+1} = U_n U_mul_n       layerstack.py:190
+                prev = next;
+            }
+            for (int k = 0; k < 4; ++k) { Dagg[(size_t)c * 4 + k] = D[k]; Uagg[(size_t)c * 4 + k] = U[k]; }
+        }
+        cd Dp[4] = {mk(1), mk(0), mk(0), mk(1)}, Up[4] = {mk(1), mk(0), mk(0), mk(1)};
+        for (int c = 0; c < nchunks; ++c) {
+            int n0 = c * chunk, n1 = std::min(NI, n0 + chunk);
+            if (c > 0) {
+                for (int n = n0; n < n1; ++n) {
+                    cd t[4];
+                    if (mode == 0) { mul22(o + (size_t)n * 4, Dp, t); mul22(Up, t, o + (size_t)n * 4); }
+                    else { mul22(Up, o + (size_t)n * 4, t); for (int k = 0; k < 4; ++k) o[(size_t)n * 4 + k] = t[k]; }
+                }
+            }
+            mul22(&Dagg[(size_t)c * 4], Dp, Dp);
+            mul22(Up, &Uagg[(size_t)c * 4], Up);
+        }
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,82 @@
+"""The exact per-layer arithmetic of the CUDA kernels (tamm_b200/csrc/tamm_core.cuh), compiled for the host by
+tests/hostsim (test-only), against the oracle.  This is how kernel numerics are checked where there is no GPU."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+import helpers as h
+import tamm_oracle as orc
+from tamm_b200 import packing
+
+dp = ctypes.POINTER(ctypes.c_double)
+
+
+@pytest.fixture(scope='module')
+def sim(built):
+    lib = ctypes.CDLL(os.path.join(os.path.dirname(__file__), 'hostsim', '_hostsim.so'))
+    return lib
+
+
+def _P(a):
+    return a.ctypes.data_as(dp)
+
+
+def sim_layers(lib, os_, f, alpha):
+    N, F = os_.N_layers, os_.N_frames
+    lay = packing.pack_layers(os_.nlm, os_.dz, os_.epsa, os_.epsc, os_.sigma)
+    lan = packing.pack_lanes(os_.beta, f)
+    c = lambda *s: np.zeros(s, dtype=np.complex128)
+    o = dict(Ai=c(F, N, 4, 4), Ai_inv=c(F, N, 4, 4), Mfwd=c(F, N, 2), Mrev=c(F, N, 2), qs=c(F, N, 4), gamma=c(F, N, 4, 3),
+             epsilon=c(F, N, 3, 3), Delta=c(F, N, 4, 4), Py=c(F, N, 3, 4))
+    st = np.zeros((F, N), dtype=np.int32)
+    lib.hostsim_layers(_P(lay), _P(lan), N, F, ctypes.c_double(float(os_.zeta(alpha))), ctypes.c_double(os_.mu),
+                       *[_P(o[k]) for k in ['Ai', 'Ai_inv', 'Mfwd', 'Mrev', 'qs', 'gamma', 'epsilon', 'Delta', 'Py']],
+                       st.ctypes.data_as(ctypes.POINTER(ctypes.c_int)))
+    o['status'] = st
+    return o
+
+
+def sim_urd(lib, os_, f, alpha, chunk, mode=0):
+    N, F = os_.N_layers, os_.N_frames
+    lay = packing.pack_layers(os_.nlm, os_.dz, os_.epsa, os_.epsc, os_.sigma)
+    lan = packing.pack_lanes(os_.beta, f)
+    out = np.zeros((F, N - 1, 2, 2), dtype=np.complex128)
+    rc = lib.hostsim_urd(_P(lay), _P(lan), N, F, ctypes.c_double(float(os_.zeta(alpha))), ctypes.c_double(os_.mu), chunk,
+                         mode, _P(out))
+    assert rc == 0
+    return out
+
+
+@pytest.mark.parametrize('name', h.golden_names())
+def test_kernel_arithmetic_layers(sim, name):
+    g = h.load_golden(name)
+    os_ = h.oracle_stack(g)
+    f, alpha = float(g['f']), float(g['alpha'])
+    L = os_.layers(f, alpha)
+    Lx = os_.layers(f, alpha, eig='factored', precision='extended')
+    H = sim_layers(sim, os_, f, alpha)
+    assert not H['status'].any()
+    assert np.abs(H['epsilon'] - L['epsilon']).max() <= 4.5e-16          # at most 1 ulp of eps
+    assert np.abs(H['Delta'] - L['Delta']).max() < 2e-15
+    # eigenvalues: same sort as the reference, and closer to the extended-precision roots than LAPACK
+    qx = Lx['qs'].astype(np.complex128)
+    assert np.abs(H['qs'] - L['qs']).max() < 5e-14
+    assert np.abs(H['qs'] - qx).max() < 2e-15
+    # gamma / A carry the reference's own eigenvalue error amplified by 1/|q_p - q_s|; compare both to the arbiter
+    for k in ('gamma', 'Ai', 'Ai_inv'):
+        ex = Lx[k].astype(np.complex128)
+        assert np.abs(H[k] - ex).max() <= max(2 * np.abs(L[k] - ex).max(), 1e-13), k
+    for k in ('Mfwd', 'Mrev'):
+        assert np.abs(H[k] - L[k]).max() < 1e-11, k
+
+
+@pytest.mark.parametrize('name', h.golden_names())
+@pytest.mark.parametrize('chunk', [1000, 16, 7, 1])
+def test_kernel_arithmetic_urd_chunked(sim, name, chunk):
+    g = h.load_golden(name)
+    os_ = h.oracle_stack(g)
+    mode = 1 if 'kw_URD' in g and str(g['kw_URD']) == 'U' else 0
+    got = sim_urd(sim, os_, float(g['f']), float(g['alpha']), chunk, mode)
+    assert h.peak_rel_err(got, g['URD'], axis=(1, 2, 3)) < h.RTOL_COMPLEX
