@@ -606,6 +606,338 @@ TAMM_HD void interface_mats(const cd prevAi[4][4], const cd prevAr[4][2], const 
     Um[2] = tpsr * next.Mrev[0]; Um[3] = tssr * next.Mrev[1];
 }
 
+// =================================================================================================
+// Hot-path formulation (stack_kernel): identical mathematics, fewer flops and half the live state.
+//
+// Write the dynamical matrix in 2x2 blocks of tangential E and H amplitudes of the transmitted (t) and reflected (r)
+// mode pairs,  A = [[Et, Er], [Ht, Hr]]  (rows 0-1 / 2-3 of layer_PPJ.py:429-433), and let Yt = Ht Et^-1, Yr = Hr Er^-1
+// be the mode-pair admittances.  Field continuity at the interface between layer n (unprimed) and n+1 (primed) gives
+//      M    = (Yt' - Yr)^-1
+//      T    = Et'^-1 M (Yt - Yr)  Et          = (Gamma[0:2,0:2])^-1                 layerstack.py:109-114
+//      R    = Er^-1  M (Yt - Yt') Et          = Gamma[2:4,0:2] T                    layerstack.py:96-106
+//      Trev = Er^-1  M (Yt' - Yr') Er'        = (Gamma_rev[2:4,2:4])^-1             layerstack.py:118-129
+// with Gamma = A^-1 A' -- the same T, R, Trev the reference obtains through two 4x4 inverses, but from 2x2 algebra
+// only, and with the small reflection matrix formed from the explicit difference Yt - Yt'.
+// =================================================================================================
+TAMM_HD void cfma(cd& acc, cd a, cd b) {   // acc += a*b, four FMAs
+    acc.re = fma(a.re, b.re, acc.re);
+    acc.re = fma(-a.im, b.im, acc.re);
+    acc.im = fma(a.re, b.im, acc.im);
+    acc.im = fma(a.im, b.re, acc.im);
+}
+TAMM_HD cd cmul_(cd a, cd b) {
+    cd r;
+    r.re = fma(a.re, b.re, -(a.im * b.im));
+    r.im = fma(a.re, b.im, a.im * b.re);
+    return r;
+}
+TAMM_HD cd dot2(cd a, cd b, cd c, cd d) {  // a*b + c*d
+    cd r = cmul_(a, b);
+    cfma(r, c, d);
+    return r;
+}
+TAMM_HD cd det2(cd a, cd b, cd c, cd d) {  // a*d - b*c
+    cd r = cmul_(a, d);
+    cfma(r, -b, c);
+    return r;
+}
+TAMM_HD void mm22(const cd a[4], const cd b[4], cd o[4]) {   // o = a b (o must not alias a or b)
+    o[0] = dot2(a[0], b[0], a[1], b[2]);
+    o[1] = dot2(a[0], b[1], a[1], b[3]);
+    o[2] = dot2(a[2], b[0], a[3], b[2]);
+    o[3] = dot2(a[2], b[1], a[3], b[3]);
+}
+TAMM_HD void inv22(const cd a[4], cd o[4]) {
+    cd id = crecip(det2(a[0], a[1], a[2], a[3]));
+    o[0] = cmul_(a[3], id); o[1] = cmul_(-a[1], id); o[2] = cmul_(-a[2], id); o[3] = cmul_(a[0], id);
+}
+
+struct LayerY {
+    cd Et[4], Er[4];     // normalised tangential-E blocks of A (row-major 2x2)
+    cd Eti[4], Eri[4];   // their inverses
+    cd Yt[4], Yr[4];     // admittances of the transmitted / reflected mode pairs
+    cd Mfwd[2], Mrev[2]; // layer.py:96-97
+};
+
+TAMM_HD double fast_abs(cd z) { return sqrt(z.re * z.re + z.im * z.im); }
+TAMM_HD cd csqrt_f(cd z) {   // principal square root, no hypot() scaling (|z| is O(1e-20 .. 1e3) here)
+    double m = fast_abs(z);
+    if (m == 0.0) return cd{0.0, 0.0};
+    double t = sqrt(0.5 * (m + fabs(z.re)));
+    double o = 0.5 * z.im / t;
+    return (z.re >= 0.0) ? cd{t, o} : cd{fabs(o), copysign(t, z.im)};
+}
+
+// eigenvalues of G = -N'^-1 N (see mslp_eigs), fused arithmetic
+TAMM_HD void mslp_eigs_f(const WaveMat& m, cd db, cd& h_big, cd& h_small) {
+    cd g00 = det2(m.dd, db, m.b, m.a);        // dd*a - db*b
+    cd g01 = det2(m.dd, db, m.d, m.b);        // dd*b - db*d
+    cd g10 = det2(m.da, db, m.a, m.b);        // da*b - db*a
+    cd g11 = det2(m.da, db, m.b, m.d);        // da*d - db*b
+    cd det1 = det2(m.da, db, db, m.dd);       // da*dd - db*db
+    cd hm = 0.5 * (g00 + g11);
+    cd hd = 0.5 * (g00 - g11);
+    cd disc = csq(hd);
+    cfma(disc, g01, g10);
+    cd s = csqrt_f(disc);
+    bool flip = (hm.re * s.re + hm.im * s.im) < 0.0;
+    s = csel(flip, -s, s);
+    cd big = hm + s;
+    cd detg = det2(g00, g01, g10, g11);
+    cd ninv = -crecip(det1);
+    cd small = (abs2(big) > 0.0) ? cmul_(detg, crecip(big)) : mk(0.0);
+    h_big = cmul_(big, ninv);
+    h_small = cmul_(small, ninv);
+}
+
+// Four roots + the (Ex, Ey) null vector of N at each root.  q0,q1: pair seeded at -sqrt(.), q2,q3: at +sqrt(.)
+TAMM_HD void eig4_fast(const WaveCoef& w, cd q[4], cd ex[4], cd ey[4]) {
+    cd c00 = w.e00 - w.e02 * (w.e02 * w.k);
+    cd c01 = w.e01 - w.e02 * w.w1;
+    cd c11 = w.d0;
+    if (w.zeta == 0.0) {
+        cd hm = 0.5 * (c00 + c11), hd = 0.5 * (c00 - c11);
+        cd s = csqrt_f(csq(hd) + csq(c01));
+        bool flip = (hm.re * s.re + hm.im * s.im) < 0.0;
+        s = csel(flip, -s, s);
+        cd lbig = hm + s;
+        cd lsmall = det2(c00, c01, c01, c11) / lbig;
+        cd r0 = csqrt_f(lbig), r1 = csqrt_f(lsmall);
+        q[0] = -r0; q[1] = -r1; q[2] = r0; q[3] = r1;
+        // N(q) = C0 - q^2 I
+        cd a0 = c00 - lbig, d0 = c11 - lbig, a1 = c00 - lsmall, d1 = c11 - lsmall;
+        bool u0 = abs2(a0) >= abs2(d0), u1 = abs2(a1) >= abs2(d1);
+        ex[0] = ex[2] = csel(u0, -c01, d0); ey[0] = ey[2] = csel(u0, a0, -c01);
+        ex[1] = ex[3] = csel(u1, -c01, d1); ey[1] = ey[3] = csel(u1, a1, -c01);
+        return;
+    }
+    cd kap = mk(1.0) + (w.zeta * w.zeta) * w.k;
+    cd qc = csqrt_f(0.5 * (c00 / kap + c11));
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int pair = 0; pair < 2; ++pair) {
+        cd centre = pair == 0 ? -qc : qc;
+        cd hb, hs;
+        {
+            WaveMat m = wave_matrix(w, centre);
+            mslp_eigs_f(m, w.db, hb, hs);
+        }
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        for (int r = 0; r < 2; ++r) {
+            cd x = centre + (r ? hs : hb);
+            // successive-linear-problem steps until the scalar Newton polish below is guaranteed to finish the job:
+            // after a step h the error is ~0.3|h|^2 and the polish turns an error e into e^2/|distance to partner|
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+            for (int it = 0; it < 24; ++it) {
+                WaveMat mm = wave_matrix(w, x);
+                cd part, h;
+                mslp_eigs_f(mm, w.db, part, h);
+                x = x + h;
+                double h2 = abs2(h);
+                if (h2 * h2 * h2 * h2 <= 1e-30 * abs2(part) * abs2(x)) break;
+            }
+            WaveMat mm = wave_matrix(w, x);
+            cd f = det2(mm.a, mm.b, mm.b, mm.d);
+            cd fp = dot2(mm.da, mm.d, mm.a, mm.dd);
+            cfma(fp, (-2.0) * mm.b, w.db);
+            cd step = (abs2(fp) > 0.0) ? cmul_(f, crecip(fp)) : mk(0.0);
+            // a polish larger than the last MSLP step means f'(x) ~ 0 (degenerate pair): keep the MSLP root
+            if (!(abs2(step) <= 1e-12 * abs2(x))) step = mk(0.0);
+            cd xr = x - step;
+            bool use0 = abs2(mm.a) >= abs2(mm.d);
+            cd vx = csel(use0, -mm.b, mm.d), vy = csel(use0, mm.a, -mm.b);
+            int idx = 2 * pair + r;
+            if (idx == 0) { q[0] = xr; ex[0] = vx; ey[0] = vy; }
+            else if (idx == 1) { q[1] = xr; ex[1] = vx; ey[1] = vy; }
+            else if (idx == 2) { q[2] = xr; ex[2] = vx; ey[2] = vy; }
+            else { q[3] = xr; ex[3] = vx; ey[3] = vy; }
+        }
+    }
+}
+
+#if defined(__CUDA_ARCH__)
+__device__ __noinline__
+#else
+inline
+#endif
+cd phase_ni(double qre, double qim, double twopif, double d, double sign) { return phase(cd{qre, qim}, twopif, d, sign); }
+
+TAMM_HD int layer_solve_fast(const LayerParams& lp, const LaneParams& ln, double zeta, double mu, LayerY& L) {
+    int status = 0;
+    const Sym3 e = permittivity(lp, ln);
+    const WaveCoef w = wave_coef(e, mu, zeta);
+    cd qu[4], vx[4], vy[4];
+    eig4_fast(w, qu, vx, vy);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < 4; ++k) qu[k] = clean_q(qu[k]);
+
+    const cd ezz = mk(e.zz, e.im);
+    const cd ib = crecip(mu * ezz);
+    const cd a20 = (-(e.xz * mu)) * ib, a21 = (-(e.yz * mu)) * ib, a24 = (-(zeta * mu)) * ib;
+    const double a51 = zeta / mu;
+    const cd D00 = zeta * a20, D02 = zeta * a21;
+    const cd iD01 = crecip(mk(mu) + zeta * a24);
+    const double imu = 1.0 / mu;
+
+    // Poynting / E-field measures for the p-s sort (layer_PPJ.py:233-276), kept as numerators and denominators
+    double px[4], ps[4], exx[4], es[4];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < 4; ++k) {
+        const cd q = qu[k];
+        cd Ex = vx[k], Ey = vy[k];
+        if (abs2(Ex) + abs2(Ey) == 0.0) { Ex = mk(1.0); Ey = mk(0.0); }
+        cd t = cmul_(q - D00, Ex);
+        cfma(t, -D02, Ey);
+        cd Hy = cmul_(t, iD01);
+        cd Hx = (-imu) * cmul_(q, Ey);
+        cd Ez = cmul_(a20, Ex);
+        cfma(Ez, a21, Ey);
+        cfma(Ez, a24, Hy);
+        cd Hz = a51 * Ey;
+        cd Px = det2(Ey, Ez, Hy, Hz);     // Ey*Hz - Ez*Hy
+        cd Py = det2(Ez, Ex, Hz, Hx);     // Ez*Hx - Ex*Hz
+        px[k] = abs2(Px); ps[k] = px[k] + abs2(Py);
+        exx[k] = abs2(Ex); es[k] = exx[k] + abs2(Ey);
+    }
+    bool has_im = (qu[0].im != 0.0) || (qu[1].im != 0.0) || (qu[2].im != 0.0) || (qu[3].im != 0.0);
+    int tmask = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < 4; ++k) {
+        bool t = has_im ? (qu[k].im >= 0.0) : (qu[k].re > 0.0);
+        tmask |= (t ? 1 : 0) << k;
+    }
+    int t0, t1, r0, r1;
+    switch (tmask) {
+        case 0x3: t0 = 0; t1 = 1; r0 = 2; r1 = 3; break;
+        case 0xC: t0 = 2; t1 = 3; r0 = 0; r1 = 1; break;
+        case 0x5: t0 = 0; t1 = 2; r0 = 1; r1 = 3; break;
+        case 0xA: t0 = 1; t1 = 3; r0 = 0; r1 = 2; break;
+        case 0x6: t0 = 1; t1 = 2; r0 = 0; r1 = 3; break;
+        case 0x9: t0 = 0; t1 = 3; r0 = 1; r1 = 2; break;
+        default:  t0 = 0; t1 = 1; r0 = 2; r1 = 3; status |= 1; break;
+    }
+    auto PX = [&](int i) { return sel4(i, px[0], px[1], px[2], px[3]); };
+    auto PS = [&](int i) { return sel4(i, ps[0], ps[1], ps[2], ps[3]); };
+    auto EX = [&](int i) { return sel4(i, exx[0], exx[1], exx[2], exx[3]); };
+    auto ES = [&](int i) { return sel4(i, es[0], es[1], es[2], es[3]); };
+    // C_a > C_b  <=>  n_a s_b > n_b s_a  for ratios C = n/s with s > 0; NaN (s = 0) compares false like the reference
+    auto gt = [](double na, double sa, double nb, double sb) { return (sa > 0.0) && (sb > 0.0) && (na * sb > nb * sa); };
+    double pa = PX(t0), sa = PS(t0), pb = PX(t1), sb = PS(t1);
+    bool biref = (sa > 0.0) && (sb > 0.0) && (fabs(pa * sb - pb * sa) > QSD_THR * (sa * sb));   // layer_PPJ.py:258
+    bool flip_t, flip_r;
+    if (biref) {
+        flip_t = gt(pb, sb, pa, sa);                                   // 260
+        flip_r = gt(PX(r1), PS(r1), PX(r0), PS(r0));                   // 263-265
+    } else {
+        flip_t = gt(EX(t1), ES(t1), EX(t0), ES(t0));                   // 269-272
+        flip_r = gt(EX(r1), ES(r1), EX(r0), ES(r0));                   // 273-276
+    }
+    int o0 = flip_t ? t1 : t0, o1 = flip_t ? t0 : t1, o2 = flip_r ? r1 : r0, o3 = flip_r ? r0 : r1;
+    const cd q0 = sel4(o0, qu[0], qu[1], qu[2], qu[3]), q1 = sel4(o1, qu[0], qu[1], qu[2], qu[3]);
+    const cd q2 = sel4(o2, qu[0], qu[1], qu[2], qu[3]), q3 = sel4(o3, qu[0], qu[1], qu[2], qu[3]);
+
+    // ---- gamma (layer_PPJ.py:309-389), unnormalised; see layer_solve for the line-by-line citations
+    const cd e00 = mk(e.xx, e.im), e11 = mk(e.yy, e.im);
+    const double m01 = mu * e.xy, m02 = mu * e.xz, m12 = mu * e.yz;
+    const cd mez = mu * ezz - zeta * zeta;
+    const cd imez = crecip(mez);
+    const cd c01m = m01 * mez;                   // mu*eps01*mez
+    const cd g23p = (-m12) * imez;               // -mu*eps21/mez
+    const double m12sq = m12 * m12;
+    const cd mzz = mu * e11 - zeta * zeta;       // mu*eps11 - zeta^2
+    const cd m00 = mu * e00;
+    cd g12, g13, g21, g23, g32, g33, g41, g43;
+    {
+        cd u0 = mk(m02) + zeta * q0, u1 = mk(m02) + zeta * q1, u2 = mk(m02) + zeta * q2, u3 = mk(m02) + zeta * q3;
+        cd g13p = (-1.0) * cmul_(u0, imez), g33p = cmul_(u2, imez);
+        // modes 0 and 2 share one form, modes 1 and 3 the other
+        cd den0 = cmul_(mez, mzz - csq(q0)) - m12sq;
+        g12 = cmul_(m12 * u0 - c01m, crecip(den0));
+        if (cisnan(g12)) g12 = mk(0.0);
+        g13 = cmul_((-1.0) * u0 - m12 * g12, imez);
+        if (cisnan(g13)) g13 = g13p;
+        cd den1 = cmul_(mez, m00 - csq(q1));
+        cfma(den1, -u1, u1);
+        g21 = cmul_(m12 * u1 - c01m, crecip(den1));
+        if (cisnan(g21)) g21 = mk(0.0);
+        cd t23 = cmul_(-u1, g21) - m12;
+        g23 = cmul_(t23, imez);
+        if (cisnan(g23)) g23 = g23p;
+        if (fast_abs(q0 - q1) < QSD_THR) { g12 = mk(0.0); g13 = g13p; g21 = mk(0.0); g23 = g23p; }
+        cd den2 = cmul_(mez, mzz - csq(q2)) - m12sq;
+        g32 = cmul_(c01m - m12 * u2, crecip(den2));
+        if (cisnan(g32)) g32 = mk(0.0);
+        g33 = cmul_(u2 + m12 * g32, imez);
+        if (cisnan(g33)) g33 = g33p;
+        cd den3 = cmul_(mez, m00 - csq(q3));
+        cfma(den3, -u3, u3);
+        g41 = cmul_(m12 * u3 - c01m, crecip(den3));
+        if (cisnan(g41)) g41 = mk(0.0);
+        cd t43 = cmul_(-u3, g41) - m12;
+        g43 = cmul_(t43, imez);
+        if (cisnan(g43)) g43 = g23p;
+        if (fast_abs(q2 - q3) < QSD_THR) { g32 = mk(0.0); g33 = g33p; g41 = mk(0.0); g43 = g23p; }
+    }
+    // row norms (layer_PPJ.py:399-402)
+    const double n0 = sqrt(1.0 + abs2(g12) + abs2(g13)), n1 = sqrt(1.0 + abs2(g21) + abs2(g23));
+    const double n2 = sqrt(1.0 + abs2(g32) + abs2(g33)), n3 = sqrt(1.0 + abs2(g41) + abs2(g43));
+    const double i0 = 1.0 / n0, i1 = 1.0 / n1, i2 = 1.0 / n2, i3 = 1.0 / n3;
+    // ---- E blocks, their inverses and the admittances
+    L.Et[0] = mk(i0); L.Et[1] = i1 * g21; L.Et[2] = i0 * g12; L.Et[3] = mk(i1);
+    L.Er[0] = mk(-i2); L.Er[1] = i3 * g41; L.Er[2] = i2 * g32; L.Er[3] = mk(i3);
+    {
+        cd idt = crecip(mk(1.0) - cmul_(g12, g21));            // 1/det [[1, g21],[g12, 1]]
+        cd ra[4] = {idt, (-1.0) * cmul_(g21, idt), (-1.0) * cmul_(g12, idt), idt};     // raw inverse
+        cd Ht[4] = {imu * (q0 - zeta * g13), imu * (cmul_(q1, g21) - zeta * g23), imu * cmul_(q0, g12), imu * q1};
+        mm22(Ht, ra, L.Yt);
+        L.Eti[0] = n0 * ra[0]; L.Eti[1] = n0 * ra[1]; L.Eti[2] = n1 * ra[2]; L.Eti[3] = n1 * ra[3];
+        cd idr = crecip(mk(-1.0) - cmul_(g32, g41));           // 1/det [[-1, g41],[g32, 1]]
+        cd rb[4] = {idr, (-1.0) * cmul_(g41, idr), (-1.0) * cmul_(g32, idr), (-1.0) * idr};
+        cd Hr[4] = {imu * ((-1.0) * q2 - zeta * g33), imu * (cmul_(q3, g41) - zeta * g43), imu * cmul_(q2, g32), imu * q3};
+        mm22(Hr, rb, L.Yr);
+        L.Eri[0] = n2 * rb[0]; L.Eri[1] = n2 * rb[1]; L.Eri[2] = n3 * rb[2]; L.Eri[3] = n3 * rb[3];
+    }
+    L.Mfwd[0] = phase_ni(q0.re, q0.im, ln.twopif, lp.dz, -1.0);
+    L.Mfwd[1] = phase_ni(q1.re, q1.im, ln.twopif, lp.dz, -1.0);
+    L.Mrev[0] = phase_ni(q2.re, q2.im, ln.twopif, lp.dz, +1.0);
+    L.Mrev[1] = phase_ni(q3.re, q3.im, ln.twopif, lp.dz, +1.0);
+    return status;
+}
+
+// Interface between layer n (carried: Et, Eri, Yt, Yr) and layer n+1 (nx).  R, Dm = Mfwd' T, Um = Trev Mrev'.
+TAMM_HD void interface_fast(const cd Et[4], const cd Eri[4], const cd Yt[4], const cd Yr[4], const LayerY& nx, cd R[4],
+                            cd Dm[4], cd Um[4]) {
+    cd S[4] = {nx.Yt[0] - Yr[0], nx.Yt[1] - Yr[1], nx.Yt[2] - Yr[2], nx.Yt[3] - Yr[3]};
+    cd M[4];
+    inv22(S, M);
+    cd d1[4] = {Yt[0] - Yr[0], Yt[1] - Yr[1], Yt[2] - Yr[2], Yt[3] - Yr[3]};
+    cd d2[4] = {Yt[0] - nx.Yt[0], Yt[1] - nx.Yt[1], Yt[2] - nx.Yt[2], Yt[3] - nx.Yt[3]};
+    cd d3[4] = {nx.Yt[0] - nx.Yr[0], nx.Yt[1] - nx.Yr[1], nx.Yt[2] - nx.Yr[2], nx.Yt[3] - nx.Yr[3]};
+    cd W[4], V[4], T[4], Tr[4];
+    mm22(d1, Et, V); mm22(M, V, W); mm22(nx.Eti, W, T);          // T = Et'^-1 M (Yt - Yr) Et
+    mm22(d2, Et, V); mm22(M, V, W); mm22(Eri, W, R);             // R = Er^-1 M (Yt - Yt') Et
+    mm22(d3, nx.Er, V); mm22(M, V, W); mm22(Eri, W, Tr);         // Trev = Er^-1 M (Yt' - Yr') Er'
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < 4; ++k) { R[k] = n2n(R[k]); T[k] = n2n(T[k]); Tr[k] = n2n(Tr[k]); }
+    Dm[0] = cmul_(nx.Mfwd[0], T[0]); Dm[1] = cmul_(nx.Mfwd[0], T[1]);
+    Dm[2] = cmul_(nx.Mfwd[1], T[2]); Dm[3] = cmul_(nx.Mfwd[1], T[3]);
+    Um[0] = cmul_(Tr[0], nx.Mrev[0]); Um[1] = cmul_(Tr[1], nx.Mrev[1]);
+    Um[2] = cmul_(Tr[2], nx.Mrev[0]); Um[3] = cmul_(Tr[3], nx.Mrev[1]);
+}
+
 TAMM_HD void mul22(const cd a[4], const cd b[4], cd o[4]) {
     cd o0 = a[0] * b[0] + a[1] * b[2];
     cd o1 = a[0] * b[1] + a[1] * b[3];

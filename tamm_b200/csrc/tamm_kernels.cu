@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/tamm_b200.h"
@@ -36,6 +37,10 @@ int fail(const char* fmt, const char* a = "", long b = 0) {
         cudaError_t e_ = (call);                                                   \
         if (e_ != cudaSuccess) return fail("%s (CUDA error %ld)", cudaGetErrorString(e_), (long)e_); \
     } while (0)
+
+#ifndef TAMM_DEFAULT_VARIANT
+#define TAMM_DEFAULT_VARIANT 0
+#endif
 
 constexpr int TL = 32;  // layers per TMA sub-tile (32 * 80 B = 2560 B)
 
@@ -76,8 +81,9 @@ __device__ __forceinline__ cd ld_cd(const cd* p) {
 
 // ---- the hot kernel ------------------------------------------------------------------------------
 // grid = (lane tiles, chunks, profiles); block = TB threads (multiple of 32).
-template <int MODE>
-__global__ void __launch_bounds__(256, 1)
+// MAXT / MINB: launch bounds (register budget): (256,1) -> 255 regs, (192,2) -> 168 regs, (256,2) -> 128 regs.
+template <int MODE, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
 stack_kernel(const double* __restrict__ layers, const double* __restrict__ lanes, int N, int QF, double zeta, double mu,
              int chunk, int nchunks, cd* __restrict__ planes, cd* __restrict__ agg, int* __restrict__ status) {
     __shared__ alignas(128) double sbuf[2][TL * LAYER_STRIDE];
@@ -115,7 +121,7 @@ stack_kernel(const double* __restrict__ layers, const double* __restrict__ lanes
         ln.twopif = c2.x; ln.w_eps0 = c2.y; ln.pad0 = 0; ln.pad1 = 0;
     }
 
-    cd prevAi[4][4], prevAr[4][2];
+    cd pEt[4], pEri[4], pYt[4], pYr[4];   // carried from the previous layer
     cd D[4] = {mk(1.0), mk(0.0), mk(0.0), mk(1.0)};
     cd U[4] = {mk(1.0), mk(0.0), mk(0.0), mk(1.0)};
     int st = 0;
@@ -144,17 +150,17 @@ stack_kernel(const double* __restrict__ layers, const double* __restrict__ lanes
                 lp.t20 = v0.x; lp.n21r = v0.y; lp.n21i = v1.x; lp.n22r = v1.y; lp.n22i = v2.x;
                 lp.mono = v2.y; lp.deps = v3.x; lp.sigma = v3.y; lp.dz = v4.x; lp.pad = 0;
             }
-            LayerMats cur;
-            st |= layer_solve(lp, ln, zeta, mu, cur, nullptr);
+            LayerY cur;
+            st |= layer_solve_fast(lp, ln, zeta, mu, cur);
             if (j > 0) {
                 const int n = n0 + j - 1;  // interface between layers n and n+1
                 cd R[4], Dm[4], Um[4];
-                interface_mats(prevAi, prevAr, cur, R, Dm, Um);
+                interface_fast(pEt, pEri, pYt, pYr, cur, R, Dm, Um);
                 cd o[4];
                 if (MODE == TAMM_MODE_URD) {
                     cd RD[4];
-                    mul22(R, D, RD);
-                    mul22(U, RD, o);
+                    mm22(R, D, RD);
+                    mm22(U, RD, o);
                 } else {
                     o[0] = U[0]; o[1] = U[1]; o[2] = U[2]; o[3] = U[3];
                 }
@@ -165,16 +171,16 @@ stack_kernel(const double* __restrict__ layers, const double* __restrict__ lanes
                     st_cd(op + 2 * (size_t)QF, o[2]);
                     st_cd(op + 3 * (size_t)QF, o[3]);
                 }
-                if (MODE == TAMM_MODE_URD) mul22(Dm, D, D);   // layerstack.py:189
-                mul22(U, Um, U);                              // layerstack.py:190
+                cd tmp[4];
+                if (MODE == TAMM_MODE_URD) {                  // layerstack.py:189
+                    mm22(Dm, D, tmp);
+                    D[0] = tmp[0]; D[1] = tmp[1]; D[2] = tmp[2]; D[3] = tmp[3];
+                }
+                mm22(U, Um, tmp);                             // layerstack.py:190
+                U[0] = tmp[0]; U[1] = tmp[1]; U[2] = tmp[2]; U[3] = tmp[3];
             }
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) prevAi[r][k] = cur.Ai[r][k];
-                prevAr[r][0] = cur.A[r][2];
-                prevAr[r][1] = cur.A[r][3];
-            }
+            for (int k = 0; k < 4; ++k) { pEt[k] = cur.Et[k]; pEri[k] = cur.Eri[k]; pYt[k] = cur.Yt[k]; pYr[k] = cur.Yr[k]; }
         }
     }
     if (live) {
@@ -423,11 +429,11 @@ __global__ void __launch_bounds__(256) fp64_probe_kernel(double* out, int iters,
 
 int nchunks_of(int N, int chunk) { return (N - 1 + chunk - 1) / chunk; }
 
-int pick_block(int QF) {
-    // smallest padding waste among multiples of 32 up to 256 (ties -> larger block)
+int pick_block(int QF, int maxt = 256) {
+    // smallest padding waste among multiples of 32 up to maxt (ties -> larger block)
     int best = 32;
     double bestw = 1e9;
-    for (int tb = 32; tb <= 256; tb += 32) {
+    for (int tb = 32; tb <= maxt; tb += 32) {
         int tiles = (QF + tb - 1) / tb;
         double waste = (double)tiles * tb / QF;
         if (waste <= bestw + 1e-12) { bestw = waste; best = tb; }
@@ -512,14 +518,30 @@ int tamm_stack_urd(const double* layers, const double* lanes, int P, int N, int 
     const int nch = nchunks_of(N, chunk);
     if (nch > 65535 || P > 65535) return fail("tamm_stack_urd: grid too large (chunks/profiles > 65535)%s", "");
     if (nch > 1 && !workspace) return fail("tamm_stack_urd: workspace required%s", "");
-    const int tb = pick_block(QF);
+    // launch-bound variant (occupancy vs spills); TAMM_STACK_VARIANT overrides for experiments
+    static int variant = -1;
+    if (variant < 0) {
+        const char* ev = getenv("TAMM_STACK_VARIANT");
+        variant = ev ? atoi(ev) : TAMM_DEFAULT_VARIANT;
+        if (variant < 0 || variant > 2) variant = TAMM_DEFAULT_VARIANT;
+    }
+    const int maxt = variant == 1 ? 192 : 256;
+    const int tb = pick_block(QF, maxt);
     dim3 grid((QF + tb - 1) / tb, nch, P);
     cd* agg = (cd*)workspace;
     cudaStream_t s = (cudaStream_t)stream;
-    if (mode == TAMM_MODE_URD)
-        stack_kernel<TAMM_MODE_URD><<<grid, tb, 0, s>>>(layers, lanes, N, QF, zeta, mu, chunk, nch, (cd*)planes, agg, status);
-    else
-        stack_kernel<TAMM_MODE_U><<<grid, tb, 0, s>>>(layers, lanes, N, QF, zeta, mu, chunk, nch, (cd*)planes, agg, status);
+#define TAMM_LAUNCH(MODE, MAXT, MINB) \
+    stack_kernel<MODE, MAXT, MINB><<<grid, tb, 0, s>>>(layers, lanes, N, QF, zeta, mu, chunk, nch, (cd*)planes, agg, status)
+    if (mode == TAMM_MODE_URD) {
+        if (variant == 0) TAMM_LAUNCH(TAMM_MODE_URD, 256, 1);
+        else if (variant == 1) TAMM_LAUNCH(TAMM_MODE_URD, 192, 2);
+        else TAMM_LAUNCH(TAMM_MODE_URD, 256, 2);
+    } else {
+        if (variant == 0) TAMM_LAUNCH(TAMM_MODE_U, 256, 1);
+        else if (variant == 1) TAMM_LAUNCH(TAMM_MODE_U, 192, 2);
+        else TAMM_LAUNCH(TAMM_MODE_U, 256, 2);
+    }
+#undef TAMM_LAUNCH
     CUDA_OK(cudaGetLastError());
     if (nch > 1) {
         long nseq = (long)P * QF;

@@ -87,4 +87,49 @@ int hostsim_urd(const double* layers, const double* lanes, int N, int F, double 
     return 0;
 }
 
+// Same as hostsim_urd but through the hot-path formulation used by stack_kernel (layer_solve_fast/interface_fast).
+int hostsim_urd_fast(const double* layers, const double* lanes, int N, int F, double zeta, double mu, int chunk, int mode,
+                     double* out) {
+    if (N < 2 || chunk < 1) return 1;
+    const int NI = N - 1;
+    const int nchunks = (NI + chunk - 1) / chunk;
+    std::vector<cd> Dagg((size_t)nchunks * 4), Uagg((size_t)nchunks * 4);
+    for (int f = 0; f < F; ++f) {
+        LaneParams ln; std::memcpy(&ln, lanes + (size_t)f * LANE_STRIDE, sizeof(ln));
+        cd* o = reinterpret_cast<cd*>(out) + (size_t)f * NI * 4;
+        for (int c = 0; c < nchunks; ++c) {
+            int n0 = c * chunk, n1 = std::min(NI, n0 + chunk);
+            LayerParams lp; std::memcpy(&lp, layers + (size_t)n0 * LAYER_STRIDE, sizeof(lp));
+            LayerY prev; layer_solve_fast(lp, ln, zeta, mu, prev);
+            cd D[4] = {mk(1), mk(0), mk(0), mk(1)}, U[4] = {mk(1), mk(0), mk(0), mk(1)};
+            for (int n = n0; n < n1; ++n) {
+                std::memcpy(&lp, layers + (size_t)(n + 1) * LAYER_STRIDE, sizeof(lp));
+                LayerY next; layer_solve_fast(lp, ln, zeta, mu, next);
+                cd R[4], Dm[4], Um[4], t[4];
+                interface_fast(prev.Et, prev.Eri, prev.Yt, prev.Yr, next, R, Dm, Um);
+                if (mode == 0) { cd RD[4]; mm22(R, D, RD); mm22(U, RD, o + (size_t)n * 4); }
+                else { for (int k = 0; k < 4; ++k) o[(size_t)n * 4 + k] = U[k]; }
+                mm22(Dm, D, t); for (int k = 0; k < 4; ++k) D[k] = t[k];
+                mm22(U, Um, t); for (int k = 0; k < 4; ++k) U[k] = t[k];
+                prev = next;
+            }
+            for (int k = 0; k < 4; ++k) { Dagg[(size_t)c * 4 + k] = D[k]; Uagg[(size_t)c * 4 + k] = U[k]; }
+        }
+        cd Dp[4] = {mk(1), mk(0), mk(0), mk(1)}, Up[4] = {mk(1), mk(0), mk(0), mk(1)};
+        for (int c = 0; c < nchunks; ++c) {
+            int n0 = c * chunk, n1 = std::min(NI, n0 + chunk);
+            if (c > 0) {
+                for (int n = n0; n < n1; ++n) {
+                    cd t[4];
+                    if (mode == 0) { mul22(o + (size_t)n * 4, Dp, t); mul22(Up, t, o + (size_t)n * 4); }
+                    else { mul22(Up, o + (size_t)n * 4, t); for (int k = 0; k < 4; ++k) o[(size_t)n * 4 + k] = t[k]; }
+                }
+            }
+            mul22(&Dagg[(size_t)c * 4], Dp, Dp);
+            mul22(Up, &Uagg[(size_t)c * 4], Up);
+        }
+    }
+    return 0;
+}
+
 }  // extern "C"
