@@ -37,6 +37,39 @@ struct cd {
     double re, im;
 };
 
+// Branch-free reciprocal and square root for the hot path: MUFU seed (~20 bits) + Newton steps, ~1 ulp, no
+// slow-path calls.  Arguments are O(1e-30..1e30) here; 0 gives NaN/inf which the callers treat like the reference's
+// 0/0 (NaN fallbacks, nan_to_num).  On the host (test-only simulator) they are the plain IEEE operations.
+TAMM_HD double frcp(double a) {
+#if defined(__CUDA_ARCH__)
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+    double e = fma(-a, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-a, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-a, r, 1.0);
+    return fma(r, e, r);
+#else
+    return 1.0 / a;
+#endif
+}
+TAMM_HD double fsqrt(double a) {
+#if defined(__CUDA_ARCH__)
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    double h = 0.5 * a;
+    y = y * fma(-h * y, y, 1.5);
+    y = y * fma(-h * y, y, 1.5);
+    y = y * fma(-h * y, y, 1.5);
+    double s = a * y;
+    s = fma(0.5 * y, fma(-s, s, a), s);
+    return (a > 0.0) ? s : ((a == 0.0) ? 0.0 : s);
+#else
+    return sqrt(a);
+#endif
+}
+
 TAMM_HD cd mk(double re, double im = 0.0) { return cd{re, im}; }
 TAMM_HD cd operator+(cd a, cd b) { return cd{a.re + b.re, a.im + b.im}; }
 TAMM_HD cd operator-(cd a, cd b) { return cd{a.re - b.re, a.im - b.im}; }
@@ -55,6 +88,10 @@ TAMM_HD cd crecip(cd b) {
     return cd{b.re * inv, -b.im * inv};
 }
 TAMM_HD cd operator/(cd a, cd b) { return a * crecip(b); }
+TAMM_HD cd crecip_f(cd b) {   // branch-free variant for the hot path
+    double inv = frcp(fma(b.re, b.re, b.im * b.im));
+    return cd{b.re * inv, -b.im * inv};
+}
 TAMM_HD bool cisnan(cd a) { return isnan(a.re) || isnan(a.im); }
 TAMM_HD cd csel(bool c, cd a, cd b) { return cd{c ? a.re : b.re, c ? a.im : b.im}; }
 
@@ -173,7 +210,7 @@ TAMM_HD WaveCoef wave_coef(const Sym3& e, double mu, double zeta) {
     w.e01 = mk(mu * e.xy, 0.0);
     w.e02 = mk(mu * e.xz, 0.0);
     cd e33 = mk(mu * e.zz - zeta * zeta, mu * e.im);
-    w.k = crecip(e33);
+    w.k = crecip_f(e33);
     double e12 = mu * e.yz;
     w.w1 = e12 * w.k;
     w.d0 = mk(mu * e.yy - zeta * zeta, mu * e.im) - e12 * w.w1;
@@ -647,10 +684,6 @@ TAMM_HD void mm22(const cd a[4], const cd b[4], cd o[4]) {   // o = a b (o must 
     o[2] = dot2(a[2], b[0], a[3], b[2]);
     o[3] = dot2(a[2], b[1], a[3], b[3]);
 }
-TAMM_HD void inv22(const cd a[4], cd o[4]) {
-    cd id = crecip(det2(a[0], a[1], a[2], a[3]));
-    o[0] = cmul_(a[3], id); o[1] = cmul_(-a[1], id); o[2] = cmul_(-a[2], id); o[3] = cmul_(a[0], id);
-}
 
 struct LayerY {
     cd Et[4], Er[4];     // normalised tangential-E blocks of A (row-major 2x2)
@@ -659,13 +692,17 @@ struct LayerY {
     cd Mfwd[2], Mrev[2]; // layer.py:96-97
 };
 
-TAMM_HD double fast_abs(cd z) { return sqrt(z.re * z.re + z.im * z.im); }
+TAMM_HD double fast_abs(cd z) { return fsqrt(fma(z.re, z.re, z.im * z.im)); }
 TAMM_HD cd csqrt_f(cd z) {   // principal square root, no hypot() scaling (|z| is O(1e-20 .. 1e3) here)
     double m = fast_abs(z);
-    if (m == 0.0) return cd{0.0, 0.0};
-    double t = sqrt(0.5 * (m + fabs(z.re)));
-    double o = 0.5 * z.im / t;
+    double t = fsqrt(0.5 * (m + fabs(z.re)));
+    double o = (t > 0.0) ? 0.5 * z.im * frcp(t) : 0.0;
     return (z.re >= 0.0) ? cd{t, o} : cd{fabs(o), copysign(t, z.im)};
+}
+
+TAMM_HD void inv22(const cd a[4], cd o[4]) {
+    cd id = crecip_f(det2(a[0], a[1], a[2], a[3]));
+    o[0] = cmul_(a[3], id); o[1] = cmul_(-a[1], id); o[2] = cmul_(-a[2], id); o[3] = cmul_(a[0], id);
 }
 
 // eigenvalues of G = -N'^-1 N (see mslp_eigs), fused arithmetic
@@ -684,8 +721,8 @@ TAMM_HD void mslp_eigs_f(const WaveMat& m, cd db, cd& h_big, cd& h_small) {
     s = csel(flip, -s, s);
     cd big = hm + s;
     cd detg = det2(g00, g01, g10, g11);
-    cd ninv = -crecip(det1);
-    cd small = (abs2(big) > 0.0) ? cmul_(detg, crecip(big)) : mk(0.0);
+    cd ninv = -crecip_f(det1);
+    cd small = (abs2(big) > 0.0) ? cmul_(detg, crecip_f(big)) : mk(0.0);
     h_big = cmul_(big, ninv);
     h_small = cmul_(small, ninv);
 }
@@ -701,7 +738,7 @@ TAMM_HD void eig4_fast(const WaveCoef& w, cd q[4], cd ex[4], cd ey[4]) {
         bool flip = (hm.re * s.re + hm.im * s.im) < 0.0;
         s = csel(flip, -s, s);
         cd lbig = hm + s;
-        cd lsmall = det2(c00, c01, c01, c11) / lbig;
+        cd lsmall = cmul_(det2(c00, c01, c01, c11), crecip_f(lbig));
         cd r0 = csqrt_f(lbig), r1 = csqrt_f(lsmall);
         q[0] = -r0; q[1] = -r1; q[2] = r0; q[3] = r1;
         // N(q) = C0 - q^2 I
@@ -712,7 +749,7 @@ TAMM_HD void eig4_fast(const WaveCoef& w, cd q[4], cd ex[4], cd ey[4]) {
         return;
     }
     cd kap = mk(1.0) + (w.zeta * w.zeta) * w.k;
-    cd qc = csqrt_f(0.5 * (c00 / kap + c11));
+    cd qc = csqrt_f(0.5 * (cmul_(c00, crecip_f(kap)) + c11));
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
@@ -745,7 +782,7 @@ TAMM_HD void eig4_fast(const WaveCoef& w, cd q[4], cd ex[4], cd ey[4]) {
             cd f = det2(mm.a, mm.b, mm.b, mm.d);
             cd fp = dot2(mm.da, mm.d, mm.a, mm.dd);
             cfma(fp, (-2.0) * mm.b, w.db);
-            cd step = (abs2(fp) > 0.0) ? cmul_(f, crecip(fp)) : mk(0.0);
+            cd step = (abs2(fp) > 0.0) ? cmul_(f, crecip_f(fp)) : mk(0.0);
             // a polish larger than the last MSLP step means f'(x) ~ 0 (degenerate pair): keep the MSLP root
             if (!(abs2(step) <= 1e-12 * abs2(x))) step = mk(0.0);
             cd xr = x - step;
@@ -779,12 +816,12 @@ TAMM_HD int layer_solve_fast(const LayerParams& lp, const LaneParams& ln, double
     for (int k = 0; k < 4; ++k) qu[k] = clean_q(qu[k]);
 
     const cd ezz = mk(e.zz, e.im);
-    const cd ib = crecip(mu * ezz);
+    const cd ib = crecip_f(mu * ezz);
     const cd a20 = (-(e.xz * mu)) * ib, a21 = (-(e.yz * mu)) * ib, a24 = (-(zeta * mu)) * ib;
-    const double a51 = zeta / mu;
+    const double a51 = zeta * frcp(mu);
     const cd D00 = zeta * a20, D02 = zeta * a21;
-    const cd iD01 = crecip(mk(mu) + zeta * a24);
-    const double imu = 1.0 / mu;
+    const cd iD01 = crecip_f(mk(mu) + zeta * a24);
+    const double imu = frcp(mu);
 
     // Poynting / E-field measures for the p-s sort (layer_PPJ.py:233-276), kept as numerators and denominators
     double px[4], ps[4], exx[4], es[4];
@@ -851,7 +888,7 @@ TAMM_HD int layer_solve_fast(const LayerParams& lp, const LaneParams& ln, double
     const cd e00 = mk(e.xx, e.im), e11 = mk(e.yy, e.im);
     const double m01 = mu * e.xy, m02 = mu * e.xz, m12 = mu * e.yz;
     const cd mez = mu * ezz - zeta * zeta;
-    const cd imez = crecip(mez);
+    const cd imez = crecip_f(mez);
     const cd c01m = m01 * mez;                   // mu*eps01*mez
     const cd g23p = (-m12) * imez;               // -mu*eps21/mez
     const double m12sq = m12 * m12;
@@ -863,26 +900,26 @@ TAMM_HD int layer_solve_fast(const LayerParams& lp, const LaneParams& ln, double
         cd g13p = (-1.0) * cmul_(u0, imez), g33p = cmul_(u2, imez);
         // modes 0 and 2 share one form, modes 1 and 3 the other
         cd den0 = cmul_(mez, mzz - csq(q0)) - m12sq;
-        g12 = cmul_(m12 * u0 - c01m, crecip(den0));
+        g12 = cmul_(m12 * u0 - c01m, crecip_f(den0));
         if (cisnan(g12)) g12 = mk(0.0);
         g13 = cmul_((-1.0) * u0 - m12 * g12, imez);
         if (cisnan(g13)) g13 = g13p;
         cd den1 = cmul_(mez, m00 - csq(q1));
         cfma(den1, -u1, u1);
-        g21 = cmul_(m12 * u1 - c01m, crecip(den1));
+        g21 = cmul_(m12 * u1 - c01m, crecip_f(den1));
         if (cisnan(g21)) g21 = mk(0.0);
         cd t23 = cmul_(-u1, g21) - m12;
         g23 = cmul_(t23, imez);
         if (cisnan(g23)) g23 = g23p;
         if (fast_abs(q0 - q1) < QSD_THR) { g12 = mk(0.0); g13 = g13p; g21 = mk(0.0); g23 = g23p; }
         cd den2 = cmul_(mez, mzz - csq(q2)) - m12sq;
-        g32 = cmul_(c01m - m12 * u2, crecip(den2));
+        g32 = cmul_(c01m - m12 * u2, crecip_f(den2));
         if (cisnan(g32)) g32 = mk(0.0);
         g33 = cmul_(u2 + m12 * g32, imez);
         if (cisnan(g33)) g33 = g33p;
         cd den3 = cmul_(mez, m00 - csq(q3));
         cfma(den3, -u3, u3);
-        g41 = cmul_(m12 * u3 - c01m, crecip(den3));
+        g41 = cmul_(m12 * u3 - c01m, crecip_f(den3));
         if (cisnan(g41)) g41 = mk(0.0);
         cd t43 = cmul_(-u3, g41) - m12;
         g43 = cmul_(t43, imez);
@@ -890,19 +927,19 @@ TAMM_HD int layer_solve_fast(const LayerParams& lp, const LaneParams& ln, double
         if (fast_abs(q2 - q3) < QSD_THR) { g32 = mk(0.0); g33 = g33p; g41 = mk(0.0); g43 = g23p; }
     }
     // row norms (layer_PPJ.py:399-402)
-    const double n0 = sqrt(1.0 + abs2(g12) + abs2(g13)), n1 = sqrt(1.0 + abs2(g21) + abs2(g23));
-    const double n2 = sqrt(1.0 + abs2(g32) + abs2(g33)), n3 = sqrt(1.0 + abs2(g41) + abs2(g43));
-    const double i0 = 1.0 / n0, i1 = 1.0 / n1, i2 = 1.0 / n2, i3 = 1.0 / n3;
+    const double n0 = fsqrt(1.0 + abs2(g12) + abs2(g13)), n1 = fsqrt(1.0 + abs2(g21) + abs2(g23));
+    const double n2 = fsqrt(1.0 + abs2(g32) + abs2(g33)), n3 = fsqrt(1.0 + abs2(g41) + abs2(g43));
+    const double i0 = frcp(n0), i1 = frcp(n1), i2 = frcp(n2), i3 = frcp(n3);
     // ---- E blocks, their inverses and the admittances
     L.Et[0] = mk(i0); L.Et[1] = i1 * g21; L.Et[2] = i0 * g12; L.Et[3] = mk(i1);
     L.Er[0] = mk(-i2); L.Er[1] = i3 * g41; L.Er[2] = i2 * g32; L.Er[3] = mk(i3);
     {
-        cd idt = crecip(mk(1.0) - cmul_(g12, g21));            // 1/det [[1, g21],[g12, 1]]
+        cd idt = crecip_f(mk(1.0) - cmul_(g12, g21));            // 1/det [[1, g21],[g12, 1]]
         cd ra[4] = {idt, (-1.0) * cmul_(g21, idt), (-1.0) * cmul_(g12, idt), idt};     // raw inverse
         cd Ht[4] = {imu * (q0 - zeta * g13), imu * (cmul_(q1, g21) - zeta * g23), imu * cmul_(q0, g12), imu * q1};
         mm22(Ht, ra, L.Yt);
         L.Eti[0] = n0 * ra[0]; L.Eti[1] = n0 * ra[1]; L.Eti[2] = n1 * ra[2]; L.Eti[3] = n1 * ra[3];
-        cd idr = crecip(mk(-1.0) - cmul_(g32, g41));           // 1/det [[-1, g41],[g32, 1]]
+        cd idr = crecip_f(mk(-1.0) - cmul_(g32, g41));           // 1/det [[-1, g41],[g32, 1]]
         cd rb[4] = {idr, (-1.0) * cmul_(g41, idr), (-1.0) * cmul_(g32, idr), (-1.0) * idr};
         cd Hr[4] = {imu * ((-1.0) * q2 - zeta * g33), imu * (cmul_(q3, g41) - zeta * g43), imu * cmul_(q2, g32), imu * q3};
         mm22(Hr, rb, L.Yr);

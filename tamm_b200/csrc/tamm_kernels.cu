@@ -39,7 +39,7 @@ int fail(const char* fmt, const char* a = "", long b = 0) {
     } while (0)
 
 #ifndef TAMM_DEFAULT_VARIANT
-#define TAMM_DEFAULT_VARIANT 0
+#define TAMM_DEFAULT_VARIANT 1
 #endif
 
 constexpr int TL = 32;  // layers per TMA sub-tile (32 * 80 B = 2560 B)
@@ -121,9 +121,16 @@ stack_kernel(const double* __restrict__ layers, const double* __restrict__ lanes
         ln.twopif = c2.x; ln.w_eps0 = c2.y; ln.pad0 = 0; ln.pad1 = 0;
     }
 
-    cd pEt[4], pEri[4], pYt[4], pYr[4];   // carried from the previous layer
-    cd D[4] = {mk(1.0), mk(0.0), mk(0.0), mk(1.0)};
-    cd U[4] = {mk(1.0), mk(0.0), mk(0.0), mk(1.0)};
+    // Per-thread state carried from layer to layer lives in shared memory (24 x 16 B per thread, conflict-free
+    // [slot][thread] layout): slots 0-15 = Et, Er^-1, Yt, Yr of the previous layer, 16-19 = D, 20-23 = U.  Keeping it
+    // out of the register file during the (register-hungry) layer solve is what allows 2 CTAs per SM.
+    extern __shared__ double2 carry[];
+    double2* cs = carry + threadIdx.x;
+    const int cstr = blockDim.x;
+#define CS_LD(slot) ld_cd(reinterpret_cast<const cd*>(cs + (slot) * cstr))
+#define CS_ST(slot, v) st_cd(reinterpret_cast<cd*>(cs + (slot) * cstr), (v))
+    CS_ST(16, mk(1.0)); CS_ST(17, mk(0.0)); CS_ST(18, mk(0.0)); CS_ST(19, mk(1.0));
+    CS_ST(20, mk(1.0)); CS_ST(21, mk(0.0)); CS_ST(22, mk(0.0)); CS_ST(23, mk(1.0));
     int st = 0;
     cd* out = planes + ((size_t)p * NI * 4) * QF + lc;
 
@@ -154,6 +161,12 @@ stack_kernel(const double* __restrict__ layers, const double* __restrict__ lanes
             st |= layer_solve_fast(lp, ln, zeta, mu, cur);
             if (j > 0) {
                 const int n = n0 + j - 1;  // interface between layers n and n+1
+                cd pEt[4], pEri[4], pYt[4], pYr[4], D[4], U[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    pEt[k] = CS_LD(k); pEri[k] = CS_LD(4 + k); pYt[k] = CS_LD(8 + k); pYr[k] = CS_LD(12 + k);
+                    D[k] = CS_LD(16 + k); U[k] = CS_LD(20 + k);
+                }
                 cd R[4], Dm[4], Um[4];
                 interface_fast(pEt, pEri, pYt, pYr, cur, R, Dm, Um);
                 cd o[4];
@@ -174,20 +187,20 @@ stack_kernel(const double* __restrict__ layers, const double* __restrict__ lanes
                 cd tmp[4];
                 if (MODE == TAMM_MODE_URD) {                  // layerstack.py:189
                     mm22(Dm, D, tmp);
-                    D[0] = tmp[0]; D[1] = tmp[1]; D[2] = tmp[2]; D[3] = tmp[3];
+                    CS_ST(16, tmp[0]); CS_ST(17, tmp[1]); CS_ST(18, tmp[2]); CS_ST(19, tmp[3]);
                 }
                 mm22(U, Um, tmp);                             // layerstack.py:190
-                U[0] = tmp[0]; U[1] = tmp[1]; U[2] = tmp[2]; U[3] = tmp[3];
+                CS_ST(20, tmp[0]); CS_ST(21, tmp[1]); CS_ST(22, tmp[2]); CS_ST(23, tmp[3]);
             }
 #pragma unroll
-            for (int k = 0; k < 4; ++k) { pEt[k] = cur.Et[k]; pEri[k] = cur.Eri[k]; pYt[k] = cur.Yt[k]; pYr[k] = cur.Yr[k]; }
+            for (int k = 0; k < 4; ++k) { CS_ST(k, cur.Et[k]); CS_ST(4 + k, cur.Eri[k]); CS_ST(8 + k, cur.Yt[k]); CS_ST(12 + k, cur.Yr[k]); }
         }
     }
     if (live) {
         if (nchunks > 1) {
             cd* a = agg + (((size_t)p * QF + l) * nchunks + c) * 8;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) { st_cd(a + k, D[k]); st_cd(a + 4 + k, U[k]); }
+            for (int k = 0; k < 4; ++k) { st_cd(a + k, CS_LD(16 + k)); st_cd(a + 4 + k, CS_LD(20 + k)); }
         }
         if (st && status) atomicOr(status + p, st);
     }
@@ -530,8 +543,18 @@ int tamm_stack_urd(const double* layers, const double* lanes, int P, int N, int 
     dim3 grid((QF + tb - 1) / tb, nch, P);
     cd* agg = (cd*)workspace;
     cudaStream_t s = (cudaStream_t)stream;
-#define TAMM_LAUNCH(MODE, MAXT, MINB) \
-    stack_kernel<MODE, MAXT, MINB><<<grid, tb, 0, s>>>(layers, lanes, N, QF, zeta, mu, chunk, nch, (cd*)planes, agg, status)
+    const size_t dyn = (size_t)24 * sizeof(double2) * tb;   // per-thread carry state, see stack_kernel
+#define TAMM_LAUNCH(MODE, MAXT, MINB)                                                                                   \
+    do {                                                                                                                \
+        static bool attr_set = false;                                                                                   \
+        if (!attr_set) {                                                                                                \
+            CUDA_OK(cudaFuncSetAttribute(stack_kernel<MODE, MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                         24 * (int)sizeof(double2) * MAXT));                                            \
+            attr_set = true;                                                                                            \
+        }                                                                                                               \
+        stack_kernel<MODE, MAXT, MINB><<<grid, tb, dyn, s>>>(layers, lanes, N, QF, zeta, mu, chunk, nch, (cd*)planes,  \
+                                                              agg, status);                                             \
+    } while (0)
     if (mode == TAMM_MODE_URD) {
         if (variant == 0) TAMM_LAUNCH(TAMM_MODE_URD, 256, 1);
         else if (variant == 1) TAMM_LAUNCH(TAMM_MODE_URD, 192, 2);
