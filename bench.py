@@ -44,7 +44,7 @@ def parse():
     ap.add_argument('--frames', type=int, default=181)
     ap.add_argument('--alpha-deg', type=float, default=10.0)
     ap.add_argument('--freq', type=float, default=179e6)
-    ap.add_argument('--batch', type=int, default=64, help='profiles per kernel launch')
+    ap.add_argument('--batch', type=int, default=128, help='profiles per kernel launch')
     ap.add_argument('--e2e-steps', type=int, default=2)
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')

@@ -225,14 +225,21 @@ struct WaveMat {
 
 TAMM_HD WaveMat wave_matrix(const WaveCoef& w, cd q) {
     WaveMat m;
-    cd u = w.e02 + w.zeta * q;
-    cd uk = u * w.k;
+    cd u = cd{fma(w.zeta, q.re, w.e02.re), fma(w.zeta, q.im, w.e02.im)};   // mu*eps_xz + zeta*q
+    cd uk = cd{fma(u.re, w.k.re, -(u.im * w.k.im)), fma(u.re, w.k.im, u.im * w.k.re)};
     cd q2 = csq(q);
-    m.a = w.e00 - q2 - u * uk;
-    m.b = w.e01 - u * w.w1;
+    cd a = w.e00 - q2;
+    a.re = fma(-u.re, uk.re, a.re); a.re = fma(u.im, uk.im, a.re);
+    a.im = fma(-u.re, uk.im, a.im); a.im = fma(-u.im, uk.re, a.im);
+    cd b = w.e01;
+    b.re = fma(-u.re, w.w1.re, b.re); b.re = fma(u.im, w.w1.im, b.re);
+    b.im = fma(-u.re, w.w1.im, b.im); b.im = fma(-u.im, w.w1.re, b.im);
+    m.a = a;
+    m.b = b;
     m.d = w.d0 - q2;
     m.dd = (-2.0) * q;
-    m.da = m.dd - (2.0 * w.zeta) * uk;
+    const double tz = 2.0 * w.zeta;
+    m.da = cd{fma(-tz, uk.re, m.dd.re), fma(-tz, uk.im, m.dd.im)};
     return m;
 }
 

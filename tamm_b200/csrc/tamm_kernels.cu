@@ -505,15 +505,29 @@ size_t tamm_stack_workspace_bytes(int P, int N, int QF, int chunk) {
 int tamm_suggest_chunk(int P, int N, int QF, int sm_count) {
     if (N < 2) return 1;
     const int NI = N - 1;
-    int tb = pick_block(QF);
-    long blocks_per_chunk = (long)P * ((QF + tb - 1) / tb);
-    // aim for >= 4 resident-CTA waves worth of blocks (1 CTA of <=256 threads per SM at 255 regs)
-    long want_blocks = 4L * (sm_count > 0 ? sm_count : 148);
-    long nch = (want_blocks + blocks_per_chunk - 1) / blocks_per_chunk;
-    if (nch < 1) nch = 1;
-    long chunk = (NI + nch - 1) / nch;
-    if (chunk < 8) chunk = 8;       // bound the 1-layer halo overhead at 12.5 %
-    if (chunk > NI) chunk = NI;
+    const int maxt = TAMM_DEFAULT_VARIANT == 1 ? 192 : 256;
+    const int ctas_per_sm = TAMM_DEFAULT_VARIANT == 0 ? 1 : 2;
+    const int tb = pick_block(QF, maxt);
+    const long bpc = (long)P * ((QF + tb - 1) / tb);                       // CTAs per chunk index
+    const long slots = (long)(sm_count > 0 ? sm_count : 148) * ctas_per_sm;  // resident CTAs per wave
+    // Every CTA walks `chunk` interfaces (+1 halo layer).  Choose the number of chunks that maximises
+    //   (CTAs / (waves * slots))  x  chunk / (chunk + 1)      wave-quantisation x halo efficiency,
+    // preferring fewer chunks on ties; chunk >= 8 bounds the halo overhead at 12.5 %.
+    long best_n = 1;
+    double best = -1.0;
+    const long max_n = NI / 8 > 0 ? NI / 8 : 1;
+    for (long n = 1; n <= max_n && n <= 65535; ++n) {
+        long chunk = (NI + n - 1) / n;
+        long nch = (NI + chunk - 1) / chunk;        // actual number of chunks for this chunk length
+        long ctas = bpc * nch;
+        long waves = (ctas + slots - 1) / slots;
+        double eff = (double)ctas / (double)(waves * slots) * (double)chunk / (double)(chunk + 1);
+        if (ctas < slots) eff *= 0.5;                // not even one CTA per slot: heavily penalised
+        if (eff > best + 1e-9) { best = eff; best_n = n; }
+        if (ctas > 64 * slots) break;
+    }
+    long chunk = (NI + best_n - 1) / best_n;
+    if (chunk < 1) chunk = 1;
     return (int)chunk;
 }
 
