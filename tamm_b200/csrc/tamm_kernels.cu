@@ -39,10 +39,11 @@ int fail(const char* fmt, const char* a = "", long b = 0) {
     } while (0)
 
 #ifndef TAMM_DEFAULT_VARIANT
-#define TAMM_DEFAULT_VARIANT 1
+#define TAMM_DEFAULT_VARIANT 2
 #endif
 
-constexpr int TL = 32;  // layers per TMA sub-tile (32 * 80 B = 2560 B)
+constexpr int TL = 16;     // layers per TMA sub-tile (16 * 80 B = 1280 B per profile)
+constexpr int NPMAX = 4;   // a CTA's lanes may span at most this many profiles (flattened lane mapping)
 
 // ---- mbarrier / bulk-copy (TMA) primitives -----------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -80,26 +81,50 @@ __device__ __forceinline__ cd ld_cd(const cd* p) {
 }
 
 // ---- the hot kernel ------------------------------------------------------------------------------
-// grid = (lane tiles, chunks, profiles); block = TB threads (multiple of 32).
+// grid = (lane blocks, chunks); block = TB threads (multiple of 32).
 // MAXT / MINB: launch bounds (register budget): (256,1) -> 255 regs, (192,2) -> 168 regs, (256,2) -> 128 regs.
 template <int MODE, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB)
-stack_kernel(const double* __restrict__ layers, const double* __restrict__ lanes, int N, int QF, double zeta, double mu,
-             int chunk, int nchunks, cd* __restrict__ planes, cd* __restrict__ agg, int* __restrict__ status) {
-    __shared__ alignas(128) double sbuf[2][TL * LAYER_STRIDE];
+stack_kernel(const double* __restrict__ layers, const double* __restrict__ lanes, int P, int N, int QF, int flat, double zeta,
+             double mu, int chunk, int nchunks, cd* __restrict__ planes, cd* __restrict__ agg, int* __restrict__ status) {
+    __shared__ alignas(128) double sbuf[2][NPMAX][TL * LAYER_STRIDE];
     __shared__ alignas(8) uint64_t bar[2];
 
+    // Lane mapping.  flat != 0: the (profile, lane) pairs of the batch are flattened, g = p*QF + l, and a CTA takes
+    // blockDim.x consecutive g (full CTAs for any QF; spans <= NPMAX profiles).  flat == 0: one CTA = one lane tile
+    // of one profile (used when QF is too small for the flattened mapping).
     const int NI = N - 1;
-    const int p = blockIdx.z;
     const int c = blockIdx.y;
-    const int l = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = l < QF;
-    const int lc = live ? l : QF - 1;
+    int p, l, p_first, np;
+    bool live;
+    if (flat) {
+        const long G = (long)P * QF;
+        const long g0 = (long)blockIdx.x * blockDim.x;
+        long g = g0 + threadIdx.x;
+        live = g < G;
+        if (!live) g = G - 1;
+        p = (int)(g / QF);
+        l = (int)(g - (long)p * QF);
+        p_first = (int)(g0 / QF);
+        long gl = g0 + blockDim.x - 1;
+        if (gl > G - 1) gl = G - 1;
+        np = (int)(gl / QF) - p_first + 1;
+    } else {
+        const int tiles = (QF + blockDim.x - 1) / blockDim.x;
+        p = blockIdx.x / tiles;
+        l = (blockIdx.x - p * tiles) * blockDim.x + threadIdx.x;
+        live = l < QF;
+        if (!live) l = QF - 1;
+        p_first = p;
+        np = 1;
+    }
+    const int lc = l;
     const int n0 = c * chunk;
     const int n1 = min(NI, n0 + chunk);
     const int cnt = n1 - n0 + 1;  // layers n0..n1
     const int ntile = (cnt + TL - 1) / TL;
-    const double* src = layers + ((size_t)p * N + n0) * LAYER_STRIDE;
+    const double* src = layers + ((size_t)p_first * N + n0) * LAYER_STRIDE;   // + pi*N*LAYER_STRIDE per spanned profile
+    const int pi = p - p_first;
 
     if (threadIdx.x == 0) {
         mbar_init(&bar[0], 1);
@@ -109,8 +134,8 @@ stack_kernel(const double* __restrict__ layers, const double* __restrict__ lanes
     __syncthreads();
     if (threadIdx.x == 0) {
         uint32_t bytes = (uint32_t)(min(TL, cnt) * LAYER_STRIDE * sizeof(double));
-        mbar_expect_tx(&bar[0], bytes);
-        tma_bulk_g2s(&sbuf[0][0], src, bytes, &bar[0]);
+        mbar_expect_tx(&bar[0], bytes * np);
+        for (int q = 0; q < np; ++q) tma_bulk_g2s(&sbuf[0][q][0], src + (size_t)q * N * LAYER_STRIDE, bytes, &bar[0]);
     }
 
     LaneParams ln;
@@ -141,11 +166,13 @@ stack_kernel(const double* __restrict__ layers, const double* __restrict__ lanes
         if (threadIdx.x == 0 && t + 1 < ntile) {
             int rem = cnt - (t + 1) * TL;
             uint32_t bytes = (uint32_t)(min(TL, rem) * LAYER_STRIDE * sizeof(double));
-            mbar_expect_tx(&bar[(t + 1) & 1], bytes);
-            tma_bulk_g2s(&sbuf[(t + 1) & 1][0], src + (size_t)(t + 1) * TL * LAYER_STRIDE, bytes, &bar[(t + 1) & 1]);
+            mbar_expect_tx(&bar[(t + 1) & 1], bytes * np);
+            for (int q = 0; q < np; ++q)
+                tma_bulk_g2s(&sbuf[(t + 1) & 1][q][0], src + ((size_t)q * N + (size_t)(t + 1) * TL) * LAYER_STRIDE, bytes,
+                             &bar[(t + 1) & 1]);
         }
         mbar_wait(&bar[t & 1], (uint32_t)((t >> 1) & 1));
-        const double* tile = &sbuf[t & 1][0];
+        const double* tile = &sbuf[t & 1][pi][0];
         const int jn = min(TL, cnt - t * TL);
 #pragma unroll 1
         for (int jj = 0; jj < jn; ++jj) {
@@ -454,6 +481,21 @@ int pick_block(int QF, int maxt = 256) {
     return best;
 }
 
+// CTA geometry of stack_kernel: flattened lanes whenever a CTA of `maxt` threads spans at most NPMAX profiles.
+void stack_geometry(int P, int QF, int maxt, int* tb, int* flat, long* gx) {
+    if ((long)(NPMAX - 1) * QF + 1 >= maxt) {
+        *flat = 1;
+        *tb = maxt;
+        long G = (long)P * QF;
+        if (G < maxt) *tb = (int)(((G + 31) / 32) * 32);
+        *gx = (G + *tb - 1) / *tb;
+    } else {
+        *flat = 0;
+        *tb = pick_block(QF, maxt);
+        *gx = (long)P * ((QF + *tb - 1) / *tb);
+    }
+}
+
 bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
 }  // namespace
@@ -507,8 +549,9 @@ int tamm_suggest_chunk(int P, int N, int QF, int sm_count) {
     const int NI = N - 1;
     const int maxt = TAMM_DEFAULT_VARIANT == 1 ? 192 : 256;
     const int ctas_per_sm = TAMM_DEFAULT_VARIANT == 0 ? 1 : 2;
-    const int tb = pick_block(QF, maxt);
-    const long bpc = (long)P * ((QF + tb - 1) / tb);                       // CTAs per chunk index
+    int tb, flat;
+    long bpc;                                                              // CTAs per chunk index
+    stack_geometry(P, QF, maxt, &tb, &flat, &bpc);
     const long slots = (long)(sm_count > 0 ? sm_count : 148) * ctas_per_sm;  // resident CTAs per wave
     // Every CTA walks `chunk` interfaces (+1 halo layer).  Choose the number of chunks that maximises
     //   (CTAs / (waves * slots))  x  chunk / (chunk + 1)      wave-quantisation x halo efficiency,
@@ -543,7 +586,7 @@ int tamm_stack_urd(const double* layers, const double* lanes, int P, int N, int 
     if (!(mu != 0.0)) return fail("tamm_stack_urd: mu must be non-zero%s", "");
     const int QF = Q * F;
     const int nch = nchunks_of(N, chunk);
-    if (nch > 65535 || P > 65535) return fail("tamm_stack_urd: grid too large (chunks/profiles > 65535)%s", "");
+    if (nch > 65535) return fail("tamm_stack_urd: grid too large (chunks > 65535)%s", "");
     if (nch > 1 && !workspace) return fail("tamm_stack_urd: workspace required%s", "");
     // launch-bound variant (occupancy vs spills); TAMM_STACK_VARIANT overrides for experiments
     static int variant = -1;
@@ -553,8 +596,11 @@ int tamm_stack_urd(const double* layers, const double* lanes, int P, int N, int 
         if (variant < 0 || variant > 2) variant = TAMM_DEFAULT_VARIANT;
     }
     const int maxt = variant == 1 ? 192 : 256;
-    const int tb = pick_block(QF, maxt);
-    dim3 grid((QF + tb - 1) / tb, nch, P);
+    int tb, flat;
+    long gx;
+    stack_geometry(P, QF, maxt, &tb, &flat, &gx);
+    if (gx > 2147483647L) return fail("tamm_stack_urd: grid too large%s", "");
+    dim3 grid((unsigned)gx, nch, 1);
     cd* agg = (cd*)workspace;
     cudaStream_t s = (cudaStream_t)stream;
     const size_t dyn = (size_t)24 * sizeof(double2) * tb;   // per-thread carry state, see stack_kernel
@@ -566,8 +612,8 @@ int tamm_stack_urd(const double* layers, const double* lanes, int P, int N, int 
                                          24 * (int)sizeof(double2) * MAXT));                                            \
             attr_set = true;                                                                                            \
         }                                                                                                               \
-        stack_kernel<MODE, MAXT, MINB><<<grid, tb, dyn, s>>>(layers, lanes, N, QF, zeta, mu, chunk, nch, (cd*)planes,  \
-                                                              agg, status);                                             \
+        stack_kernel<MODE, MAXT, MINB><<<grid, tb, dyn, s>>>(layers, lanes, P, N, QF, flat, zeta, mu, chunk, nch,       \
+                                                              (cd*)planes, agg, status);                                \
     } while (0)
     if (mode == TAMM_MODE_URD) {
         if (variant == 0) TAMM_LAUNCH(TAMM_MODE_URD, 256, 1);
