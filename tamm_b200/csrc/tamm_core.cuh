@@ -734,8 +734,11 @@ TAMM_HD void mslp_eigs_f(const WaveMat& m, cd db, cd& h_big, cd& h_small) {
     h_small = cmul_(small, ninv);
 }
 
-// Four roots + the (Ex, Ey) null vector of N at each root.  q0,q1: pair seeded at -sqrt(.), q2,q3: at +sqrt(.)
-TAMM_HD void eig4_fast(const WaveCoef& w, cd q[4], cd ex[4], cd ey[4]) {
+// Four roots + the (Ex, Ey) null vector of N at each root, written to rv[k] = {q, Ex, Ey}.  rv is indexed with run-time
+// indices on purpose: it lives in (L1-resident) local memory, which costs a few 16-byte loads/stores instead of the
+// long select/move chains a register-resident array needs in rolled loops.
+// rv[0],rv[1]: pair seeded at -sqrt(.), rv[2],rv[3]: pair seeded at +sqrt(.)
+TAMM_HD void eig4_fast(const WaveCoef& w, cd rv[4][3]) {
     cd c00 = w.e00 - w.e02 * (w.e02 * w.k);
     cd c01 = w.e01 - w.e02 * w.w1;
     cd c11 = w.d0;
@@ -747,12 +750,15 @@ TAMM_HD void eig4_fast(const WaveCoef& w, cd q[4], cd ex[4], cd ey[4]) {
         cd lbig = hm + s;
         cd lsmall = cmul_(det2(c00, c01, c01, c11), crecip_f(lbig));
         cd r0 = csqrt_f(lbig), r1 = csqrt_f(lsmall);
-        q[0] = -r0; q[1] = -r1; q[2] = r0; q[3] = r1;
         // N(q) = C0 - q^2 I
         cd a0 = c00 - lbig, d0 = c11 - lbig, a1 = c00 - lsmall, d1 = c11 - lsmall;
         bool u0 = abs2(a0) >= abs2(d0), u1 = abs2(a1) >= abs2(d1);
-        ex[0] = ex[2] = csel(u0, -c01, d0); ey[0] = ey[2] = csel(u0, a0, -c01);
-        ex[1] = ex[3] = csel(u1, -c01, d1); ey[1] = ey[3] = csel(u1, a1, -c01);
+        cd x0 = csel(u0, -c01, d0), y0 = csel(u0, a0, -c01);
+        cd x1 = csel(u1, -c01, d1), y1 = csel(u1, a1, -c01);
+        rv[0][0] = -r0; rv[0][1] = x0; rv[0][2] = y0;
+        rv[1][0] = -r1; rv[1][1] = x1; rv[1][2] = y1;
+        rv[2][0] = r0; rv[2][1] = x0; rv[2][2] = y0;
+        rv[3][0] = r1; rv[3][1] = x1; rv[3][2] = y1;
         return;
     }
     cd kap = mk(1.0) + (w.zeta * w.zeta) * w.k;
@@ -783,23 +789,21 @@ TAMM_HD void eig4_fast(const WaveCoef& w, cd q[4], cd ex[4], cd ey[4]) {
                 mslp_eigs_f(mm, w.db, part, h);
                 x = x + h;
                 double h2 = abs2(h);
-                if (h2 * h2 * h2 * h2 <= 1e-30 * abs2(part) * abs2(x)) break;
+                h2 = h2 * h2;
+                if (h2 * h2 <= 1e-30 * abs2(part) * abs2(x)) break;
             }
             WaveMat mm = wave_matrix(w, x);
             cd f = det2(mm.a, mm.b, mm.b, mm.d);
             cd fp = dot2(mm.da, mm.d, mm.a, mm.dd);
             cfma(fp, (-2.0) * mm.b, w.db);
-            cd step = (abs2(fp) > 0.0) ? cmul_(f, crecip_f(fp)) : mk(0.0);
-            // a polish larger than the last MSLP step means f'(x) ~ 0 (degenerate pair): keep the MSLP root
+            cd step = cmul_(f, crecip_f(fp));
+            // a NaN / large polish means f'(x) ~ 0 (degenerate pair): keep the MSLP root
             if (!(abs2(step) <= 1e-12 * abs2(x))) step = mk(0.0);
-            cd xr = x - step;
             bool use0 = abs2(mm.a) >= abs2(mm.d);
-            cd vx = csel(use0, -mm.b, mm.d), vy = csel(use0, mm.a, -mm.b);
-            int idx = 2 * pair + r;
-            if (idx == 0) { q[0] = xr; ex[0] = vx; ey[0] = vy; }
-            else if (idx == 1) { q[1] = xr; ex[1] = vx; ey[1] = vy; }
-            else if (idx == 2) { q[2] = xr; ex[2] = vx; ey[2] = vy; }
-            else { q[3] = xr; ex[3] = vx; ey[3] = vy; }
+            const int idx = 2 * pair + r;
+            rv[idx][0] = x - step;
+            rv[idx][1] = csel(use0, -mm.b, mm.d);
+            rv[idx][2] = csel(use0, mm.a, -mm.b);
         }
     }
 }
@@ -815,29 +819,32 @@ TAMM_HD int layer_solve_fast(const LayerParams& lp, const LaneParams& ln, double
     int status = 0;
     const Sym3 e = permittivity(lp, ln);
     const WaveCoef w = wave_coef(e, mu, zeta);
-    cd qu[4], vx[4], vy[4];
-    eig4_fast(w, qu, vx, vy);
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (int k = 0; k < 4; ++k) qu[k] = clean_q(qu[k]);
+    cd rv[4][3];
+    eig4_fast(w, rv);
 
     const cd ezz = mk(e.zz, e.im);
     const cd ib = crecip_f(mu * ezz);
     const cd a20 = (-(e.xz * mu)) * ib, a21 = (-(e.yz * mu)) * ib, a24 = (-(zeta * mu)) * ib;
-    const double a51 = zeta * frcp(mu);
+    const double imu = frcp(mu);
+    const double a51 = zeta * imu;
     const cd D00 = zeta * a20, D02 = zeta * a21;
     const cd iD01 = crecip_f(mk(mu) + zeta * a24);
-    const double imu = frcp(mu);
 
-    // Poynting / E-field measures for the p-s sort (layer_PPJ.py:233-276), kept as numerators and denominators
-    double px[4], ps[4], exx[4], es[4];
+    // clean-up (layer_PPJ.py:199-203), Poynting / E-field measures for the p-s sort (233-276) kept as numerators and
+    // denominators {|Px|^2, |Px|^2+|Py|^2, |Ex|^2, |Ex|^2+|Ey|^2}, and the transmitted/reflected flags (216-231)
+    double ms[4][4];
+    int im_mask = 0, re_mask = 0;
+    bool has_im = false;
 #if defined(__CUDA_ARCH__)
-#pragma unroll
+#pragma unroll 1
 #endif
     for (int k = 0; k < 4; ++k) {
-        const cd q = qu[k];
-        cd Ex = vx[k], Ey = vy[k];
+        const cd q = clean_q(rv[k][0]);
+        rv[k][0] = q;
+        has_im = has_im || (q.im != 0.0);
+        im_mask |= (q.im >= 0.0 ? 1 : 0) << k;
+        re_mask |= (q.re > 0.0 ? 1 : 0) << k;
+        cd Ex = rv[k][1], Ey = rv[k][2];
         if (abs2(Ex) + abs2(Ey) == 0.0) { Ex = mk(1.0); Ey = mk(0.0); }
         cd t = cmul_(q - D00, Ex);
         cfma(t, -D02, Ey);
@@ -849,47 +856,31 @@ TAMM_HD int layer_solve_fast(const LayerParams& lp, const LaneParams& ln, double
         cd Hz = a51 * Ey;
         cd Px = det2(Ey, Ez, Hy, Hz);     // Ey*Hz - Ez*Hy
         cd Py = det2(Ez, Ex, Hz, Hx);     // Ez*Hx - Ex*Hz
-        px[k] = abs2(Px); ps[k] = px[k] + abs2(Py);
-        exx[k] = abs2(Ex); es[k] = exx[k] + abs2(Ey);
+        double pxx = abs2(Px), exx = abs2(Ex);
+        ms[k][0] = pxx; ms[k][1] = pxx + abs2(Py); ms[k][2] = exx; ms[k][3] = exx + abs2(Ey);
     }
-    bool has_im = (qu[0].im != 0.0) || (qu[1].im != 0.0) || (qu[2].im != 0.0) || (qu[3].im != 0.0);
-    int tmask = 0;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (int k = 0; k < 4; ++k) {
-        bool t = has_im ? (qu[k].im >= 0.0) : (qu[k].re > 0.0);
-        tmask |= (t ? 1 : 0) << k;
-    }
+    const int tmask = has_im ? im_mask : re_mask;
     int t0, t1, r0, r1;
-    switch (tmask) {
-        case 0x3: t0 = 0; t1 = 1; r0 = 2; r1 = 3; break;
-        case 0xC: t0 = 2; t1 = 3; r0 = 0; r1 = 1; break;
-        case 0x5: t0 = 0; t1 = 2; r0 = 1; r1 = 3; break;
-        case 0xA: t0 = 1; t1 = 3; r0 = 0; r1 = 2; break;
-        case 0x6: t0 = 1; t1 = 2; r0 = 0; r1 = 3; break;
-        case 0x9: t0 = 0; t1 = 3; r0 = 1; r1 = 2; break;
-        default:  t0 = 0; t1 = 1; r0 = 2; r1 = 3; status |= 1; break;
+    if (tmask == 0x3) { t0 = 0; t1 = 1; r0 = 2; r1 = 3; }
+    else if (tmask == 0xC) { t0 = 2; t1 = 3; r0 = 0; r1 = 1; }
+    else {
+        switch (tmask) {
+            case 0x5: t0 = 0; t1 = 2; r0 = 1; r1 = 3; break;
+            case 0xA: t0 = 1; t1 = 3; r0 = 0; r1 = 2; break;
+            case 0x6: t0 = 1; t1 = 2; r0 = 0; r1 = 3; break;
+            case 0x9: t0 = 0; t1 = 3; r0 = 1; r1 = 2; break;
+            default:  t0 = 0; t1 = 1; r0 = 2; r1 = 3; status |= 1; break;
+        }
     }
-    auto PX = [&](int i) { return sel4(i, px[0], px[1], px[2], px[3]); };
-    auto PS = [&](int i) { return sel4(i, ps[0], ps[1], ps[2], ps[3]); };
-    auto EX = [&](int i) { return sel4(i, exx[0], exx[1], exx[2], exx[3]); };
-    auto ES = [&](int i) { return sel4(i, es[0], es[1], es[2], es[3]); };
     // C_a > C_b  <=>  n_a s_b > n_b s_a  for ratios C = n/s with s > 0; NaN (s = 0) compares false like the reference
     auto gt = [](double na, double sa, double nb, double sb) { return (sa > 0.0) && (sb > 0.0) && (na * sb > nb * sa); };
-    double pa = PX(t0), sa = PS(t0), pb = PX(t1), sb = PS(t1);
-    bool biref = (sa > 0.0) && (sb > 0.0) && (fabs(pa * sb - pb * sa) > QSD_THR * (sa * sb));   // layer_PPJ.py:258
-    bool flip_t, flip_r;
-    if (biref) {
-        flip_t = gt(pb, sb, pa, sa);                                   // 260
-        flip_r = gt(PX(r1), PS(r1), PX(r0), PS(r0));                   // 263-265
-    } else {
-        flip_t = gt(EX(t1), ES(t1), EX(t0), ES(t0));                   // 269-272
-        flip_r = gt(EX(r1), ES(r1), EX(r0), ES(r0));                   // 273-276
-    }
-    int o0 = flip_t ? t1 : t0, o1 = flip_t ? t0 : t1, o2 = flip_r ? r1 : r0, o3 = flip_r ? r0 : r1;
-    const cd q0 = sel4(o0, qu[0], qu[1], qu[2], qu[3]), q1 = sel4(o1, qu[0], qu[1], qu[2], qu[3]);
-    const cd q2 = sel4(o2, qu[0], qu[1], qu[2], qu[3]), q3 = sel4(o3, qu[0], qu[1], qu[2], qu[3]);
+    const double pa = ms[t0][0], sa = ms[t0][1], pb = ms[t1][0], sb = ms[t1][1];
+    const bool biref = (sa > 0.0) && (sb > 0.0) && (fabs(pa * sb - pb * sa) > QSD_THR * (sa * sb));   // layer_PPJ.py:258
+    const int mo = biref ? 0 : 2;        // Poynting measures (260-265) or E-field measures (269-276)
+    const bool flip_t = gt(ms[t1][mo], ms[t1][mo + 1], ms[t0][mo], ms[t0][mo + 1]);
+    const bool flip_r = gt(ms[r1][mo], ms[r1][mo + 1], ms[r0][mo], ms[r0][mo + 1]);
+    const int o0 = flip_t ? t1 : t0, o1 = flip_t ? t0 : t1, o2 = flip_r ? r1 : r0, o3 = flip_r ? r0 : r1;
+    const cd q0 = rv[o0][0], q1 = rv[o1][0], q2 = rv[o2][0], q3 = rv[o3][0];
 
     // ---- gamma (layer_PPJ.py:309-389), unnormalised; see layer_solve for the line-by-line citations
     const cd e00 = mk(e.xx, e.im), e11 = mk(e.yy, e.im);
@@ -972,10 +963,18 @@ TAMM_HD void interface_fast(const cd Et[4], const cd Eri[4], const cd Yt[4], con
     mm22(d1, Et, V); mm22(M, V, W); mm22(nx.Eti, W, T);          // T = Et'^-1 M (Yt - Yr) Et
     mm22(d2, Et, V); mm22(M, V, W); mm22(Eri, W, R);             // R = Er^-1 M (Yt - Yt') Et
     mm22(d3, nx.Er, V); mm22(M, V, W); mm22(Eri, W, Tr);         // Trev = Er^-1 M (Yt' - Yr') Er'
+    // nan_to_num (layerstack.py:101-127) only matters for singular interfaces: one finite-check, rare slow path.
+    // x - x is 0 for finite x and NaN for inf/NaN, so the sum below is NaN iff any entry is not finite.
+    double chk = 0.0;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    for (int k = 0; k < 4; ++k) { R[k] = n2n(R[k]); T[k] = n2n(T[k]); Tr[k] = n2n(Tr[k]); }
+    for (int k = 0; k < 4; ++k)
+        chk += (R[k].re - R[k].re) + (R[k].im - R[k].im) + (T[k].re - T[k].re) + (T[k].im - T[k].im) + (Tr[k].re - Tr[k].re) +
+               (Tr[k].im - Tr[k].im);
+    if (chk != chk) {
+        for (int k = 0; k < 4; ++k) { R[k] = n2n(R[k]); T[k] = n2n(T[k]); Tr[k] = n2n(Tr[k]); }
+    }
     Dm[0] = cmul_(nx.Mfwd[0], T[0]); Dm[1] = cmul_(nx.Mfwd[0], T[1]);
     Dm[2] = cmul_(nx.Mfwd[1], T[2]); Dm[3] = cmul_(nx.Mfwd[1], T[3]);
     Um[0] = cmul_(Tr[0], nx.Mrev[0]); Um[1] = cmul_(Tr[1], nx.Mrev[1]);

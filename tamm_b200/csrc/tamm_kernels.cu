@@ -185,7 +185,13 @@ stack_kernel(const double* __restrict__ layers, const double* __restrict__ lanes
                 lp.mono = v2.y; lp.deps = v3.x; lp.sigma = v3.y; lp.dz = v4.x; lp.pad = 0;
             }
             LayerY cur;
+#ifdef TAMM_SYNC_PER_LAYER
+            __syncthreads();
+#endif
             st |= layer_solve_fast(lp, ln, zeta, mu, cur);
+#ifdef TAMM_SYNC_PER_LAYER
+            __syncthreads();
+#endif
             if (j > 0) {
                 const int n = n0 + j - 1;  // interface between layers n and n+1
                 cd pEt[4], pEri[4], pYt[4], pYr[4], D[4], U[4];
@@ -547,8 +553,11 @@ size_t tamm_stack_workspace_bytes(int P, int N, int QF, int chunk) {
 int tamm_suggest_chunk(int P, int N, int QF, int sm_count) {
     if (N < 2) return 1;
     const int NI = N - 1;
-    const int maxt = TAMM_DEFAULT_VARIANT == 1 ? 192 : 256;
-    const int ctas_per_sm = TAMM_DEFAULT_VARIANT == 0 ? 1 : 2;
+    const char* ev = getenv("TAMM_STACK_VARIANT");
+    int variant = ev ? atoi(ev) : TAMM_DEFAULT_VARIANT;
+    if (variant < 0 || variant > 3) variant = TAMM_DEFAULT_VARIANT;
+    const int maxt = variant == 1 ? 192 : (variant == 3 ? 512 : 256);
+    const int ctas_per_sm = (variant == 0 || variant == 3) ? 1 : 2;
     int tb, flat;
     long bpc;                                                              // CTAs per chunk index
     stack_geometry(P, QF, maxt, &tb, &flat, &bpc);
@@ -593,9 +602,9 @@ int tamm_stack_urd(const double* layers, const double* lanes, int P, int N, int 
     if (variant < 0) {
         const char* ev = getenv("TAMM_STACK_VARIANT");
         variant = ev ? atoi(ev) : TAMM_DEFAULT_VARIANT;
-        if (variant < 0 || variant > 2) variant = TAMM_DEFAULT_VARIANT;
+        if (variant < 0 || variant > 3) variant = TAMM_DEFAULT_VARIANT;
     }
-    const int maxt = variant == 1 ? 192 : 256;
+    const int maxt = variant == 1 ? 192 : (variant == 3 ? 512 : 256);
     int tb, flat;
     long gx;
     stack_geometry(P, QF, maxt, &tb, &flat, &gx);
@@ -618,10 +627,12 @@ int tamm_stack_urd(const double* layers, const double* lanes, int P, int N, int 
     if (mode == TAMM_MODE_URD) {
         if (variant == 0) TAMM_LAUNCH(TAMM_MODE_URD, 256, 1);
         else if (variant == 1) TAMM_LAUNCH(TAMM_MODE_URD, 192, 2);
+        else if (variant == 3) TAMM_LAUNCH(TAMM_MODE_URD, 512, 1);
         else TAMM_LAUNCH(TAMM_MODE_URD, 256, 2);
     } else {
         if (variant == 0) TAMM_LAUNCH(TAMM_MODE_U, 256, 1);
         else if (variant == 1) TAMM_LAUNCH(TAMM_MODE_U, 192, 2);
+        else if (variant == 3) TAMM_LAUNCH(TAMM_MODE_U, 512, 1);
         else TAMM_LAUNCH(TAMM_MODE_U, 256, 2);
     }
 #undef TAMM_LAUNCH
