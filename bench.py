@@ -49,6 +49,8 @@ def parse():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--cpu-seconds', type=float, default=15.0)
+    ap.add_argument('--gather', default='fields', choices=['none', 'power', 'fields', 'jones'],
+                    help='N>1 only: additionally time the final NCCL all-gather of results (reported separately)')
     return ap.parse_args()
 
 
@@ -157,12 +159,10 @@ def main():
 
     import torch
     import torch.distributed as dist
-    rank = int(os.environ.get('RANK', '0'))
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
+    from tamm_b200 import distributed as tdist
+    rank, world, local = tdist.world()
     torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    tdist.init('nccl')
     import __graft_entry__ as g
     if rank == 0:
         g.build()
@@ -273,6 +273,29 @@ def main():
                                result_check=float(np.nanmax(res['Pm_HH'])))
         except Exception as e:  # e.g. not enough pinned host memory
             line['e2e'] = dict(value=None, error=repr(e)[:200])
+
+    # final all-gather of results over NVLink (north_star) -- NOT part of `value`: profiles are independent, the
+    # compute path has no exchange step; this is what a caller pays when every rank needs the whole ensemble.
+    if world > 1 and args.gather != 'none':
+        names = dict(power=['dP_HH', 'dP_HV'], fields=['E_HH', 'E_HV'], jones=['E_HH', 'E_HV', 'c_HHVV', 'dP_HH', 'dP_HV'])[args.gather]
+        try:
+            g0 = torch.cuda.Event(enable_timing=True); g1 = torch.cuda.Event(enable_timing=True)
+            got = [tdist.all_gather_profiles(out[n], P) for n in names[:1]]    # warm-up (NCCL channel setup)
+            del got
+            sync_all()
+            g0.record()
+            got = [tdist.all_gather_profiles(out[n], P) for n in names]
+            g1.record()
+            sync_all()
+            gm = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
+            dist.all_reduce(gm, op=dist.ReduceOp.MAX)
+            nbytes = sum(t.numel() * t.element_size() for t in got)
+            del got
+            line['gather'] = dict(what=args.gather, arrays=names, bytes_per_rank=nbytes, ms=float(gm.item()),
+                                  algbw_gbs=nbytes / (float(gm.item()) * 1e-3) / 1e9, included_in_value=False,
+                                  value_with_gather=evals_job / ((ms_per_step + float(gm.item())) * 1e-3))
+        except Exception as e:
+            line['gather'] = dict(what=args.gather, error=repr(e)[:200])
 
     if rank == 0:
         line['clocks'] = sampler.summary()

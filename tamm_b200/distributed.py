@@ -1,0 +1,77 @@
+"""
+Multi-GPU layer: one process per GPU (torch.distributed, NCCL over NVLink/NVSwitch; gloo on CPU for the tests).
+
+The path shards by PROFILE: every (profile, frequency, azimuth) lane is independent through the whole
+pipeline and the only cross-lane operation, the azimuth mean in Pm/dP (layerstack.py:262,266), stays inside a profile.
+So the compute path has no collective at all; the one collective offered here is the final all-gather of results
+(`all_gather_profiles`), which callers use when every rank (or rank 0) needs the whole ensemble.
+"""
+import os
+
+import numpy as np
+
+from .ensemble import shard_range
+
+
+def world():
+    """(rank, world_size, local_rank) from the torchrun environment (single process: 0, 1, 0)."""
+    return int(os.environ.get('RANK', '0')), int(os.environ.get('WORLD_SIZE', '1')), int(os.environ.get('LOCAL_RANK', '0'))
+
+
+def init(backend=None):
+    """Initialise torch.distributed from the environment if WORLD_SIZE > 1.  Returns (rank, world_size)."""
+    import torch
+    import torch.distributed as dist
+    rank, ws, local = world()
+    if ws > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = 'nccl' if torch.cuda.is_available() else 'gloo'
+        if backend == 'nccl':
+            torch.cuda.set_device(local)
+            dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+        else:
+            dist.init_process_group(backend)
+    return rank, ws
+
+
+def shard_sizes(P, ws):
+    return [shard_range(P, r, ws)[1] - shard_range(P, r, ws)[0] for r in range(ws)]
+
+
+def all_gather_profiles(local, P_total, group=None):
+    """All-gather a tensor whose leading axis is this rank's profile shard into the full (P_total, ...) tensor.
+    Works for uneven shards (pads to the largest shard).  `local` may live on the GPU (NCCL) or the CPU (gloo)."""
+    import torch
+    import torch.distributed as dist
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return local
+    ws = dist.get_world_size(group)
+    sizes = shard_sizes(P_total, ws)
+    assert local.shape[0] == sizes[dist.get_rank(group)], (local.shape, sizes)
+    m = max(sizes)
+    cplx = local.is_complex()
+    x = torch.view_as_real(local) if cplx else local        # NCCL moves raw doubles
+    if x.shape[0] < m:
+        pad = torch.zeros((m - x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        x = torch.cat([x, pad], dim=0)
+    x = x.contiguous()
+    out = torch.empty((ws * m,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    dist.all_gather_into_tensor(out, x, group=group)
+    parts = [out[r * m: r * m + sizes[r]] for r in range(ws)]
+    full = torch.cat(parts, dim=0) if len(set(sizes)) > 1 else out
+    return torch.view_as_complex(full.contiguous()) if cplx else full
+
+
+def all_reduce_azimuth_sums(sums, group=None):
+    """For the alternative azimuth sharding of a single profile (configs[1], [3]): the per-depth sums of |E| over the
+    local azimuths are summed over ranks before the dB step (layerstack.py:262).  Tiny: (N-1) x 2 doubles."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+    return sums
+
+
+def gather_bytes(P_total, N, Q, F, what='jones'):
+    """Bytes each rank RECEIVES in the final all-gather (SURVEY.md 8e budget check)."""
+    per_eval = {'jones': 64, 'fields': 32, 'power': 16}[what]
+    return int(per_eval) * int(P_total) * int(N - 1) * int(Q) * int(F)
