@@ -43,30 +43,37 @@ struct cd {
 TAMM_HD double frcp(double a) {
 #if defined(__CUDA_ARCH__)
     double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));     // >= 20 good bits
     double e = fma(-a, r, 1.0);
-    r = fma(r, e, r);
+    r = fma(r, e, r);                                           // 40
     e = fma(-a, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-a, r, 1.0);
-    return fma(r, e, r);
+    r = fma(r, e, r);                                           // 80 -> rounding-limited
+    return r;
 #else
     return 1.0 / a;
 #endif
 }
-TAMM_HD double fsqrt(double a) {
+// y ~ 1/sqrt(a) to full precision (a > 0)
+TAMM_HD double frsqrt(double a) {
 #if defined(__CUDA_ARCH__)
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
-    double h = 0.5 * a;
+    const double h = 0.5 * a;
     y = y * fma(-h * y, y, 1.5);
     y = y * fma(-h * y, y, 1.5);
-    y = y * fma(-h * y, y, 1.5);
-    double s = a * y;
-    s = fma(0.5 * y, fma(-s, s, a), s);
-    return (a > 0.0) ? s : ((a == 0.0) ? 0.0 : s);
+    return y;
 #else
-    return sqrt(a);
+    return 1.0 / sqrt(a);
+#endif
+}
+TAMM_HD double fsqrt(double a) {
+#if defined(__CUDA_ARCH__)
+    double y = frsqrt(a);
+    double s = a * y;
+    s = fma(0.5 * y, fma(-s, s, a), s);       // one correction step on sqrt itself
+    return (a > 0.0) ? s : 0.0;               // sqrt(0) = 0 (the rsqrt path gives NaN there); negative inputs do not occur
+#else
+    return a > 0.0 ? sqrt(a) : 0.0;
 #endif
 }
 
@@ -702,8 +709,17 @@ struct LayerY {
 TAMM_HD double fast_abs(cd z) { return fsqrt(fma(z.re, z.re, z.im * z.im)); }
 TAMM_HD cd csqrt_f(cd z) {   // principal square root, no hypot() scaling (|z| is O(1e-20 .. 1e3) here)
     double m = fast_abs(z);
-    double t = fsqrt(0.5 * (m + fabs(z.re)));
-    double o = (t > 0.0) ? 0.5 * z.im * frcp(t) : 0.0;
+    double v = 0.5 * (m + fabs(z.re));
+#if defined(__CUDA_ARCH__)
+    double y = frsqrt(v);                      // 1/t
+    double t = v * y;
+    t = fma(0.5 * y, fma(-t, t, v), t);
+    double o = (v > 0.0) ? 0.5 * z.im * y : 0.0;
+    t = (v > 0.0) ? t : 0.0;
+#else
+    double t = v > 0.0 ? sqrt(v) : 0.0;
+    double o = (t > 0.0) ? 0.5 * z.im / t : 0.0;
+#endif
     return (z.re >= 0.0) ? cd{t, o} : cd{fabs(o), copysign(t, z.im)};
 }
 
@@ -961,6 +977,8 @@ TAMM_HD void interface_fast(const cd Et[4], const cd Eri[4], const cd Yt[4], con
     cd d3[4] = {nx.Yt[0] - nx.Yr[0], nx.Yt[1] - nx.Yr[1], nx.Yt[2] - nx.Yr[2], nx.Yt[3] - nx.Yr[3]};
     cd W[4], V[4], T[4], Tr[4];
     mm22(d1, Et, V); mm22(M, V, W); mm22(nx.Eti, W, T);          // T = Et'^-1 M (Yt - Yr) Et
+    // R from the EXPLICIT difference Yt - Yt': the two admittances carry nearly identical rounding errors which cancel
+    // in the difference; the algebraically equal shortcut W - Et doubles the error of the weakest returns (measured)
     mm22(d2, Et, V); mm22(M, V, W); mm22(Eri, W, R);             // R = Er^-1 M (Yt - Yt') Et
     mm22(d3, nx.Er, V); mm22(M, V, W); mm22(Eri, W, Tr);         // Trev = Er^-1 M (Yt' - Yr') Er'
     // nan_to_num (layerstack.py:101-127) only matters for singular interfaces: one finite-check, rare slow path.

@@ -72,7 +72,7 @@ WORKER = textwrap.dedent('''
     assert np.allclose(20 * np.log10(sums / F), 20 * np.log10(ref.mean(axis=0)), rtol=0, atol=1e-12)
     dist.barrier()
     dist.destroy_process_group()
-    print('rank', rank, 'ok')
+    open(os.path.join(%(out)r, 'rank%%d.ok' %% rank), 'w').write('ok')
 ''')
 
 
@@ -83,10 +83,10 @@ def _free_port():
 
 def test_two_rank_gloo_sharding_and_gather(built, tmp_path):
     script = tmp_path / 'worker.py'
-    script.write_text(WORKER % dict(root=ROOT))
+    script.write_text(WORKER % dict(root=ROOT, out=str(tmp_path)))
     env = dict(os.environ, CUDA_VISIBLE_DEVICES='', OMP_NUM_THREADS='1')
     cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2', '--master-addr', '127.0.0.1',
            '--master-port', str(_free_port()), str(script)]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
-    assert 'rank 0 ok' in r.stdout and 'rank 1 ok' in r.stdout
+    assert (tmp_path / 'rank0.ok').exists() and (tmp_path / 'rank1.ok').exists()
