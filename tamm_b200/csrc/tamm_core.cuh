@@ -728,26 +728,30 @@ TAMM_HD void inv22(const cd a[4], cd o[4]) {
     o[0] = cmul_(a[3], id); o[1] = cmul_(-a[1], id); o[2] = cmul_(-a[2], id); o[3] = cmul_(a[0], id);
 }
 
-// eigenvalues of G = -N'^-1 N (see mslp_eigs), fused arithmetic
-TAMM_HD void mslp_eigs_f(const WaveMat& m, cd db, cd& h_big, cd& h_small) {
-    cd g00 = det2(m.dd, db, m.b, m.a);        // dd*a - db*b
-    cd g01 = det2(m.dd, db, m.d, m.b);        // dd*b - db*d
-    cd g10 = det2(m.da, db, m.a, m.b);        // da*b - db*a
-    cd g11 = det2(m.da, db, m.b, m.d);        // da*d - db*b
-    cd det1 = det2(m.da, db, db, m.dd);       // da*dd - db*db
-    cd hm = 0.5 * (g00 + g11);
-    cd hd = 0.5 * (g00 - g11);
-    cd disc = csq(hd);
-    cfma(disc, g01, g10);
+// Eigenvalues of G = -N'^-1 N (see mslp_eigs) from three scalars only.  With G' = adj(N') N:
+//   tr G' = dd*a + da*d - 2 db*b (= d/dq det N),  det G' = det N' * det N,
+//   lambda_big = tr/2 + sqrt((tr/2)^2 - det G'),  h_small = -lambda_small/det N' = -det N / lambda_big,
+//   h_big = -lambda_big / det N'.
+// Returns lambda_big and det N' instead of h_big so callers that only need |h_big| avoid a division.
+TAMM_HD void mslp_core(const WaveMat& m, cd db, cd& big, cd& det1, cd& h_small) {
+    cd tr = cmul_(m.dd, m.a);
+    cfma(tr, m.da, m.d);
+    cfma(tr, (-2.0) * db, m.b);
+    cd detN = det2(m.a, m.b, m.b, m.d);
+    det1 = det2(m.da, db, db, m.dd);
+    cd hm = 0.5 * tr;
+    cd disc = csq(hm);
+    cfma(disc, -det1, detN);
     cd s = csqrt_f(disc);
     bool flip = (hm.re * s.re + hm.im * s.im) < 0.0;
     s = csel(flip, -s, s);
-    cd big = hm + s;
-    cd detg = det2(g00, g01, g10, g11);
-    cd ninv = -crecip_f(det1);
-    cd small = (abs2(big) > 0.0) ? cmul_(detg, crecip_f(big)) : mk(0.0);
-    h_big = cmul_(big, ninv);
-    h_small = cmul_(small, ninv);
+    big = hm + s;
+    h_small = (abs2(big) > 0.0) ? (-1.0) * cmul_(detN, crecip_f(big)) : mk(0.0);
+}
+TAMM_HD void mslp_eigs_f(const WaveMat& m, cd db, cd& h_big, cd& h_small) {
+    cd big, det1;
+    mslp_core(m, db, big, det1, h_small);
+    h_big = (-1.0) * cmul_(big, crecip_f(det1));
 }
 
 // Four roots + the (Ex, Ey) null vector of N at each root, written to rv[k] = {q, Ex, Ey}.  rv is indexed with run-time
@@ -801,12 +805,13 @@ TAMM_HD void eig4_fast(const WaveCoef& w, cd rv[4][3]) {
 #endif
             for (int it = 0; it < 24; ++it) {
                 WaveMat mm = wave_matrix(w, x);
-                cd part, h;
-                mslp_eigs_f(mm, w.db, part, h);
+                cd big, det1, h;
+                mslp_core(mm, w.db, big, det1, h);
                 x = x + h;
                 double h2 = abs2(h);
                 h2 = h2 * h2;
-                if (h2 * h2 <= 1e-30 * abs2(part) * abs2(x)) break;
+                // |h|^8 <= 1e-30 |h_big|^2 |x|^2 with |h_big| = |big|/|det N'|  (no division)
+                if (h2 * h2 * abs2(det1) <= 1e-30 * abs2(big) * abs2(x)) break;
             }
             WaveMat mm = wave_matrix(w, x);
             cd f = det2(mm.a, mm.b, mm.b, mm.d);

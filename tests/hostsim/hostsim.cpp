@@ -87,6 +87,22 @@ int hostsim_urd(const double* layers, const double* lanes, int N, int F, double 
     return 0;
 }
 
+// Unsorted roots of the hot-path eigen-solver (eig4_fast) for every (lane, layer): out complex128 (F, N, 4).
+int hostsim_roots_fast(const double* layers, const double* lanes, int N, int F, double zeta, double mu, double* out) {
+    for (int f = 0; f < F; ++f) {
+        LaneParams ln; std::memcpy(&ln, lanes + (size_t)f * LANE_STRIDE, sizeof(ln));
+        for (int n = 0; n < N; ++n) {
+            LayerParams lp; std::memcpy(&lp, layers + (size_t)n * LAYER_STRIDE, sizeof(lp));
+            const Sym3 e = permittivity(lp, ln);
+            const WaveCoef w = wave_coef(e, mu, zeta);
+            cd rv[4][3];
+            eig4_fast(w, rv);
+            for (int k = 0; k < 4; ++k) put(out + (((size_t)f * N + n) * 4 + k) * 2, rv[k][0]);
+        }
+    }
+    return 0;
+}
+
 // Same as hostsim_urd but through the hot-path formulation used by stack_kernel (layer_solve_fast/interface_fast).
 int hostsim_urd_fast(const double* layers, const double* lanes, int N, int F, double zeta, double mu, int chunk, int mode,
                      double* out) {

@@ -38,13 +38,16 @@ def sim_layers(lib, os_, f, alpha):
     return o
 
 
-def sim_urd(lib, os_, f, alpha, chunk, mode=0):
+def sim_urd(lib, os_, f, alpha, chunk, mode=0, fast=True):
+    """fast=True: the formulation stack_kernel runs (layer_solve_fast / interface_fast); False: the A, A^-1 route of
+    the diagnostic kernel."""
     N, F = os_.N_layers, os_.N_frames
     lay = packing.pack_layers(os_.nlm, os_.dz, os_.epsa, os_.epsc, os_.sigma)
     lan = packing.pack_lanes(os_.beta, f)
     out = np.zeros((F, N - 1, 2, 2), dtype=np.complex128)
-    rc = lib.hostsim_urd(_P(lay), _P(lan), N, F, ctypes.c_double(float(os_.zeta(alpha))), ctypes.c_double(os_.mu), chunk,
-                         mode, _P(out))
+    fn = lib.hostsim_urd_fast if fast else lib.hostsim_urd
+    rc = fn(_P(lay), _P(lan), N, F, ctypes.c_double(float(os_.zeta(alpha))), ctypes.c_double(os_.mu), chunk,
+            mode, _P(out))
     assert rc == 0
     return out
 
@@ -74,9 +77,52 @@ def test_kernel_arithmetic_layers(sim, name):
 
 @pytest.mark.parametrize('name', h.golden_names())
 @pytest.mark.parametrize('chunk', [1000, 16, 7, 1])
-def test_kernel_arithmetic_urd_chunked(sim, name, chunk):
+@pytest.mark.parametrize('fast', [True, False])
+def test_kernel_arithmetic_urd_chunked(sim, name, chunk, fast):
     g = h.load_golden(name)
     os_ = h.oracle_stack(g)
     mode = 1 if 'kw_URD' in g and str(g['kw_URD']) == 'U' else 0
-    got = sim_urd(sim, os_, float(g['f']), float(g['alpha']), chunk, mode)
+    got = sim_urd(sim, os_, float(g['f']), float(g['alpha']), chunk, mode, fast)
     assert h.peak_rel_err(got, g['URD'], axis=(1, 2, 3)) < h.RTOL_COMPLEX
+
+
+def test_hot_path_closer_to_exact_than_reference(sim):
+    """The hot-path arithmetic against the extended-precision arbiter on the fixtures: at least as close to the exact
+    Jones matrices as the reference's own arithmetic."""
+    for name in ('demo_a10', 'tilted_a10', 'rathmann_t4_a10', 'perlayer_eps'):
+        g = h.load_golden(name)
+        os_ = h.oracle_stack(g)
+        f, a = float(g['f']), float(g['alpha'])
+        x = os_.get_URD(f, a, eig='factored', precision='extended').astype(np.complex128)
+        got = sim_urd(sim, os_, f, a, 16)
+        assert h.peak_rel_err(got, x, axis=(1, 2, 3)) <= max(h.peak_rel_err(g['URD'], x, axis=(1, 2, 3)), 1e-12), name
+
+
+def _roots_fast(lib, os_, f, alpha):
+    N, F = os_.N_layers, os_.N_frames
+    lay = packing.pack_layers(os_.nlm, os_.dz, os_.epsa, os_.epsc, os_.sigma)
+    lan = packing.pack_lanes(os_.beta, f)
+    out = np.zeros((F, N, 4), dtype=np.complex128)
+    assert lib.hostsim_roots_fast(_P(lay), _P(lan), N, F, ctypes.c_double(float(os_.zeta(alpha))), ctypes.c_double(os_.mu),
+                                  _P(out)) == 0
+    return out
+
+
+@pytest.mark.parametrize('alpha_deg', [0.0, 10.0, 40.0])
+def test_eigen_solver_near_degenerate_and_strong_anisotropy(sim, alpha_deg):
+    """Roots of the hot-path eigen-solver against the extended-precision roots for mode splittings |q_p - q_s| from
+    ~1e-2 down to 0 (anisotropy scaled by 1 ... 1e-14 and exactly isotropic) and for a strongly anisotropic medium."""
+    from tamm_b200 import profiles
+    base, z = profiles.tilted(24, 100, seed=21)
+    scales = [1.0, 1e-2, 1e-4, 1e-6, 1e-8, 1e-10, 1e-12, 1e-14, 0.0]
+    for deps, tol in ((0.034, 3e-15), (1.2, 2e-14)):
+        for sc in scales:
+            nlm = base.copy()
+            nlm[:, 1:] *= sc
+            os_ = orc.OracleStack(nlm, z, N_frames=5, epsa=[3.17 - deps], epsc=[3.17])
+            alpha = np.deg2rad(alpha_deg)
+            got = np.sort_complex(_roots_fast(sim, os_, 179e6, alpha))
+            L = os_.layers(179e6, alpha, eig='factored', precision='extended')
+            want = np.sort_complex(L['qs_unsorted'].astype(np.complex128))
+            assert np.isfinite(got.view(np.float64)).all(), (deps, sc)
+            assert np.abs(got - want).max() < tol, (deps, sc, np.abs(got - want).max())
