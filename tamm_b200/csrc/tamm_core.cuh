@@ -829,12 +829,78 @@ TAMM_HD void eig4_fast(const WaveCoef& w, cd rv[4][3]) {
     }
 }
 
+// ---- lean, branch-free exp(i*theta) * exp(x) for the layer phases ---------------------------------------------
+// sincos: n = rint(t * 2/pi), three-term Cody-Waite reduction with FMAs (exact to ~2^-150 for |t| < 2^30, far beyond
+// any k0*q*d here), fdlibm __kernel_sin/__kernel_cos minimax polynomials on [-pi/4, pi/4] (< 1 ulp).
+// exp: n = rint(x * log2 e), two-term reduction, Taylor degree 13 on |r| <= ln2/2 (truncation 4e-18), 2^n by exponent
+// arithmetic; x is clamped to +-700 (|exp| outside 1e+-304 cannot occur for a physical layer).
+TAMM_HD void sincos_f(double t, double& sn, double& cs) {
+    const double n = rint(t * 0.6366197723675814);
+    double r = fma(-n, 1.5707963267948966, t);
+    r = fma(-n, 6.123233995736766e-17, r);
+    r = fma(-n, -1.4973849048591698e-33, r);
+    const double z = r * r;
+    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    ps = fma(z, ps, 2.75573137070700676789e-06);
+    ps = fma(z, ps, -1.98412698298579493134e-04);
+    ps = fma(z, ps, 8.33333333332248946124e-03);
+    ps = fma(z, ps, -1.66666666666666324348e-01);
+    const double s = fma(r * z, ps, r);
+    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+    pc = fma(z, pc, -2.75573143513906633035e-07);
+    pc = fma(z, pc, 2.48015872894767294178e-05);
+    pc = fma(z, pc, -1.38888888888741095749e-03);
+    pc = fma(z, pc, 4.16666666666666019037e-02);
+    const double c = fma(z * z, pc, fma(-0.5, z, 1.0));
+    const int q = (int)n & 3;
+    const double a = (q & 1) ? c : s, b = (q & 1) ? s : c;
+    sn = (q & 2) ? -a : a;
+    cs = ((q + 1) & 2) ? -b : b;
+}
+TAMM_HD double exp_f(double x) {
+    x = fmin(fmax(x, -700.0), 700.0);
+    const double n = rint(x * 1.4426950408889634);
+    double r = fma(-n, 0.6931471805598903, x);
+    r = fma(-n, 5.497923018708371e-14, r);
+    double p = fma(r, 1.6059043836821613e-10, 2.08767569878681e-09);   // 1/13!, 1/12!
+    p = fma(r, p, 2.505210838544172e-08);      // 1/11!
+    p = fma(r, p, 2.755731922398589e-07);      // 1/10!
+    p = fma(r, p, 2.7557319223985893e-06);     // 1/9!
+    p = fma(r, p, 2.48015873015873e-05);       // 1/8!
+    p = fma(r, p, 1.984126984126984e-04);      // 1/7!
+    p = fma(r, p, 1.388888888888889e-03);      // 1/6!
+    p = fma(r, p, 8.333333333333333e-03);      // 1/5!
+    p = fma(r, p, 4.1666666666666664e-02);     // 1/4!
+    p = fma(r, p, 1.6666666666666666e-01);     // 1/3!
+    p = fma(r, p, 0.5);
+    p = fma(r, p, 1.0);
+    p = fma(r, p, 1.0);
+    // 2^n, |n| <= 1010: split so neither factor leaves the normal range
+    const int ni = (int)n;
+    const int n1 = ni / 2, n2 = ni - n1;
 #if defined(__CUDA_ARCH__)
+    const double s1 = __hiloint2double((n1 + 1023) << 20, 0), s2 = __hiloint2double((n2 + 1023) << 20, 0);
+#else
+    const double s1 = ldexp(1.0, n1), s2 = ldexp(1.0, n2);
+#endif
+    return (p * s1) * s2;
+}
+// exp(-+ i (2 pi f q d)/c): same argument arithmetic as phase() (layer_PPJ.py:437)
+#if defined(__CUDA_ARCH__) && defined(TAMM_PHASE_NOINLINE)
 __device__ __noinline__
 #else
-inline
+TAMM_HD
 #endif
-cd phase_ni(double qre, double qim, double twopif, double d, double sign) { return phase(cd{qre, qim}, twopif, d, sign); }
+cd phase_f(cd q, double twopif, double d, double sign) {
+    const double rc = 1.0 / C_CONST;
+    cd z = (twopif * q) * d;
+    double ar = sign * (z.im * rc);
+    double ai = sign * (-(z.re * rc));
+    double sn, cs;
+    sincos_f(ai, sn, cs);
+    double m = exp_f(ar);
+    return cd{m * cs, m * sn};
+}
 
 TAMM_HD int layer_solve_fast(const LayerParams& lp, const LaneParams& ln, double zeta, double mu, LayerY& L) {
     int status = 0;
@@ -930,7 +996,7 @@ TAMM_HD int layer_solve_fast(const LayerParams& lp, const LaneParams& ln, double
         cd t23 = cmul_(-u1, g21) - m12;
         g23 = cmul_(t23, imez);
         if (cisnan(g23)) g23 = g23p;
-        if (fast_abs(q0 - q1) < QSD_THR) { g12 = mk(0.0); g13 = g13p; g21 = mk(0.0); g23 = g23p; }
+        if (abs2(q0 - q1) < QSD_THR * QSD_THR) { g12 = mk(0.0); g13 = g13p; g21 = mk(0.0); g23 = g23p; }   // |q0-q1| < qsd_thr
         cd den2 = cmul_(mez, mzz - csq(q2)) - m12sq;
         g32 = cmul_(c01m - m12 * u2, crecip_f(den2));
         if (cisnan(g32)) g32 = mk(0.0);
@@ -943,12 +1009,13 @@ TAMM_HD int layer_solve_fast(const LayerParams& lp, const LaneParams& ln, double
         cd t43 = cmul_(-u3, g41) - m12;
         g43 = cmul_(t43, imez);
         if (cisnan(g43)) g43 = g23p;
-        if (fast_abs(q2 - q3) < QSD_THR) { g32 = mk(0.0); g33 = g33p; g41 = mk(0.0); g43 = g23p; }
+        if (abs2(q2 - q3) < QSD_THR * QSD_THR) { g32 = mk(0.0); g33 = g33p; g41 = mk(0.0); g43 = g23p; }
     }
     // row norms (layer_PPJ.py:399-402)
-    const double n0 = fsqrt(1.0 + abs2(g12) + abs2(g13)), n1 = fsqrt(1.0 + abs2(g21) + abs2(g23));
-    const double n2 = fsqrt(1.0 + abs2(g32) + abs2(g33)), n3 = fsqrt(1.0 + abs2(g41) + abs2(g43));
-    const double i0 = frcp(n0), i1 = frcp(n1), i2 = frcp(n2), i3 = frcp(n3);
+    const double s0 = 1.0 + abs2(g12) + abs2(g13), s1 = 1.0 + abs2(g21) + abs2(g23);
+    const double s2 = 1.0 + abs2(g32) + abs2(g33), s3 = 1.0 + abs2(g41) + abs2(g43);
+    const double i0 = frsqrt(s0), i1 = frsqrt(s1), i2 = frsqrt(s2), i3 = frsqrt(s3);     // 1/norm
+    const double n0 = s0 * i0, n1 = s1 * i1, n2 = s2 * i2, n3 = s3 * i3;                 // norm
     // ---- E blocks, their inverses and the admittances
     L.Et[0] = mk(i0); L.Et[1] = i1 * g21; L.Et[2] = i0 * g12; L.Et[3] = mk(i1);
     L.Er[0] = mk(-i2); L.Er[1] = i3 * g41; L.Er[2] = i2 * g32; L.Er[3] = mk(i3);
@@ -964,10 +1031,10 @@ TAMM_HD int layer_solve_fast(const LayerParams& lp, const LaneParams& ln, double
         mm22(Hr, rb, L.Yr);
         L.Eri[0] = n2 * rb[0]; L.Eri[1] = n2 * rb[1]; L.Eri[2] = n3 * rb[2]; L.Eri[3] = n3 * rb[3];
     }
-    L.Mfwd[0] = phase_ni(q0.re, q0.im, ln.twopif, lp.dz, -1.0);
-    L.Mfwd[1] = phase_ni(q1.re, q1.im, ln.twopif, lp.dz, -1.0);
-    L.Mrev[0] = phase_ni(q2.re, q2.im, ln.twopif, lp.dz, +1.0);
-    L.Mrev[1] = phase_ni(q3.re, q3.im, ln.twopif, lp.dz, +1.0);
+    L.Mfwd[0] = phase_f(q0, ln.twopif, lp.dz, -1.0);
+    L.Mfwd[1] = phase_f(q1, ln.twopif, lp.dz, -1.0);
+    L.Mrev[0] = phase_f(q2, ln.twopif, lp.dz, +1.0);
+    L.Mrev[1] = phase_f(q3, ln.twopif, lp.dz, +1.0);
     return status;
 }
 

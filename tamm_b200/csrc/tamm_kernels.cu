@@ -39,7 +39,7 @@ int fail(const char* fmt, const char* a = "", long b = 0) {
     } while (0)
 
 #ifndef TAMM_DEFAULT_VARIANT
-#define TAMM_DEFAULT_VARIANT 2
+#define TAMM_DEFAULT_VARIANT 0
 #endif
 
 constexpr int TL = 16;     // layers per TMA sub-tile (16 * 80 B = 1280 B per profile)
@@ -82,10 +82,9 @@ __device__ __forceinline__ cd ld_cd(const cd* p) {
 
 // ---- the hot kernel ------------------------------------------------------------------------------
 // grid = (lane blocks, chunks); block = TB threads (multiple of 32).
-// MAXT / MINB: launch bounds (register budget): (256,1) -> 255 regs, (192,2) -> 168 regs, (256,2) -> 128 regs.
-template <int MODE, int MAXT, int MINB>
-__global__ void __launch_bounds__(MAXT, MINB)
-stack_kernel(const double* __restrict__ layers, const double* __restrict__ lanes, int P, int N, int QF, int flat, double zeta,
+template <int MODE>
+__device__ __forceinline__ void
+stack_body(const double* __restrict__ layers, const double* __restrict__ lanes, int P, int N, int QF, int flat, double zeta,
              double mu, int chunk, int nchunks, cd* __restrict__ planes, cd* __restrict__ agg, int* __restrict__ status) {
     __shared__ alignas(128) double sbuf[2][NPMAX][TL * LAYER_STRIDE];
     __shared__ alignas(8) uint64_t bar[2];
@@ -238,6 +237,17 @@ stack_kernel(const double* __restrict__ layers, const double* __restrict__ lanes
         if (st && status) atomicOr(status + p, st);
     }
 }
+
+#define TAMM_STACK_ARGS                                                                                              \
+    const double *__restrict__ layers, const double *__restrict__ lanes, int P, int N, int QF, int flat, double zeta, \
+        double mu, int chunk, int nchunks, cd *__restrict__ planes, cd *__restrict__ agg, int *__restrict__ status
+#define TAMM_STACK_PASS layers, lanes, P, N, QF, flat, zeta, mu, chunk, nchunks, planes, agg, status
+// MAXT / MINB: launch bounds (register budget): (256,1) -> 255 regs, (192,2) -> 168 regs, (256,2) -> 128 regs, ...
+template <int MODE, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) stack_kernel(TAMM_STACK_ARGS) { stack_body<MODE>(TAMM_STACK_PASS); }
+// explicit register cap (ptxas otherwise rounds the 320-thread budget down to 168)
+template <int MODE, int NREG>
+__global__ void __maxnreg__(NREG) stack_kernel_nreg(TAMM_STACK_ARGS) { stack_body<MODE>(TAMM_STACK_PASS); }
 
 // ---- chunk prefix scan: one warp per (profile, lane) ---------------------------------------------
 struct DU {
@@ -487,6 +497,18 @@ int pick_block(int QF, int maxt = 256) {
     return best;
 }
 
+// launch-bound variants of stack_kernel: threads per CTA (CTAs per SM, registers):
+//   0: 256 (1, 255)   1: 192 (2, 168)   2: 256 (2, 128)   3: 512 (1, 128)   4: 320 (1, 204)   5: 384 (1, 168)
+int variant_threads(int v) {
+    switch (v) {
+        case 1: return 192;
+        case 3: return 512;
+        case 4: return 320;
+        case 5: return 384;
+        default: return 256;
+    }
+}
+
 // CTA geometry of stack_kernel: flattened lanes whenever a CTA of `maxt` threads spans at most NPMAX profiles.
 void stack_geometry(int P, int QF, int maxt, int* tb, int* flat, long* gx) {
     if ((long)(NPMAX - 1) * QF + 1 >= maxt) {
@@ -555,9 +577,9 @@ int tamm_suggest_chunk(int P, int N, int QF, int sm_count) {
     const int NI = N - 1;
     const char* ev = getenv("TAMM_STACK_VARIANT");
     int variant = ev ? atoi(ev) : TAMM_DEFAULT_VARIANT;
-    if (variant < 0 || variant > 3) variant = TAMM_DEFAULT_VARIANT;
-    const int maxt = variant == 1 ? 192 : (variant == 3 ? 512 : 256);
-    const int ctas_per_sm = (variant == 0 || variant == 3) ? 1 : 2;
+    if (variant < 0 || variant > 5) variant = TAMM_DEFAULT_VARIANT;
+    const int maxt = variant_threads(variant);
+    const int ctas_per_sm = (variant == 1 || variant == 2) ? 2 : 1;
     int tb, flat;
     long bpc;                                                              // CTAs per chunk index
     stack_geometry(P, QF, maxt, &tb, &flat, &bpc);
@@ -602,9 +624,9 @@ int tamm_stack_urd(const double* layers, const double* lanes, int P, int N, int 
     if (variant < 0) {
         const char* ev = getenv("TAMM_STACK_VARIANT");
         variant = ev ? atoi(ev) : TAMM_DEFAULT_VARIANT;
-        if (variant < 0 || variant > 3) variant = TAMM_DEFAULT_VARIANT;
+        if (variant < 0 || variant > 5) variant = TAMM_DEFAULT_VARIANT;
     }
-    const int maxt = variant == 1 ? 192 : (variant == 3 ? 512 : 256);
+    const int maxt = variant_threads(variant);
     int tb, flat;
     long gx;
     stack_geometry(P, QF, maxt, &tb, &flat, &gx);
@@ -624,18 +646,34 @@ int tamm_stack_urd(const double* layers, const double* lanes, int P, int N, int 
         stack_kernel<MODE, MAXT, MINB><<<grid, tb, dyn, s>>>(layers, lanes, P, N, QF, flat, zeta, mu, chunk, nch,       \
                                                               (cd*)planes, agg, status);                                \
     } while (0)
+#define TAMM_LAUNCH_NREG(MODE, NREG, MAXT)                                                                             \
+    do {                                                                                                                \
+        static bool attr_set = false;                                                                                   \
+        if (!attr_set) {                                                                                                \
+            CUDA_OK(cudaFuncSetAttribute(stack_kernel_nreg<MODE, NREG>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                         24 * (int)sizeof(double2) * MAXT));                                            \
+            attr_set = true;                                                                                            \
+        }                                                                                                               \
+        stack_kernel_nreg<MODE, NREG><<<grid, tb, dyn, s>>>(layers, lanes, P, N, QF, flat, zeta, mu, chunk, nch,        \
+                                                             (cd*)planes, agg, status);                                 \
+    } while (0)
     if (mode == TAMM_MODE_URD) {
         if (variant == 0) TAMM_LAUNCH(TAMM_MODE_URD, 256, 1);
         else if (variant == 1) TAMM_LAUNCH(TAMM_MODE_URD, 192, 2);
         else if (variant == 3) TAMM_LAUNCH(TAMM_MODE_URD, 512, 1);
+        else if (variant == 4) TAMM_LAUNCH_NREG(TAMM_MODE_URD, 192, 320);
+        else if (variant == 5) TAMM_LAUNCH(TAMM_MODE_URD, 384, 1);
         else TAMM_LAUNCH(TAMM_MODE_URD, 256, 2);
     } else {
         if (variant == 0) TAMM_LAUNCH(TAMM_MODE_U, 256, 1);
         else if (variant == 1) TAMM_LAUNCH(TAMM_MODE_U, 192, 2);
         else if (variant == 3) TAMM_LAUNCH(TAMM_MODE_U, 512, 1);
+        else if (variant == 4) TAMM_LAUNCH_NREG(TAMM_MODE_U, 192, 320);
+        else if (variant == 5) TAMM_LAUNCH(TAMM_MODE_U, 384, 1);
         else TAMM_LAUNCH(TAMM_MODE_U, 256, 2);
     }
 #undef TAMM_LAUNCH
+#undef TAMM_LAUNCH_NREG
     CUDA_OK(cudaGetLastError());
     if (nch > 1) {
         long nseq = (long)P * QF;

@@ -87,6 +87,16 @@ int hostsim_urd(const double* layers, const double* lanes, int N, int F, double 
     return 0;
 }
 
+// Elementary functions of the hot path: out[i] = {sin, cos, exp} of x[i] through sincos_f / exp_f.
+int hostsim_elementary(const double* x, int n, double* out) {
+    for (int i = 0; i < n; ++i) {
+        double s, c;
+        sincos_f(x[i], s, c);
+        out[3 * i] = s; out[3 * i + 1] = c; out[3 * i + 2] = exp_f(x[i]);
+    }
+    return 0;
+}
+
 // Unsorted roots of the hot-path eigen-solver (eig4_fast) for every (lane, layer): out complex128 (F, N, 4).
 int hostsim_roots_fast(const double* layers, const double* lanes, int N, int F, double zeta, double mu, double* out) {
     for (int f = 0; f < F; ++f) {

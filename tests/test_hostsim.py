@@ -126,3 +126,20 @@ def test_eigen_solver_near_degenerate_and_strong_anisotropy(sim, alpha_deg):
             want = np.sort_complex(L['qs_unsorted'].astype(np.complex128))
             assert np.isfinite(got.view(np.float64)).all(), (deps, sc)
             assert np.abs(got - want).max() < tol, (deps, sc, np.abs(got - want).max())
+
+
+def test_hot_path_elementary_functions(sim):
+    """sincos_f / exp_f (the branch-free versions the stack kernel inlines) against libm in extended precision."""
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.uniform(-50, 50, 20000), rng.uniform(-3e4, 3e4, 20000), rng.uniform(-1e-3, 1e-3, 2000),
+                        np.array([0.0, np.pi / 4, -np.pi / 4, np.pi / 2, 1e5, -1e5, 699.0, -699.0, 710.0, -710.0])])
+    out = np.zeros((x.size, 3))
+    assert sim.hostsim_elementary(_P(x), x.size, _P(out)) == 0
+    xl = x.astype(np.longdouble)
+    assert np.abs(out[:, 0] - np.sin(xl).astype(np.float64)).max() < 2.3e-16
+    assert np.abs(out[:, 1] - np.cos(xl).astype(np.float64)).max() < 2.3e-16
+    xe = np.clip(x, -700, 700)
+    small = np.abs(xe) < 700
+    rel = np.abs(out[:, 2] / np.exp(xe.astype(np.longdouble)).astype(np.float64) - 1)
+    assert rel[small].max() < 4.5e-16
+    assert np.isfinite(out).all()
