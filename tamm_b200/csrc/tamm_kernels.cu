@@ -375,6 +375,98 @@ returns_kernel(const cd* __restrict__ planes, const cd* __restrict__ pre, int N,
     }
 }
 
+
+// Fused returns + power for 32 <= F <= 1024: one CTA = all F azimuths of one (profile, frequency) x TN consecutive depths,
+// so the azimuth mean (layerstack.py:262,266) is a CTA reduction and |E| never goes to HBM.  128 B/eval instead of 225.
+// (TN below is TNF, the fused kernel's own depth tile.)
+constexpr int TNF = 4;   // depths per CTA of the fused returns kernel (keeps it at ~64 registers)
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+returns_fused_kernel(const cd* __restrict__ planes, const cd* __restrict__ pre, int N, int Q, int F, int mode, int chunk,
+                     int nchunks, cd e0, cd e1, int gtm_phase, cd* __restrict__ E_HH, cd* __restrict__ E_HV,
+                     cd* __restrict__ c_HHVV, double* __restrict__ dP_HH, double* __restrict__ dP_HV,
+                     double* __restrict__ Pm_HH, double* __restrict__ Pm_HV) {
+    constexpr int NW = BLOCK / 32;
+    __shared__ double red[NW][2 * TNF];
+    __shared__ double tot[2 * TNF];
+    const int NI = N - 1, QF = Q * F;
+    const int p = blockIdx.z, iq = blockIdx.y;
+    const int ifr = threadIdx.x;
+    const bool live = ifr < F;
+    const int l = iq * F + (live ? ifr : F - 1);
+    const int nb = blockIdx.x * TNF, ne = min(NI, nb + TNF);
+    const cd* in = planes + ((size_t)p * NI * 4) * QF + l;
+    const size_t obase = (((size_t)p * Q + iq) * NI) * F + (live ? ifr : F - 1);
+    double ah[TNF], av[TNF];
+    cd Dp[4], Up[4];
+    int cc = -1;
+#pragma unroll
+    for (int k = 0; k < TNF; ++k) {
+        const int n = nb + k;
+        ah[k] = 0.0; av[k] = 0.0;
+        if (n < ne) {
+            const cd* ip = in + (size_t)n * 4 * QF;
+            cd m[4] = {ld_cd(ip), ld_cd(ip + QF), ld_cd(ip + 2 * (size_t)QF), ld_cd(ip + 3 * (size_t)QF)};
+            if (nchunks > 1) {
+                int c = n / chunk;
+                if (c != cc) { load_prefix(pre, (size_t)p * QF + l, nchunks, c, Dp, Up); cc = c; }
+                if (c > 0) apply_prefix(mode, Dp, Up, m);
+            }
+            cd hh = m[0] * e0 + m[1] * e1;             // get_Rx_all (layerstack.py:298)
+            cd hv = m[2] * e0 + m[3] * e1;
+            cd num = m[0] * conj(m[3]);                // c_HHVV (layerstack.py:271-278): num / (|m0| |m3|)
+            double iden = tamm::frsqrt(abs2(m[0]) * abs2(m[3]));
+            cd c = cd{num.re * iden, num.im * iden};
+            if (gtm_phase) c = cd{-c.re, c.im};
+            double a = tamm::fsqrt(abs2(hh)), b = tamm::fsqrt(abs2(hv));
+            if (live) {
+                const size_t o = obase + (size_t)n * F;
+                st_cd(E_HH + o, hh);
+                st_cd(E_HV + o, hv);
+                st_cd(c_HHVV + o, c);
+                ah[k] = a; av[k] = b;
+            }
+        }
+    }
+    // CTA reduction of the 2*TNF sums over azimuth (fixed order -> deterministic)
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < TNF; ++k) {
+        double x = ah[k], y = av[k];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            x += __shfl_xor_sync(0xffffffffu, x, off);
+            y += __shfl_xor_sync(0xffffffffu, y, off);
+        }
+        if (lane == 0) { red[w][2 * k] = x; red[w][2 * k + 1] = y; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * TNF) {
+        double sum = 0.0;
+#pragma unroll
+        for (int i = 0; i < NW; ++i) sum += red[i][threadIdx.x];
+        const double pm = 20.0 * log10(sum / (double)F);
+        tot[threadIdx.x] = pm;
+        const int k = threadIdx.x >> 1, n = nb + k;
+        if (n < ne) {
+            const size_t row = ((size_t)p * Q + iq) * NI + n;
+            if (threadIdx.x & 1) Pm_HV[row] = pm; else Pm_HH[row] = pm;
+        }
+    }
+    __syncthreads();
+    if (live) {
+#pragma unroll
+        for (int k = 0; k < TNF; ++k) {
+            const int n = nb + k;
+            if (n < ne) {
+                const size_t o = obase + (size_t)n * F;
+                dP_HH[o] = 20.0 * log10(ah[k]) - tot[2 * k];      // layerstack.py:261-267
+                dP_HV[o] = 20.0 * log10(av[k]) - tot[2 * k + 1];
+            }
+        }
+    }
+}
+
 // one warp per (p, iq, n): azimuth mean of |E|, dB, anomaly (layerstack.py:257-267).  a* hold |E| on entry, dP on exit.
 __global__ void __launch_bounds__(256)
 power_kernel(double* __restrict__ aHH, double* __restrict__ aHV, double* __restrict__ Pm_HH, double* __restrict__ Pm_HV,
@@ -706,6 +798,23 @@ int tamm_returns(const void* planes, const void* workspace, int P, int N, int Q,
     const int QF = Q * F, NI = N - 1, nch = nchunks_of(N, chunk);
     const cd* pre = nch > 1 ? (const cd*)workspace + (size_t)P * QF * nch * 8 : nullptr;
     cudaStream_t s = (cudaStream_t)stream;
+    if (F >= 32 && F <= 1024 && Q <= 65535 && P <= 65535) {
+        // fused path: azimuth reduction inside the CTA
+        dim3 grid((NI + TNF - 1) / TNF, Q, P);
+        const cd e0 = cd{etx[0], etx[1]}, e1 = cd{etx[2], etx[3]};
+#define TAMM_RF(BLK)                                                                                                     \
+    returns_fused_kernel<BLK><<<grid, BLK, 0, s>>>((const cd*)planes, pre, N, Q, F, mode, chunk, nch, e0, e1, gtm_phase, \
+                                                   (cd*)E_HH, (cd*)E_HV, (cd*)c_HHVV, dP_HH, dP_HV, Pm_HH, Pm_HV)
+        if (F <= 64) TAMM_RF(64);
+        else if (F <= 128) TAMM_RF(128);
+        else if (F <= 192) TAMM_RF(192);
+        else if (F <= 256) TAMM_RF(256);
+        else if (F <= 512) TAMM_RF(512);
+        else TAMM_RF(1024);
+#undef TAMM_RF
+        CUDA_OK(cudaGetLastError());
+        return 0;
+    }
     dim3 grid((QF + 127) / 128, (NI + TN - 1) / TN, P);
     returns_kernel<<<grid, 128, 0, s>>>((const cd*)planes, pre, N, Q, F, mode, chunk, nch, cd{etx[0], etx[1]},
                                         cd{etx[2], etx[3]}, gtm_phase, (cd*)E_HH, (cd*)E_HV, (cd*)c_HHVV, dP_HH, dP_HV);

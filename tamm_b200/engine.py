@@ -122,7 +122,7 @@ class Engine:
                                    out['c_HHVV'].data_ptr(), out['dP_HH'].data_ptr(), out['dP_HV'].data_ptr(),
                                    out['Pm_HH'].data_ptr(), out['Pm_HV'].data_ptr(), self._stream())
         _lib.check(rc, self.lib)
-        self.launches += 2
+        self.launches += 1 if 32 <= F <= 1024 else 2      # fused returns+power kernel, or returns + power
         return out
 
     def layer_matrices(self, layers, lanes, N, QF, zeta, mu=1.0):
