@@ -85,6 +85,16 @@ int tamm_stack_urd(const double* layers, const double* lanes, int P, int N, int 
                    int mode, int chunk, void* planes, void* workspace, int* status, void* stream);
 
 /*
+ * The same for modeltype 'FP' (Fujita--Paren): replaces Layer.set_matrices FP branch (layer.py:100-128) and the FP
+ * branch of get_URD (layerstack.py:158-181, T = Trev = I, Paren reflection).  Always mode URD.
+ *   layers_fp : double [P][N][10] = { ai_horiz[0], ai_horiz[1], cos(eigang), sin(eigang), Re epsa, Re epsc, sigma, dz, 0, 0 }
+ *               (ai_horiz, eigang: layer.py:77-79, evaluated on the host with the reference's numpy.linalg.eig)
+ * Output and workspace exactly as tamm_stack_urd; continue with tamm_returns (gtm_phase = 0) / tamm_export_jones.
+ */
+int tamm_stack_urd_fp(const double* layers_fp, const double* lanes, int P, int N, int Q, int F, int chunk, void* planes,
+                      void* workspace, void* stream);
+
+/*
  * Per-depth Jones matrices in the reference's layout: complex128 [P][Q][F][N-1][2][2]
  * (layerstack.py:194 / 225, with leading profile and frequency axes).
  */

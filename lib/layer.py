@@ -7,7 +7,7 @@ import numpy as np
 import numpy.linalg as lag
 
 from layer_PPJ import *  # noqa: F401,F403  (reference does the same: layer.py:10)
-from layer_PPJ import Layer_PPJ, c_const, eps0
+from layer_PPJ import Layer_PPJ, c_const, eps0, mu0
 
 import os as _os
 import sys as _sys
@@ -94,7 +94,15 @@ class Layer(Layer_PPJ):
             self.Mrev = np.diag(d['Mrev']).astype(np.complex128)   # layer.py:97
             self.status = int(d['status'])
         if self.modeltype == 'FP':
-            raise NotImplementedError('modeltype="FP" (Fujita-Paren) is not implemented on the device yet')
+            # layer.py:100-121.  These per-object attributes are O(1) host arithmetic; LayerStack.get_returns evaluates the
+            # same expressions for all (azimuth, layer) pairs on the device (tamm_core.cuh: fp_layer).
+            epsxy = self.epsa + self.ai_horiz * (self.epsc - self.epsa)
+            kxy = np.sqrt(epsxy * (self.q2k) ** 2 + 1j * mu0 * self.sigma * self.omega)
+            (kx, ky) = kxy
+            self.ks = +np.array([kx, ky, kx, ky], dtype=np.complex128)
+            self.qs = 1 / self.q2k * self.ks
+            self.Mfwd = self.eig_to_meas_frame(np.diag(np.exp(+1j * self.ks[[0, 1]] * self.thick)))
+            self.Mrev = self.eig_to_meas_frame(np.diag(np.exp(+1j * self.ks[[2, 3]] * self.thick)))
 
     def eig_to_meas_frame(self, mat_eig_frame):
         """layer.py:123-128."""

@@ -7,7 +7,6 @@ per method).  Differences, all additive:
   * `get_returns(..., f=)` also accepts a 1-D array of frequencies; the outputs then gain a leading frequency axis;
   * `frm_layers` is a lazy view: `frm_layers[ff][nn]` materialises a `Layer` (attributes fetched from the device) on
     demand instead of holding N_frames x N_layers Python objects (SURVEY.md 7.3-8);
-  * `modeltype='FP'` is accepted by the constructor but not yet solvable on the device.
 """
 import numpy as np
 
@@ -30,6 +29,8 @@ class _FrameLayers:
         return self.stack.N_layers
 
     def _fetch(self):
+        if self.stack.modeltype != 'GTM':
+            return None
         if self._dev is None:
             st = self.stack
             eng = _get_engine()
@@ -47,7 +48,7 @@ class _FrameLayers:
         if nn < 0:
             nn += st.N_layers
         d = self._fetch()
-        one = {k: v[nn] for k, v in d.items()}
+        one = None if d is None else {k: v[nn] for k, v in d.items()}
         return Layer(st.nlm[nn], self.beta, st.dz[nn], self.f, self.zeta, st.epsa[nn], st.epsc[nn], st.sigma[nn], st.mu,
                      modeltype=st.modeltype, _device_result=one)
 
@@ -116,20 +117,19 @@ class LayerStack:
     def _packed_layers(self):
         return _packing.pack_layers(self.nlm, self.dz, self.epsa, self.epsc, self.sigma)
 
-    def _require_gtm(self):
-        if self.modeltype != 'GTM':
-            raise NotImplementedError('modeltype="FP" (Fujita-Paren) is not implemented on the device yet')
-
     def _run(self, betas, f, zeta, mode):
         """Hot path on the device for this stack: returns (engine, StackResult)."""
-        self._require_gtm()
         if self.N_layers < 2:
             raise ValueError('need at least two layers to form an interface')
         eng = _get_engine()
         fa = np.atleast_1d(np.asarray(f, dtype=np.float64))
-        layers = eng.to_device(self._packed_layers()[None])
         lanes = eng.to_device(_packing.pack_lanes(betas, fa))
-        res = eng.stack(layers, lanes, 1, self.N_layers, fa.size, len(betas), zeta, self.mu, mode)
+        if self.modeltype == 'FP':     # layer.py:100-128, layerstack.py:158-181
+            lay = _packing.pack_layers_fp(self.nlm, self.dz, self.epsa, self.epsc, self.sigma)
+            res = eng.stack_fp(eng.to_device(lay[None]), lanes, 1, self.N_layers, fa.size, len(betas))
+        else:
+            layers = eng.to_device(self._packed_layers()[None])
+            res = eng.stack(layers, lanes, 1, self.N_layers, fa.size, len(betas), zeta, self.mu, mode)
         return eng, res
 
     # ------------------------------------------------------------------------------------------
@@ -150,6 +150,8 @@ class LayerStack:
     def get_propconst(self):
         """layerstack.py:69-71: k_s = omega/c q_s of frame 0, shape (N_layers, 4)."""
         fr = self.frm_layers[0]
+        if self.modeltype == 'FP':
+            return np.array([fr[nn].ks[:] for nn in self.layerlist], dtype=np.complex128)
         d = fr._fetch()
         q2k = (2 * np.pi * fr.f) / c_const
         return np.array(q2k * d['qs'], dtype=np.complex128)

@@ -18,7 +18,7 @@ from tamm_b200 import profiles  # noqa: E402
 def run_case(name, nlm, z, F, alpha, f=179e6, E0=1e3, keep_layers=((0, 0), (1, 3)), **kw):
     sys.path.insert(0, REF)
     import layerstack as ref
-    stack_kw = {k: kw[k] for k in ('epsa', 'epsc', 'sigma', 'mu') if k in kw}
+    stack_kw = {k: kw[k] for k in ('epsa', 'epsc', 'sigma', 'mu', 'modeltype') if k in kw}
     ret_kw = {k: kw[k] for k in ('Tx_pol', 'URD', 'nn') if k in kw}
     ls = ref.LayerStack(nlm, z, N_frames=F, VERBOSE=0, **stack_kw)
     r = ls.get_returns(E0, f=f, alpha=alpha, **ret_kw)
@@ -34,8 +34,13 @@ def run_case(name, nlm, z, F, alpha, f=179e6, E0=1e3, keep_layers=((0, 0), (1, 3
     else:
         d['URD'] = ls.get_U(ls.frm_layers)
     d['propconst'] = ls.get_propconst()
+    fp = stack_kw.get('modeltype', 'GTM') == 'FP'
     for (ff, nn) in keep_layers:
         L = ls.frm_layers[ff][nn]
+        if fp:
+            for attr in ['ai_horiz', 'eigang', 'ks', 'qs', 'Mfwd', 'Mrev']:
+                d['layer_%d_%d_%s' % (ff, nn, attr)] = np.asarray(getattr(L, attr))
+            continue
         for attr in ['epsilon', 'Delta', 'qs', 'gamma', 'Ai', 'Ai_inv', 'Ki', 'Mfwd', 'Mrev', 'Py', 'ccavg', 'nlm']:
             d['layer_%d_%d_%s' % (ff, nn, attr)] = np.asarray(getattr(L, attr))
     np.savez_compressed(os.path.join(OUT, name + '.npz'), **d)
@@ -63,5 +68,20 @@ def main():
     run_case('rathmann_t4_a10', nlm, z, 24, np.deg2rad(10), keep_layers=((6, 30),))
 
 
+def main_fp():
+    nlm, z = profiles.demo(60, 900)
+    run_case('fp_demo', nlm, z, 12, 0.0, modeltype='FP', keep_layers=((0, 0), (5, 30)))
+    nlm, z = profiles.rathmann_transition(41, 800, fabric_type=4)
+    run_case('fp_rathmann_t4', nlm, z, 10, 0.0, modeltype='FP', Tx_pol=([0.6, 0.8],), keep_layers=((3, 20),))
+    N = 30
+    nlm, z = profiles.tilted(N, 300, seed=8)
+    rng = np.random.default_rng(6)
+    run_case('fp_perlayer', nlm, z, 7, 0.0, f=300e6, modeltype='FP', epsa=3.10 + 0.05 * rng.random(N),
+             epsc=3.17 + 0.02 * rng.random(N), sigma=1e-5 * (1 + rng.random(N)), nn=11, keep_layers=((2, 9),))
+
+
 if __name__ == '__main__':
+    if len(sys.argv) > 1 and sys.argv[1] == 'fp':
+        main_fp()
+        sys.exit(0)
     main()

@@ -681,11 +681,88 @@ def returns_from_URD(URD, E0, Tx_pol=([1, 0],), nn=None, modeltype='GTM'):
             np.squeeze(c_HHVV.T), np.squeeze(E_HH.T), np.squeeze(E_HV.T))
 
 
+# ---------------------------------------------------------------------------------------------
+# Fujita--Paren model (modeltype='FP'): layer.py:100-128, layerstack.py:158-181
+# ---------------------------------------------------------------------------------------------
+
+def fp_layer_constants(nlm):
+    """Per-layer horizontal eigenvalues / eigen-angle of <c^2> in the fabric frame (layer.py:77-79), with the very
+    numpy.linalg.eig call of the reference (its ordering and eigenvector signs define ai_horiz and eigang)."""
+    nlm = np.asarray(nlm)[:, :6]
+    cc0 = nlm_to_c2(nlm)
+    N = nlm.shape[0]
+    ai = np.zeros((N, 2)); eigang = np.zeros(N)
+    for n in range(N):
+        a, Q = np.linalg.eig(cc0[n, :2, :2])
+        ai[n] = a
+        eigang[n] = np.arctan2(Q[1, 0], Q[0, 0])
+    return ai, eigang
+
+
+def _rot2(ang):
+    c, s = np.cos(ang), np.sin(ang)
+    return np.stack([np.stack([c, -s], -1), np.stack([s, c], -1)], -2)
+
+
+def fp_layers(nlm, beta, dz, f, epsa, epsc, sigma, faithful=False):
+    """Mfwd, Mrev (F,N,2,2) in the measurement frame, ks/qs (N,4), ai_horiz (N,2), ang (F,N)  -- layer.py:100-128."""
+    ai, eigang = fp_layer_constants(nlm)
+    epsa = np.asarray(epsa); epsc = np.asarray(epsc); sigma = np.asarray(sigma)
+    omega = 2 * np.pi * f                                                   # layer.py:31
+    q2k = omega / c_const                                                   # layer.py:32
+    epsxy = epsa[:, None] + ai * (epsc - epsa)[:, None]                     # layer.py:104
+    kxy = np.sqrt(epsxy * (q2k) ** 2 + 1j * mu0 * sigma[:, None] * omega)   # layer.py:107
+    ks = np.concatenate([kxy, kxy], axis=1).astype(np.complex128)           # layer.py:110
+    qs = 1 / q2k * ks                                                       # layer.py:111
+    dz = np.asarray(dz)
+    Md = np.exp(+1j * kxy * dz[:, None])                                    # layer.py:115-116 (Mfwd and Mrev coincide)
+    beta = np.asarray(beta)
+    ang = -beta[:, None] + eigang[None, :]                                  # layer.py:125
+    Qz = _rot2(ang)                                                         # (F,N,2,2)
+    if faithful:
+        M = np.zeros(ang.shape + (2, 2), dtype=np.complex128)
+        for ff in range(ang.shape[0]):
+            for nn in range(ang.shape[1]):
+                M[ff, nn] = np.matmul(Qz[ff, nn], np.matmul(np.diag(Md[nn]), Qz[ff, nn].T))     # layer.py:128
+    else:
+        M = np.einsum('fnij,nj,fnkj->fnik', Qz, Md, Qz)
+    return dict(Mfwd=M, Mrev=M.copy(), ks=ks, qs=qs, ai_horiz=ai, eigang=eigang, ang=ang, Qz=Qz)
+
+
+def get_URD_FP(L, epsa, epsc, faithful=False):
+    """layerstack.py:158-194 for modeltype 'FP'."""
+    M = L['Mfwd']
+    F, N = M.shape[:2]
+    ai = L['ai_horiz']
+    epsa = np.asarray(epsa); epsc = np.asarray(epsc)
+    R0 = np.zeros((N - 1, 2, 2), dtype=np.complex128)
+    R0f = (ai[:-1] - ai[1:]) * (epsc[:-1] - epsa[:-1])[:, None]                                # 171-173
+    R0[:, 0, 0] = R0f[:, 0]; R0[:, 1, 1] = R0f[:, 1]
+    Qn = L['Qz'][:, 1:]                                                                         # rotation of layer n+1 (181)
+    if faithful:
+        R = np.zeros((F, N - 1, 2, 2), dtype=np.complex128)
+        for ff in range(F):
+            for nn in range(N - 1):
+                R[ff, nn] = np.matmul(Qn[ff, nn], np.matmul(R0[nn], Qn[ff, nn].T))
+    else:
+        R = np.einsum('fnij,njk,fnlk->fnil', Qn, R0, Qn)
+    T = np.zeros((F, N - 1, 2, 2), dtype=np.complex128); T[:, :, 0, 0] = 1; T[:, :, 1, 1] = 1     # 165-167
+    D_mul = np.einsum('fnij,fnjk->fnik', L['Mfwd'][:, 1:], T)                                   # 185
+    U_mul = np.einsum('fnij,fnjk->fnik', T, L['Mrev'][:, 1:])                                   # 186
+    D = np.zeros((F, N, 2, 2), dtype=np.complex128); U = np.zeros((F, N, 2, 2), dtype=np.complex128)
+    D[:, 0] = np.eye(2); U[:, 0] = np.eye(2)
+    for nn in range(N - 1):
+        D[:, nn + 1] = np.einsum('fij,fjk->fik', D_mul[:, nn], D[:, nn])
+        U[:, nn + 1] = np.einsum('fij,fjk->fik', U[:, nn], U_mul[:, nn])
+    return np.einsum('fnij,fnjk->fnik', U[:, :-1], np.einsum('fnij,fnjk->fnik', R, D[:, :-1]))   # 194
+
+
 class OracleStack:
     """Mirror of LayerStack's constructor state (layerstack.py:14-47) + get_returns (232-288), GTM only."""
 
-    def __init__(self, nlm, z, N_frames=100, epsa=[3.17 - 0.034], epsc=[3.17], sigma=[1e-5], mu=1):
+    def __init__(self, nlm, z, N_frames=100, epsa=[3.17 - 0.034], epsc=[3.17], sigma=[1e-5], mu=1, modeltype='GTM'):
         nlm = np.asarray(nlm)
+        self.modeltype = modeltype
         self.N_layers = nlm.shape[0]
         self.N_frames = N_frames
         self.beta = np.linspace(0, np.pi, N_frames)
@@ -712,6 +789,12 @@ class OracleStack:
                               self.mu, eig=eig, precision=precision, faithful=faithful)
 
     def get_URD(self, f=179.0e6, alpha=0, mode='URD', eig='lapack', precision='double', beta=None, faithful=False):
+        if self.modeltype == 'FP':
+            if mode != 'URD':
+                raise ValueError('Only GTM model type supported')
+            b = self.beta if beta is None else beta
+            L = fp_layers(self.nlm, b, self.dz, f, self.epsa, self.epsc, self.sigma, faithful)
+            return get_URD_FP(L, self.epsa, self.epsc, faithful)
         return get_URD(self.layers(f, alpha, eig, precision, beta, faithful), mode)
 
     def get_returns(self, E0, f=179.0e6, alpha=0, Tx_pol=([1, 0],), URD='URD', nn=None, eig='lapack',
@@ -719,4 +802,4 @@ class OracleStack:
         if URD not in ('URD', 'U'):
             raise ValueError('get_returns(): argument URD="%s" not understood' % (URD))
         urd = self.get_URD(f, alpha, URD, eig, precision, faithful=faithful)
-        return returns_from_URD(urd, E0, Tx_pol, nn)
+        return returns_from_URD(urd, E0, Tx_pol, nn, self.modeltype)

@@ -19,6 +19,7 @@ SIGNATURES = {
     'tamm_stack_workspace_bytes': (ctypes.c_size_t, [_i, _i, _i, _i]),
     'tamm_suggest_chunk': (_i, [_i, _i, _i, _i]),
     'tamm_stack_urd': (_i, [_vp, _vp, _i, _i, _i, _i, _d, _d, _i, _i, _vp, _vp, _vp, _vp]),
+    'tamm_stack_urd_fp': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     'tamm_export_jones': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     'tamm_returns': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, ctypes.POINTER(_d), _i] + [_vp] * 7 + [_vp]),
 }

@@ -1079,4 +1079,49 @@ TAMM_HD void mul22(const cd a[4], const cd b[4], cd o[4]) {
     o[0] = o0; o[1] = o1; o[2] = o2; o[3] = o3;
 }
 
+// =================================================================================================
+// Fujita--Paren model (modeltype='FP'): layer.py:100-128, layerstack.py:158-181.
+// Per layer the host supplies the horizontal eigenvalues ai_horiz and the eigen-angle of <c^2> in the fabric frame
+// (layer.py:77-79, computed with the reference's own numpy.linalg.eig so ordering and signs are its own).
+// =================================================================================================
+constexpr double MU0 = 1.25663706212e-6;   // layer_PPJ.py:16
+
+struct FpLayerParams {   // 10 doubles, same stride as LayerParams
+    double ai0, ai1;     // ai_horiz                              layer.py:77
+    double ce, se;       // cos/sin(eigang)                       layer.py:79
+    double epsa, epsc;   // real parts
+    double sigma, dz;
+    double pad0, pad1;
+};
+
+// symmetric 2x2 Qz diag(m0, m1) Qz^T with Qz = [[c, -s], [s, c]]   (layer.py:123-128), row-major
+TAMM_HD void rot_diag(double c, double s, cd m0, cd m1, cd o[4]) {
+    const double cc = c * c, ss = s * s, cs = c * s;
+    o[0] = cc * m0 + ss * m1;
+    o[1] = cs * (m0 - m1);
+    o[2] = o[1];
+    o[3] = ss * m0 + cc * m1;
+}
+
+// Mfwd (= Mrev) of one layer in the measurement frame and the rotation (c, s) of its eigen frame
+TAMM_HD void fp_layer(const FpLayerParams& lp, const LaneParams& ln, cd M[4], double& c, double& s) {
+    const double omega = ln.twopif;
+    const double q2k = omega / C_CONST;                                   // layer.py:32
+    const double ex = lp.epsa + lp.ai0 * (lp.epsc - lp.epsa);              // layer.py:104
+    const double ey = lp.epsa + lp.ai1 * (lp.epsc - lp.epsa);
+    const double im = MU0 * lp.sigma * omega;
+    const cd kx = csqrt_(cd{ex * (q2k * q2k), im});                        // layer.py:107
+    const cd ky = csqrt_(cd{ey * (q2k * q2k), im});
+    // exp(+i k d)                                                          layer.py:115-116
+    double sn, cs_;
+    double a0 = exp(-kx.im * lp.dz); sincos(kx.re * lp.dz, &sn, &cs_);
+    const cd m0 = cd{a0 * cs_, a0 * sn};
+    double a1 = exp(-ky.im * lp.dz); sincos(ky.re * lp.dz, &sn, &cs_);
+    const cd m1 = cd{a1 * cs_, a1 * sn};
+    // ang = -beta + eigang                                                 layer.py:125
+    c = lp.ce * ln.c1 + lp.se * ln.s1;
+    s = lp.se * ln.c1 - lp.ce * ln.s1;
+    rot_diag(c, s, m0, m1, M);
+}
+
 }  // namespace tamm

@@ -249,6 +249,51 @@ __global__ void __launch_bounds__(MAXT, MINB) stack_kernel(TAMM_STACK_ARGS) { st
 template <int MODE, int NREG>
 __global__ void __maxnreg__(NREG) stack_kernel_nreg(TAMM_STACK_ARGS) { stack_body<MODE>(TAMM_STACK_PASS); }
 
+// ---- Fujita--Paren stack (modeltype 'FP'): thread = (profile, lane, chunk); same planes/aggregate layout as stack_kernel
+__global__ void __launch_bounds__(128)
+fp_stack_kernel(const double* __restrict__ layers, const double* __restrict__ lanes, int P, int N, int QF, int chunk, int nchunks,
+                cd* __restrict__ planes, cd* __restrict__ agg) {
+    const int NI = N - 1;
+    const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (long)P * QF) return;
+    const int p = (int)(g / QF), l = (int)(g - (long)p * QF), c = blockIdx.y;
+    const int n0 = c * chunk, n1 = min(NI, n0 + chunk);
+    LaneParams ln;
+    const double* b = lanes + (size_t)l * LANE_STRIDE;
+    ln.c1 = __ldg(b); ln.s1 = __ldg(b + 1); ln.c2 = 0; ln.s2 = 0; ln.twopif = __ldg(b + 4); ln.w_eps0 = 0; ln.pad0 = 0; ln.pad1 = 0;
+    cd D[4] = {mk(1.0), mk(0.0), mk(0.0), mk(1.0)}, U[4] = {mk(1.0), mk(0.0), mk(0.0), mk(1.0)};
+    cd* out = planes + ((size_t)p * NI * 4) * QF + l;
+    const double* lay = layers + (size_t)p * N * LAYER_STRIDE;
+    FpLayerParams prev;
+    {
+        const double* a = lay + (size_t)n0 * LAYER_STRIDE;
+        prev.ai0 = __ldg(a); prev.ai1 = __ldg(a + 1); prev.epsa = __ldg(a + 4); prev.epsc = __ldg(a + 5);
+    }
+    for (int n = n0; n < n1; ++n) {
+        FpLayerParams nx;
+        const double* a = lay + (size_t)(n + 1) * LAYER_STRIDE;
+        nx.ai0 = __ldg(a); nx.ai1 = __ldg(a + 1); nx.ce = __ldg(a + 2); nx.se = __ldg(a + 3); nx.epsa = __ldg(a + 4);
+        nx.epsc = __ldg(a + 5); nx.sigma = __ldg(a + 6); nx.dz = __ldg(a + 7); nx.pad0 = 0; nx.pad1 = 0;
+        cd M[4], R[4], t[4], o[4];
+        double cr, sr;
+        fp_layer(nx, ln, M, cr, sr);
+        // Paren reflection (layerstack.py:171-181): diag((ai_n - ai_{n+1}) (epsc_n - epsa_n)) rotated with layer n+1
+        const double de = prev.epsc - prev.epsa;
+        rot_diag(cr, sr, mk((prev.ai0 - nx.ai0) * de), mk((prev.ai1 - nx.ai1) * de), R);
+        mul22(R, D, t);
+        mul22(U, t, o);                                                  // URD_n = U_n R_n D_n     (194)
+        cd* op = out + (size_t)n * 4 * QF;
+        st_cd(op, o[0]); st_cd(op + QF, o[1]); st_cd(op + 2 * (size_t)QF, o[2]); st_cd(op + 3 * (size_t)QF, o[3]);
+        mul22(M, D, D);                                                  // D_{n+1} = Mfwd_{n+1} D_n (T = I, 165-167, 189)
+        mul22(U, M, U);                                                  // U_{n+1} = U_n Mrev_{n+1} (190)
+        prev = nx;
+    }
+    if (nchunks > 1) {
+        cd* a = agg + (((size_t)p * QF + l) * nchunks + c) * 8;
+        for (int k = 0; k < 4; ++k) { st_cd(a + k, D[k]); st_cd(a + 4 + k, U[k]); }
+    }
+}
+
 // ---- chunk prefix scan: one warp per (profile, lane) ---------------------------------------------
 struct DU {
     cd D[4], U[4];
@@ -772,6 +817,30 @@ int tamm_stack_urd(const double* layers, const double* lanes, int P, int N, int 
         cd* pre = agg + (size_t)nseq * nch * 8;
         int grid2 = (int)((nseq + 3) / 4);
         chunk_scan_kernel<<<grid2, 128, 0, s>>>(agg, pre, nseq, nch);
+        CUDA_OK(cudaGetLastError());
+    }
+    return 0;
+}
+
+int tamm_stack_urd_fp(const double* layers_fp, const double* lanes, int P, int N, int Q, int F, int chunk, void* planes,
+                      void* workspace, void* stream) {
+    if (!layers_fp || !lanes || !planes) return fail("tamm_stack_urd_fp: null pointer%s", "");
+    if (P < 1 || Q < 1 || F < 1) return fail("tamm_stack_urd_fp: empty batch%s", "");
+    if (N < 2) return fail("tamm_stack_urd_fp: need at least 2 layers (N=%s%ld)", "", N);
+    if (chunk < 1) return fail("tamm_stack_urd_fp: chunk must be >= 1%s", "");
+    if (!aligned16(planes) || !aligned16(workspace)) return fail("tamm_stack_urd_fp: buffers must be 16-byte aligned%s", "");
+    const int QF = Q * F, nch = nchunks_of(N, chunk);
+    if (nch > 65535) return fail("tamm_stack_urd_fp: grid too large (chunks > 65535)%s", "");
+    if (nch > 1 && !workspace) return fail("tamm_stack_urd_fp: workspace required%s", "");
+    const long G = (long)P * QF;
+    dim3 grid((unsigned)((G + 127) / 128), nch, 1);
+    cudaStream_t s = (cudaStream_t)stream;
+    cd* agg = (cd*)workspace;
+    fp_stack_kernel<<<grid, 128, 0, s>>>(layers_fp, lanes, P, N, QF, chunk, nch, (cd*)planes, agg);
+    CUDA_OK(cudaGetLastError());
+    if (nch > 1) {
+        cd* pre = agg + (size_t)G * nch * 8;
+        chunk_scan_kernel<<<(int)((G + 3) / 4), 128, 0, s>>>(agg, pre, G, nch);
         CUDA_OK(cudaGetLastError());
     }
     return 0;

@@ -96,6 +96,25 @@ class Engine:
         self.launches += 1 if (N - 1 + chunk - 1) // chunk <= 1 else 2
         return StackResult(planes, workspace, P, N, Q, F, mode, chunk, status)
 
+    def stack_fp(self, layers_fp, lanes, P, N, Q, F, chunk=None, planes=None, workspace=None):
+        """Fujita--Paren stack (modeltype 'FP').  layers_fp: packing.pack_layers_fp device tensor (P, N, 10)."""
+        torch = _torch()
+        QF = Q * F
+        assert layers_fp.dtype == torch.float64 and layers_fp.is_contiguous() and layers_fp.numel() == P * N * packing.LAYER_STRIDE
+        if chunk is None:
+            chunk = self.suggest_chunk(P, N, QF)
+        chunk = max(1, min(int(chunk), N - 1))
+        if planes is None:
+            planes = self.empty((P, N - 1, 4, QF), torch.complex128)
+        wsb = int(self.lib.tamm_stack_workspace_bytes(P, N, QF, chunk))
+        if workspace is None or workspace.numel() * 8 < wsb:
+            workspace = self.empty(((wsb + 7) // 8,), torch.float64)
+        rc = self.lib.tamm_stack_urd_fp(layers_fp.data_ptr(), lanes.data_ptr(), P, N, Q, F, chunk, planes.data_ptr(),
+                                        workspace.data_ptr(), self._stream())
+        _lib.check(rc, self.lib)
+        self.launches += 1 if (N - 1 + chunk - 1) // chunk <= 1 else 2
+        return StackResult(planes, workspace, P, N, Q, F, MODE_URD, chunk, None)
+
     def export_jones(self, res, out=None):
         """-> complex128 device tensor (P, Q, F, N-1, 2, 2)  (layerstack.py:194/225 layout per profile/frequency)."""
         torch = _torch()

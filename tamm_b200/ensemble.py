@@ -67,22 +67,24 @@ class EnsembleStack:
         epsiso = (2 * self.epsa[0, 0] + self.epsc[0, 0]) / 3              # layerstack.py:236
         return np.sqrt(epsiso) * np.sin(alpha)
 
-    def packed_layers(self, lo=None, hi=None):
+    def packed_layers(self, lo=None, hi=None, fp=False):
         lo = self.lo if lo is None else lo
         hi = self.hi if hi is None else hi
         sl = slice(lo, hi)
         dz = np.broadcast_to(self.dz, (hi - lo, self.N_layers))
-        return packing.pack_layers(self.nlm[sl], dz, self.epsa[sl], self.epsc[sl], self.sigma[sl])
+        pack = packing.pack_layers_fp if fp else packing.pack_layers
+        return pack(self.nlm[sl], dz, self.epsa[sl], self.epsc[sl], self.sigma[sl])
 
     def get_returns(self, E0, f=179.0e6, alpha=0, Tx_pol=([1, 0],), URD='URD', batch=None, out=None, outputs=RETURN_NAMES):
         """-> dict name -> host array for the local shard, shapes (P_local, [Q,] N-1, F) / (P_local, [Q,] N-1).
         Same numbers as LayerStack.get_returns per profile (layerstack.py:232-288)."""
         import torch
-        if self.modeltype != 'GTM':
-            raise NotImplementedError('modeltype="FP" (Fujita-Paren) is not implemented on the device yet')
         if URD not in ('URD', 'U'):
             raise ValueError('get_returns(): argument URD="%s" not understood' % (URD))
+        if URD == 'U' and self.modeltype != 'GTM':
+            raise ValueError('Only GTM model type supported')
         mode = MODE_URD if URD == 'URD' else MODE_U
+        fp = (self.modeltype == 'FP')
         eng = get_engine()
         fa = np.atleast_1d(np.asarray(f, dtype=np.float64))
         Q, F, N, NI, Pl = fa.size, self.N_frames, self.N_layers, self.N_layers - 1, self.P_local
@@ -105,13 +107,16 @@ class EnsembleStack:
             k = bi & 1
             if done[k] is not None:
                 compute.wait_event(done[k])       # the previous D2H from this buffer set must have finished
-            lay_h = torch.from_numpy(self.packed_layers(self.lo + b0, self.lo + b1)).pin_memory()
+            lay_h = torch.from_numpy(self.packed_layers(self.lo + b0, self.lo + b1, fp)).pin_memory()
             lay = lay_h.to(eng.device, non_blocking=True)
             if planes[k] is None or planes[k].shape[0] != b1 - b0:
                 planes[k] = eng.empty((b1 - b0, NI, 4, Q * F), torch.complex128)
                 dev[k] = None
-            res = eng.stack(lay, lanes, b1 - b0, N, Q, F, zeta, self.mu, mode, planes=planes[k])
-            dev[k] = eng.returns(res, etx, gtm_phase=True, out=dev[k])
+            if fp:
+                res = eng.stack_fp(lay, lanes, b1 - b0, N, Q, F, planes=planes[k])
+            else:
+                res = eng.stack(lay, lanes, b1 - b0, N, Q, F, zeta, self.mu, mode, planes=planes[k])
+            dev[k] = eng.returns(res, etx, gtm_phase=not fp, out=dev[k])
             ready = torch.cuda.Event()
             ready.record(compute)
             with torch.cuda.stream(copy):

@@ -48,3 +48,35 @@ def pack_lanes(beta, f):
     out[..., 4] = (2 * np.pi * f)[:, None]                      # layer.py:31
     out[..., 5] = (2 * np.pi * f * eps0)[:, None]               # layer.py:65
     return out.reshape(f.size * beta.size, LANE_STRIDE)
+
+
+def fp_layer_constants(nlm):
+    """ai_horiz (N, 2) and eigang (N,) of the fabric-frame <c^2> (layer.py:77-79) with the reference's own
+    numpy.linalg.eig call per layer -- its eigenvalue ordering and eigenvector signs define both."""
+    nlm = np.asarray(nlm, dtype=np.complex128)
+    nn = np.divide(nlm[..., :6], nlm[..., 0:1])                          # layer.py:137
+    t = np.real(np.sqrt(2 / 3) * nn[..., 3])
+    n22 = nn[..., 5]
+    c2 = np.zeros(nlm.shape[:-1] + (2, 2))
+    c2[..., 0, 0] = 1 / 3 + np.sqrt(2 / 15) * (np.real(n22) - t / 2)   # layer.py:145-157, horizontal block
+    c2[..., 1, 1] = 1 / 3 + np.sqrt(2 / 15) * (-np.real(n22) - t / 2)
+    c2[..., 0, 1] = c2[..., 1, 0] = np.sqrt(2 / 15) * (-np.imag(n22))
+    flat = c2.reshape(-1, 2, 2)
+    ai = np.zeros((flat.shape[0], 2)); ang = np.zeros(flat.shape[0])
+    for i in range(flat.shape[0]):
+        a, Q = np.linalg.eig(flat[i])                                   # layer.py:77
+        ai[i] = a
+        ang[i] = np.arctan2(Q[1, 0], Q[0, 0])                           # layer.py:79
+    return ai.reshape(nlm.shape[:-1] + (2,)), ang.reshape(nlm.shape[:-1])
+
+
+def pack_layers_fp(nlm, dz, epsa, epsc, sigma):
+    """Layer records of the Fujita--Paren model (include/tamm_b200.h: tamm_stack_urd_fp).  Returns float64 (..., N, 10)."""
+    ai, ang = fp_layer_constants(nlm)
+    out = np.zeros(ai.shape[:-1] + (LAYER_STRIDE,), dtype=np.float64)
+    out[..., 0] = ai[..., 0]; out[..., 1] = ai[..., 1]
+    out[..., 2] = np.cos(ang); out[..., 3] = np.sin(ang)
+    out[..., 4] = np.real(np.asarray(epsa)); out[..., 5] = np.real(np.asarray(epsc))
+    out[..., 6] = np.asarray(sigma, dtype=np.float64)
+    out[..., 7] = np.asarray(dz, dtype=np.float64)
+    return out

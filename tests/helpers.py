@@ -14,8 +14,10 @@ RTOL_COMPLEX = 1e-9   # complex reflection coefficients (URD, E_HH, E_HV), relat
 ATOL_DB = 1e-6        # return power in dB
 
 
-def golden_names():
-    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, '*.npz')))
+def golden_names(model='GTM'):
+    """Fixture names; the Fujita--Paren fixtures are prefixed fp_."""
+    names = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, '*.npz')))
+    return [n for n in names if n.startswith('fp_') == (model == 'FP')]
 
 
 def load_golden(name):
@@ -41,8 +43,12 @@ def returns_kwargs(g):
     return kw
 
 
+def modeltype(g):
+    return str(g['kw_modeltype']) if 'kw_modeltype' in g else 'GTM'
+
+
 def oracle_stack(g):
-    return orc.OracleStack(g['nlm'], g['z'], N_frames=int(g['F']), **stack_kwargs(g))
+    return orc.OracleStack(g['nlm'], g['z'], N_frames=int(g['F']), modeltype=modeltype(g), **stack_kwargs(g))
 
 
 def peak_rel_err(got, want, axis):

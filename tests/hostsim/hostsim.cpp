@@ -87,6 +87,30 @@ int hostsim_urd(const double* layers, const double* lanes, int N, int F, double 
     return 0;
 }
 
+// Fujita--Paren stack with the kernel's arithmetic (fp_layer / rot_diag), sequential over depth.  out (F, N-1, 2, 2).
+int hostsim_urd_fp(const double* layers_fp, const double* lanes, int N, int F, double* out) {
+    if (N < 2) return 1;
+    const int NI = N - 1;
+    for (int f = 0; f < F; ++f) {
+        LaneParams ln; std::memcpy(&ln, lanes + (size_t)f * LANE_STRIDE, sizeof(ln));
+        cd* o = reinterpret_cast<cd*>(out) + (size_t)f * NI * 4;
+        cd D[4] = {mk(1), mk(0), mk(0), mk(1)}, U[4] = {mk(1), mk(0), mk(0), mk(1)};
+        FpLayerParams prev; std::memcpy(&prev, layers_fp, sizeof(prev));
+        for (int n = 0; n < NI; ++n) {
+            FpLayerParams nx; std::memcpy(&nx, layers_fp + (size_t)(n + 1) * LAYER_STRIDE, sizeof(nx));
+            cd M[4], R[4], t[4];
+            double cr, sr;
+            fp_layer(nx, ln, M, cr, sr);
+            const double de = prev.epsc - prev.epsa;
+            rot_diag(cr, sr, mk((prev.ai0 - nx.ai0) * de), mk((prev.ai1 - nx.ai1) * de), R);
+            mul22(R, D, t); mul22(U, t, o + (size_t)n * 4);
+            mul22(M, D, D); mul22(U, M, U);
+            prev = nx;
+        }
+    }
+    return 0;
+}
+
 // Elementary functions of the hot path: out[i] = {sin, cos, exp} of x[i] through sincos_f / exp_f.
 int hostsim_elementary(const double* x, int n, double* out) {
     for (int i = 0; i < n; ++i) {

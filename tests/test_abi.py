@@ -17,7 +17,8 @@ def declared_symbols():
 def test_header_declares_expected_entry_points():
     syms = declared_symbols()
     for s in ['tamm_stack_urd', 'tamm_returns', 'tamm_export_jones', 'tamm_layer_matrices', 'tamm_last_error',
-              'tamm_stack_workspace_bytes', 'tamm_suggest_chunk', 'tamm_check_device', 'tamm_version', 'tamm_fp64_probe']:
+              'tamm_stack_workspace_bytes', 'tamm_suggest_chunk', 'tamm_check_device', 'tamm_version', 'tamm_fp64_probe',
+              'tamm_stack_urd_fp']:
         assert s in syms
 
 

@@ -27,7 +27,7 @@ def eng(built):
 
 def _stack(g):
     import layerstack as ls
-    return ls.LayerStack(g['nlm'], g['z'], N_frames=int(g['F']), VERBOSE=0, **h.stack_kwargs(g))
+    return ls.LayerStack(g['nlm'], g['z'], N_frames=int(g['F']), VERBOSE=0, modeltype=h.modeltype(g), **h.stack_kwargs(g))
 
 
 def _check_returns(got, want, arbiter=None):
@@ -298,3 +298,40 @@ def test_two_layer_minimum_and_abi_errors(eng):
     assert lib.tamm_stack_urd(p + 8, p, 1, 5, 1, 1, 0.0, 1.0, 0, 4, p, p, None, None) != 0   # misaligned
     with pytest.raises(_lib.TammLibraryError):
         _lib.check(1, lib)
+
+
+@pytest.mark.parametrize('name', h.golden_names('FP'))
+def test_fujita_paren_model_matches_reference_fixture(eng, name):
+    """modeltype='FP' (layer.py:100-128, layerstack.py:158-181) through the drop-in API."""
+    g = h.load_golden(name)
+    s = _stack(g)
+    got = s.get_returns(float(g['E0']), f=float(g['f']), alpha=float(g['alpha']), **h.returns_kwargs(g))
+    for n, a in zip(h.RET_NAMES, got):
+        b = g['ret_' + n]
+        assert np.shape(a) == b.shape and np.asarray(a).dtype == b.dtype, n
+        fin = np.isfinite(b)
+        tol = 1e-9 if n in ('Pm_HH', 'Pm_HV', 'dP_HH', 'dP_HV') else 1e-12 * max(1.0, np.abs(b[fin]).max())
+        assert np.abs(np.asarray(a) - b)[fin].max() < tol, n
+    assert np.abs(s.get_propconst() - g['propconst']).max() < 1e-12
+    frames = [s.get_layerstack(b, float(g['f']), 0.0) for b in s.beta]
+    assert h.peak_rel_err(s.get_URD(frames), g['URD'], axis=(1, 2, 3)) < 1e-12
+    with pytest.raises(ValueError, match='Only GTM model type supported'):
+        s.get_U(frames)
+    with pytest.raises(ValueError, match='Only GTM model type supported'):
+        s.get_returns(1e3, URD='U')
+    for key in g:
+        if key.startswith('layer_'):
+            _, ff, nn, attr = key.split('_', 3)
+            lay = s.frm_layers[int(ff)][int(nn)]
+            assert np.allclose(getattr(lay, attr), g[key], rtol=1e-13, atol=1e-15), key
+
+
+def test_fujita_paren_agrees_with_gtm_coherence(eng):
+    """the two models are different physics that must agree closely on the HH-VV coherence of the demo
+    profile (median 7e-5, max 1e-2 in the oracle)."""
+    import layerstack as ls
+    nlm, z = profiles.demo(100, 1500)
+    g = ls.LayerStack(nlm, z, N_frames=20, VERBOSE=0).get_returns(1e3, f=179e6, alpha=0)
+    f = ls.LayerStack(nlm, z, N_frames=20, VERBOSE=0, modeltype='FP').get_returns(1e3, f=179e6, alpha=0)
+    d = np.abs(g[4] - f[4])
+    assert np.nanmedian(d) < 2e-4 and np.nanmax(d) < 2e-2

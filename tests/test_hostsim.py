@@ -143,3 +143,19 @@ def test_hot_path_elementary_functions(sim):
     rel = np.abs(out[:, 2] / np.exp(xe.astype(np.longdouble)).astype(np.float64) - 1)
     assert rel[small].max() < 4.5e-16
     assert np.isfinite(out).all()
+
+
+@pytest.mark.parametrize('name', h.golden_names('FP'))
+def test_kernel_arithmetic_fp(sim, name):
+    """Fujita--Paren kernel arithmetic (tamm_core.cuh: fp_layer, rot_diag) against the reference fixture."""
+    g = h.load_golden(name)
+    os_ = h.oracle_stack(g)
+    N, F = os_.N_layers, os_.N_frames
+    lay = packing.pack_layers_fp(os_.nlm, os_.dz, os_.epsa, os_.epsc, os_.sigma)
+    lan = packing.pack_lanes(os_.beta, float(g['f']))
+    out = np.zeros((F, N - 1, 2, 2), dtype=np.complex128)
+    assert sim.hostsim_urd_fp(_P(lay), _P(lan), N, F, _P(out)) == 0
+    assert h.peak_rel_err(out, g['URD'], axis=(1, 2, 3)) < 1e-12
+    ai, ang = packing.fp_layer_constants(os_.nlm)
+    L = orc.fp_layers(os_.nlm, os_.beta, os_.dz, float(g['f']), os_.epsa, os_.epsc, os_.sigma)
+    assert np.array_equal(ai, L['ai_horiz']) and np.array_equal(ang, L['eigang'])

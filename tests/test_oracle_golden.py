@@ -81,3 +81,27 @@ def test_reference_spot_values():
     r0 = os_.get_returns(1e3, f=179e6, alpha=0)
     assert np.allclose(r0[0][:3], [-12.79568151, -48.14941445, -48.42882211], atol=1e-7)
     assert abs(r0[5][1, 0] - (-0.0011409126238392416 + 0.00066780121932077j)) < 1e-12
+
+
+@pytest.mark.parametrize('name', h.golden_names('FP'))
+def test_oracle_fp_bit_exact_against_reference_fixture(name):
+    """Fujita--Paren branch (layer.py:100-128, layerstack.py:158-181)."""
+    g = h.load_golden(name)
+    os_ = h.oracle_stack(g)
+    kw = h.returns_kwargs(g)
+    urd = os_.get_URD(float(g['f']), float(g['alpha']), faithful=True)
+    assert np.array_equal(urd, g['URD'])
+    got = orc.returns_from_URD(urd, float(g['E0']), kw.get('Tx_pol', ([1, 0],)), kw.get('nn'), 'FP')
+    for n, a in zip(h.RET_NAMES, got):
+        assert a.shape == g['ret_' + n].shape and np.array_equal(a, g['ret_' + n], equal_nan=True), n
+    L = orc.fp_layers(os_.nlm, os_.beta, os_.dz, float(g['f']), os_.epsa, os_.epsc, os_.sigma, faithful=True)
+    assert np.array_equal(L['ks'], g['propconst'])
+    for key in g:
+        if key.startswith('layer_'):
+            _, ff, nn, attr = key.split('_', 3)
+            ff, nn = int(ff), int(nn)
+            have = {'ai_horiz': L['ai_horiz'][nn], 'eigang': L['eigang'][nn], 'ks': L['ks'][nn], 'qs': L['qs'][nn],
+                    'Mfwd': L['Mfwd'][ff, nn], 'Mrev': L['Mrev'][ff, nn]}[attr]
+            assert np.array_equal(have, g[key]), key
+    fast = os_.get_URD(float(g['f']), float(g['alpha']))
+    assert h.peak_rel_err(fast, g['URD'], axis=(1, 2, 3)) < 1e-13
