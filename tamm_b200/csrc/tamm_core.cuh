@@ -99,6 +99,13 @@ TAMM_HD cd crecip_f(cd b) {   // branch-free variant for the hot path
     double inv = frcp(fma(b.re, b.re, b.im * b.im));
     return cd{b.re * inv, -b.im * inv};
 }
+// 1/b with 1/0 := 0 instead of NaN/inf (TINY is far below the square of any quantity that occurs): replaces the
+// `isnan -> 0` fallbacks of the reference (layer_PPJ.py:332,348,368,382) and the zero guards of the eigen-solver
+constexpr double TINY = 1e-280;
+TAMM_HD cd crecip_s(cd b) {
+    double inv = frcp(fma(b.re, b.re, fma(b.im, b.im, TINY)));
+    return cd{b.re * inv, -b.im * inv};
+}
 TAMM_HD bool cisnan(cd a) { return isnan(a.re) || isnan(a.im); }
 TAMM_HD cd csel(bool c, cd a, cd b) { return cd{c ? a.re : b.re, c ? a.im : b.im}; }
 
@@ -708,15 +715,20 @@ struct LayerY {
 
 TAMM_HD double fast_abs(cd z) { return fsqrt(fma(z.re, z.re, z.im * z.im)); }
 TAMM_HD cd csqrt_f(cd z) {   // principal square root, no hypot() scaling (|z| is O(1e-20 .. 1e3) here)
-    double m = fast_abs(z);
-    double v = 0.5 * (m + fabs(z.re));
 #if defined(__CUDA_ARCH__)
-    double y = frsqrt(v);                      // 1/t
+    // TINY offsets keep rsqrt away from 0 (sqrt(0) then returns ~1e-70 instead of 0, which is harmless here)
+    const double m2 = fma(z.re, z.re, fma(z.im, z.im, TINY));
+    double y = frsqrt(m2);
+    double m = m2 * y;
+    m = fma(0.5 * y, fma(-m, m, m2), m);       // |z|
+    const double v = 0.5 * (m + fabs(z.re)) + 1e-140;
+    y = frsqrt(v);                             // 1/t
     double t = v * y;
     t = fma(0.5 * y, fma(-t, t, v), t);
-    double o = (v > 0.0) ? 0.5 * z.im * y : 0.0;
-    t = (v > 0.0) ? t : 0.0;
+    const double o = 0.5 * z.im * y;
 #else
+    double m = sqrt(z.re * z.re + z.im * z.im);
+    double v = 0.5 * (m + fabs(z.re));
     double t = v > 0.0 ? sqrt(v) : 0.0;
     double o = (t > 0.0) ? 0.5 * z.im / t : 0.0;
 #endif
@@ -746,12 +758,12 @@ TAMM_HD void mslp_core(const WaveMat& m, cd db, cd& big, cd& det1, cd& h_small) 
     bool flip = (hm.re * s.re + hm.im * s.im) < 0.0;
     s = csel(flip, -s, s);
     big = hm + s;
-    h_small = (abs2(big) > 0.0) ? (-1.0) * cmul_(detN, crecip_f(big)) : mk(0.0);
+    h_small = -cmul_(detN, crecip_s(big));
 }
 TAMM_HD void mslp_eigs_f(const WaveMat& m, cd db, cd& h_big, cd& h_small) {
     cd big, det1;
     mslp_core(m, db, big, det1, h_small);
-    h_big = (-1.0) * cmul_(big, crecip_f(det1));
+    h_big = -cmul_(big, crecip_f(det1));
 }
 
 // Four roots + the (Ex, Ey) null vector of N at each root, written to rv[k] = {q, Ex, Ey}.  rv is indexed with run-time
@@ -817,8 +829,8 @@ TAMM_HD void eig4_fast(const WaveCoef& w, cd rv[4][3]) {
             cd f = det2(mm.a, mm.b, mm.b, mm.d);
             cd fp = dot2(mm.da, mm.d, mm.a, mm.dd);
             cfma(fp, (-2.0) * mm.b, w.db);
-            cd step = cmul_(f, crecip_f(fp));
-            // a NaN / large polish means f'(x) ~ 0 (degenerate pair): keep the MSLP root
+            cd step = cmul_(f, crecip_s(fp));
+            // a large polish means f'(x) ~ 0 (degenerate pair): keep the MSLP root
             if (!(abs2(step) <= 1e-12 * abs2(x))) step = mk(0.0);
             bool use0 = abs2(mm.a) >= abs2(mm.d);
             const int idx = 2 * pair + r;
@@ -973,7 +985,7 @@ TAMM_HD int layer_solve_fast(const LayerParams& lp, const LaneParams& ln, double
     const cd e00 = mk(e.xx, e.im), e11 = mk(e.yy, e.im);
     const double m01 = mu * e.xy, m02 = mu * e.xz, m12 = mu * e.yz;
     const cd mez = mu * ezz - zeta * zeta;
-    const cd imez = crecip_f(mez);
+    const cd imez = crecip_s(mez);
     const cd c01m = m01 * mez;                   // mu*eps01*mez
     const cd g23p = (-m12) * imez;               // -mu*eps21/mez
     const double m12sq = m12 * m12;
@@ -982,33 +994,24 @@ TAMM_HD int layer_solve_fast(const LayerParams& lp, const LaneParams& ln, double
     cd g12, g13, g21, g23, g32, g33, g41, g43;
     {
         cd u0 = mk(m02) + zeta * q0, u1 = mk(m02) + zeta * q1, u2 = mk(m02) + zeta * q2, u3 = mk(m02) + zeta * q3;
-        cd g13p = (-1.0) * cmul_(u0, imez), g33p = cmul_(u2, imez);
-        // modes 0 and 2 share one form, modes 1 and 3 the other
+        cd g13p = -cmul_(u0, imez), g33p = cmul_(u2, imez);
+        // modes 0 and 2 share one form, modes 1 and 3 the other.  crecip_s(den) makes x/0 := 0, which is the reference's
+        // `if isnan(gamma): gamma = 0` fallback (0/0) without the NaN tests.
         cd den0 = cmul_(mez, mzz - csq(q0)) - m12sq;
-        g12 = cmul_(m12 * u0 - c01m, crecip_f(den0));
-        if (cisnan(g12)) g12 = mk(0.0);
-        g13 = cmul_((-1.0) * u0 - m12 * g12, imez);
-        if (cisnan(g13)) g13 = g13p;
+        g12 = cmul_(m12 * u0 - c01m, crecip_s(den0));
+        g13 = cmul_(-u0 - m12 * g12, imez);
         cd den1 = cmul_(mez, m00 - csq(q1));
         cfma(den1, -u1, u1);
-        g21 = cmul_(m12 * u1 - c01m, crecip_f(den1));
-        if (cisnan(g21)) g21 = mk(0.0);
-        cd t23 = cmul_(-u1, g21) - m12;
-        g23 = cmul_(t23, imez);
-        if (cisnan(g23)) g23 = g23p;
+        g21 = cmul_(m12 * u1 - c01m, crecip_s(den1));
+        g23 = cmul_(cmul_(-u1, g21) - m12, imez);
         if (abs2(q0 - q1) < QSD_THR * QSD_THR) { g12 = mk(0.0); g13 = g13p; g21 = mk(0.0); g23 = g23p; }   // |q0-q1| < qsd_thr
         cd den2 = cmul_(mez, mzz - csq(q2)) - m12sq;
-        g32 = cmul_(c01m - m12 * u2, crecip_f(den2));
-        if (cisnan(g32)) g32 = mk(0.0);
+        g32 = cmul_(c01m - m12 * u2, crecip_s(den2));
         g33 = cmul_(u2 + m12 * g32, imez);
-        if (cisnan(g33)) g33 = g33p;
         cd den3 = cmul_(mez, m00 - csq(q3));
         cfma(den3, -u3, u3);
-        g41 = cmul_(m12 * u3 - c01m, crecip_f(den3));
-        if (cisnan(g41)) g41 = mk(0.0);
-        cd t43 = cmul_(-u3, g41) - m12;
-        g43 = cmul_(t43, imez);
-        if (cisnan(g43)) g43 = g23p;
+        g41 = cmul_(m12 * u3 - c01m, crecip_s(den3));
+        g43 = cmul_(cmul_(-u3, g41) - m12, imez);
         if (abs2(q2 - q3) < QSD_THR * QSD_THR) { g32 = mk(0.0); g33 = g33p; g41 = mk(0.0); g43 = g23p; }
     }
     // row norms (layer_PPJ.py:399-402)
@@ -1021,13 +1024,13 @@ TAMM_HD int layer_solve_fast(const LayerParams& lp, const LaneParams& ln, double
     L.Er[0] = mk(-i2); L.Er[1] = i3 * g41; L.Er[2] = i2 * g32; L.Er[3] = mk(i3);
     {
         cd idt = crecip_f(mk(1.0) - cmul_(g12, g21));            // 1/det [[1, g21],[g12, 1]]
-        cd ra[4] = {idt, (-1.0) * cmul_(g21, idt), (-1.0) * cmul_(g12, idt), idt};     // raw inverse
+        cd ra[4] = {idt, -cmul_(g21, idt), -cmul_(g12, idt), idt};     // raw inverse
         cd Ht[4] = {imu * (q0 - zeta * g13), imu * (cmul_(q1, g21) - zeta * g23), imu * cmul_(q0, g12), imu * q1};
         mm22(Ht, ra, L.Yt);
         L.Eti[0] = n0 * ra[0]; L.Eti[1] = n0 * ra[1]; L.Eti[2] = n1 * ra[2]; L.Eti[3] = n1 * ra[3];
         cd idr = crecip_f(mk(-1.0) - cmul_(g32, g41));           // 1/det [[-1, g41],[g32, 1]]
-        cd rb[4] = {idr, (-1.0) * cmul_(g41, idr), (-1.0) * cmul_(g32, idr), (-1.0) * idr};
-        cd Hr[4] = {imu * ((-1.0) * q2 - zeta * g33), imu * (cmul_(q3, g41) - zeta * g43), imu * cmul_(q2, g32), imu * q3};
+        cd rb[4] = {idr, -cmul_(g41, idr), -cmul_(g32, idr), -idr};
+        cd Hr[4] = {imu * (-q2 - zeta * g33), imu * (cmul_(q3, g41) - zeta * g43), imu * cmul_(q2, g32), imu * q3};
         mm22(Hr, rb, L.Yr);
         L.Eri[0] = n2 * rb[0]; L.Eri[1] = n2 * rb[1]; L.Eri[2] = n3 * rb[2]; L.Eri[3] = n3 * rb[3];
     }
