@@ -243,8 +243,14 @@ def main():
     except Exception:
         peak, peak_src = FP64_PEAK_FALLBACK, 'fallback: tools/dfma_peak.cu on this pool (profiles/r01_dfma_peak.log)'
     achieved = stack_evals_per_s * F_ALG_STACK / 1e12
+    traffic = None
+    try:   # DRAM bytes per eval of this kernel from the committed ncu capture, scaled to this run's launch size
+        tj = json.load(open(os.path.join(ROOT, 'profiles', 'r01_stack_traffic.json')))
+        traffic = tj['dram_bytes_per_eval'] * float(B) * N * F
+    except Exception:
+        pass
     roofline = dict(bound='fp64', kernel='stack_kernel<URD>', achieved=achieved, peak=peak, unit='TFLOP/s', frac=achieved / peak,
-                    traffic=None, peak_source=peak_src, flop_per_eval=F_ALG_STACK, evals_per_launch=float(B) * N * F,
+                    traffic=traffic, traffic_source='profiles/r01_stack_traffic.json (ncu dram__bytes_read+write per eval x evals per launch)', peak_source=peak_src, flop_per_eval=F_ALG_STACK, evals_per_launch=float(B) * N * F,
                     avg_launch_ms=stack_ms / max(1, len(stack_events)), share_of_step=stack_ms / ms if world == 1 else None,
                     hbm_alg_bytes_per_eval=64.5, hbm_achieved_gbs=stack_evals_per_s * 64.5 / 1e9)
 

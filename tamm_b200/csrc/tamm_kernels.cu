@@ -426,7 +426,7 @@ returns_kernel(const cd* __restrict__ planes, const cd* __restrict__ pre, int N,
 // (TN below is TNF, the fused kernel's own depth tile.)
 constexpr int TNF = 4;   // depths per CTA of the fused returns kernel (keeps it at ~64 registers)
 template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK)
+__global__ void __launch_bounds__(BLOCK, (BLOCK <= 256 ? 768 / BLOCK : 1))
 returns_fused_kernel(const cd* __restrict__ planes, const cd* __restrict__ pre, int N, int Q, int F, int mode, int chunk,
                      int nchunks, cd e0, cd e1, int gtm_phase, cd* __restrict__ E_HH, cd* __restrict__ E_HV,
                      cd* __restrict__ c_HHVV, double* __restrict__ dP_HH, double* __restrict__ dP_HV,
