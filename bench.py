@@ -94,7 +94,7 @@ def cpu_baseline(args, seconds):
                            cores, args.layers, frames, args.frames, evals, wall)), wall
 
 
-def run_reference(args):
+def run_reference(args, emit):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
@@ -114,7 +114,7 @@ def run_reference(args):
                 config=workload_config(args), cpu_baseline=base,
                 e2e=dict(value=v, unit='layer*freq*azimuth evals/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 gpu_launches=0, note='CPU arm: ms_per_step is the whole workload extrapolated from the bounded sample rate')
-    print(json.dumps(line))
+    emit(json.dumps(line))
 
 
 def workload_config(args):
@@ -152,10 +152,26 @@ class ClockSampler(threading.Thread):
                     power_w_max=max(float(x[2]) for x in s), reasons=reasons)
 
 
+def _claim_stdout():
+    """Libraries (NCCL's version banner, torchrun notices) write to stdout; the contract is ONE JSON line there.  Point
+    fd 1 at stderr for the whole run and return a writer bound to the real stdout."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(os.dup(2), 'w', buffering=1)
+
+    def emit(line):
+        with os.fdopen(real, 'w') as f:
+            f.write(line + '\n')
+            f.flush()
+    return emit
+
+
 def main():
     args = parse()
+    emit = _claim_stdout()
     if args.impl == 'reference':
-        return run_reference(args)
+        return run_reference(args, emit)
 
     import torch
     import torch.distributed as dist
@@ -307,7 +323,7 @@ def main():
         line['clocks'] = sampler.summary()
         if world == 1 and not args.no_cpu:
             line['cpu_baseline'], _ = cpu_baseline(args, args.cpu_seconds)
-        print(json.dumps(line))
+        emit(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
