@@ -335,3 +335,39 @@ def test_fujita_paren_agrees_with_gtm_coherence(eng):
     f = ls.LayerStack(nlm, z, N_frames=20, VERBOSE=0, modeltype='FP').get_returns(1e3, f=179e6, alpha=0)
     d = np.abs(g[4] - f[4])
     assert np.nanmedian(d) < 2e-4 and np.nanmax(d) < 2e-2
+
+
+def test_config0_demo_full_size(eng):
+    """configs[0]: demo.ipynb stack, 500 layers from a structure-tensor profile, normal incidence, 181 azimuths."""
+    import layerstack as ls
+    nlm, z = profiles.demo(500, 1500)
+    got = ls.LayerStack(nlm, z, N_frames=181, VERBOSE=0).get_returns(1e3, f=179e6, alpha=0)
+    os_ = orc.OracleStack(nlm, z, N_frames=181)
+    want = os_.get_returns(1e3, f=179e6, alpha=0)
+    arb = os_.get_returns(1e3, f=179e6, alpha=0, eig='factored', precision='extended')   # near-nulls of HH: see helpers
+    _check_returns(got, want, arb)
+
+
+def test_config2_wideband_full_size(eng):
+    """configs[2]: 4096 frequency bins (150-450 MHz) x 3000 layers, both Tx polarisations (full 2x2 Jones matrices),
+    one azimuth.  All 4096 bins run in one launch; 6 sampled bins are checked against the oracle, and the whole sweep
+    against a second launch with a different chunking and against single-frequency launches."""
+    nlm, z = profiles.rathmann_transition(3000, 3000, fabric_type=4)
+    fs = np.linspace(150e6, 450e6, 4096)
+    beta = np.array([0.3])
+    alpha = np.deg2rad(10)
+    got, res = _run(eng, nlm, z, beta, fs, alpha)
+    assert got.shape == (1, 4096, 1, 2999, 2, 2) and np.isfinite(got.view(np.float64)).all()
+    assert int(res.status.cpu().numpy().max()) == 0
+    other, _ = _run(eng, nlm, z, beta, fs, alpha, chunk=97)
+    assert h.peak_rel_err(other[0, :, 0], got[0, :, 0], axis=(1, 2, 3)) < 1e-12
+    for iq in (0, 1, 1365, 2048, 3000, 4095):
+        want = orc.OracleStack(nlm, z, N_frames=1).get_URD(float(fs[iq]), alpha, beta=beta)
+        assert h.peak_rel_err(got[0, iq], want, axis=(1, 2, 3)) < h.RTOL_COMPLEX, iq
+        one, _ = _run(eng, nlm, z, beta, float(fs[iq]), alpha)
+        assert h.peak_rel_err(one[0, 0], got[0, iq], axis=(1, 2, 3)) < 1e-12
+    # returns through the public API with a frequency vector: VV of the second Tx polarisation is URD[1,1]
+    import layerstack as ls
+    s = ls.LayerStack(nlm, z, N_frames=2, VERBOSE=0)
+    r = s.get_returns(1e3, f=fs[::512], alpha=alpha, Tx_pol=([0, 1],))
+    assert r[5].shape == (8, 2999, 2) and np.isfinite(r[0]).all()
