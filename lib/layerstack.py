@@ -130,6 +130,12 @@ class LayerStack:
         else:
             layers = eng.to_device(self._packed_layers()[None])
             res = eng.stack(layers, lanes, 1, self.N_layers, fa.size, len(betas), zeta, self.mu, mode)
+            if int(res.status.cpu()[0]) & 1:
+                # layer_PPJ.py:216-231 assumes two transmitted and two reflected modes; the reference indexes out of
+                # bounds (IndexError) or mis-sorts silently when that fails.  The device flags it instead.
+                import warnings
+                warnings.warn('tamm_b200: a layer did not have 2 transmitted + 2 reflected modes '
+                              '(layer_PPJ.py:216-231); results for this stack are unreliable', UserWarning)
         return eng, res
 
     # ------------------------------------------------------------------------------------------
