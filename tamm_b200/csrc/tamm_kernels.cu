@@ -39,10 +39,11 @@ int fail(const char* fmt, const char* a = "", long b = 0) {
     } while (0)
 
 #ifndef TAMM_DEFAULT_VARIANT
-#define TAMM_DEFAULT_VARIANT 0
+#define TAMM_DEFAULT_VARIANT 5
 #endif
 
 constexpr int TL = 16;     // layers per TMA sub-tile (16 * 80 B = 1280 B per profile)
+constexpr int CARRY_SLOTS = 20;   // 16-byte shared-memory slots per thread of stack_kernel
 constexpr int NPMAX = 4;   // a CTA's lanes may span at most this many profiles (flattened lane mapping)
 
 // ---- mbarrier / bulk-copy (TMA) primitives -----------------------------------------------------
@@ -145,16 +146,17 @@ stack_body(const double* __restrict__ layers, const double* __restrict__ lanes, 
         ln.twopif = c2.x; ln.w_eps0 = c2.y; ln.pad0 = 0; ln.pad1 = 0;
     }
 
-    // Per-thread state carried from layer to layer lives in shared memory (24 x 16 B per thread, conflict-free
-    // [slot][thread] layout): slots 0-15 = Et, Er^-1, Yt, Yr of the previous layer, 16-19 = D, 20-23 = U.  Keeping it
-    // out of the register file during the (register-hungry) layer solve is what allows 2 CTAs per SM.
+    // Per-thread state carried from layer to layer lives in shared memory (CARRY_SLOTS x 16 B per thread, conflict-free
+    // [slot][thread] layout): slots 0-7 = Yt, Yr of the previous layer, 8-11 = D', 12-15 = U' (field basis, see
+    // tamm_core.cuh: LayerF), 16-19 = Er of the previous layer (MODE_U only).  Keeping it out of the register file
+    // during the register-hungry layer solve keeps the kernel spill-free.
     extern __shared__ double2 carry[];
     double2* cs = carry + threadIdx.x;
     const int cstr = blockDim.x;
 #define CS_LD(slot) ld_cd(reinterpret_cast<const cd*>(cs + (slot) * cstr))
 #define CS_ST(slot, v) st_cd(reinterpret_cast<cd*>(cs + (slot) * cstr), (v))
-    CS_ST(16, mk(1.0)); CS_ST(17, mk(0.0)); CS_ST(18, mk(0.0)); CS_ST(19, mk(1.0));
-    CS_ST(20, mk(1.0)); CS_ST(21, mk(0.0)); CS_ST(22, mk(0.0)); CS_ST(23, mk(1.0));
+    CS_ST(8, mk(1.0)); CS_ST(9, mk(0.0)); CS_ST(10, mk(0.0)); CS_ST(11, mk(1.0));
+    CS_ST(12, mk(1.0)); CS_ST(13, mk(0.0)); CS_ST(14, mk(0.0)); CS_ST(15, mk(1.0));
     int st = 0;
     cd* out = planes + ((size_t)p * NI * 4) * QF + lc;
 
@@ -183,31 +185,35 @@ stack_body(const double* __restrict__ layers, const double* __restrict__ lanes, 
                 lp.t20 = v0.x; lp.n21r = v0.y; lp.n21i = v1.x; lp.n22r = v1.y; lp.n22i = v2.x;
                 lp.mono = v2.y; lp.deps = v3.x; lp.sigma = v3.y; lp.dz = v4.x; lp.pad = 0;
             }
-            LayerY cur;
+            LayerF cur;
 #ifdef TAMM_SYNC_PER_LAYER
             __syncthreads();
 #endif
-            st |= layer_solve_fast(lp, ln, zeta, mu, cur);
+            {
+                LayerY y;
+                st |= layer_solve_fast(lp, ln, zeta, mu, y);
+                to_field_basis(y, cur);
+            }
 #ifdef TAMM_SYNC_PER_LAYER
             __syncthreads();
 #endif
-            if (j > 0) {
-                const int n = n0 + j - 1;  // interface between layers n and n+1
-                cd pEt[4], pEri[4], pYt[4], pYr[4], D[4], U[4];
+            if (j == 0) {
+                if (c == 0) {   // the stack starts in the tangential-field basis of the top layer: D'_0 = Et_0, U'_0 = Er_0^-1
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    pEt[k] = CS_LD(k); pEri[k] = CS_LD(4 + k); pYt[k] = CS_LD(8 + k); pYr[k] = CS_LD(12 + k);
-                    D[k] = CS_LD(16 + k); U[k] = CS_LD(20 + k);
+                    for (int k = 0; k < 4; ++k) { CS_ST(8 + k, cur.Et[k]); CS_ST(12 + k, cur.Eri[k]); }
                 }
-                cd R[4], Dm[4], Um[4];
-                interface_fast(pEt, pEri, pYt, pYr, cur, R, Dm, Um);
-                cd o[4];
+            } else {
+                const int n = n0 + j - 1;  // interface between layers n and n+1
+                cd pYt[4], pYr[4], D[4], U[4], o[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { pYt[k] = CS_LD(k); pYr[k] = CS_LD(4 + k); D[k] = CS_LD(8 + k); U[k] = CS_LD(12 + k); }
                 if (MODE == TAMM_MODE_URD) {
-                    cd RD[4];
-                    mm22(R, D, RD);
-                    mm22(U, RD, o);
+                    interface_fb<true>(pYt, pYr, cur, D, U, o);
                 } else {
-                    o[0] = U[0]; o[1] = U[1]; o[2] = U[2]; o[3] = U[3];
+                    cd pEr[4] = {CS_LD(16), CS_LD(17), CS_LD(18), CS_LD(19)};
+                    mm22(U, pEr, o);                          // U_n = U'_n Er_n (layerstack.py:225), before the update
+                    cd dummy[4];
+                    interface_fb<false>(pYt, pYr, cur, D, U, dummy);
                 }
                 if (live) {
                     cd* op = out + (size_t)n * 4 * QF;
@@ -216,23 +222,18 @@ stack_body(const double* __restrict__ layers, const double* __restrict__ lanes, 
                     st_cd(op + 2 * (size_t)QF, o[2]);
                     st_cd(op + 3 * (size_t)QF, o[3]);
                 }
-                cd tmp[4];
-                if (MODE == TAMM_MODE_URD) {                  // layerstack.py:189
-                    mm22(Dm, D, tmp);
-                    CS_ST(16, tmp[0]); CS_ST(17, tmp[1]); CS_ST(18, tmp[2]); CS_ST(19, tmp[3]);
-                }
-                mm22(U, Um, tmp);                             // layerstack.py:190
-                CS_ST(20, tmp[0]); CS_ST(21, tmp[1]); CS_ST(22, tmp[2]); CS_ST(23, tmp[3]);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { if (MODE == TAMM_MODE_URD) CS_ST(8 + k, D[k]); CS_ST(12 + k, U[k]); }
             }
 #pragma unroll
-            for (int k = 0; k < 4; ++k) { CS_ST(k, cur.Et[k]); CS_ST(4 + k, cur.Eri[k]); CS_ST(8 + k, cur.Yt[k]); CS_ST(12 + k, cur.Yr[k]); }
+            for (int k = 0; k < 4; ++k) { CS_ST(k, cur.Yt[k]); CS_ST(4 + k, cur.Yr[k]); if (MODE == TAMM_MODE_U) CS_ST(16 + k, cur.Er[k]); }
         }
     }
     if (live) {
         if (nchunks > 1) {
             cd* a = agg + (((size_t)p * QF + l) * nchunks + c) * 8;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) { st_cd(a + k, CS_LD(16 + k)); st_cd(a + 4 + k, CS_LD(20 + k)); }
+            for (int k = 0; k < 4; ++k) { st_cd(a + k, CS_LD(8 + k)); st_cd(a + 4 + k, CS_LD(12 + k)); }
         }
         if (st && status) atomicOr(status + p, st);
     }
@@ -635,12 +636,12 @@ int pick_block(int QF, int maxt = 256) {
 }
 
 // launch-bound variants of stack_kernel: threads per CTA (CTAs per SM, registers):
-//   0: 256 (1, 255)   1: 192 (2, 168)   2: 256 (2, 128)   3: 512 (1, 128)   4: 320 (1, 204)   5: 384 (1, 168)
+//   0: 256 (1, 255)   1: 192 (2, 168)   2: 256 (2, 128)   3: 512 (1, 128)   4: 448 (1, 144)   5: 384 (1, 168)
 int variant_threads(int v) {
     switch (v) {
         case 1: return 192;
         case 3: return 512;
-        case 4: return 320;
+        case 4: return 448;
         case 5: return 384;
         default: return 256;
     }
@@ -771,13 +772,13 @@ int tamm_stack_urd(const double* layers, const double* lanes, int P, int N, int 
     dim3 grid((unsigned)gx, nch, 1);
     cd* agg = (cd*)workspace;
     cudaStream_t s = (cudaStream_t)stream;
-    const size_t dyn = (size_t)24 * sizeof(double2) * tb;   // per-thread carry state, see stack_kernel
+    const size_t dyn = (size_t)CARRY_SLOTS * sizeof(double2) * tb;   // per-thread carry state, see stack_kernel
 #define TAMM_LAUNCH(MODE, MAXT, MINB)                                                                                   \
     do {                                                                                                                \
         static bool attr_set = false;                                                                                   \
         if (!attr_set) {                                                                                                \
             CUDA_OK(cudaFuncSetAttribute(stack_kernel<MODE, MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                                         24 * (int)sizeof(double2) * MAXT));                                            \
+                                         CARRY_SLOTS * (int)sizeof(double2) * MAXT));                                   \
             attr_set = true;                                                                                            \
         }                                                                                                               \
         stack_kernel<MODE, MAXT, MINB><<<grid, tb, dyn, s>>>(layers, lanes, P, N, QF, flat, zeta, mu, chunk, nch,       \
@@ -788,7 +789,7 @@ int tamm_stack_urd(const double* layers, const double* lanes, int P, int N, int 
         static bool attr_set = false;                                                                                   \
         if (!attr_set) {                                                                                                \
             CUDA_OK(cudaFuncSetAttribute(stack_kernel_nreg<MODE, NREG>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
-                                         24 * (int)sizeof(double2) * MAXT));                                            \
+                                         CARRY_SLOTS * (int)sizeof(double2) * MAXT));                                   \
             attr_set = true;                                                                                            \
         }                                                                                                               \
         stack_kernel_nreg<MODE, NREG><<<grid, tb, dyn, s>>>(layers, lanes, P, N, QF, flat, zeta, mu, chunk, nch,        \
@@ -798,14 +799,14 @@ int tamm_stack_urd(const double* layers, const double* lanes, int P, int N, int 
         if (variant == 0) TAMM_LAUNCH(TAMM_MODE_URD, 256, 1);
         else if (variant == 1) TAMM_LAUNCH(TAMM_MODE_URD, 192, 2);
         else if (variant == 3) TAMM_LAUNCH(TAMM_MODE_URD, 512, 1);
-        else if (variant == 4) TAMM_LAUNCH_NREG(TAMM_MODE_URD, 192, 320);
+        else if (variant == 4) TAMM_LAUNCH(TAMM_MODE_URD, 448, 1);
         else if (variant == 5) TAMM_LAUNCH(TAMM_MODE_URD, 384, 1);
         else TAMM_LAUNCH(TAMM_MODE_URD, 256, 2);
     } else {
         if (variant == 0) TAMM_LAUNCH(TAMM_MODE_U, 256, 1);
         else if (variant == 1) TAMM_LAUNCH(TAMM_MODE_U, 192, 2);
         else if (variant == 3) TAMM_LAUNCH(TAMM_MODE_U, 512, 1);
-        else if (variant == 4) TAMM_LAUNCH_NREG(TAMM_MODE_U, 192, 320);
+        else if (variant == 4) TAMM_LAUNCH(TAMM_MODE_U, 448, 1);
         else if (variant == 5) TAMM_LAUNCH(TAMM_MODE_U, 384, 1);
         else TAMM_LAUNCH(TAMM_MODE_U, 256, 2);
     }

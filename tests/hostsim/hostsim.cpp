@@ -137,6 +137,56 @@ int hostsim_roots_fast(const double* layers, const double* lanes, int N, int F, 
     return 0;
 }
 
+// Field-basis formulation (LayerF / interface_fb), chunked exactly like stack_kernel: chunk 0 starts from D' = Et_0,
+// U' = Er_0^-1, later chunks from identity; MODE_U output is U' Er.
+int hostsim_urd_fb(const double* layers, const double* lanes, int N, int F, double zeta, double mu, int chunk, int mode,
+                   double* out) {
+    if (N < 2 || chunk < 1) return 1;
+    const int NI = N - 1;
+    const int nchunks = (NI + chunk - 1) / chunk;
+    std::vector<cd> Dagg((size_t)nchunks * 4), Uagg((size_t)nchunks * 4);
+    for (int f = 0; f < F; ++f) {
+        LaneParams ln; std::memcpy(&ln, lanes + (size_t)f * LANE_STRIDE, sizeof(ln));
+        cd* o = reinterpret_cast<cd*>(out) + (size_t)f * NI * 4;
+        for (int c = 0; c < nchunks; ++c) {
+            int n0 = c * chunk, n1 = std::min(NI, n0 + chunk);
+            LayerParams lp; std::memcpy(&lp, layers + (size_t)n0 * LAYER_STRIDE, sizeof(lp));
+            LayerY y; LayerF prev, next;
+            layer_solve_fast(lp, ln, zeta, mu, y); to_field_basis(y, prev);
+            cd D[4] = {mk(1), mk(0), mk(0), mk(1)}, U[4] = {mk(1), mk(0), mk(0), mk(1)};
+            if (c == 0) for (int k = 0; k < 4; ++k) { D[k] = prev.Et[k]; U[k] = prev.Eri[k]; }
+            for (int n = n0; n < n1; ++n) {
+                std::memcpy(&lp, layers + (size_t)(n + 1) * LAYER_STRIDE, sizeof(lp));
+                layer_solve_fast(lp, ln, zeta, mu, y); to_field_basis(y, next);
+                cd res[4];
+                if (mode == 0) interface_fb<true>(prev.Yt, prev.Yr, next, D, U, res);
+                else {
+                    mm22(U, prev.Er, res);                    // U_n = U'_n Er_n, before the update
+                    cd dummy[4];
+                    interface_fb<false>(prev.Yt, prev.Yr, next, D, U, dummy);
+                }
+                for (int k = 0; k < 4; ++k) o[(size_t)n * 4 + k] = res[k];
+                prev = next;
+            }
+            for (int k = 0; k < 4; ++k) { Dagg[(size_t)c * 4 + k] = D[k]; Uagg[(size_t)c * 4 + k] = U[k]; }
+        }
+        cd Dp[4] = {mk(1), mk(0), mk(0), mk(1)}, Up[4] = {mk(1), mk(0), mk(0), mk(1)};
+        for (int c = 0; c < nchunks; ++c) {
+            int n0 = c * chunk, n1 = std::min(NI, n0 + chunk);
+            if (c > 0) {
+                for (int n = n0; n < n1; ++n) {
+                    cd t[4];
+                    if (mode == 0) { mul22(o + (size_t)n * 4, Dp, t); mul22(Up, t, o + (size_t)n * 4); }
+                    else { mul22(Up, o + (size_t)n * 4, t); for (int k = 0; k < 4; ++k) o[(size_t)n * 4 + k] = t[k]; }
+                }
+            }
+            mul22(&Dagg[(size_t)c * 4], Dp, Dp);
+            mul22(Up, &Uagg[(size_t)c * 4], Up);
+        }
+    }
+    return 0;
+}
+
 // Same as hostsim_urd but through the hot-path formulation used by stack_kernel (layer_solve_fast/interface_fast).
 int hostsim_urd_fast(const double* layers, const double* lanes, int N, int F, double zeta, double mu, int chunk, int mode,
                      double* out) {

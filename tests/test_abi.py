@@ -39,11 +39,11 @@ def test_host_side_entry_points_without_gpu(built):
     assert lib.tamm_stack_workspace_bytes(0, 100, 181, 10) == 0
     c = lib.tamm_suggest_chunk(1, 3001, 181, 148)
     assert 8 <= c <= 3000
-    # the heuristic fills whole waves of resident CTAs (default variant: one 256-thread CTA per SM, flattened lanes)
+    # the heuristic fills whole waves of resident CTAs (default variant: one 384-thread CTA per SM, flattened lanes)
     for P in (16, 64, 128, 1024):
         c = lib.tamm_suggest_chunk(P, 5000, 181, 148)
         nch = -(-4999 // c)
-        ctas = -(-P * 181 // 256) * nch
+        ctas = -(-P * 181 // 384) * nch
         waves = -(-ctas // 148)
         assert ctas / (waves * 148) > 0.93, (P, c, ctas)
     assert lib.tamm_suggest_chunk(1, 2, 1, 148) == 1

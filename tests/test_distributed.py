@@ -47,7 +47,7 @@ WORKER = textwrap.dedent('''
         lay = ens.packed_layers(lo, hi); lan = packing.pack_lanes(betas, 179e6)
         out = np.zeros((hi - lo, len(betas), N - 1, 2, 2), dtype=np.complex128)
         for i in range(hi - lo):
-            rc = lib.hostsim_urd_fast(lay[i].ctypes.data_as(dp), lan.ctypes.data_as(dp), N, len(betas),
+            rc = lib.hostsim_urd_fb(lay[i].ctypes.data_as(dp), lan.ctypes.data_as(dp), N, len(betas),
                                       ctypes.c_double(float(ens.zeta(alpha))), ctypes.c_double(1.0), 16, 0,
                                       out[i].ctypes.data_as(dp))
             assert rc == 0

@@ -38,14 +38,15 @@ def sim_layers(lib, os_, f, alpha):
     return o
 
 
-def sim_urd(lib, os_, f, alpha, chunk, mode=0, fast=True):
-    """fast=True: the formulation stack_kernel runs (layer_solve_fast / interface_fast); False: the A, A^-1 route of
-    the diagnostic kernel."""
+def sim_urd(lib, os_, f, alpha, chunk, mode=0, fast=True, field_basis=False):
+    """field_basis=True: exactly what stack_kernel runs (layer_solve_fast + to_field_basis + interface_fb, chunk 0
+    starting from Et_0 / Er_0^-1); fast=True: the same layer solve with the amplitude-basis interface (interface_fast);
+    fast=False: the A, A^-1 route of the diagnostic kernel."""
     N, F = os_.N_layers, os_.N_frames
     lay = packing.pack_layers(os_.nlm, os_.dz, os_.epsa, os_.epsc, os_.sigma)
     lan = packing.pack_lanes(os_.beta, f)
     out = np.zeros((F, N - 1, 2, 2), dtype=np.complex128)
-    fn = lib.hostsim_urd_fast if fast else lib.hostsim_urd
+    fn = lib.hostsim_urd_fb if field_basis else (lib.hostsim_urd_fast if fast else lib.hostsim_urd)
     rc = fn(_P(lay), _P(lan), N, F, ctypes.c_double(float(os_.zeta(alpha))), ctypes.c_double(os_.mu), chunk,
             mode, _P(out))
     assert rc == 0
@@ -86,6 +87,18 @@ def test_kernel_arithmetic_urd_chunked(sim, name, chunk, fast):
     assert h.peak_rel_err(got, g['URD'], axis=(1, 2, 3)) < h.RTOL_COMPLEX
 
 
+@pytest.mark.parametrize('name', h.golden_names())
+@pytest.mark.parametrize('chunk', [1000, 16, 7, 1])
+def test_stack_kernel_arithmetic_field_basis(sim, name, chunk):
+    g = h.load_golden(name)
+    os_ = h.oracle_stack(g)
+    mode = 1 if 'kw_URD' in g and str(g['kw_URD']) == 'U' else 0
+    got = sim_urd(sim, os_, float(g['f']), float(g['alpha']), chunk, mode, field_basis=True)
+    assert h.peak_rel_err(got, g['URD'], axis=(1, 2, 3)) < h.RTOL_COMPLEX
+    amp = sim_urd(sim, os_, float(g['f']), float(g['alpha']), chunk, mode, fast=True)
+    assert h.peak_rel_err(got, amp, axis=(1, 2, 3)) < 1e-13          # the two bases are the same mathematics
+
+
 def test_hot_path_closer_to_exact_than_reference(sim):
     """The hot-path arithmetic against the extended-precision arbiter on the fixtures: at least as close to the exact
     Jones matrices as the reference's own arithmetic."""
@@ -94,7 +107,7 @@ def test_hot_path_closer_to_exact_than_reference(sim):
         os_ = h.oracle_stack(g)
         f, a = float(g['f']), float(g['alpha'])
         x = os_.get_URD(f, a, eig='factored', precision='extended').astype(np.complex128)
-        got = sim_urd(sim, os_, f, a, 16)
+        got = sim_urd(sim, os_, f, a, 16, field_basis=True)
         assert h.peak_rel_err(got, x, axis=(1, 2, 3)) <= max(h.peak_rel_err(g['URD'], x, axis=(1, 2, 3)), 1e-12), name
 
 
