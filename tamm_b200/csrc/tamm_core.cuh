@@ -928,7 +928,13 @@ cd phase_f(cd q, double twopif, double d, double sign) {
     return cd{m * cs, m * sn};
 }
 
-TAMM_HD int layer_solve_fast(const LayerParams& lp, const LaneParams& ln, double zeta, double mu, LayerY& L) {
+struct ModeSet {          // sorted roots and unnormalised gamma entries of one layer (layer_PPJ.py:280-283, 309-389)
+    cd q0, q1, q2, q3;
+    cd g12, g13, g21, g23, g32, g33, g41, g43;
+};
+
+// Everything up to the unnormalised field vectors: permittivity, roots, clean-up, partition, p/s sort, gamma.
+TAMM_HD int layer_modes(const LayerParams& lp, const LaneParams& ln, double zeta, double mu, ModeSet& ms_out) {
     int status = 0;
     const Sym3 e = permittivity(lp, ln);
     const WaveCoef w = wave_coef(e, mu, zeta);
@@ -945,7 +951,7 @@ TAMM_HD int layer_solve_fast(const LayerParams& lp, const LaneParams& ln, double
 
     // clean-up (layer_PPJ.py:199-203), Poynting / E-field measures for the p-s sort (233-276) kept as numerators and
     // denominators {|Px|^2, |Px|^2+|Py|^2, |Ex|^2, |Ex|^2+|Ey|^2}, and the transmitted/reflected flags (216-231)
-    double ms[4][4];
+    double ms[4][4];   // sort measures
     int im_mask = 0, re_mask = 0;
     bool has_im = false;
 #if defined(__CUDA_ARCH__)
@@ -1028,6 +1034,19 @@ TAMM_HD int layer_solve_fast(const LayerParams& lp, const LaneParams& ln, double
         g43 = cmul_(cmul_(-u3, g41) - m12, imez);
         if (abs2(q2 - q3) < QSD_THR * QSD_THR) { g32 = mk(0.0); g33 = g33p; g41 = mk(0.0); g43 = g23p; }
     }
+    ms_out.q0 = q0; ms_out.q1 = q1; ms_out.q2 = q2; ms_out.q3 = q3;
+    ms_out.g12 = g12; ms_out.g13 = g13; ms_out.g21 = g21; ms_out.g23 = g23;
+    ms_out.g32 = g32; ms_out.g33 = g33; ms_out.g41 = g41; ms_out.g43 = g43;
+    return status;
+}
+
+// Amplitude-basis layer record (normalised E blocks, their inverses, admittances, phases).
+TAMM_HD int layer_solve_fast(const LayerParams& lp, const LaneParams& ln, double zeta, double mu, LayerY& L) {
+    ModeSet m;
+    int status = layer_modes(lp, ln, zeta, mu, m);
+    const cd q0 = m.q0, q1 = m.q1, q2 = m.q2, q3 = m.q3;
+    const cd g12 = m.g12, g13 = m.g13, g21 = m.g21, g23 = m.g23, g32 = m.g32, g33 = m.g33, g41 = m.g41, g43 = m.g43;
+    const double imu = frcp(mu);
     // row norms (layer_PPJ.py:399-402)
     const double s0 = 1.0 + abs2(g12) + abs2(g13), s1 = 1.0 + abs2(g21) + abs2(g23);
     const double s2 = 1.0 + abs2(g32) + abs2(g33), s3 = 1.0 + abs2(g41) + abs2(g43);
@@ -1053,6 +1072,56 @@ TAMM_HD int layer_solve_fast(const LayerParams& lp, const LaneParams& ln, double
     L.Mrev[0] = phase_f(q2, ln.twopif, lp.dz, +1.0);
     L.Mrev[1] = phase_f(q3, ln.twopif, lp.dz, +1.0);
     return status;
+}
+
+// Field-basis layer record straight from the unnormalised field vectors: P = Et diag(Mfwd) Et^-1, Q = Er diag(Mrev) Er^-1
+// and the admittances are invariant under the row normalisation of gamma (layer_PPJ.py:399-402), so the norms are only
+// evaluated when the normalised blocks themselves are needed (first layer of a stack, MODE_U).
+template <bool WANT_E>
+TAMM_HD int layer_solve_field(const LayerParams& lp, const LaneParams& ln, double zeta, double mu, LayerF& F) {
+    ModeSet m;
+    int status = layer_modes(lp, ln, zeta, mu, m);
+    const double imu = frcp(mu);
+    const cd Mf0 = phase_f(m.q0, ln.twopif, lp.dz, -1.0), Mf1 = phase_f(m.q1, ln.twopif, lp.dz, -1.0);
+    const cd Mr0 = phase_f(m.q2, ln.twopif, lp.dz, +1.0), Mr1 = phase_f(m.q3, ln.twopif, lp.dz, +1.0);
+    cd ra[4], rb[4];
+    {
+        cd idt = crecip_f(mk(1.0) - cmul_(m.g12, m.g21));            // 1/det [[1, g21],[g12, 1]]
+        ra[0] = idt; ra[1] = -cmul_(m.g21, idt); ra[2] = -cmul_(m.g12, idt); ra[3] = idt;
+        cd Ht[4] = {imu * (m.q0 - zeta * m.g13), imu * (cmul_(m.q1, m.g21) - zeta * m.g23), imu * cmul_(m.q0, m.g12), imu * m.q1};
+        mm22(Ht, ra, F.Yt);
+        cd t[4] = {Mf0, cmul_(m.g21, Mf1), cmul_(m.g12, Mf0), Mf1};   // [[1, g21],[g12, 1]] diag(Mfwd)
+        mm22(t, ra, F.P);
+        cd idr = crecip_f(mk(-1.0) - cmul_(m.g32, m.g41));           // 1/det [[-1, g41],[g32, 1]]
+        rb[0] = idr; rb[1] = -cmul_(m.g41, idr); rb[2] = -cmul_(m.g32, idr); rb[3] = -idr;
+        cd Hr[4] = {imu * (-m.q2 - zeta * m.g33), imu * (cmul_(m.q3, m.g41) - zeta * m.g43), imu * cmul_(m.q2, m.g32), imu * m.q3};
+        mm22(Hr, rb, F.Yr);
+        cd r[4] = {-Mr0, cmul_(m.g41, Mr1), cmul_(m.g32, Mr0), Mr1};  // [[-1, g41],[g32, 1]] diag(Mrev)
+        mm22(r, rb, F.Q);
+    }
+    if (WANT_E) {
+        const double s0 = 1.0 + abs2(m.g12) + abs2(m.g13), s1 = 1.0 + abs2(m.g21) + abs2(m.g23);
+        const double s2 = 1.0 + abs2(m.g32) + abs2(m.g33), s3 = 1.0 + abs2(m.g41) + abs2(m.g43);
+        const double i0 = frsqrt(s0), i1 = frsqrt(s1), i2 = frsqrt(s2), i3 = frsqrt(s3);     // 1/norm
+        const double n2 = s2 * i2, n3 = s3 * i3;
+        F.Et[0] = mk(i0); F.Et[1] = i1 * m.g21; F.Et[2] = i0 * m.g12; F.Et[3] = mk(i1);
+        F.Er[0] = mk(-i2); F.Er[1] = i3 * m.g41; F.Er[2] = i2 * m.g32; F.Er[3] = mk(i3);
+        F.Eri[0] = n2 * rb[0]; F.Eri[1] = n2 * rb[1]; F.Eri[2] = n3 * rb[2]; F.Eri[3] = n3 * rb[3];
+    }
+    return status;
+}
+
+// Cold path: the normalised E blocks of one layer (start of a stack: D'_0 = Et_0, U'_0 = Er_0^-1).  Never inlined, so the
+// hot loop of stack_kernel carries no normalisation code or registers for it.
+#if defined(__CUDA_ARCH__)
+__device__ __noinline__
+#else
+inline
+#endif
+void layer_start_blocks(const LayerParams* lp, const LaneParams* ln, double zeta, double mu, cd Et[4], cd Eri[4]) {
+    LayerF F;
+    layer_solve_field<true>(*lp, *ln, zeta, mu, F);
+    for (int k = 0; k < 4; ++k) { Et[k] = F.Et[k]; Eri[k] = F.Eri[k]; }
 }
 
 // Interface between layer n (carried: Et, Eri, Yt, Yr) and layer n+1 (nx).  R, Dm = Mfwd' T, Um = Trev Mrev'.
@@ -1109,19 +1178,18 @@ TAMM_HD void interface_fb(const cd pYt[4], const cd pYr[4], const LayerF& nx, cd
     cd d3[4] = {nx.Yt[0] - nx.Yr[0], nx.Yt[1] - nx.Yr[1], nx.Yt[2] - nx.Yr[2], nx.Yt[3] - nx.Yr[3]};
     cd X[4], V[4], W[4];
     if (WITH_D) {
-        // R from the EXPLICIT difference Yt - Yt' (correlated rounding of the two admittances cancels)
+        // X2 = M d2 from the EXPLICIT difference d2 = Yt - Yt' (correlated rounding of the two admittances cancels).
+        // Since d1 - d2 = Yt' - Yr = M^-1, M d1 = I + X2: V = X2 D' serves both URD_n and D'_{n+1}.
         cd d2[4] = {pYt[0] - nx.Yt[0], pYt[1] - nx.Yt[1], pYt[2] - nx.Yt[2], pYt[3] - nx.Yt[3]};
         mm22(M, d2, X);
         mm22(X, D, V);
-        mm22(U, V, out);                                  // URD_n = U'_n (M d2) D'_n          layerstack.py:194
-        cd d1[4] = {pYt[0] - pYr[0], pYt[1] - pYr[1], pYt[2] - pYr[2], pYt[3] - pYr[3]};
-        mm22(M, d1, X);
-        mm22(X, D, V);
-        mm22(nx.P, V, D);                                 // D'_{n+1} = P' (M d1) D'_n         layerstack.py:189
+        mm22(U, V, out);                                  // URD_n = U'_n (M d2) D'_n                 layerstack.py:194
+        cd T[4] = {D[0] + V[0], D[1] + V[1], D[2] + V[2], D[3] + V[3]};
+        mm22(nx.P, T, D);                                 // D'_{n+1} = P' (M d1) D'_n = P' (D' + V)   layerstack.py:189
     }
     mm22(M, d3, X);
     mm22(U, X, V);
-    mm22(V, nx.Q, W);                                     // U'_{n+1} = U'_n (M d3) Q'         layerstack.py:190
+    mm22(V, nx.Q, W);                                     // U'_{n+1} = U'_n (M d3) Q'                layerstack.py:190
     // nan_to_num (layerstack.py:101-127) only matters for singular interfaces: one finite-check, rare slow path
     double chk = 0.0;
 #if defined(__CUDA_ARCH__)

@@ -189,18 +189,16 @@ stack_body(const double* __restrict__ layers, const double* __restrict__ lanes, 
 #ifdef TAMM_SYNC_PER_LAYER
             __syncthreads();
 #endif
-            {
-                LayerY y;
-                st |= layer_solve_fast(lp, ln, zeta, mu, y);
-                to_field_basis(y, cur);
-            }
+            // normalised E blocks are only needed for MODE_U here; the start of a stack uses the cold helper below
+            st |= layer_solve_field<MODE == TAMM_MODE_U>(lp, ln, zeta, mu, cur);
 #ifdef TAMM_SYNC_PER_LAYER
             __syncthreads();
 #endif
             if (j == 0) {
                 if (c == 0) {   // the stack starts in the tangential-field basis of the top layer: D'_0 = Et_0, U'_0 = Er_0^-1
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) { CS_ST(8 + k, cur.Et[k]); CS_ST(12 + k, cur.Eri[k]); }
+                    cd e0[4], e1[4];
+                    layer_start_blocks(&lp, &ln, zeta, mu, e0, e1);
+                    for (int k = 0; k < 4; ++k) { CS_ST(8 + k, e0[k]); CS_ST(12 + k, e1[k]); }
                 }
             } else {
                 const int n = n0 + j - 1;  // interface between layers n and n+1

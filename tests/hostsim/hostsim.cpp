@@ -151,13 +151,13 @@ int hostsim_urd_fb(const double* layers, const double* lanes, int N, int F, doub
         for (int c = 0; c < nchunks; ++c) {
             int n0 = c * chunk, n1 = std::min(NI, n0 + chunk);
             LayerParams lp; std::memcpy(&lp, layers + (size_t)n0 * LAYER_STRIDE, sizeof(lp));
-            LayerY y; LayerF prev, next;
-            layer_solve_fast(lp, ln, zeta, mu, y); to_field_basis(y, prev);
+            LayerF prev, next;
+            layer_solve_field<true>(lp, ln, zeta, mu, prev);
             cd D[4] = {mk(1), mk(0), mk(0), mk(1)}, U[4] = {mk(1), mk(0), mk(0), mk(1)};
             if (c == 0) for (int k = 0; k < 4; ++k) { D[k] = prev.Et[k]; U[k] = prev.Eri[k]; }
             for (int n = n0; n < n1; ++n) {
                 std::memcpy(&lp, layers + (size_t)(n + 1) * LAYER_STRIDE, sizeof(lp));
-                layer_solve_fast(lp, ln, zeta, mu, y); to_field_basis(y, next);
+                if (mode != 0) layer_solve_field<true>(lp, ln, zeta, mu, next); else layer_solve_field<false>(lp, ln, zeta, mu, next);
                 cd res[4];
                 if (mode == 0) interface_fb<true>(prev.Yt, prev.Yr, next, D, U, res);
                 else {
