@@ -822,33 +822,54 @@ TAMM_HD void eig4_fast(const WaveCoef& w, cd rv[4][3]) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
+        const double sep2 = abs2(hb - hs);      // |distance between the two roots of the pair|^2 (estimate)
         for (int r = 0; r < 2; ++r) {
-            cd x = centre + (r ? hs : hb);
-            // successive-linear-problem steps until the scalar Newton polish below is guaranteed to finish the job:
-            // after a step h the error is ~0.3|h|^2 and the polish turns an error e into e^2/|distance to partner|
+            const cd h0 = r ? hs : hb;
+            cd x = centre + h0;
+            // Refinement loop.  Every iteration evaluates N(x), f = det N and f' = tr(adj(N') N).  While the error of x may
+            // be comparable to the pair splitting the step is the MSLP step (smaller eigenvalue of -N'^-1 N, needs a
+            // complex sqrt; converges quadratically whatever the splitting); once the error is well below the splitting
+            // the plain Newton step -f/f' is taken (error e -> e^2/splitting).  err2 tracks the squared error estimate.
+            double err2 = abs2(h0);
+            err2 = 0.09 * err2 * err2;              // pair step: error ~ 0.3 |h|^2
+            WaveMat mm;
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
             for (int it = 0; it < 24; ++it) {
-                WaveMat mm = wave_matrix(w, x);
-                cd big, det1, h;
-                mslp_core(mm, w.db, big, det1, h);
-                x = x + h;
-                double h2 = abs2(h);
-                h2 = h2 * h2;
-                // |h|^8 <= 1e-30 |h_big|^2 |x|^2 with |h_big| = |big|/|det N'|  (no division)
-                if (h2 * h2 * abs2(det1) <= 1e-30 * abs2(big) * abs2(x)) break;
+                mm = wave_matrix(w, x);
+                const cd f = det2(mm.a, mm.b, mm.b, mm.d);
+                cd tr = cmul_(mm.dd, mm.a);
+                cfma(tr, mm.da, mm.d);
+                cfma(tr, (-2.0) * w.db, mm.b);
+                const double x2 = abs2(x);
+                cd h;
+                if (err2 * 400.0 < sep2) {           // error < splitting / 20: scalar Newton
+                    h = -cmul_(f, crecip_s(tr));
+                    const double hh = abs2(h);
+                    // a Newton step larger than the estimated error means f' ~ 0: discard it
+                    if (!(hh <= 100.0 * err2 + 1e-30 * x2)) h = mk(0.0);
+                    x = x + h;
+                    err2 = hh * hh * frcp(sep2);     // e^2/splitting, squared
+                } else {                              // MSLP step
+                    const cd det1 = det2(mm.da, w.db, w.db, mm.dd);
+                    const cd hm = 0.5 * tr;
+                    cd disc = csq(hm);
+                    cfma(disc, -det1, f);
+                    cd sq = csqrt_f(disc);
+                    const bool flip = (hm.re * sq.re + hm.im * sq.im) < 0.0;
+                    sq = csel(flip, -sq, sq);
+                    h = -cmul_(f, crecip_s(hm + sq));
+                    x = x + h;
+                    const double hh = abs2(h);
+                    err2 = 0.09 * hh * hh;
+                }
+                if (err2 <= 1e-32 * x2) break;       // estimated error below 1e-16 |x|
             }
-            WaveMat mm = wave_matrix(w, x);
-            cd f = det2(mm.a, mm.b, mm.b, mm.d);
-            cd fp = dot2(mm.da, mm.d, mm.a, mm.dd);
-            cfma(fp, (-2.0) * mm.b, w.db);
-            cd step = cmul_(f, crecip_s(fp));
-            // a large polish means f'(x) ~ 0 (degenerate pair): keep the MSLP root
-            if (!(abs2(step) <= 1e-12 * abs2(x))) step = mk(0.0);
+            // null vector of N from the last evaluation (one step before x: accurate to the size of that step)
             bool use0 = abs2(mm.a) >= abs2(mm.d);
             const int idx = 2 * pair + r;
-            rv[idx][0] = x - step;
+            rv[idx][0] = x;
             rv[idx][1] = csel(use0, -mm.b, mm.d);
             rv[idx][2] = csel(use0, mm.a, -mm.b);
         }
