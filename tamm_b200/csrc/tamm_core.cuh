@@ -77,6 +77,9 @@ TAMM_HD double fsqrt(double a) {
 #endif
 }
 
+// 1/mu; folds to the constant 1 when the kernel is specialised for mu == 1 (the reference's default, layerstack.py:14)
+TAMM_HD double rcp_mu(double mu) { return mu == 1.0 ? 1.0 : frcp(mu); }
+
 TAMM_HD cd mk(double re, double im = 0.0) { return cd{re, im}; }
 TAMM_HD cd operator+(cd a, cd b) { return cd{a.re + b.re, a.im + b.im}; }
 TAMM_HD cd operator-(cd a, cd b) { return cd{a.re - b.re, a.im - b.im}; }
@@ -965,7 +968,7 @@ TAMM_HD int layer_modes(const LayerParams& lp, const LaneParams& ln, double zeta
     const cd ezz = mk(e.zz, e.im);
     const cd ib = crecip_f(mu * ezz);
     const cd a20 = (-(e.xz * mu)) * ib, a21 = (-(e.yz * mu)) * ib, a24 = (-(zeta * mu)) * ib;
-    const double imu = frcp(mu);
+    const double imu = rcp_mu(mu);
     const double a51 = zeta * imu;
     const cd D00 = zeta * a20, D02 = zeta * a21;
     const cd iD01 = crecip_f(mk(mu) + zeta * a24);
@@ -1067,7 +1070,7 @@ TAMM_HD int layer_solve_fast(const LayerParams& lp, const LaneParams& ln, double
     int status = layer_modes(lp, ln, zeta, mu, m);
     const cd q0 = m.q0, q1 = m.q1, q2 = m.q2, q3 = m.q3;
     const cd g12 = m.g12, g13 = m.g13, g21 = m.g21, g23 = m.g23, g32 = m.g32, g33 = m.g33, g41 = m.g41, g43 = m.g43;
-    const double imu = frcp(mu);
+    const double imu = rcp_mu(mu);
     // row norms (layer_PPJ.py:399-402)
     const double s0 = 1.0 + abs2(g12) + abs2(g13), s1 = 1.0 + abs2(g21) + abs2(g23);
     const double s2 = 1.0 + abs2(g32) + abs2(g33), s3 = 1.0 + abs2(g41) + abs2(g43);
@@ -1102,7 +1105,7 @@ template <bool WANT_E>
 TAMM_HD int layer_solve_field(const LayerParams& lp, const LaneParams& ln, double zeta, double mu, LayerF& F) {
     ModeSet m;
     int status = layer_modes(lp, ln, zeta, mu, m);
-    const double imu = frcp(mu);
+    const double imu = rcp_mu(mu);
     const cd Mf0 = phase_f(m.q0, ln.twopif, lp.dz, -1.0), Mf1 = phase_f(m.q1, ln.twopif, lp.dz, -1.0);
     const cd Mr0 = phase_f(m.q2, ln.twopif, lp.dz, +1.0), Mr1 = phase_f(m.q3, ln.twopif, lp.dz, +1.0);
     cd ra[4], rb[4];

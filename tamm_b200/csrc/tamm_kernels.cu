@@ -83,10 +83,12 @@ __device__ __forceinline__ cd ld_cd(const cd* p) {
 
 // ---- the hot kernel ------------------------------------------------------------------------------
 // grid = (lane blocks, chunks); block = TB threads (multiple of 32).
-template <int MODE>
+// MU1: specialisation for mu == 1 (every multiplication by mu or 1/mu folds away)
+template <int MODE, bool MU1>
 __device__ __forceinline__ void
 stack_body(const double* __restrict__ layers, const double* __restrict__ lanes, int P, int N, int QF, int flat, double zeta,
-             double mu, int chunk, int nchunks, cd* __restrict__ planes, cd* __restrict__ agg, int* __restrict__ status) {
+             double mu_arg, int chunk, int nchunks, cd* __restrict__ planes, cd* __restrict__ agg, int* __restrict__ status) {
+    const double mu = MU1 ? 1.0 : mu_arg;
     __shared__ alignas(128) double sbuf[2][NPMAX][TL * LAYER_STRIDE];
     __shared__ alignas(8) uint64_t bar[2];
 
@@ -242,11 +244,8 @@ stack_body(const double* __restrict__ layers, const double* __restrict__ lanes, 
         double mu, int chunk, int nchunks, cd *__restrict__ planes, cd *__restrict__ agg, int *__restrict__ status
 #define TAMM_STACK_PASS layers, lanes, P, N, QF, flat, zeta, mu, chunk, nchunks, planes, agg, status
 // MAXT / MINB: launch bounds (register budget): (256,1) -> 255 regs, (192,2) -> 168 regs, (256,2) -> 128 regs, ...
-template <int MODE, int MAXT, int MINB>
-__global__ void __launch_bounds__(MAXT, MINB) stack_kernel(TAMM_STACK_ARGS) { stack_body<MODE>(TAMM_STACK_PASS); }
-// explicit register cap (ptxas otherwise rounds the 320-thread budget down to 168)
-template <int MODE, int NREG>
-__global__ void __maxnreg__(NREG) stack_kernel_nreg(TAMM_STACK_ARGS) { stack_body<MODE>(TAMM_STACK_PASS); }
+template <int MODE, int MAXT, int MINB, bool MU1>
+__global__ void __launch_bounds__(MAXT, MINB) stack_kernel(TAMM_STACK_ARGS) { stack_body<MODE, MU1>(TAMM_STACK_PASS); }
 
 // ---- Fujita--Paren stack (modeltype 'FP'): thread = (profile, lane, chunk); same planes/aggregate layout as stack_kernel
 __global__ void __launch_bounds__(128)
@@ -634,12 +633,10 @@ int pick_block(int QF, int maxt = 256) {
 }
 
 // launch-bound variants of stack_kernel: threads per CTA (CTAs per SM, registers):
-//   0: 256 (1, 255)   1: 192 (2, 168)   2: 256 (2, 128)   3: 512 (1, 128)   4: 448 (1, 144)   5: 384 (1, 168)
+//   0: 256 (1, 255)   2: 256 (2, 128)   3: 512 (1, 128)   5: 384 (1, 168, default)
 int variant_threads(int v) {
     switch (v) {
-        case 1: return 192;
         case 3: return 512;
-        case 4: return 448;
         case 5: return 384;
         default: return 256;
     }
@@ -715,7 +712,7 @@ int tamm_suggest_chunk(int P, int N, int QF, int sm_count) {
     int variant = ev ? atoi(ev) : TAMM_DEFAULT_VARIANT;
     if (variant < 0 || variant > 5) variant = TAMM_DEFAULT_VARIANT;
     const int maxt = variant_threads(variant);
-    const int ctas_per_sm = (variant == 1 || variant == 2) ? 2 : 1;
+    const int ctas_per_sm = (variant == 2) ? 2 : 1;
     int tb, flat;
     long bpc;                                                              // CTAs per chunk index
     stack_geometry(P, QF, maxt, &tb, &flat, &bpc);
@@ -775,41 +772,33 @@ int tamm_stack_urd(const double* layers, const double* lanes, int P, int N, int 
     do {                                                                                                                \
         static bool attr_set = false;                                                                                   \
         if (!attr_set) {                                                                                                \
-            CUDA_OK(cudaFuncSetAttribute(stack_kernel<MODE, MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+            CUDA_OK(cudaFuncSetAttribute(stack_kernel<MODE, MAXT, MINB, true>,                                          \
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,                                   \
+                                         CARRY_SLOTS * (int)sizeof(double2) * MAXT));                                   \
+            CUDA_OK(cudaFuncSetAttribute(stack_kernel<MODE, MAXT, MINB, false>,                                         \
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,                                   \
                                          CARRY_SLOTS * (int)sizeof(double2) * MAXT));                                   \
             attr_set = true;                                                                                            \
         }                                                                                                               \
-        stack_kernel<MODE, MAXT, MINB><<<grid, tb, dyn, s>>>(layers, lanes, P, N, QF, flat, zeta, mu, chunk, nch,       \
-                                                              (cd*)planes, agg, status);                                \
-    } while (0)
-#define TAMM_LAUNCH_NREG(MODE, NREG, MAXT)                                                                             \
-    do {                                                                                                                \
-        static bool attr_set = false;                                                                                   \
-        if (!attr_set) {                                                                                                \
-            CUDA_OK(cudaFuncSetAttribute(stack_kernel_nreg<MODE, NREG>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
-                                         CARRY_SLOTS * (int)sizeof(double2) * MAXT));                                   \
-            attr_set = true;                                                                                            \
-        }                                                                                                               \
-        stack_kernel_nreg<MODE, NREG><<<grid, tb, dyn, s>>>(layers, lanes, P, N, QF, flat, zeta, mu, chunk, nch,        \
-                                                             (cd*)planes, agg, status);                                 \
+        if (mu == 1.0)                                                                                                  \
+            stack_kernel<MODE, MAXT, MINB, true><<<grid, tb, dyn, s>>>(layers, lanes, P, N, QF, flat, zeta, mu, chunk,  \
+                                                                        nch, (cd*)planes, agg, status);                 \
+        else                                                                                                            \
+            stack_kernel<MODE, MAXT, MINB, false><<<grid, tb, dyn, s>>>(layers, lanes, P, N, QF, flat, zeta, mu, chunk, \
+                                                                         nch, (cd*)planes, agg, status);                \
     } while (0)
     if (mode == TAMM_MODE_URD) {
         if (variant == 0) TAMM_LAUNCH(TAMM_MODE_URD, 256, 1);
-        else if (variant == 1) TAMM_LAUNCH(TAMM_MODE_URD, 192, 2);
         else if (variant == 3) TAMM_LAUNCH(TAMM_MODE_URD, 512, 1);
-        else if (variant == 4) TAMM_LAUNCH(TAMM_MODE_URD, 448, 1);
         else if (variant == 5) TAMM_LAUNCH(TAMM_MODE_URD, 384, 1);
         else TAMM_LAUNCH(TAMM_MODE_URD, 256, 2);
     } else {
         if (variant == 0) TAMM_LAUNCH(TAMM_MODE_U, 256, 1);
-        else if (variant == 1) TAMM_LAUNCH(TAMM_MODE_U, 192, 2);
         else if (variant == 3) TAMM_LAUNCH(TAMM_MODE_U, 512, 1);
-        else if (variant == 4) TAMM_LAUNCH(TAMM_MODE_U, 448, 1);
         else if (variant == 5) TAMM_LAUNCH(TAMM_MODE_U, 384, 1);
         else TAMM_LAUNCH(TAMM_MODE_U, 256, 2);
     }
 #undef TAMM_LAUNCH
-#undef TAMM_LAUNCH_NREG
     CUDA_OK(cudaGetLastError());
     if (nch > 1) {
         long nseq = (long)P * QF;

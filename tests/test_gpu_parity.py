@@ -371,3 +371,15 @@ def test_config2_wideband_full_size(eng):
     s = ls.LayerStack(nlm, z, N_frames=2, VERBOSE=0)
     r = s.get_returns(1e3, f=fs[::512], alpha=alpha, Tx_pol=([0, 1],))
     assert r[5].shape == (8, 2999, 2) and np.isfinite(r[0]).all()
+
+
+def test_nonunit_permeability(eng):
+    """mu != 1 exercises the generic (non-specialised) kernel instantiation and the mu-dependent formulas
+    (layer_PPJ.py:122, 315-389, 432-433)."""
+    import layerstack as ls
+    nlm, z = profiles.tilted(80, 400, seed=12)
+    for mu in (1.7, 0.8):
+        for alpha in (0.0, np.deg2rad(12)):
+            got = ls.LayerStack(nlm, z, N_frames=33, mu=mu, VERBOSE=0).get_returns(1e3, f=179e6, alpha=alpha)
+            want = orc.OracleStack(nlm, z, N_frames=33, mu=mu).get_returns(1e3, f=179e6, alpha=alpha)
+            _check_returns(got, want)

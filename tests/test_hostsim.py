@@ -172,3 +172,17 @@ def test_kernel_arithmetic_fp(sim, name):
     ai, ang = packing.fp_layer_constants(os_.nlm)
     L = orc.fp_layers(os_.nlm, os_.beta, os_.dz, float(g['f']), os_.epsa, os_.epsc, os_.sigma)
     assert np.array_equal(ai, L['ai_horiz']) and np.array_equal(ang, L['eigang'])
+
+
+@pytest.mark.parametrize('mu', [1.0, 1.7])
+def test_stack_kernel_arithmetic_permeability(sim, mu):
+    """mu != 1 runs the generic instantiation of the kernels (mu == 1 is specialised); the reference carries mu through
+    M[3:6,3:6] (layer_PPJ.py:122), A rows 2-3 (432-433) and gamma (315-389)."""
+    from tamm_b200 import profiles
+    nlm, z = profiles.tilted(50, 300, seed=12)
+    os_ = orc.OracleStack(nlm, z, N_frames=9, mu=mu)
+    for alpha in (0.0, np.deg2rad(12)):
+        want = os_.get_URD(179e6, alpha)
+        for fb in (True, False):
+            got = sim_urd(sim, os_, 179e6, alpha, 16, field_basis=fb)
+            assert h.peak_rel_err(got, want, axis=(1, 2, 3)) < h.RTOL_COMPLEX, (mu, alpha, fb)
