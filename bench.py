@@ -126,30 +126,73 @@ def workload_config(args):
 
 # ---------------------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
+    """SM clock, power and clock-event (throttle) reasons sampled DURING the timed region: NVML every 10 ms (falls back
+    to nvidia-smi subprocesses every ~0.3 s when pynvml is unavailable)."""
+    REASONS = (('hw_slowdown', 0x8), ('hw_thermal_slowdown', 0x40), ('sw_thermal_slowdown', 0x20), ('sw_power_cap', 0x4))
+
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.stop_flag = index, [], False
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices; honour CUDA_VISIBLE_DEVICES if it is a plain index list
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            phys = index
+            if vis and all(t.strip().isdigit() for t in vis.split(',')):
+                phys = int(vis.split(',')[index])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+        try:
+            pw = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+        except Exception:
+            pw = float('nan')
+        try:
+            rs = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+        except Exception:
+            try:
+                rs = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+            except Exception:
+                rs = 0
+        return sm, self.max_sm, pw, rs
 
     def run(self):
         q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
         while not self.stop_flag:
             try:
+                if self.nvml is not None:
+                    self.samples.append(self._sample_nvml())
+                    time.sleep(0.01)
+                    continue
                 o = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q, '--format=csv,noheader,nounits'],
                                    capture_output=True, text=True, timeout=5).stdout.strip().split(',')
-                self.samples.append([x.strip() for x in o])
+                o = [x.strip() for x in o]
+                mask = sum(bit for (name, bit), v in zip(self.REASONS, o[3:7]) if v.lower().startswith('active'))
+                self.samples.append((float(o[0]), float(o[1]), float(o[2]), mask))
             except Exception:
-                pass
-            time.sleep(0.1)
+                time.sleep(0.05)
 
     def summary(self):
-        s = [x for x in self.samples if len(x) >= 7 and x[0].isdigit()]
+        s = self.samples
         if not s:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=['unavailable'])
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = [n for i, n in enumerate(names) if any(x[3 + i].lower().startswith('active') for x in s)]
-        return dict(sm_mhz=float(np.median([float(x[0]) for x in s])), sm_max_mhz=float(s[0][1]), samples=len(s),
-                    power_w_max=max(float(x[2]) for x in s), reasons=reasons)
+        mask = 0
+        for x in s:
+            mask |= int(x[3])
+        reasons = [name for name, bit in self.REASONS if mask & bit]
+        pw = [x[2] for x in s if x[2] == x[2]]
+        return dict(sm_mhz=float(np.median([x[0] for x in s])), sm_max_mhz=float(s[0][1]), samples=len(s),
+                    power_w_max=max(pw) if pw else None, reasons=reasons,
+                    source='nvml' if self.nvml is not None else 'nvidia-smi')
 
 
 def _claim_stdout():
