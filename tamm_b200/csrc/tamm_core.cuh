@@ -822,10 +822,11 @@ TAMM_HD void eig4_fast(const WaveCoef& w, cd rv[4][3]) {
             WaveMat m = wave_matrix(w, centre);
             mslp_eigs_f(m, w.db, hb, hs);
         }
+        const double sep2 = abs2(hb - hs);      // |distance between the two roots of the pair|^2 (estimate)
+        const double isep2 = frcp(sep2 + TINY);
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
-        const double sep2 = abs2(hb - hs);      // |distance between the two roots of the pair|^2 (estimate)
         for (int r = 0; r < 2; ++r) {
             const cd h0 = r ? hs : hb;
             cd x = centre + h0;
@@ -853,7 +854,7 @@ TAMM_HD void eig4_fast(const WaveCoef& w, cd rv[4][3]) {
                     // a Newton step larger than the estimated error means f' ~ 0: discard it
                     if (!(hh <= 100.0 * err2 + 1e-30 * x2)) h = mk(0.0);
                     x = x + h;
-                    err2 = hh * hh * frcp(sep2);     // e^2/splitting, squared
+                    err2 = hh * hh * isep2;          // e^2/splitting, squared
                 } else {                              // MSLP step
                     const cd det1 = det2(mm.da, w.db, w.db, mm.dd);
                     const cd hm = 0.5 * tr;
@@ -992,13 +993,16 @@ TAMM_HD int layer_modes(const LayerParams& lp, const LaneParams& ln, double zeta
         cd t = cmul_(q - D00, Ex);
         cfma(t, -D02, Ey);
         cd Hy = cmul_(t, iD01);
-        cd Hx = (-imu) * cmul_(q, Ey);
         cd Ez = cmul_(a20, Ex);
         cfma(Ez, a21, Ey);
         cfma(Ez, a24, Hy);
-        cd Hz = a51 * Ey;
-        cd Px = det2(Ey, Ez, Hy, Hz);     // Ey*Hz - Ez*Hy
-        cd Py = det2(Ez, Ex, Hz, Hx);     // Ez*Hx - Ex*Hz
+        // with Hz = a51 Ey and Hx = -q Ey / mu (layer_PPJ.py:236-241):
+        //   Px = Ey Hz - Ez Hy = a51 Ey^2 - Ez Hy ,   Py = Ez Hx - Ex Hz = -Ey (q Ez / mu + a51 Ex)
+        cd Px = a51 * csq(Ey);
+        cfma(Px, -Ez, Hy);
+        cd u = imu * cmul_(q, Ez);
+        u = cd{fma(a51, Ex.re, u.re), fma(a51, Ex.im, u.im)};
+        cd Py = -cmul_(Ey, u);
         double pxx = abs2(Px), exx = abs2(Ex);
         ms[k][0] = pxx; ms[k][1] = pxx + abs2(Py); ms[k][2] = exx; ms[k][3] = exx + abs2(Ey);
     }
