@@ -783,11 +783,119 @@ TAMM_HD void mslp_eigs_f(const WaveMat& m, cd db, cd& h_big, cd& h_small) {
     h_big = -cmul_(big, crecip_f(det1));
 }
 
+// Refinement of one root.  Every iteration evaluates N(x), f = det N and f' = tr(adj(N') N) entry-wise.  While the error
+// of x may be comparable to the distance to the nearest other root (sep2 = that distance squared) the step is the MSLP
+// step (smaller eigenvalue of -N'^-1 N; needs a complex sqrt, converges quadratically whatever the separation); once the
+// error is well below the separation the plain Newton step -f/f' is taken (error e -> e^2/separation).  err2 carries
+// the squared error estimate in and out; mm returns the last evaluated wave matrix (for the null vector).
+TAMM_HD void refine_root(const WaveCoef& w, cd& x, double sep2, double isep2, double err2, WaveMat& mm) {
+    // error model: a linearised step h leaves an error ~ |h|^2/|x| (curvature of det N ~ 1/|q|); a Newton step near a
+    // second root at distance d leaves ~ |h|^2 (1/d + 1/|x|)
+    const double ix2 = frcp(abs2(x) + TINY);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int it = 0; it < 24; ++it) {
+        mm = wave_matrix(w, x);
+        const cd f = det2(mm.a, mm.b, mm.b, mm.d);
+        cd tr = cmul_(mm.dd, mm.a);
+        cfma(tr, mm.da, mm.d);
+        cfma(tr, (-2.0) * w.db, mm.b);
+        cd h = -cmul_(f, crecip_s(tr));        // Newton step
+        double hh = abs2(h);
+        // Newton only when the error is well below the separation AND the step it proposes is small against it
+        if ((err2 * 400.0 < sep2) && (hh * 16.0 <= sep2)) {
+            x = x + h;
+            err2 = hh * hh * (isep2 + ix2);
+        } else {                              // MSLP step
+            const cd det1 = det2(mm.da, w.db, w.db, mm.dd);
+            const cd hm = 0.5 * tr;
+            cd disc = csq(hm);
+            cfma(disc, -det1, f);
+            cd sq = csqrt_f(disc);
+            const bool flip = (hm.re * sq.re + hm.im * sq.im) < 0.0;
+            sq = csel(flip, -sq, sq);
+            h = -cmul_(f, crecip_s(hm + sq));
+            x = x + h;
+            hh = abs2(h);
+            err2 = hh * hh * ix2;
+        }
+        if (err2 <= 1e-31 * abs2(x)) break;       // conservative error bound below 3e-16 |x|
+    }
+}
+
+// Coefficients of the characteristic quartic det N(q) = c4 q^4 + c3 q^3 + c2 q^2 + c1 q + c0 (only used to VERIFY the
+// roots through Vieta's relations and by the cold fallback; the roots themselves come from entry-wise evaluation).
+TAMM_HD void quartic_coef(const WaveCoef& w, cd c[5]) {
+    const cd A0 = w.e00 - w.k * (w.e02 * w.e02), A1 = (-2.0 * w.zeta) * (w.k * w.e02), A2 = -(mk(1.0) + (w.zeta * w.zeta) * w.k);
+    const cd B0 = w.e01 - w.e02 * w.w1, B1 = w.db;
+    c[4] = -A2;
+    c[3] = -A1;
+    c[2] = A2 * w.d0 - A0 - B1 * B1;
+    c[1] = A1 * w.d0 - 2.0 * (B0 * B1);
+    c[0] = A0 * w.d0 - B0 * B0;
+}
+
+// Cold path: all four roots from scratch by Aberth-Ehrlich iteration on the quartic, each then refined entry-wise.
+// Used when the pair-based solve fails Vieta's check (grazing incidence: the four roots are O(0.1) apart and the
+// transmitted / reflected pairs are no longer separated).
+#if defined(__CUDA_ARCH__)
+__device__ __noinline__
+#else
+inline
+#endif
+void eig4_fallback(double exx, double exy, double exz, double eyy, double eyz, double ezz, double eim, double mu,
+                   double zeta, cd rv[4][3]) {
+    // all inputs by value: taking the address of the caller's WaveCoef would force it into local memory on the hot path
+    Sym3 e;
+    e.xx = exx; e.xy = exy; e.xz = exz; e.yy = eyy; e.yz = eyz; e.zz = ezz; e.im = eim;
+    const WaveCoef w = wave_coef(e, mu, zeta);
+    cd c[5];
+    quartic_coef(w, c);
+    // start on a circle of the Cauchy-type radius 1 + max|c_k/c_4|
+    const cd i4 = crecip(c[4]);
+    double rad = 0.0;
+    for (int k = 0; k < 4; ++k) rad = fmax(rad, sqrt(abs2(c[k] * i4)));
+    rad = fmin(1.0 + rad, 2.0 * sqrt(sqrt(rad)) + 1e-3);
+    cd q[4] = {mk(0.7 * rad, 0.4 * rad), mk(-0.5 * rad, 0.8 * rad), mk(-0.8 * rad, -0.3 * rad), mk(0.4 * rad, -0.9 * rad)};
+    for (int it = 0; it < 60; ++it) {
+        double worst = 0.0;
+        for (int k = 0; k < 4; ++k) {
+            const cd x = q[k];
+            cd p = c[4], dp = mk(0.0);
+            for (int j = 3; j >= 0; --j) { dp = dp * x + p; p = p * x + c[j]; }
+            cd nw = p / dp;
+            cd sum = mk(0.0);
+            for (int j = 0; j < 4; ++j)
+                if (j != k) sum = sum + crecip(x - q[j] + mk(1e-300));
+            cd step = nw / (mk(1.0) - nw * sum);
+            if (!(abs2(step) == abs2(step))) step = nw;      // NaN guard
+            q[k] = x - step;
+            worst = fmax(worst, abs2(step) / (abs2(q[k]) + 1e-300));
+        }
+        if (worst < 1e-24) break;
+    }
+    for (int k = 0; k < 4; ++k) {
+        double sep2 = 1e300;
+        for (int j = 0; j < 4; ++j)
+            if (j != k) sep2 = fmin(sep2, abs2(q[k] - q[j]));
+        cd x = q[k];
+        WaveMat mm;
+        // coefficient-form roots are good to ~sqrt(eps) at worst (double roots): start the refinement from there
+        refine_root(w, x, sep2, frcp(sep2 + TINY), 1e-16 * (abs2(x) + 1e-300) + 1e-20, mm);
+        bool use0 = abs2(mm.a) >= abs2(mm.d);
+        rv[k][0] = x;
+        rv[k][1] = csel(use0, -mm.b, mm.d);
+        rv[k][2] = csel(use0, mm.a, -mm.b);
+    }
+}
+
 // Four roots + the (Ex, Ey) null vector of N at each root, written to rv[k] = {q, Ex, Ey}.  rv is indexed with run-time
 // indices on purpose: it lives in (L1-resident) local memory, which costs a few 16-byte loads/stores instead of the
 // long select/move chains a register-resident array needs in rolled loops.
 // rv[0],rv[1]: pair seeded at -sqrt(.), rv[2],rv[3]: pair seeded at +sqrt(.)
-TAMM_HD void eig4_fast(const WaveCoef& w, cd rv[4][3]) {
+// Returns false when the roots fail Vieta's product check (the caller then runs the cold fallback).
+TAMM_HD bool eig4_fast(const WaveCoef& w, cd rv[4][3]) {
     cd c00 = w.e00 - w.e02 * (w.e02 * w.k);
     cd c01 = w.e01 - w.e02 * w.w1;
     cd c11 = w.d0;
@@ -808,10 +916,13 @@ TAMM_HD void eig4_fast(const WaveCoef& w, cd rv[4][3]) {
         rv[1][0] = -r1; rv[1][1] = x1; rv[1][2] = y1;
         rv[2][0] = r0; rv[2][1] = x0; rv[2][2] = y0;
         rv[3][0] = r1; rv[3][1] = x1; rv[3][2] = y1;
-        return;
+        return true;
     }
-    cd kap = mk(1.0) + (w.zeta * w.zeta) * w.k;
-    cd qc = csqrt_f(0.5 * (cmul_(c00, crecip_f(kap)) + c11));
+    const cd kap = mk(1.0) + (w.zeta * w.zeta) * w.k;
+    const cd ikap = crecip_f(kap);
+    cd qc = csqrt_f(0.5 * (cmul_(c00, ikap) + c11));
+    double reach2 = 0.0;      // largest |distance from a pair centre to one of its roots|^2
+    const double iq2c = frcp(abs2(qc) + TINY);
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
@@ -822,6 +933,7 @@ TAMM_HD void eig4_fast(const WaveCoef& w, cd rv[4][3]) {
             WaveMat m = wave_matrix(w, centre);
             mslp_eigs_f(m, w.db, hb, hs);
         }
+        reach2 = fmax(reach2, fmax(abs2(hb), abs2(hs)));
         const double sep2 = abs2(hb - hs);      // |distance between the two roots of the pair|^2 (estimate)
         const double isep2 = frcp(sep2 + TINY);
 #if defined(__CUDA_ARCH__)
@@ -830,46 +942,10 @@ TAMM_HD void eig4_fast(const WaveCoef& w, cd rv[4][3]) {
         for (int r = 0; r < 2; ++r) {
             const cd h0 = r ? hs : hb;
             cd x = centre + h0;
-            // Refinement loop.  Every iteration evaluates N(x), f = det N and f' = tr(adj(N') N).  While the error of x may
-            // be comparable to the pair splitting the step is the MSLP step (smaller eigenvalue of -N'^-1 N, needs a
-            // complex sqrt; converges quadratically whatever the splitting); once the error is well below the splitting
-            // the plain Newton step -f/f' is taken (error e -> e^2/splitting).  err2 tracks the squared error estimate.
             double err2 = abs2(h0);
-            err2 = 0.09 * err2 * err2;              // pair step: error ~ 0.3 |h|^2
+            err2 = err2 * err2 * iq2c;              // pair step: error ~ |h|^2/|q|
             WaveMat mm;
-#if defined(__CUDA_ARCH__)
-#pragma unroll 1
-#endif
-            for (int it = 0; it < 24; ++it) {
-                mm = wave_matrix(w, x);
-                const cd f = det2(mm.a, mm.b, mm.b, mm.d);
-                cd tr = cmul_(mm.dd, mm.a);
-                cfma(tr, mm.da, mm.d);
-                cfma(tr, (-2.0) * w.db, mm.b);
-                const double x2 = abs2(x);
-                cd h;
-                if (err2 * 400.0 < sep2) {           // error < splitting / 20: scalar Newton
-                    h = -cmul_(f, crecip_s(tr));
-                    const double hh = abs2(h);
-                    // a Newton step larger than the estimated error means f' ~ 0: discard it
-                    if (!(hh <= 100.0 * err2 + 1e-30 * x2)) h = mk(0.0);
-                    x = x + h;
-                    err2 = hh * hh * isep2;          // e^2/splitting, squared
-                } else {                              // MSLP step
-                    const cd det1 = det2(mm.da, w.db, w.db, mm.dd);
-                    const cd hm = 0.5 * tr;
-                    cd disc = csq(hm);
-                    cfma(disc, -det1, f);
-                    cd sq = csqrt_f(disc);
-                    const bool flip = (hm.re * sq.re + hm.im * sq.im) < 0.0;
-                    sq = csel(flip, -sq, sq);
-                    h = -cmul_(f, crecip_s(hm + sq));
-                    x = x + h;
-                    const double hh = abs2(h);
-                    err2 = 0.09 * hh * hh;
-                }
-                if (err2 <= 1e-32 * x2) break;       // estimated error below 1e-16 |x|
-            }
+            refine_root(w, x, sep2, isep2, err2, mm);
             // null vector of N from the last evaluation (one step before x: accurate to the size of that step)
             bool use0 = abs2(mm.a) >= abs2(mm.d);
             const int idx = 2 * pair + r;
@@ -878,6 +954,18 @@ TAMM_HD void eig4_fast(const WaveCoef& w, cd rv[4][3]) {
             rv[idx][2] = csel(use0, mm.a, -mm.b);
         }
     }
+    // The pair-based solve is only at risk when the roots of a pair are not close to their centre compared with the
+    // distance 2|qc| to the other pair (grazing incidence, very strong anisotropy):
+    //   reach < 0.02 |qc|  : safe (ice at any practical incidence is < 0.004)
+    //   reach > 0.1  |qc|  : use the fallback
+    //   in between         : Vieta check -- the product of the four roots must equal c0/c4 = det N(0)/kappa; a
+    //                        duplicated / missed root changes it by O(1) relative, rounding by ~1e-15.
+    const double q2c = abs2(qc);
+    if (reach2 <= 4e-4 * q2c) return true;
+    if (reach2 > 1e-2 * q2c) return false;
+    const cd prod = cmul_(cmul_(rv[0][0], rv[1][0]), cmul_(rv[2][0], rv[3][0]));
+    const cd pwant = cmul_(det2(c00, c01, c01, c11), ikap);
+    return abs2(prod - pwant) <= 1e-16 * abs2(pwant);
 }
 
 // ---- lean, branch-free exp(i*theta) * exp(x) for the layer phases ---------------------------------------------
@@ -964,7 +1052,7 @@ TAMM_HD int layer_modes(const LayerParams& lp, const LaneParams& ln, double zeta
     const Sym3 e = permittivity(lp, ln);
     const WaveCoef w = wave_coef(e, mu, zeta);
     cd rv[4][3];
-    eig4_fast(w, rv);
+    if (!eig4_fast(w, rv)) eig4_fallback(e.xx, e.xy, e.xz, e.yy, e.yz, e.zz, e.im, mu, zeta, rv);
 
     const cd ezz = mk(e.zz, e.im);
     const cd ib = crecip_f(mu * ezz);

@@ -130,7 +130,7 @@ int hostsim_roots_fast(const double* layers, const double* lanes, int N, int F, 
             const Sym3 e = permittivity(lp, ln);
             const WaveCoef w = wave_coef(e, mu, zeta);
             cd rv[4][3];
-            eig4_fast(w, rv);
+            if (!eig4_fast(w, rv)) eig4_fallback(e.xx, e.xy, e.xz, e.yy, e.yz, e.zz, e.im, mu, zeta, rv);
             for (int k = 0; k < 4; ++k) put(out + (((size_t)f * N + n) * 4 + k) * 2, rv[k][0]);
         }
     }

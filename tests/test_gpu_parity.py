@@ -383,3 +383,19 @@ def test_nonunit_permeability(eng):
             got = ls.LayerStack(nlm, z, N_frames=33, mu=mu, VERBOSE=0).get_returns(1e3, f=179e6, alpha=alpha)
             want = orc.OracleStack(nlm, z, N_frames=33, mu=mu).get_returns(1e3, f=179e6, alpha=alpha)
             _check_returns(got, want)
+
+
+@pytest.mark.parametrize('name,kw,alpha_deg', [('lossless_tilted', dict(sigma=[0.0]), 10.0), ('lossless_demo', dict(sigma=[0.0]), 0.0),
+                                               ('grazing_demo', {}, 88.0), ('grazing_tilted', {}, 89.0),
+                                               ('strong_loss', dict(sigma=[1e-2]), 30.0), ('steep_tilted', {}, 60.0)])
+def test_unusual_regimes(eng, name, kw, alpha_deg):
+    """Lossless media, grazing incidence with evanescent modes (eigen-solver fallback), strong loss, steep incidence."""
+    import layerstack as ls
+    nlm, z = profiles.demo(60, 600) if 'demo' in name else profiles.tilted(60, 300, seed=5)
+    alpha = np.deg2rad(alpha_deg)
+    s = ls.LayerStack(nlm, z, N_frames=33, VERBOSE=0, **kw)
+    zeta = np.sqrt((2 * s.epsa[0] + s.epsc[0]) / 3) * np.sin(alpha)
+    got = s.get_URD([s.get_layerstack(b, 179e6, zeta) for b in s.beta])
+    want = orc.OracleStack(nlm, z, N_frames=33, **kw).get_URD(179e6, alpha)
+    assert np.isfinite(got.view(np.float64)).all()
+    assert h.peak_rel_err(got, want, axis=(1, 2, 3)) < h.RTOL_COMPLEX

@@ -186,3 +186,29 @@ def test_stack_kernel_arithmetic_permeability(sim, mu):
         for fb in (True, False):
             got = sim_urd(sim, os_, 179e6, alpha, 16, field_basis=fb)
             assert h.peak_rel_err(got, want, axis=(1, 2, 3)) < h.RTOL_COMPLEX, (mu, alpha, fb)
+
+
+EDGE_CASES = [('lossless_tilted', dict(sigma=[0.0]), 10.0), ('lossless_demo', dict(sigma=[0.0]), 0.0),
+              ('grazing_demo', {}, 88.0), ('grazing_tilted', {}, 89.0), ('strong_loss', dict(sigma=[1e-2]), 30.0),
+              ('steep_tilted', {}, 60.0)]
+
+
+def edge_profile(name):
+    from tamm_b200 import profiles
+    return profiles.demo(60, 600) if 'demo' in name else profiles.tilted(60, 300, seed=5)
+
+
+@pytest.mark.parametrize('name,kw,alpha_deg', EDGE_CASES)
+def test_unusual_regimes(sim, name, kw, alpha_deg):
+    """Lossless media (real q: the Re q > 0 partition branch of layer_PPJ.py:224-231), grazing incidence (evanescent
+    modes, transmitted / reflected pairs no longer separated -> Vieta check + Aberth fallback), strong loss."""
+    nlm, z = edge_profile(name)
+    os_ = orc.OracleStack(nlm, z, N_frames=9, **kw)
+    alpha = np.deg2rad(alpha_deg)
+    L = os_.layers(179e6, alpha)
+    assert (L['n_trans'] == 2).all()
+    got = np.sort_complex(_roots_fast(sim, os_, 179e6, alpha))
+    assert np.abs(got - np.sort_complex(L['qs_unsorted'])).max() < 5e-14
+    urd = sim_urd(sim, os_, 179e6, alpha, 16, field_basis=True)
+    assert np.isfinite(urd.view(np.float64)).all()
+    assert h.peak_rel_err(urd, orc.get_URD(L), axis=(1, 2, 3)) < h.RTOL_COMPLEX
