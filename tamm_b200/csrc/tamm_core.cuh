@@ -33,6 +33,24 @@ constexpr double EPS0 = 8.8541878128e-12;
 constexpr double QSD_THR = 1e-10;
 constexpr double ZERO_THR = 1e-10;
 
+// Host-side instrumentation for the test simulator (tests/hostsim): counts how often the eigen-solver leaves its
+// straight path.  Compiled out everywhere else.
+#if defined(TAMM_HOST_STATS) && !defined(__CUDA_ARCH__)
+struct SolverStats { long roots, newton, quad, recentre, collapsed, vieta, fallback; };
+inline SolverStats& solver_stats() { static SolverStats s = {0, 0, 0, 0, 0, 0, 0}; return s; }
+#define TAMM_STAT(field) (++tamm::solver_stats().field)
+#else
+#define TAMM_STAT(field) ((void)0)
+#endif
+// Block-placement hints: keep rarely taken paths out of the straight-line instruction stream of the hot loop.
+#if defined(__GNUC__) || defined(__CUDACC__)
+#define TAMM_RARE(x) __builtin_expect(!!(x), 0)
+#define TAMM_USUAL(x) __builtin_expect(!!(x), 1)
+#else
+#define TAMM_RARE(x) (x)
+#define TAMM_USUAL(x) (x)
+#endif
+
 struct cd {
     double re, im;
 };
@@ -804,10 +822,12 @@ TAMM_HD void refine_root(const WaveCoef& w, cd& x, double sep2, double isep2, do
         cd h = -cmul_(f, crecip_s(tr));        // Newton step
         double hh = abs2(h);
         // Newton only when the error is well below the separation AND the step it proposes is small against it
-        if ((err2 * 400.0 < sep2) && (hh * 16.0 <= sep2)) {
+        if (TAMM_USUAL((err2 * 400.0 < sep2) && (hh * 16.0 <= sep2))) {
+            TAMM_STAT(newton);
             x = x + h;
             err2 = hh * hh * (isep2 + ix2);
         } else {                              // MSLP step
+            TAMM_STAT(quad);
             const cd det1 = det2(mm.da, w.db, w.db, mm.dd);
             const cd hm = 0.5 * tr;
             cd disc = csq(hm);
@@ -890,16 +910,34 @@ void eig4_fallback(double exx, double exy, double exz, double eyy, double eyz, d
     }
 }
 
+// ---- per-thread scratch of the mode solve -------------------------------------------------------------------------
+// rv[k] = {q_k, Ex_k, Ey_k} (roots + null vectors) and ms[k] = four sort measures are indexed with RUN-TIME indices (the
+// p/s sort is a permutation), which a register-resident array can only serve with long select/move chains.  They live
+// in addressable memory instead: plain arrays on the host and in the diagnostics kernel (ScratchArrays), per-thread
+// shared-memory slots in stack_kernel (ScratchShared in tamm_kernels.cu: local memory thrashed the small L1 left next
+// to the carry state).  A policy provides
+//   cd rv(k, j) / set_rv(k, j, v)          k = 0..3, j = 0..2
+//   ms_pair(k, h, a, b) / set_ms_pair(...)  h = 0: Poynting measures {|Px|^2, |Px|^2+|Py|^2}, h = 1: E-field measures
+struct ScratchArrays {
+    cd rv_[4][3];
+    double ms_[4][4];
+    TAMM_HD cd rv(int k, int j) const { return rv_[k][j]; }
+    TAMM_HD void set_rv(int k, int j, cd v) { rv_[k][j] = v; }
+    TAMM_HD void ms_pair(int k, int h, double& a, double& b) const { a = ms_[k][2 * h]; b = ms_[k][2 * h + 1]; }
+    TAMM_HD void set_ms_pair(int k, int h, double a, double b) { ms_[k][2 * h] = a; ms_[k][2 * h + 1] = b; }
+};
+
 // Four roots + the (Ex, Ey) null vector of N at each root, written to rv[k] = {q, Ex, Ey}.  rv is indexed with run-time
 // indices on purpose: it lives in (L1-resident) local memory, which costs a few 16-byte loads/stores instead of the
 // long select/move chains a register-resident array needs in rolled loops.
 // rv[0],rv[1]: pair seeded at -sqrt(.), rv[2],rv[3]: pair seeded at +sqrt(.)
 // Returns false when the roots fail Vieta's product check (the caller then runs the cold fallback).
-TAMM_HD bool eig4_fast(const WaveCoef& w, cd rv[4][3]) {
+template <class SC>
+TAMM_HD bool eig4_fast(const WaveCoef& w, SC& sc) {
     cd c00 = w.e00 - w.e02 * (w.e02 * w.k);
     cd c01 = w.e01 - w.e02 * w.w1;
     cd c11 = w.d0;
-    if (w.zeta == 0.0) {
+    if (TAMM_RARE(w.zeta == 0.0)) {
         cd hm = 0.5 * (c00 + c11), hd = 0.5 * (c00 - c11);
         cd s = csqrt_f(csq(hd) + csq(c01));
         bool flip = (hm.re * s.re + hm.im * s.im) < 0.0;
@@ -912,10 +950,10 @@ TAMM_HD bool eig4_fast(const WaveCoef& w, cd rv[4][3]) {
         bool u0 = abs2(a0) >= abs2(d0), u1 = abs2(a1) >= abs2(d1);
         cd x0 = csel(u0, -c01, d0), y0 = csel(u0, a0, -c01);
         cd x1 = csel(u1, -c01, d1), y1 = csel(u1, a1, -c01);
-        rv[0][0] = -r0; rv[0][1] = x0; rv[0][2] = y0;
-        rv[1][0] = -r1; rv[1][1] = x1; rv[1][2] = y1;
-        rv[2][0] = r0; rv[2][1] = x0; rv[2][2] = y0;
-        rv[3][0] = r1; rv[3][1] = x1; rv[3][2] = y1;
+        sc.set_rv(0, 0, -r0); sc.set_rv(0, 1, x0); sc.set_rv(0, 2, y0);
+        sc.set_rv(1, 0, -r1); sc.set_rv(1, 1, x1); sc.set_rv(1, 2, y1);
+        sc.set_rv(2, 0, r0); sc.set_rv(2, 1, x0); sc.set_rv(2, 2, y0);
+        sc.set_rv(3, 0, r1); sc.set_rv(3, 1, x1); sc.set_rv(3, 2, y1);
         return true;
     }
     const cd kap = mk(1.0) + (w.zeta * w.zeta) * w.k;
@@ -923,19 +961,37 @@ TAMM_HD bool eig4_fast(const WaveCoef& w, cd rv[4][3]) {
     cd qc = csqrt_f(0.5 * (cmul_(c00, ikap) + c11));
     double reach2 = 0.0;      // largest |distance from a pair centre to one of its roots|^2
     const double iq2c = frcp(abs2(qc) + TINY);
+    // c0/c4 = product of the four roots (Vieta); also the reference value of the check at the end
+    const cd pwant = cmul_(det2(c00, c01, c01, c11), ikap);
+    const cd rsum = ((-2.0 * w.zeta) * w.e02.re) * cmul_(w.k, ikap);      // -c3/c4 = sum of the four roots
+    const double q2c = abs2(qc);
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
     for (int pair = 0; pair < 2; ++pair) {
-        cd centre = pair == 0 ? -qc : qc;
-        cd hb, hs;
-        {
+        cd centre, hb, hs;
+        double errv = -1.0;
+        if (pair == 1) {
+            // second pair from the refined first one through Vieta: sum' = -c3/c4 - (x0 + x1), prod' = (c0/c4)/(x0 x1);
+            // roots = sum'/2 +- sqrt((sum'/2)^2 - prod').  The cancellation in the radicand leaves ~eps |q|^2 / split
+            // in the roots -- a starting point one Newton step away from full accuracy (instead of a pair step + two),
+            // as long as the splitting is not itself down at that level (then: pair step like the first pair).
+            const cd x0 = sc.rv(0, 0), x1 = sc.rv(1, 0);
+            centre = 0.5 * (rsum - (x0 + x1));
+            const cd pr = cmul_(pwant, crecip_s(cmul_(x0, x1)));
+            hb = csqrt_f(csq(centre) - pr);
+            hs = -hb;
+            if (TAMM_USUAL(4.0 * abs2(hb) >= 1e-10 * q2c)) errv = 4e-30 * q2c * q2c;
+        }
+        if (errv < 0.0) {
+            // one MSLP step from the seed -+sqrt(.) gives both roots of the pair to O(h^2/|q|)
+            centre = pair == 0 ? -qc : qc;
             WaveMat m = wave_matrix(w, centre);
             mslp_eigs_f(m, w.db, hb, hs);
         }
-        reach2 = fmax(reach2, fmax(abs2(hb), abs2(hs)));
         const double sep2 = abs2(hb - hs);      // |distance between the two roots of the pair|^2 (estimate)
         const double isep2 = frcp(sep2 + TINY);
+        const cd seed = pair == 0 ? -qc : qc;
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
@@ -943,15 +999,17 @@ TAMM_HD bool eig4_fast(const WaveCoef& w, cd rv[4][3]) {
             const cd h0 = r ? hs : hb;
             cd x = centre + h0;
             double err2 = abs2(h0);
-            err2 = err2 * err2 * iq2c;              // pair step: error ~ |h|^2/|q|
+            err2 = errv < 0.0 ? err2 * err2 * iq2c : errv * isep2;     // pair step: error ~ |h|^2/|q|
+            TAMM_STAT(roots);
             WaveMat mm;
             refine_root(w, x, sep2, isep2, err2, mm);
+            reach2 = fmax(reach2, abs2(x - seed));
             // null vector of N from the last evaluation (one step before x: accurate to the size of that step)
             bool use0 = abs2(mm.a) >= abs2(mm.d);
             const int idx = 2 * pair + r;
-            rv[idx][0] = x;
-            rv[idx][1] = csel(use0, -mm.b, mm.d);
-            rv[idx][2] = csel(use0, mm.a, -mm.b);
+            sc.set_rv(idx, 0, x);
+            sc.set_rv(idx, 1, csel(use0, -mm.b, mm.d));
+            sc.set_rv(idx, 2, csel(use0, mm.a, -mm.b));
         }
     }
     // The pair-based solve is only at risk when the roots of a pair are not close to their centre compared with the
@@ -960,11 +1018,10 @@ TAMM_HD bool eig4_fast(const WaveCoef& w, cd rv[4][3]) {
     //   reach > 0.1  |qc|  : use the fallback
     //   in between         : Vieta check -- the product of the four roots must equal c0/c4 = det N(0)/kappa; a
     //                        duplicated / missed root changes it by O(1) relative, rounding by ~1e-15.
-    const double q2c = abs2(qc);
     if (reach2 <= 4e-4 * q2c) return true;
     if (reach2 > 1e-2 * q2c) return false;
-    const cd prod = cmul_(cmul_(rv[0][0], rv[1][0]), cmul_(rv[2][0], rv[3][0]));
-    const cd pwant = cmul_(det2(c00, c01, c01, c11), ikap);
+    TAMM_STAT(vieta);
+    const cd prod = cmul_(cmul_(sc.rv(0, 0), sc.rv(1, 0)), cmul_(sc.rv(2, 0), sc.rv(3, 0)));
     return abs2(prod - pwant) <= 1e-16 * abs2(pwant);
 }
 
@@ -1047,12 +1104,17 @@ struct ModeSet {          // sorted roots and unnormalised gamma entries of one 
 };
 
 // Everything up to the unnormalised field vectors: permittivity, roots, clean-up, partition, p/s sort, gamma.
-TAMM_HD int layer_modes(const LayerParams& lp, const LaneParams& ln, double zeta, double mu, ModeSet& ms_out) {
+template <class SC>
+TAMM_HD int layer_modes(const LayerParams& lp, const LaneParams& ln, double zeta, double mu, ModeSet& ms_out, SC& sc) {
     int status = 0;
     const Sym3 e = permittivity(lp, ln);
     const WaveCoef w = wave_coef(e, mu, zeta);
-    cd rv[4][3];
-    if (!eig4_fast(w, rv)) eig4_fallback(e.xx, e.xy, e.xz, e.yy, e.yz, e.zz, e.im, mu, zeta, rv);
+    if (TAMM_RARE(!eig4_fast(w, sc))) {
+        TAMM_STAT(fallback);
+        cd rv[4][3];
+        eig4_fallback(e.xx, e.xy, e.xz, e.yy, e.yz, e.zz, e.im, mu, zeta, rv);
+        for (int k = 0; k < 4; ++k) { sc.set_rv(k, 0, rv[k][0]); sc.set_rv(k, 1, rv[k][1]); sc.set_rv(k, 2, rv[k][2]); }
+    }
 
     const cd ezz = mk(e.zz, e.im);
     const cd ib = crecip_f(mu * ezz);
@@ -1064,19 +1126,18 @@ TAMM_HD int layer_modes(const LayerParams& lp, const LaneParams& ln, double zeta
 
     // clean-up (layer_PPJ.py:199-203), Poynting / E-field measures for the p-s sort (233-276) kept as numerators and
     // denominators {|Px|^2, |Px|^2+|Py|^2, |Ex|^2, |Ex|^2+|Ey|^2}, and the transmitted/reflected flags (216-231)
-    double ms[4][4];   // sort measures
     int im_mask = 0, re_mask = 0;
     bool has_im = false;
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
     for (int k = 0; k < 4; ++k) {
-        const cd q = clean_q(rv[k][0]);
-        rv[k][0] = q;
+        const cd q = clean_q(sc.rv(k, 0));
+        sc.set_rv(k, 0, q);
         has_im = has_im || (q.im != 0.0);
         im_mask |= (q.im >= 0.0 ? 1 : 0) << k;
         re_mask |= (q.re > 0.0 ? 1 : 0) << k;
-        cd Ex = rv[k][1], Ey = rv[k][2];
+        cd Ex = sc.rv(k, 1), Ey = sc.rv(k, 2);
         if (abs2(Ex) + abs2(Ey) == 0.0) { Ex = mk(1.0); Ey = mk(0.0); }
         cd t = cmul_(q - D00, Ex);
         cfma(t, -D02, Ey);
@@ -1092,7 +1153,8 @@ TAMM_HD int layer_modes(const LayerParams& lp, const LaneParams& ln, double zeta
         u = cd{fma(a51, Ex.re, u.re), fma(a51, Ex.im, u.im)};
         cd Py = -cmul_(Ey, u);
         double pxx = abs2(Px), exx = abs2(Ex);
-        ms[k][0] = pxx; ms[k][1] = pxx + abs2(Py); ms[k][2] = exx; ms[k][3] = exx + abs2(Ey);
+        sc.set_ms_pair(k, 0, pxx, pxx + abs2(Py));
+        sc.set_ms_pair(k, 1, exx, exx + abs2(Ey));
     }
     const int tmask = has_im ? im_mask : re_mask;
     int t0, t1, r0, r1;
@@ -1109,13 +1171,20 @@ TAMM_HD int layer_modes(const LayerParams& lp, const LaneParams& ln, double zeta
     }
     // C_a > C_b  <=>  n_a s_b > n_b s_a  for ratios C = n/s with s > 0; NaN (s = 0) compares false like the reference
     auto gt = [](double na, double sa, double nb, double sb) { return (sa > 0.0) && (sb > 0.0) && (na * sb > nb * sa); };
-    const double pa = ms[t0][0], sa = ms[t0][1], pb = ms[t1][0], sb = ms[t1][1];
+    double pa, sa, pb, sb;
+    sc.ms_pair(t0, 0, pa, sa);
+    sc.ms_pair(t1, 0, pb, sb);
     const bool biref = (sa > 0.0) && (sb > 0.0) && (fabs(pa * sb - pb * sa) > QSD_THR * (sa * sb));   // layer_PPJ.py:258
-    const int mo = biref ? 0 : 2;        // Poynting measures (260-265) or E-field measures (269-276)
-    const bool flip_t = gt(ms[t1][mo], ms[t1][mo + 1], ms[t0][mo], ms[t0][mo + 1]);
-    const bool flip_r = gt(ms[r1][mo], ms[r1][mo + 1], ms[r0][mo], ms[r0][mo + 1]);
+    const int mo = biref ? 0 : 1;        // Poynting measures (260-265) or E-field measures (269-276)
+    double n0, d0, n1, d1;
+    sc.ms_pair(t1, mo, n1, d1);
+    sc.ms_pair(t0, mo, n0, d0);
+    const bool flip_t = gt(n1, d1, n0, d0);
+    sc.ms_pair(r1, mo, n1, d1);
+    sc.ms_pair(r0, mo, n0, d0);
+    const bool flip_r = gt(n1, d1, n0, d0);
     const int o0 = flip_t ? t1 : t0, o1 = flip_t ? t0 : t1, o2 = flip_r ? r1 : r0, o3 = flip_r ? r0 : r1;
-    const cd q0 = rv[o0][0], q1 = rv[o1][0], q2 = rv[o2][0], q3 = rv[o3][0];
+    const cd q0 = sc.rv(o0, 0), q1 = sc.rv(o1, 0), q2 = sc.rv(o2, 0), q3 = sc.rv(o3, 0);
 
     // ---- gamma (layer_PPJ.py:309-389), unnormalised; see layer_solve for the line-by-line citations
     const cd e00 = mk(e.xx, e.im), e11 = mk(e.yy, e.im);
@@ -1159,7 +1228,8 @@ TAMM_HD int layer_modes(const LayerParams& lp, const LaneParams& ln, double zeta
 // Amplitude-basis layer record (normalised E blocks, their inverses, admittances, phases).
 TAMM_HD int layer_solve_fast(const LayerParams& lp, const LaneParams& ln, double zeta, double mu, LayerY& L) {
     ModeSet m;
-    int status = layer_modes(lp, ln, zeta, mu, m);
+    ScratchArrays sc;
+    int status = layer_modes(lp, ln, zeta, mu, m, sc);
     const cd q0 = m.q0, q1 = m.q1, q2 = m.q2, q3 = m.q3;
     const cd g12 = m.g12, g13 = m.g13, g21 = m.g21, g23 = m.g23, g32 = m.g32, g33 = m.g33, g41 = m.g41, g43 = m.g43;
     const double imu = rcp_mu(mu);
@@ -1193,10 +1263,10 @@ TAMM_HD int layer_solve_fast(const LayerParams& lp, const LaneParams& ln, double
 // Field-basis layer record straight from the unnormalised field vectors: P = Et diag(Mfwd) Et^-1, Q = Er diag(Mrev) Er^-1
 // and the admittances are invariant under the row normalisation of gamma (layer_PPJ.py:399-402), so the norms are only
 // evaluated when the normalised blocks themselves are needed (first layer of a stack, MODE_U).
-template <bool WANT_E>
-TAMM_HD int layer_solve_field(const LayerParams& lp, const LaneParams& ln, double zeta, double mu, LayerF& F) {
+template <bool WANT_E, class SC>
+TAMM_HD int layer_solve_field(const LayerParams& lp, const LaneParams& ln, double zeta, double mu, LayerF& F, SC& sc) {
     ModeSet m;
-    int status = layer_modes(lp, ln, zeta, mu, m);
+    int status = layer_modes(lp, ln, zeta, mu, m, sc);
     const double imu = rcp_mu(mu);
     const cd Mf0 = phase_f(m.q0, ln.twopif, lp.dz, -1.0), Mf1 = phase_f(m.q1, ln.twopif, lp.dz, -1.0);
     const cd Mr0 = phase_f(m.q2, ln.twopif, lp.dz, +1.0), Mr1 = phase_f(m.q3, ln.twopif, lp.dz, +1.0);
@@ -1225,6 +1295,12 @@ TAMM_HD int layer_solve_field(const LayerParams& lp, const LaneParams& ln, doubl
         F.Eri[0] = n2 * rb[0]; F.Eri[1] = n2 * rb[1]; F.Eri[2] = n3 * rb[2]; F.Eri[3] = n3 * rb[3];
     }
     return status;
+}
+
+template <bool WANT_E>
+TAMM_HD int layer_solve_field(const LayerParams& lp, const LaneParams& ln, double zeta, double mu, LayerF& F) {
+    ScratchArrays sc;
+    return layer_solve_field<WANT_E>(lp, ln, zeta, mu, F, sc);
 }
 
 // Cold path: the normalised E blocks of one layer (start of a stack: D'_0 = Et_0, U'_0 = Er_0^-1).  Never inlined, so the
@@ -1264,7 +1340,7 @@ TAMM_HD void interface_fast(const cd Et[4], const cd Eri[4], const cd Yt[4], con
     for (int k = 0; k < 4; ++k)
         chk += (R[k].re - R[k].re) + (R[k].im - R[k].im) + (T[k].re - T[k].re) + (T[k].im - T[k].im) + (Tr[k].re - Tr[k].re) +
                (Tr[k].im - Tr[k].im);
-    if (chk != chk) {
+    if (TAMM_RARE(chk != chk)) {
         for (int k = 0; k < 4; ++k) { R[k] = n2n(R[k]); T[k] = n2n(T[k]); Tr[k] = n2n(Tr[k]); }
     }
     Dm[0] = cmul_(nx.Mfwd[0], T[0]); Dm[1] = cmul_(nx.Mfwd[0], T[1]);
@@ -1312,7 +1388,7 @@ TAMM_HD void interface_fb(const cd pYt[4], const cd pYr[4], const LayerF& nx, cd
 #pragma unroll
 #endif
     for (int k = 0; k < 4; ++k) chk += (W[k].re - W[k].re) + (W[k].im - W[k].im) + (D[k].re - D[k].re) + (D[k].im - D[k].im);
-    if (chk != chk) {
+    if (TAMM_RARE(chk != chk)) {
         for (int k = 0; k < 4; ++k) { W[k] = n2n(W[k]); D[k] = n2n(D[k]); out[k] = n2n(out[k]); }
     }
     U[0] = W[0]; U[1] = W[1]; U[2] = W[2]; U[3] = W[3];

@@ -43,7 +43,7 @@ int fail(const char* fmt, const char* a = "", long b = 0) {
 #endif
 
 constexpr int TL = 16;     // layers per TMA sub-tile (16 * 80 B = 1280 B per profile)
-constexpr int CARRY_SLOTS = 20;   // 16-byte shared-memory slots per thread of stack_kernel
+constexpr int CARRY_SLOTS = 36;   // 16-byte shared-memory slots per thread of stack_kernel (carry state + mode scratch)
 constexpr int NPMAX = 4;   // a CTA's lanes may span at most this many profiles (flattened lane mapping)
 
 // ---- mbarrier / bulk-copy (TMA) primitives -----------------------------------------------------
@@ -80,6 +80,25 @@ __device__ __forceinline__ cd ld_cd(const cd* p) {
     double2 v = *reinterpret_cast<const double2*>(p);
     return cd{v.x, v.y};
 }
+
+// Mode-solve scratch (tamm_core.cuh: ScratchArrays) in per-thread shared-memory slots: slot s of thread t sits at
+// base[s * stride + t], so any run-time slot index is bank-conflict free.  Slots 0-11: rv[k][j], 12-19: ms pairs.
+struct ScratchShared {
+    double2* base;
+    int stride;
+    __device__ __forceinline__ cd rv(int k, int j) const {
+        const double2 v = base[(3 * k + j) * stride];
+        return cd{v.x, v.y};
+    }
+    __device__ __forceinline__ void set_rv(int k, int j, cd v) { base[(3 * k + j) * stride] = make_double2(v.re, v.im); }
+    __device__ __forceinline__ void ms_pair(int k, int h, double& a, double& b) const {
+        const double2 v = base[(12 + 2 * k + h) * stride];
+        a = v.x; b = v.y;
+    }
+    __device__ __forceinline__ void set_ms_pair(int k, int h, double a, double b) {
+        base[(12 + 2 * k + h) * stride] = make_double2(a, b);
+    }
+};
 
 // ---- the hot kernel ------------------------------------------------------------------------------
 // grid = (lane blocks, chunks); block = TB threads (multiple of 32).
@@ -149,9 +168,10 @@ stack_body(const double* __restrict__ layers, const double* __restrict__ lanes, 
     }
 
     // Per-thread state carried from layer to layer lives in shared memory (CARRY_SLOTS x 16 B per thread, conflict-free
-    // [slot][thread] layout): slots 0-7 = Yt, Yr of the previous layer, 8-11 = D', 12-15 = U' (field basis, see
-    // tamm_core.cuh: LayerF), 16-19 = Er of the previous layer (MODE_U only).  Keeping it out of the register file
-    // during the register-hungry layer solve keeps the kernel spill-free.
+    // [slot][thread] layout): slots 0-7 = Yt, Yr of the previous layer, 8-11 = D' (MODE_URD) or Er of the previous layer
+    // (MODE_U, which carries no D'), 12-15 = U' (field basis, see tamm_core.cuh: LayerF), 16-35 = scratch of the mode
+    // solve (ScratchShared).  Keeping all of it out of the register file and out of local memory matters twice: the
+    // register-hungry layer solve stays (nearly) spill-free, and nothing competes for the small L1 that remains.
     extern __shared__ double2 carry[];
     double2* cs = carry + threadIdx.x;
     const int cstr = blockDim.x;
@@ -159,6 +179,7 @@ stack_body(const double* __restrict__ layers, const double* __restrict__ lanes, 
 #define CS_ST(slot, v) st_cd(reinterpret_cast<cd*>(cs + (slot) * cstr), (v))
     CS_ST(8, mk(1.0)); CS_ST(9, mk(0.0)); CS_ST(10, mk(0.0)); CS_ST(11, mk(1.0));
     CS_ST(12, mk(1.0)); CS_ST(13, mk(0.0)); CS_ST(14, mk(0.0)); CS_ST(15, mk(1.0));
+    ScratchShared sc{cs + 16 * cstr, cstr};
     int st = 0;
     cd* out = planes + ((size_t)p * NI * 4) * QF + lc;
 
@@ -192,14 +213,28 @@ stack_body(const double* __restrict__ layers, const double* __restrict__ lanes, 
             __syncthreads();
 #endif
             // normalised E blocks are only needed for MODE_U here; the start of a stack uses the cold helper below
-            st |= layer_solve_field<MODE == TAMM_MODE_U>(lp, ln, zeta, mu, cur);
+            st |= layer_solve_field<MODE == TAMM_MODE_U>(lp, ln, zeta, mu, cur, sc);
 #ifdef TAMM_SYNC_PER_LAYER
             __syncthreads();
 #endif
-            if (j == 0) {
+            if (TAMM_RARE(j == 0)) {
                 if (c == 0) {   // the stack starts in the tangential-field basis of the top layer: D'_0 = Et_0, U'_0 = Er_0^-1
                     cd e0[4], e1[4];
-                    layer_start_blocks(&lp, &ln, zeta, mu, e0, e1);
+                    // fresh copies of the parameters: taking the address of lp / ln themselves would put them in local
+                    // memory for every layer
+                    LayerParams lp0;
+                    {
+                        const volatile double* r = tile + jj * LAYER_STRIDE;
+                        lp0.t20 = r[0]; lp0.n21r = r[1]; lp0.n21i = r[2]; lp0.n22r = r[3]; lp0.n22i = r[4];
+                        lp0.mono = r[5]; lp0.deps = r[6]; lp0.sigma = r[7]; lp0.dz = r[8]; lp0.pad = 0;
+                    }
+                    LaneParams ln0;
+                    {
+                        const volatile double* r = lanes + (size_t)lc * LANE_STRIDE;
+                        ln0.c1 = r[0]; ln0.s1 = r[1]; ln0.c2 = r[2]; ln0.s2 = r[3]; ln0.twopif = r[4]; ln0.w_eps0 = r[5];
+                        ln0.pad0 = 0; ln0.pad1 = 0;
+                    }
+                    layer_start_blocks(&lp0, &ln0, zeta, mu, e0, e1);
                     for (int k = 0; k < 4; ++k) { CS_ST(8 + k, e0[k]); CS_ST(12 + k, e1[k]); }
                 }
             } else {
@@ -210,7 +245,7 @@ stack_body(const double* __restrict__ layers, const double* __restrict__ lanes, 
                 if (MODE == TAMM_MODE_URD) {
                     interface_fb<true>(pYt, pYr, cur, D, U, o);
                 } else {
-                    cd pEr[4] = {CS_LD(16), CS_LD(17), CS_LD(18), CS_LD(19)};
+                    cd pEr[4] = {CS_LD(8), CS_LD(9), CS_LD(10), CS_LD(11)};
                     mm22(U, pEr, o);                          // U_n = U'_n Er_n (layerstack.py:225), before the update
                     cd dummy[4];
                     interface_fb<false>(pYt, pYr, cur, D, U, dummy);
@@ -226,14 +261,17 @@ stack_body(const double* __restrict__ layers, const double* __restrict__ lanes, 
                 for (int k = 0; k < 4; ++k) { if (MODE == TAMM_MODE_URD) CS_ST(8 + k, D[k]); CS_ST(12 + k, U[k]); }
             }
 #pragma unroll
-            for (int k = 0; k < 4; ++k) { CS_ST(k, cur.Yt[k]); CS_ST(4 + k, cur.Yr[k]); if (MODE == TAMM_MODE_U) CS_ST(16 + k, cur.Er[k]); }
+            for (int k = 0; k < 4; ++k) { CS_ST(k, cur.Yt[k]); CS_ST(4 + k, cur.Yr[k]); if (MODE == TAMM_MODE_U) CS_ST(8 + k, cur.Er[k]); }
         }
     }
     if (live) {
         if (nchunks > 1) {
             cd* a = agg + (((size_t)p * QF + l) * nchunks + c) * 8;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) { st_cd(a + k, CS_LD(8 + k)); st_cd(a + 4 + k, CS_LD(12 + k)); }
+            for (int k = 0; k < 4; ++k) {
+                st_cd(a + k, MODE == TAMM_MODE_URD ? CS_LD(8 + k) : mk((k == 0 || k == 3) ? 1.0 : 0.0));   // MODE_U carries no D'
+                st_cd(a + 4 + k, CS_LD(12 + k));
+            }
         }
         if (st && status) atomicOr(status + p, st);
     }
@@ -633,14 +671,9 @@ int pick_block(int QF, int maxt = 256) {
 }
 
 // launch-bound variants of stack_kernel: threads per CTA (CTAs per SM, registers):
-//   0: 256 (1, 255)   2: 256 (2, 128)   3: 512 (1, 128)   5: 384 (1, 168, default)
-int variant_threads(int v) {
-    switch (v) {
-        case 3: return 512;
-        case 5: return 384;
-        default: return 256;
-    }
-}
+//   0: 256 (1, 255)   5: 384 (1, 168, default).  One CTA per SM either way: the per-thread shared-memory state
+//   (CARRY_SLOTS x 16 B) of 384 threads fills the SM's 227 KB.
+int variant_threads(int v) { return v == 0 ? 256 : 384; }
 
 // CTA geometry of stack_kernel: flattened lanes whenever a CTA of `maxt` threads spans at most NPMAX profiles.
 void stack_geometry(int P, int QF, int maxt, int* tb, int* flat, long* gx) {
@@ -712,7 +745,7 @@ int tamm_suggest_chunk(int P, int N, int QF, int sm_count) {
     int variant = ev ? atoi(ev) : TAMM_DEFAULT_VARIANT;
     if (variant < 0 || variant > 5) variant = TAMM_DEFAULT_VARIANT;
     const int maxt = variant_threads(variant);
-    const int ctas_per_sm = (variant == 2) ? 2 : 1;
+    const int ctas_per_sm = 1;
     int tb, flat;
     long bpc;                                                              // CTAs per chunk index
     stack_geometry(P, QF, maxt, &tb, &flat, &bpc);
@@ -789,14 +822,10 @@ int tamm_stack_urd(const double* layers, const double* lanes, int P, int N, int 
     } while (0)
     if (mode == TAMM_MODE_URD) {
         if (variant == 0) TAMM_LAUNCH(TAMM_MODE_URD, 256, 1);
-        else if (variant == 3) TAMM_LAUNCH(TAMM_MODE_URD, 512, 1);
-        else if (variant == 5) TAMM_LAUNCH(TAMM_MODE_URD, 384, 1);
-        else TAMM_LAUNCH(TAMM_MODE_URD, 256, 2);
+        else TAMM_LAUNCH(TAMM_MODE_URD, 384, 1);
     } else {
         if (variant == 0) TAMM_LAUNCH(TAMM_MODE_U, 256, 1);
-        else if (variant == 3) TAMM_LAUNCH(TAMM_MODE_U, 512, 1);
-        else if (variant == 5) TAMM_LAUNCH(TAMM_MODE_U, 384, 1);
-        else TAMM_LAUNCH(TAMM_MODE_U, 256, 2);
+        else TAMM_LAUNCH(TAMM_MODE_U, 384, 1);
     }
 #undef TAMM_LAUNCH
     CUDA_OK(cudaGetLastError());

@@ -1,6 +1,7 @@
 // TEST INFRASTRUCTURE ONLY -- compiles tamm_b200/csrc/tamm_core.cuh with the host compiler so the exact
 // per-layer arithmetic of the CUDA kernels can be checked against the oracle on a machine without a GPU.
 // Nothing in the product (tamm_b200/, lib/) loads this library.
+#define TAMM_HOST_STATS 1
 #include "../../tamm_b200/csrc/tamm_core.cuh"
 #include <cstring>
 #include <vector>
@@ -121,6 +122,16 @@ int hostsim_elementary(const double* x, int n, double* out) {
     return 0;
 }
 
+// Eigen-solver path counters since the last reset: {roots, newton steps, quadratic-model steps, recentres, collapsed
+// pairs, Vieta checks, fallbacks}.
+int hostsim_solver_stats(long* out, int reset) {
+    SolverStats& s = solver_stats();
+    out[0] = s.roots; out[1] = s.newton; out[2] = s.quad; out[3] = s.recentre; out[4] = s.collapsed; out[5] = s.vieta;
+    out[6] = s.fallback;
+    if (reset) s = SolverStats{0, 0, 0, 0, 0, 0, 0};
+    return 0;
+}
+
 // Unsorted roots of the hot-path eigen-solver (eig4_fast) for every (lane, layer): out complex128 (F, N, 4).
 int hostsim_roots_fast(const double* layers, const double* lanes, int N, int F, double zeta, double mu, double* out) {
     for (int f = 0; f < F; ++f) {
@@ -129,9 +140,12 @@ int hostsim_roots_fast(const double* layers, const double* lanes, int N, int F, 
             LayerParams lp; std::memcpy(&lp, layers + (size_t)n * LAYER_STRIDE, sizeof(lp));
             const Sym3 e = permittivity(lp, ln);
             const WaveCoef w = wave_coef(e, mu, zeta);
-            cd rv[4][3];
-            if (!eig4_fast(w, rv)) eig4_fallback(e.xx, e.xy, e.xz, e.yy, e.yz, e.zz, e.im, mu, zeta, rv);
-            for (int k = 0; k < 4; ++k) put(out + (((size_t)f * N + n) * 4 + k) * 2, rv[k][0]);
+            ScratchArrays sc;
+            if (!eig4_fast(w, sc)) {
+                TAMM_STAT(fallback);
+                eig4_fallback(e.xx, e.xy, e.xz, e.yy, e.yz, e.zz, e.im, mu, zeta, sc.rv_);
+            }
+            for (int k = 0; k < 4; ++k) put(out + (((size_t)f * N + n) * 4 + k) * 2, sc.rv(k, 0));
         }
     }
     return 0;
