@@ -149,6 +149,18 @@ TAMM_HD double n2n(double x) {
     return x;
 }
 TAMM_HD cd n2n(cd a) { return cd{n2n(a.re), n2n(a.im)}; }
+// Cold, out-of-line numpy.nan_to_num of three 2x2 blocks at once (values in, values out: taking the address of the
+// caller's arrays would move them to local memory on the hot path).
+struct Blocks3 { cd a[12]; };
+#if defined(__CUDA_ARCH__)
+__device__ __noinline__
+#else
+inline
+#endif
+Blocks3 n2n_blocks(Blocks3 b) {
+    for (int k = 0; k < 12; ++k) b.a[k] = n2n(b.a[k]);
+    return b;
+}
 
 // -------------------------------------------------------------------------------------------------
 // Inputs.  One LayerParams per (profile, layer); one LaneParams per (frequency, azimuth) lane.
@@ -801,6 +813,23 @@ TAMM_HD void mslp_eigs_f(const WaveMat& m, cd db, cd& h_big, cd& h_small) {
     h_big = -cmul_(big, crecip_f(det1));
 }
 
+// Smaller root of the local quadratic model of det N (the MSLP step of refine_root); rare, kept out of line on the device.
+#if defined(__CUDA_ARCH__)
+__device__ __noinline__
+#else
+inline
+#endif
+cd mslp_step_cold(cd f, cd tr, cd da, cd dd, cd db) {
+    const cd det1 = det2(da, db, db, dd);
+    const cd hm = 0.5 * tr;
+    cd disc = csq(hm);
+    cfma(disc, -det1, f);
+    cd sq = csqrt_f(disc);
+    const bool flip = (hm.re * sq.re + hm.im * sq.im) < 0.0;
+    sq = csel(flip, -sq, sq);
+    return -cmul_(f, crecip_s(hm + sq));
+}
+
 // Refinement of one root.  Every iteration evaluates N(x), f = det N and f' = tr(adj(N') N) entry-wise.  While the error
 // of x may be comparable to the distance to the nearest other root (sep2 = that distance squared) the step is the MSLP
 // step (smaller eigenvalue of -N'^-1 N; needs a complex sqrt, converges quadratically whatever the separation); once the
@@ -828,14 +857,7 @@ TAMM_HD void refine_root(const WaveCoef& w, cd& x, double sep2, double isep2, do
             err2 = hh * hh * (isep2 + ix2);
         } else {                              // MSLP step
             TAMM_STAT(quad);
-            const cd det1 = det2(mm.da, w.db, w.db, mm.dd);
-            const cd hm = 0.5 * tr;
-            cd disc = csq(hm);
-            cfma(disc, -det1, f);
-            cd sq = csqrt_f(disc);
-            const bool flip = (hm.re * sq.re + hm.im * sq.im) < 0.0;
-            sq = csel(flip, -sq, sq);
-            h = -cmul_(f, crecip_s(hm + sq));
+            h = mslp_step_cold(f, tr, mm.da, mm.dd, w.db);
             x = x + h;
             hh = abs2(h);
             err2 = hh * hh * ix2;
@@ -927,9 +949,35 @@ struct ScratchArrays {
     TAMM_HD void set_ms_pair(int k, int h, double a, double b) { ms_[k][2 * h] = a; ms_[k][2 * h + 1] = b; }
 };
 
-// Four roots + the (Ex, Ey) null vector of N at each root, written to rv[k] = {q, Ex, Ey}.  rv is indexed with run-time
-// indices on purpose: it lives in (L1-resident) local memory, which costs a few 16-byte loads/stores instead of the
-// long select/move chains a register-resident array needs in rolled loops.
+// Normal incidence: N(q) = C0 - q^2 I, closed form (q^2 = eigenvalues of the 2x2 C0).  Out of line on the device so the
+// oblique-incidence loop carries none of it.
+template <class SC>
+#if defined(__CUDA_ARCH__)
+__device__ __noinline__
+#else
+inline
+#endif
+void eig4_zeta0(cd c00, cd c01, cd c11, SC& sc) {
+    cd hm = 0.5 * (c00 + c11), hd = 0.5 * (c00 - c11);
+    cd s = csqrt_f(csq(hd) + csq(c01));
+    bool flip = (hm.re * s.re + hm.im * s.im) < 0.0;
+    s = csel(flip, -s, s);
+    cd lbig = hm + s;
+    cd lsmall = cmul_(det2(c00, c01, c01, c11), crecip_f(lbig));
+    cd r0 = csqrt_f(lbig), r1 = csqrt_f(lsmall);
+    // N(q) = C0 - q^2 I
+    cd a0 = c00 - lbig, d0 = c11 - lbig, a1 = c00 - lsmall, d1 = c11 - lsmall;
+    bool u0 = abs2(a0) >= abs2(d0), u1 = abs2(a1) >= abs2(d1);
+    cd x0 = csel(u0, -c01, d0), y0 = csel(u0, a0, -c01);
+    cd x1 = csel(u1, -c01, d1), y1 = csel(u1, a1, -c01);
+    sc.set_rv(0, 0, -r0); sc.set_rv(0, 1, x0); sc.set_rv(0, 2, y0);
+    sc.set_rv(1, 0, -r1); sc.set_rv(1, 1, x1); sc.set_rv(1, 2, y1);
+    sc.set_rv(2, 0, r0); sc.set_rv(2, 1, x0); sc.set_rv(2, 2, y0);
+    sc.set_rv(3, 0, r1); sc.set_rv(3, 1, x1); sc.set_rv(3, 2, y1);
+}
+
+// Four roots + the (Ex, Ey) null vector of N at each root, written to the scratch policy's rv[k] = {q, Ex, Ey} (indexed
+// with run-time indices on purpose, see ScratchArrays).
 // rv[0],rv[1]: pair seeded at -sqrt(.), rv[2],rv[3]: pair seeded at +sqrt(.)
 // Returns false when the roots fail Vieta's product check (the caller then runs the cold fallback).
 template <class SC>
@@ -938,22 +986,7 @@ TAMM_HD bool eig4_fast(const WaveCoef& w, SC& sc) {
     cd c01 = w.e01 - w.e02 * w.w1;
     cd c11 = w.d0;
     if (TAMM_RARE(w.zeta == 0.0)) {
-        cd hm = 0.5 * (c00 + c11), hd = 0.5 * (c00 - c11);
-        cd s = csqrt_f(csq(hd) + csq(c01));
-        bool flip = (hm.re * s.re + hm.im * s.im) < 0.0;
-        s = csel(flip, -s, s);
-        cd lbig = hm + s;
-        cd lsmall = cmul_(det2(c00, c01, c01, c11), crecip_f(lbig));
-        cd r0 = csqrt_f(lbig), r1 = csqrt_f(lsmall);
-        // N(q) = C0 - q^2 I
-        cd a0 = c00 - lbig, d0 = c11 - lbig, a1 = c00 - lsmall, d1 = c11 - lsmall;
-        bool u0 = abs2(a0) >= abs2(d0), u1 = abs2(a1) >= abs2(d1);
-        cd x0 = csel(u0, -c01, d0), y0 = csel(u0, a0, -c01);
-        cd x1 = csel(u1, -c01, d1), y1 = csel(u1, a1, -c01);
-        sc.set_rv(0, 0, -r0); sc.set_rv(0, 1, x0); sc.set_rv(0, 2, y0);
-        sc.set_rv(1, 0, -r1); sc.set_rv(1, 1, x1); sc.set_rv(1, 2, y1);
-        sc.set_rv(2, 0, r0); sc.set_rv(2, 1, x0); sc.set_rv(2, 2, y0);
-        sc.set_rv(3, 0, r1); sc.set_rv(3, 1, x1); sc.set_rv(3, 2, y1);
+        eig4_zeta0(c00, c01, c11, sc);
         return true;
     }
     const cd kap = mk(1.0) + (w.zeta * w.zeta) * w.k;
@@ -1030,47 +1063,65 @@ TAMM_HD bool eig4_fast(const WaveCoef& w, SC& sc) {
 // any k0*q*d here), fdlibm __kernel_sin/__kernel_cos minimax polynomials on [-pi/4, pi/4] (< 1 ulp).
 // exp: n = rint(x * log2 e), two-term reduction, Taylor degree 13 on |r| <= ln2/2 (truncation 4e-18), 2^n by exponent
 // arithmetic; x is clamped to +-700 (|exp| outside 1e+-304 cannot occur for a physical layer).
+// On the device the polynomial coefficients sit in constant memory: FP64 instructions take a constant-bank operand
+// directly, whereas a literal costs two uniform-register moves to materialise.
+#if defined(__CUDA_ARCH__) || defined(__CUDACC__)
+#define TAMM_KTAB static __constant__ double
+#else
+#define TAMM_KTAB static const double
+#endif
+TAMM_KTAB K_SC[18] = {
+    0.6366197723675814, 1.5707963267948966, 6.123233995736766e-17, -1.4973849048591698e-33,
+    1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06, -1.98412698298579493134e-04,
+    8.33333333332248946124e-03, -1.66666666666666324348e-01,
+    -1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07, 2.48015872894767294178e-05,
+    -1.38888888888741095749e-03, 4.16666666666666019037e-02, -0.5, 1.0};
+TAMM_KTAB K_EXP[17] = {
+    1.4426950408889634, 0.6931471805598903, 5.497923018708371e-14,
+    1.6059043836821613e-10, 2.08767569878681e-09, 2.505210838544172e-08, 2.755731922398589e-07, 2.7557319223985893e-06,
+    2.48015873015873e-05, 1.984126984126984e-04, 1.388888888888889e-03, 8.333333333333333e-03, 4.1666666666666664e-02,
+    1.6666666666666666e-01, 0.5, 1.0, 700.0};
 TAMM_HD void sincos_f(double t, double& sn, double& cs) {
-    const double n = rint(t * 0.6366197723675814);
-    double r = fma(-n, 1.5707963267948966, t);
-    r = fma(-n, 6.123233995736766e-17, r);
-    r = fma(-n, -1.4973849048591698e-33, r);
+    const double n = rint(t * K_SC[0]);
+    double r = fma(-n, K_SC[1], t);
+    r = fma(-n, K_SC[2], r);
+    r = fma(-n, K_SC[3], r);
     const double z = r * r;
-    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
-    ps = fma(z, ps, 2.75573137070700676789e-06);
-    ps = fma(z, ps, -1.98412698298579493134e-04);
-    ps = fma(z, ps, 8.33333333332248946124e-03);
-    ps = fma(z, ps, -1.66666666666666324348e-01);
+    double ps = fma(z, K_SC[4], K_SC[5]);
+    ps = fma(z, ps, K_SC[6]);
+    ps = fma(z, ps, K_SC[7]);
+    ps = fma(z, ps, K_SC[8]);
+    ps = fma(z, ps, K_SC[9]);
     const double s = fma(r * z, ps, r);
-    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
-    pc = fma(z, pc, -2.75573143513906633035e-07);
-    pc = fma(z, pc, 2.48015872894767294178e-05);
-    pc = fma(z, pc, -1.38888888888741095749e-03);
-    pc = fma(z, pc, 4.16666666666666019037e-02);
-    const double c = fma(z * z, pc, fma(-0.5, z, 1.0));
+    double pc = fma(z, K_SC[10], K_SC[11]);
+    pc = fma(z, pc, K_SC[12]);
+    pc = fma(z, pc, K_SC[13]);
+    pc = fma(z, pc, K_SC[14]);
+    pc = fma(z, pc, K_SC[15]);
+    const double c = fma(z * z, pc, fma(K_SC[16], z, K_SC[17]));
     const int q = (int)n & 3;
     const double a = (q & 1) ? c : s, b = (q & 1) ? s : c;
     sn = (q & 2) ? -a : a;
     cs = ((q + 1) & 2) ? -b : b;
 }
 TAMM_HD double exp_f(double x) {
-    x = fmin(fmax(x, -700.0), 700.0);
-    const double n = rint(x * 1.4426950408889634);
-    double r = fma(-n, 0.6931471805598903, x);
-    r = fma(-n, 5.497923018708371e-14, r);
-    double p = fma(r, 1.6059043836821613e-10, 2.08767569878681e-09);   // 1/13!, 1/12!
-    p = fma(r, p, 2.505210838544172e-08);      // 1/11!
-    p = fma(r, p, 2.755731922398589e-07);      // 1/10!
-    p = fma(r, p, 2.7557319223985893e-06);     // 1/9!
-    p = fma(r, p, 2.48015873015873e-05);       // 1/8!
-    p = fma(r, p, 1.984126984126984e-04);      // 1/7!
-    p = fma(r, p, 1.388888888888889e-03);      // 1/6!
-    p = fma(r, p, 8.333333333333333e-03);      // 1/5!
-    p = fma(r, p, 4.1666666666666664e-02);     // 1/4!
-    p = fma(r, p, 1.6666666666666666e-01);     // 1/3!
-    p = fma(r, p, 0.5);
-    p = fma(r, p, 1.0);
-    p = fma(r, p, 1.0);
+    x = fmin(fmax(x, -K_EXP[16]), K_EXP[16]);
+    const double n = rint(x * K_EXP[0]);
+    double r = fma(-n, K_EXP[1], x);
+    r = fma(-n, K_EXP[2], r);
+    double p = fma(r, K_EXP[3], K_EXP[4]);   // 1/13!, 1/12!
+    p = fma(r, p, K_EXP[5]);      // 1/11!
+    p = fma(r, p, K_EXP[6]);      // 1/10!
+    p = fma(r, p, K_EXP[7]);      // 1/9!
+    p = fma(r, p, K_EXP[8]);      // 1/8!
+    p = fma(r, p, K_EXP[9]);      // 1/7!
+    p = fma(r, p, K_EXP[10]);     // 1/6!
+    p = fma(r, p, K_EXP[11]);     // 1/5!
+    p = fma(r, p, K_EXP[12]);     // 1/4!
+    p = fma(r, p, K_EXP[13]);     // 1/3!
+    p = fma(r, p, K_EXP[14]);
+    p = fma(r, p, K_EXP[15]);
+    p = fma(r, p, K_EXP[15]);
     // 2^n, |n| <= 1010: split so neither factor leaves the normal range
     const int ni = (int)n;
     const int n1 = ni / 2, n2 = ni - n1;
@@ -1096,6 +1147,68 @@ cd phase_f(cd q, double twopif, double d, double sign) {
     sincos_f(ai, sn, cs);
     double m = exp_f(ar);
     return cd{m * cs, m * sn};
+}
+
+// The four layer phases at once: Mf0 = exp(+i k0 q0 d), Mf1 = exp(+i k0 q1 d), Mr0 = exp(-i k0 q2 d), Mr1 = exp(-i k0 q3 d)
+// (K^-1 and K diagonals, layer.py:96-97 / layer_PPJ.py:437).  q1, -q2 and -q3 differ from q0 by the birefringence and the
+// tilt-induced asymmetry only, so for a thin layer the last three are Mf0 times exp(w) with |w| = k0 d |dq| small:
+// when every |w| < 2^-5 they come from short Taylor polynomials (no range reduction, no 2^n scaling; truncation below
+// 3e-17), otherwise from the general routine.
+TAMM_HD double exp_small_re(double x) {   // exp(x) for |x| < 2^-5
+    double e = fma(x, 1.984126984126984e-04, 1.388888888888889e-03);
+    e = fma(x, e, 8.333333333333333e-03);
+    e = fma(x, e, 4.1666666666666664e-02);
+    e = fma(x, e, 1.6666666666666666e-01);
+    e = fma(x, e, 0.5);
+    e = fma(x, e, 1.0);
+    return fma(x, e, 1.0);
+}
+TAMM_HD cd exp_small(cd w) {       // exp(w) for |w| < 2^-5
+    const double e = exp_small_re(w.re);
+    const double z = w.im * w.im;
+    double sp = fma(z, -1.984126984126984e-04, 8.333333333333333e-03);
+    sp = fma(z, sp, -1.6666666666666666e-01);
+    sp = fma(z, sp, 1.0);
+    double cp = fma(z, 2.48015873015873e-05, -1.388888888888889e-03);
+    cp = fma(z, cp, 4.1666666666666664e-02);
+    cp = fma(z, cp, -0.5);
+    cp = fma(z, cp, 1.0);
+    return cd{e * cp, e * (sp * w.im)};
+}
+// general case, out of line on the device: thick layers are not what the hot loop is laid out for
+#if defined(__CUDA_ARCH__)
+__device__ __noinline__
+#else
+inline
+#endif
+void layer_phases_full(cd q0, cd q1, cd q2, cd q3, double twopif, double d, cd* M) {
+    M[0] = phase_f(q0, twopif, d, -1.0);
+    M[1] = phase_f(q1, twopif, d, -1.0);
+    M[2] = phase_f(q2, twopif, d, +1.0);
+    M[3] = phase_f(q3, twopif, d, +1.0);
+}
+TAMM_HD void layer_phases(cd q0, cd q1, cd q2, cd q3, double twopif, double d, cd& Mf0, cd& Mf1, cd& Mr0, cd& Mr1) {
+    const double rc = 1.0 / C_CONST;
+    const cd z = (twopif * q0) * d;              // same argument arithmetic as phase_f(q0, ., ., -1)
+    const double ar = -(z.im * rc), ai = z.re * rc;
+    const double kd = (twopif * d) * rc;
+    // w = i k0 d dq
+    const cd d1 = q1 - q0, d2 = -(q2 + q0), d3 = -(q3 + q0);
+    const cd w1 = cd{-kd * d1.im, kd * d1.re}, w2 = cd{-kd * d2.im, kd * d2.re}, w3 = cd{-kd * d3.im, kd * d3.re};
+    const double wmax = fmax(fmax(abs2(w1), ar * ar), fmax(abs2(w2), abs2(w3)));
+    if (TAMM_USUAL(wmax < 9.765625e-04)) {         // 2^-10: thin layer, weak attenuation across it
+        double sn, cs;
+        sincos_f(ai, sn, cs);
+        const double m = exp_small_re(ar);
+        Mf0 = cd{m * cs, m * sn};
+        Mf1 = cmul_(Mf0, exp_small(w1));
+        Mr0 = cmul_(Mf0, exp_small(w2));
+        Mr1 = cmul_(Mf0, exp_small(w3));
+    } else {
+        cd M[4];
+        layer_phases_full(q0, q1, q2, q3, twopif, d, M);
+        Mf0 = M[0]; Mf1 = M[1]; Mr0 = M[2]; Mr1 = M[3];
+    }
 }
 
 struct ModeSet {          // sorted roots and unnormalised gamma entries of one layer (layer_PPJ.py:280-283, 309-389)
@@ -1268,8 +1381,8 @@ TAMM_HD int layer_solve_field(const LayerParams& lp, const LaneParams& ln, doubl
     ModeSet m;
     int status = layer_modes(lp, ln, zeta, mu, m, sc);
     const double imu = rcp_mu(mu);
-    const cd Mf0 = phase_f(m.q0, ln.twopif, lp.dz, -1.0), Mf1 = phase_f(m.q1, ln.twopif, lp.dz, -1.0);
-    const cd Mr0 = phase_f(m.q2, ln.twopif, lp.dz, +1.0), Mr1 = phase_f(m.q3, ln.twopif, lp.dz, +1.0);
+    cd Mf0, Mf1, Mr0, Mr1;
+    layer_phases(m.q0, m.q1, m.q2, m.q3, ln.twopif, lp.dz, Mf0, Mf1, Mr0, Mr1);
     cd ra[4], rb[4];
     {
         cd idt = crecip_f(mk(1.0) - cmul_(m.g12, m.g21));            // 1/det [[1, g21],[g12, 1]]
@@ -1389,7 +1502,10 @@ TAMM_HD void interface_fb(const cd pYt[4], const cd pYr[4], const LayerF& nx, cd
 #endif
     for (int k = 0; k < 4; ++k) chk += (W[k].re - W[k].re) + (W[k].im - W[k].im) + (D[k].re - D[k].re) + (D[k].im - D[k].im);
     if (TAMM_RARE(chk != chk)) {
-        for (int k = 0; k < 4; ++k) { W[k] = n2n(W[k]); D[k] = n2n(D[k]); out[k] = n2n(out[k]); }
+        Blocks3 b;
+        for (int k = 0; k < 4; ++k) { b.a[k] = W[k]; b.a[4 + k] = D[k]; b.a[8 + k] = out[k]; }
+        b = n2n_blocks(b);
+        for (int k = 0; k < 4; ++k) { W[k] = b.a[k]; D[k] = b.a[4 + k]; out[k] = b.a[8 + k]; }
     }
     U[0] = W[0]; U[1] = W[1]; U[2] = W[2]; U[3] = W[3];
 }

@@ -122,6 +122,17 @@ int hostsim_elementary(const double* x, int n, double* out) {
     return 0;
 }
 
+// The four layer phases (layer_phases) of n root quadruples: q complex128 (n, 4), d (n), out complex128 (n, 4).
+int hostsim_phases(const double* q, const double* d, int n, double twopif, double* out) {
+    for (int i = 0; i < n; ++i) {
+        const cd* qi = reinterpret_cast<const cd*>(q) + 4 * (size_t)i;
+        cd m[4];
+        layer_phases(qi[0], qi[1], qi[2], qi[3], twopif, d[i], m[0], m[1], m[2], m[3]);
+        for (int k = 0; k < 4; ++k) put(out + (4 * (size_t)i + k) * 2, m[k]);
+    }
+    return 0;
+}
+
 // Eigen-solver path counters since the last reset: {roots, newton steps, quadratic-model steps, recentres, collapsed
 // pairs, Vieta checks, fallbacks}.
 int hostsim_solver_stats(long* out, int reset) {

@@ -158,6 +158,31 @@ def test_hot_path_elementary_functions(sim):
     assert np.isfinite(out).all()
 
 
+def test_layer_phases_thin_and_thick_layers(sim):
+    """layer_phases (one full exp(i k0 q0 d) + three small-argument corrections for thin layers, four full evaluations
+    otherwise) against exp() in extended precision: K^-1 / K diagonals of layer.py:96-97."""
+    rng = np.random.default_rng(3)
+    n = 40000
+    q0 = rng.uniform(0.5, 2.0, n) - 1j * rng.uniform(0, 2e-3, n)
+    spread = 10.0 ** rng.uniform(-9, -0.5, n)                      # birefringence / asymmetry from 1e-9 to 0.3
+    dq = lambda: spread * (rng.standard_normal(n) + 1e-2j * rng.standard_normal(n))
+    q = np.stack([q0, q0 + dq(), -q0 + dq(), -q0 + dq()], axis=1)
+    d = 10.0 ** rng.uniform(-3, 2, n)                               # 1 mm ... 100 m
+    twopif = 2 * np.pi * 179e6
+    out = np.zeros((n, 4), dtype=np.complex128)
+    assert sim.hostsim_phases(_P(np.ascontiguousarray(q)), _P(d), n, ctypes.c_double(twopif), _P(out)) == 0
+    k0d = (np.longdouble(twopif) * d.astype(np.longdouble)) / np.longdouble(299792458.0)
+    sign = np.array([1, 1, -1, -1])
+    arg = 1j * (k0d[:, None] * sign) * q.astype(np.clongdouble)
+    want = np.exp(arg)
+    # |M| can be far from 1 for thick lossy layers: relative error; the argument k0 q d itself carries three roundings
+    rel = np.abs(out - want) / np.abs(want)
+    bound = 6e-16 + 4e-16 * np.abs(arg)
+    assert (rel < bound).all(), float((rel / bound).max())
+    thin = np.abs(arg[:, 1:] - arg[:, :1]).max(axis=1) < 2.0 ** -5
+    assert 0.2 < thin.mean() < 0.95            # both regimes are exercised
+
+
 @pytest.mark.parametrize('name', h.golden_names('FP'))
 def test_kernel_arithmetic_fp(sim, name):
     """Fujita--Paren kernel arithmetic (tamm_core.cuh: fp_layer, rot_diag) against the reference fixture."""
