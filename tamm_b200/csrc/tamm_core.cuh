@@ -835,10 +835,12 @@ cd mslp_step_cold(cd f, cd tr, cd da, cd dd, cd db) {
 // step (smaller eigenvalue of -N'^-1 N; needs a complex sqrt, converges quadratically whatever the separation); once the
 // error is well below the separation the plain Newton step -f/f' is taken (error e -> e^2/separation).  err2 carries
 // the squared error estimate in and out; mm returns the last evaluated wave matrix (for the null vector).
-TAMM_HD void refine_root(const WaveCoef& w, cd& x, double sep2, double isep2, double err2, WaveMat& mm) {
+// ix2 ~ 1/|x|^2 and tol2 = the squared error to stop at come from the caller (the hot path knows |x| ~ |qc| beforehand).
+TAMM_HD void refine_root(const WaveCoef& w, cd& x, double sep2, double isep2, double ix2, double tol2, double err2,
+                         WaveMat& mm) {
     // error model: a linearised step h leaves an error ~ |h|^2/|x| (curvature of det N ~ 1/|q|); a Newton step near a
     // second root at distance d leaves ~ |h|^2 (1/d + 1/|x|)
-    const double ix2 = frcp(abs2(x) + TINY);
+    const double sep2_400 = sep2 * 0.0025, sep2_16 = sep2 * 0.0625, inewt = isep2 + ix2;
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
@@ -851,10 +853,10 @@ TAMM_HD void refine_root(const WaveCoef& w, cd& x, double sep2, double isep2, do
         cd h = -cmul_(f, crecip_s(tr));        // Newton step
         double hh = abs2(h);
         // Newton only when the error is well below the separation AND the step it proposes is small against it
-        if (TAMM_USUAL((err2 * 400.0 < sep2) && (hh * 16.0 <= sep2))) {
+        if (TAMM_USUAL((err2 < sep2_400) && (hh <= sep2_16))) {
             TAMM_STAT(newton);
             x = x + h;
-            err2 = hh * hh * (isep2 + ix2);
+            err2 = hh * hh * inewt;
         } else {                              // MSLP step
             TAMM_STAT(quad);
             h = mslp_step_cold(f, tr, mm.da, mm.dd, w.db);
@@ -862,7 +864,7 @@ TAMM_HD void refine_root(const WaveCoef& w, cd& x, double sep2, double isep2, do
             hh = abs2(h);
             err2 = hh * hh * ix2;
         }
-        if (err2 <= 1e-31 * abs2(x)) break;       // conservative error bound below 3e-16 |x|
+        if (err2 <= tol2) break;                  // conservative error bound below 3e-16 |x|
     }
 }
 
@@ -924,7 +926,7 @@ void eig4_fallback(double exx, double exy, double exz, double eyy, double eyz, d
         cd x = q[k];
         WaveMat mm;
         // coefficient-form roots are good to ~sqrt(eps) at worst (double roots): start the refinement from there
-        refine_root(w, x, sep2, frcp(sep2 + TINY), 1e-16 * (abs2(x) + 1e-300) + 1e-20, mm);
+        refine_root(w, x, sep2, frcp(sep2 + TINY), frcp(abs2(x) + TINY), 1e-31 * abs2(x), 1e-16 * (abs2(x) + 1e-300) + 1e-20, mm);
         bool use0 = abs2(mm.a) >= abs2(mm.d);
         rv[k][0] = x;
         rv[k][1] = csel(use0, -mm.b, mm.d);
@@ -994,6 +996,7 @@ TAMM_HD bool eig4_fast(const WaveCoef& w, SC& sc) {
     cd qc = csqrt_f(0.5 * (cmul_(c00, ikap) + c11));
     double reach2 = 0.0;      // largest |distance from a pair centre to one of its roots|^2
     const double iq2c = frcp(abs2(qc) + TINY);
+    const double tol2 = 0.8e-31 * abs2(qc);      // every accepted root is within 10 % of +-qc
     // c0/c4 = product of the four roots (Vieta); also the reference value of the check at the end
     const cd pwant = cmul_(det2(c00, c01, c01, c11), ikap);
     const cd rsum = ((-2.0 * w.zeta) * w.e02.re) * cmul_(w.k, ikap);      // -c3/c4 = sum of the four roots
@@ -1035,7 +1038,7 @@ TAMM_HD bool eig4_fast(const WaveCoef& w, SC& sc) {
             err2 = errv < 0.0 ? err2 * err2 * iq2c : errv * isep2;     // pair step: error ~ |h|^2/|q|
             TAMM_STAT(roots);
             WaveMat mm;
-            refine_root(w, x, sep2, isep2, err2, mm);
+            refine_root(w, x, sep2, isep2, iq2c, tol2, err2, mm);
             reach2 = fmax(reach2, abs2(x - seed));
             // null vector of N from the last evaluation (one step before x: accurate to the size of that step)
             bool use0 = abs2(mm.a) >= abs2(mm.d);

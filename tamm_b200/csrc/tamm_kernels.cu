@@ -461,12 +461,56 @@ returns_kernel(const cd* __restrict__ planes, const cd* __restrict__ pre, int N,
 // so the azimuth mean (layerstack.py:262,266) is a CTA reduction and |E| never goes to HBM.  128 B/eval instead of 225.
 // (TN below is TNF, the fused kernel's own depth tile.)
 constexpr int TNF = 4;   // depths per CTA of the fused returns kernel (keeps it at ~64 registers)
+
+// log10 for the dB conversions: fdlibm's e_log kernel (x = 2^e m, m in [sqrt(1/2), sqrt 2), s = f/(2+f), degree-14
+// minimax in s; < 1 ulp in ln m) with the reciprocal from frcp and none of libm's special-case ladder on the fast path.
+// Zero, denormals, negatives, inf and NaN take the library routine.
+__device__ __forceinline__ double log10_dev(double x) {
+    int hi = __double2hiint(x);
+    if (TAMM_RARE((unsigned)(hi - 0x00100000) >= 0x7fe00000u)) return log10(x);
+    int e = (hi >> 20) - 1023;
+    double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
+    if (m > 1.4142135623730951) { m *= 0.5; e += 1; }
+    const double f = m - 1.0;
+    const double s = f * tamm::frcp(2.0 + f);
+    const double z = s * s, w = z * z;
+    const double t1 = w * fma(w, fma(w, 1.531383769920937332e-01, 2.222219843214978396e-01), 3.999999999940941908e-01);
+    const double t2 = z * fma(w, fma(w, fma(w, 1.479819860511658591e-01, 1.818357216161805012e-01), 2.857142874366239149e-01),
+                              6.666666666666735130e-01);
+    const double hfsq = 0.5 * f * f;
+    const double lnm = f - (hfsq - s * (hfsq + (t1 + t2)));
+    return fma((double)e, 3.010299956639812e-01, lnm * 4.342944819032518e-01);
+}
+
+// Sum of 8 per-lane values over the warp in 9 shuffles: each butterfly step halves the number of values a lane carries
+// (lanes with the step's bit set keep the odd-indexed partial sums, the others the even-indexed ones).  On return lane L
+// holds the warp total of v[idx], idx = bit4(L) | bit3(L) << 1 | bit2(L) << 2; fixed summation order (deterministic).
+__device__ __forceinline__ double warp_sum8(const double v[8], int lane) {
+    double u[4], t[2];
+    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const double a = v[2 * i], b = v[2 * i + 1];
+        u[i] = (h16 ? b : a) + __shfl_xor_sync(0xffffffffu, h16 ? a : b, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const double a = u[2 * i], b = u[2 * i + 1];
+        t[i] = (h8 ? b : a) + __shfl_xor_sync(0xffffffffu, h8 ? a : b, 8);
+    }
+    double r = (h4 ? t[1] : t[0]) + __shfl_xor_sync(0xffffffffu, h4 ? t[0] : t[1], 4);
+    r += __shfl_xor_sync(0xffffffffu, r, 2);
+    r += __shfl_xor_sync(0xffffffffu, r, 1);
+    return r;
+}
+
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK, (BLOCK <= 256 ? 768 / BLOCK : 1))
 returns_fused_kernel(const cd* __restrict__ planes, const cd* __restrict__ pre, int N, int Q, int F, int mode, int chunk,
                      int nchunks, cd e0, cd e1, int gtm_phase, cd* __restrict__ E_HH, cd* __restrict__ E_HV,
                      cd* __restrict__ c_HHVV, double* __restrict__ dP_HH, double* __restrict__ dP_HV,
                      double* __restrict__ Pm_HH, double* __restrict__ Pm_HV) {
+    static_assert(TNF == 4, "warp_sum8 reduces 2 * TNF = 8 values");
     constexpr int NW = BLOCK / 32;
     __shared__ double red[NW][2 * TNF];
     __shared__ double tot[2 * TNF];
@@ -476,50 +520,49 @@ returns_fused_kernel(const cd* __restrict__ planes, const cd* __restrict__ pre, 
     const bool live = ifr < F;
     const int l = iq * F + (live ? ifr : F - 1);
     const int nb = blockIdx.x * TNF, ne = min(NI, nb + TNF);
-    const cd* in = planes + ((size_t)p * NI * 4) * QF + l;
-    const size_t obase = (((size_t)p * Q + iq) * NI) * F + (live ? ifr : F - 1);
-    double ah[TNF], av[TNF];
+    const size_t istride = (size_t)4 * QF;                                   // elements between consecutive depths
+    const cd* ip = planes + ((size_t)p * NI + nb) * istride + l;
+    size_t o = (((size_t)p * Q + iq) * NI + nb) * F + (live ? ifr : F - 1);   // output element of depth nb
+    double amp[2 * TNF];
     cd Dp[4], Up[4];
     int cc = -1;
 #pragma unroll
     for (int k = 0; k < TNF; ++k) {
         const int n = nb + k;
-        ah[k] = 0.0; av[k] = 0.0;
+        amp[2 * k] = 0.0; amp[2 * k + 1] = 0.0;
         if (n < ne) {
-            const cd* ip = in + (size_t)n * 4 * QF;
             cd m[4] = {ld_cd(ip), ld_cd(ip + QF), ld_cd(ip + 2 * (size_t)QF), ld_cd(ip + 3 * (size_t)QF)};
             if (nchunks > 1) {
-                int c = n / chunk;
+                const int c = n / chunk;
                 if (c != cc) { load_prefix(pre, (size_t)p * QF + l, nchunks, c, Dp, Up); cc = c; }
-                if (c > 0) apply_prefix(mode, Dp, Up, m);
+                if (c > 0) {
+                    cd t[4];
+                    if (mode == TAMM_MODE_URD) { mm22(m, Dp, t); mm22(Up, t, m); }
+                    else { mm22(Up, m, t); m[0] = t[0]; m[1] = t[1]; m[2] = t[2]; m[3] = t[3]; }
+                }
             }
-            cd hh = m[0] * e0 + m[1] * e1;             // get_Rx_all (layerstack.py:298)
-            cd hv = m[2] * e0 + m[3] * e1;
-            cd num = m[0] * conj(m[3]);                // c_HHVV (layerstack.py:271-278): num / (|m0| |m3|)
-            double iden = tamm::frsqrt(abs2(m[0]) * abs2(m[3]));
+            const cd hh = dot2(m[0], e0, m[1], e1);    // get_Rx_all (layerstack.py:298)
+            const cd hv = dot2(m[2], e0, m[3], e1);
+            const cd num = cmul_(m[0], conj(m[3]));    // c_HHVV (layerstack.py:271-278): num / (|m0| |m3|)
+            const double iden = tamm::frsqrt(abs2(m[0]) * abs2(m[3]));
             cd c = cd{num.re * iden, num.im * iden};
             if (gtm_phase) c = cd{-c.re, c.im};
-            double a = tamm::fsqrt(abs2(hh)), b = tamm::fsqrt(abs2(hv));
             if (live) {
-                const size_t o = obase + (size_t)n * F;
                 st_cd(E_HH + o, hh);
                 st_cd(E_HV + o, hv);
                 st_cd(c_HHVV + o, c);
-                ah[k] = a; av[k] = b;
+                amp[2 * k] = tamm::fsqrt(abs2(hh));
+                amp[2 * k + 1] = tamm::fsqrt(abs2(hv));
             }
         }
+        ip += istride;
+        o += F;
     }
     // CTA reduction of the 2*TNF sums over azimuth (fixed order -> deterministic)
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-#pragma unroll
-    for (int k = 0; k < TNF; ++k) {
-        double x = ah[k], y = av[k];
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            x += __shfl_xor_sync(0xffffffffu, x, off);
-            y += __shfl_xor_sync(0xffffffffu, y, off);
-        }
-        if (lane == 0) { red[w][2 * k] = x; red[w][2 * k + 1] = y; }
+    {
+        const double r = warp_sum8(amp, lane);
+        if ((lane & 3) == 0) red[w][((lane >> 4) & 1) | (((lane >> 3) & 1) << 1) | (((lane >> 2) & 1) << 2)] = r;
     }
     __syncthreads();
     if (threadIdx.x < 2 * TNF) {
@@ -536,14 +579,14 @@ returns_fused_kernel(const cd* __restrict__ planes, const cd* __restrict__ pre, 
     }
     __syncthreads();
     if (live) {
+        o -= (size_t)TNF * F;
 #pragma unroll
         for (int k = 0; k < TNF; ++k) {
-            const int n = nb + k;
-            if (n < ne) {
-                const size_t o = obase + (size_t)n * F;
-                dP_HH[o] = 20.0 * log10(ah[k]) - tot[2 * k];      // layerstack.py:261-267
-                dP_HV[o] = 20.0 * log10(av[k]) - tot[2 * k + 1];
+            if (nb + k < ne) {
+                dP_HH[o] = 20.0 * log10_dev(amp[2 * k]) - tot[2 * k];      // layerstack.py:261-267
+                dP_HV[o] = 20.0 * log10_dev(amp[2 * k + 1]) - tot[2 * k + 1];
             }
+            o += F;
         }
     }
 }
