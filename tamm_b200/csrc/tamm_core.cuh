@@ -1066,24 +1066,32 @@ TAMM_HD bool eig4_fast(const WaveCoef& w, SC& sc) {
 // any k0*q*d here), fdlibm __kernel_sin/__kernel_cos minimax polynomials on [-pi/4, pi/4] (< 1 ulp).
 // exp: n = rint(x * log2 e), two-term reduction, Taylor degree 13 on |r| <= ln2/2 (truncation 4e-18), 2^n by exponent
 // arithmetic; x is clamped to +-700 (|exp| outside 1e+-304 cannot occur for a physical layer).
-// On the device the polynomial coefficients sit in constant memory: FP64 instructions take a constant-bank operand
-// directly, whereas a literal costs two uniform-register moves to materialise.
-#if defined(__CUDA_ARCH__) || defined(__CUDACC__)
-#define TAMM_KTAB static __constant__ double
-#else
-#define TAMM_KTAB static const double
+// On the device the polynomial coefficients sit in constant memory (an FP64 instruction takes them through a uniform
+// register loaded two at a time, whereas a literal costs two moves to materialise); the host pass reads a plain table.
+#define TAMM_K_SC_VALUES { \
+    0.6366197723675814, 1.5707963267948966, 6.123233995736766e-17, -1.4973849048591698e-33, \
+    1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06, -1.98412698298579493134e-04, \
+    8.33333333332248946124e-03, -1.66666666666666324348e-01, \
+    -1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07, 2.48015872894767294178e-05, \
+    -1.38888888888741095749e-03, 4.16666666666666019037e-02, -0.5, 1.0}
+#define TAMM_K_EXP_VALUES { \
+    1.4426950408889634, 0.6931471805598903, 5.497923018708371e-14, \
+    1.6059043836821613e-10, 2.08767569878681e-09, 2.505210838544172e-08, 2.755731922398589e-07, 2.7557319223985893e-06, \
+    2.48015873015873e-05, 1.984126984126984e-04, 1.388888888888889e-03, 8.333333333333333e-03, 4.1666666666666664e-02, \
+    1.6666666666666666e-01, 0.5, 1.0, 700.0}
+#if defined(__CUDACC__)
+static __constant__ double K_SC_D[18] = TAMM_K_SC_VALUES;
+static __constant__ double K_EXP_D[17] = TAMM_K_EXP_VALUES;
 #endif
-TAMM_KTAB K_SC[18] = {
-    0.6366197723675814, 1.5707963267948966, 6.123233995736766e-17, -1.4973849048591698e-33,
-    1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06, -1.98412698298579493134e-04,
-    8.33333333332248946124e-03, -1.66666666666666324348e-01,
-    -1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07, 2.48015872894767294178e-05,
-    -1.38888888888741095749e-03, 4.16666666666666019037e-02, -0.5, 1.0};
-TAMM_KTAB K_EXP[17] = {
-    1.4426950408889634, 0.6931471805598903, 5.497923018708371e-14,
-    1.6059043836821613e-10, 2.08767569878681e-09, 2.505210838544172e-08, 2.755731922398589e-07, 2.7557319223985893e-06,
-    2.48015873015873e-05, 1.984126984126984e-04, 1.388888888888889e-03, 8.333333333333333e-03, 4.1666666666666664e-02,
-    1.6666666666666666e-01, 0.5, 1.0, 700.0};
+#if defined(__CUDA_ARCH__)
+#define K_SC K_SC_D
+#define K_EXP K_EXP_D
+#else
+static const double K_SC_H[18] = TAMM_K_SC_VALUES;
+static const double K_EXP_H[17] = TAMM_K_EXP_VALUES;
+#define K_SC K_SC_H
+#define K_EXP K_EXP_H
+#endif
 TAMM_HD void sincos_f(double t, double& sn, double& cs) {
     const double n = rint(t * K_SC[0]);
     double r = fma(-n, K_SC[1], t);

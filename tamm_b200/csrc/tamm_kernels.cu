@@ -460,7 +460,8 @@ returns_kernel(const cd* __restrict__ planes, const cd* __restrict__ pre, int N,
 // Fused returns + power for 32 <= F <= 1024: one CTA = all F azimuths of one (profile, frequency) x TN consecutive depths,
 // so the azimuth mean (layerstack.py:262,266) is a CTA reduction and |E| never goes to HBM.  128 B/eval instead of 225.
 // (TN below is TNF, the fused kernel's own depth tile.)
-constexpr int TNF = 4;   // depths per CTA of the fused returns kernel (keeps it at ~64 registers)
+constexpr int TNF = 4;   // depths per reduction group of the fused returns kernel (keeps it at ~80 registers)
+constexpr int TNG = 4;   // groups per CTA
 
 // log10 for the dB conversions: fdlibm's e_log kernel (x = 2^e m, m in [sqrt(1/2), sqrt 2), s = f/(2+f), degree-14
 // minimax in s; < 1 ulp in ln m) with the reciprocal from frcp and none of libm's special-case ladder on the fast path.
@@ -519,75 +520,81 @@ returns_fused_kernel(const cd* __restrict__ planes, const cd* __restrict__ pre, 
     const int ifr = threadIdx.x;
     const bool live = ifr < F;
     const int l = iq * F + (live ? ifr : F - 1);
-    const int nb = blockIdx.x * TNF, ne = min(NI, nb + TNF);
+    const int ne = min(NI, (int)(blockIdx.x + 1) * (TNF * TNG));
     const size_t istride = (size_t)4 * QF;                                   // elements between consecutive depths
-    const cd* ip = planes + ((size_t)p * NI + nb) * istride + l;
-    size_t o = (((size_t)p * Q + iq) * NI + nb) * F + (live ? ifr : F - 1);   // output element of depth nb
-    double amp[2 * TNF];
+    const cd* ip = planes + ((size_t)p * NI + (size_t)blockIdx.x * (TNF * TNG)) * istride + l;
+    size_t o = (((size_t)p * Q + iq) * NI + (size_t)blockIdx.x * (TNF * TNG)) * F + (live ? ifr : F - 1);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     cd Dp[4], Up[4];
     int cc = -1;
-#pragma unroll
-    for (int k = 0; k < TNF; ++k) {
-        const int n = nb + k;
-        amp[2 * k] = 0.0; amp[2 * k + 1] = 0.0;
-        if (n < ne) {
-            cd m[4] = {ld_cd(ip), ld_cd(ip + QF), ld_cd(ip + 2 * (size_t)QF), ld_cd(ip + 3 * (size_t)QF)};
-            if (nchunks > 1) {
-                const int c = n / chunk;
-                if (c != cc) { load_prefix(pre, (size_t)p * QF + l, nchunks, c, Dp, Up); cc = c; }
-                if (c > 0) {
-                    cd t[4];
-                    if (mode == TAMM_MODE_URD) { mm22(m, Dp, t); mm22(Up, t, m); }
-                    else { mm22(Up, m, t); m[0] = t[0]; m[1] = t[1]; m[2] = t[2]; m[3] = t[3]; }
-                }
-            }
-            const cd hh = dot2(m[0], e0, m[1], e1);    // get_Rx_all (layerstack.py:298)
-            const cd hv = dot2(m[2], e0, m[3], e1);
-            const cd num = cmul_(m[0], conj(m[3]));    // c_HHVV (layerstack.py:271-278): num / (|m0| |m3|)
-            const double iden = tamm::frsqrt(abs2(m[0]) * abs2(m[3]));
-            cd c = cd{num.re * iden, num.im * iden};
-            if (gtm_phase) c = cd{-c.re, c.im};
-            if (live) {
-                st_cd(E_HH + o, hh);
-                st_cd(E_HV + o, hv);
-                st_cd(c_HHVV + o, c);
-                amp[2 * k] = tamm::fsqrt(abs2(hh));
-                amp[2 * k + 1] = tamm::fsqrt(abs2(hv));
-            }
-        }
-        ip += istride;
-        o += F;
-    }
-    // CTA reduction of the 2*TNF sums over azimuth (fixed order -> deterministic)
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    {
-        const double r = warp_sum8(amp, lane);
-        if ((lane & 3) == 0) red[w][((lane >> 4) & 1) | (((lane >> 3) & 1) << 1) | (((lane >> 2) & 1) << 2)] = r;
-    }
-    __syncthreads();
-    if (threadIdx.x < 2 * TNF) {
-        double sum = 0.0;
-#pragma unroll
-        for (int i = 0; i < NW; ++i) sum += red[i][threadIdx.x];
-        const double pm = 20.0 * log10(sum / (double)F);
-        tot[threadIdx.x] = pm;
-        const int k = threadIdx.x >> 1, n = nb + k;
-        if (n < ne) {
-            const size_t row = ((size_t)p * Q + iq) * NI + n;
-            if (threadIdx.x & 1) Pm_HV[row] = pm; else Pm_HH[row] = pm;
-        }
-    }
-    __syncthreads();
-    if (live) {
-        o -= (size_t)TNF * F;
+    // TNG groups of TNF depths per CTA: the chunk prefix stays in registers from group to group
+#pragma unroll 1
+    for (int nb = blockIdx.x * (TNF * TNG); nb < ne; nb += TNF) {
+        double amp[2 * TNF];
 #pragma unroll
         for (int k = 0; k < TNF; ++k) {
-            if (nb + k < ne) {
-                dP_HH[o] = 20.0 * log10_dev(amp[2 * k]) - tot[2 * k];      // layerstack.py:261-267
-                dP_HV[o] = 20.0 * log10_dev(amp[2 * k + 1]) - tot[2 * k + 1];
+            const int n = nb + k;
+            amp[2 * k] = 0.0; amp[2 * k + 1] = 0.0;
+            if (n < ne) {
+                cd m[4] = {ld_cd(ip), ld_cd(ip + QF), ld_cd(ip + 2 * (size_t)QF), ld_cd(ip + 3 * (size_t)QF)};
+                if (nchunks > 1) {
+                    const int c = n / chunk;
+                    if (c != cc) { load_prefix(pre, (size_t)p * QF + l, nchunks, c, Dp, Up); cc = c; }
+                    if (c > 0) {
+                        cd t[4];
+                        if (mode == TAMM_MODE_URD) { mm22(m, Dp, t); mm22(Up, t, m); }
+                        else { mm22(Up, m, t); m[0] = t[0]; m[1] = t[1]; m[2] = t[2]; m[3] = t[3]; }
+                    }
+                }
+                const cd hh = dot2(m[0], e0, m[1], e1);    // get_Rx_all (layerstack.py:298)
+                const cd hv = dot2(m[2], e0, m[3], e1);
+                const cd num = cmul_(m[0], conj(m[3]));    // c_HHVV (layerstack.py:271-278): num / (|m0| |m3|)
+                const double iden = tamm::frsqrt(abs2(m[0]) * abs2(m[3]));
+                cd c = cd{num.re * iden, num.im * iden};
+                if (gtm_phase) c = cd{-c.re, c.im};
+                if (live) {
+                    st_cd(E_HH + o, hh);
+                    st_cd(E_HV + o, hv);
+                    st_cd(c_HHVV + o, c);
+                    amp[2 * k] = tamm::fsqrt(abs2(hh));
+                    amp[2 * k + 1] = tamm::fsqrt(abs2(hv));
+                }
             }
+            ip += istride;
             o += F;
         }
+        // CTA reduction of the 2*TNF sums over azimuth (fixed order -> deterministic)
+        {
+            const double r = warp_sum8(amp, lane);
+            if ((lane & 3) == 0) red[w][((lane >> 4) & 1) | (((lane >> 3) & 1) << 1) | (((lane >> 2) & 1) << 2)] = r;
+        }
+        __syncthreads();
+        if (threadIdx.x < 2 * TNF) {
+            double sum = 0.0;
+#pragma unroll
+            for (int i = 0; i < NW; ++i) sum += red[i][threadIdx.x];
+            const double pm = 20.0 * log10(sum / (double)F);
+            tot[threadIdx.x] = pm;
+            const int k = threadIdx.x >> 1, n = nb + k;
+            if (n < ne) {
+                const size_t row = ((size_t)p * Q + iq) * NI + n;
+                if (threadIdx.x & 1) Pm_HV[row] = pm; else Pm_HH[row] = pm;
+            }
+        }
+        __syncthreads();
+        if (live) {
+            size_t od = o - (size_t)TNF * F;
+#pragma unroll
+            for (int k = 0; k < TNF; ++k) {
+                if (nb + k < ne) {
+                    dP_HH[od] = 20.0 * log10_dev(amp[2 * k]) - tot[2 * k];      // layerstack.py:261-267
+                    dP_HV[od] = 20.0 * log10_dev(amp[2 * k + 1]) - tot[2 * k + 1];
+                }
+                od += F;
+            }
+        }
+        // red / tot are rewritten by the next group only after its own barrier on red; tot is read above before the next
+        // group's first barrier, and written after it -> no extra barrier needed
     }
 }
 
@@ -929,7 +936,7 @@ int tamm_returns(const void* planes, const void* workspace, int P, int N, int Q,
     cudaStream_t s = (cudaStream_t)stream;
     if (F >= 32 && F <= 1024 && Q <= 65535 && P <= 65535) {
         // fused path: azimuth reduction inside the CTA
-        dim3 grid((NI + TNF - 1) / TNF, Q, P);
+        dim3 grid((NI + TNF * TNG - 1) / (TNF * TNG), Q, P);
         const cd e0 = cd{etx[0], etx[1]}, e1 = cd{etx[2], etx[3]};
 #define TAMM_RF(BLK)                                                                                                     \
     returns_fused_kernel<BLK><<<grid, BLK, 0, s>>>((const cd*)planes, pre, N, Q, F, mode, chunk, nch, e0, e1, gtm_phase, \
