@@ -941,14 +941,15 @@ void eig4_fallback(double exx, double exy, double exz, double eyy, double eyz, d
 // shared-memory slots in stack_kernel (ScratchShared in tamm_kernels.cu: local memory thrashed the small L1 left next
 // to the carry state).  A policy provides
 //   cd rv(k, j) / set_rv(k, j, v)          k = 0..3, j = 0..2
-//   ms_pair(k, h, a, b) / set_ms_pair(...)  h = 0: Poynting measures {|Px|^2, |Px|^2+|Py|^2}, h = 1: E-field measures
+//   ms_pair(k, a, b) / set_ms_pair(...)     Poynting measures {|Px|^2, |Px|^2+|Py|^2} of mode k
+// (the E-field measures of the rarely taken branch are recomputed from rv when needed).
 struct ScratchArrays {
     cd rv_[4][3];
-    double ms_[4][4];
+    double ms_[4][2];
     TAMM_HD cd rv(int k, int j) const { return rv_[k][j]; }
     TAMM_HD void set_rv(int k, int j, cd v) { rv_[k][j] = v; }
-    TAMM_HD void ms_pair(int k, int h, double& a, double& b) const { a = ms_[k][2 * h]; b = ms_[k][2 * h + 1]; }
-    TAMM_HD void set_ms_pair(int k, int h, double a, double b) { ms_[k][2 * h] = a; ms_[k][2 * h + 1] = b; }
+    TAMM_HD void ms_pair(int k, double& a, double& b) const { a = ms_[k][0]; b = ms_[k][1]; }
+    TAMM_HD void set_ms_pair(int k, double a, double b) { ms_[k][0] = a; ms_[k][1] = b; }
 };
 
 // Normal incidence: N(q) = C0 - q^2 I, closed form (q^2 = eigenvalues of the 2x2 C0).  Out of line on the device so the
@@ -1276,9 +1277,8 @@ TAMM_HD int layer_modes(const LayerParams& lp, const LaneParams& ln, double zeta
         cd u = imu * cmul_(q, Ez);
         u = cd{fma(a51, Ex.re, u.re), fma(a51, Ex.im, u.im)};
         cd Py = -cmul_(Ey, u);
-        double pxx = abs2(Px), exx = abs2(Ex);
-        sc.set_ms_pair(k, 0, pxx, pxx + abs2(Py));
-        sc.set_ms_pair(k, 1, exx, exx + abs2(Ey));
+        const double pxx = abs2(Px);
+        sc.set_ms_pair(k, pxx, pxx + abs2(Py));
     }
     const int tmask = has_im ? im_mask : re_mask;
     int t0, t1, r0, r1;
@@ -1296,17 +1296,28 @@ TAMM_HD int layer_modes(const LayerParams& lp, const LaneParams& ln, double zeta
     // C_a > C_b  <=>  n_a s_b > n_b s_a  for ratios C = n/s with s > 0; NaN (s = 0) compares false like the reference
     auto gt = [](double na, double sa, double nb, double sb) { return (sa > 0.0) && (sb > 0.0) && (na * sb > nb * sa); };
     double pa, sa, pb, sb;
-    sc.ms_pair(t0, 0, pa, sa);
-    sc.ms_pair(t1, 0, pb, sb);
+    sc.ms_pair(t0, pa, sa);
+    sc.ms_pair(t1, pb, sb);
     const bool biref = (sa > 0.0) && (sb > 0.0) && (fabs(pa * sb - pb * sa) > QSD_THR * (sa * sb));   // layer_PPJ.py:258
-    const int mo = biref ? 0 : 1;        // Poynting measures (260-265) or E-field measures (269-276)
-    double n0, d0, n1, d1;
-    sc.ms_pair(t1, mo, n1, d1);
-    sc.ms_pair(t0, mo, n0, d0);
-    const bool flip_t = gt(n1, d1, n0, d0);
-    sc.ms_pair(r1, mo, n1, d1);
-    sc.ms_pair(r0, mo, n0, d0);
-    const bool flip_r = gt(n1, d1, n0, d0);
+    bool flip_t, flip_r;
+    if (TAMM_USUAL(biref)) {             // Poynting measures (layer_PPJ.py:260-265)
+        double pc, sc_, pd, sd;
+        sc.ms_pair(r0, pc, sc_);
+        sc.ms_pair(r1, pd, sd);
+        flip_t = gt(pb, sb, pa, sa);
+        flip_r = gt(pd, sd, pc, sc_);
+    } else {                             // E-field measures {|Ex|^2, |Ex|^2+|Ey|^2} (269-276), from the stored null vectors
+        double en[4], es[4];
+        const int idx[4] = {t0, t1, r0, r1};
+        for (int i = 0; i < 4; ++i) {
+            cd Ex = sc.rv(idx[i], 1), Ey = sc.rv(idx[i], 2);
+            if (abs2(Ex) + abs2(Ey) == 0.0) { Ex = mk(1.0); Ey = mk(0.0); }
+            en[i] = abs2(Ex);
+            es[i] = en[i] + abs2(Ey);
+        }
+        flip_t = gt(en[1], es[1], en[0], es[0]);
+        flip_r = gt(en[3], es[3], en[2], es[2]);
+    }
     const int o0 = flip_t ? t1 : t0, o1 = flip_t ? t0 : t1, o2 = flip_r ? r1 : r0, o3 = flip_r ? r0 : r1;
     const cd q0 = sc.rv(o0, 0), q1 = sc.rv(o1, 0), q2 = sc.rv(o2, 0), q3 = sc.rv(o3, 0);
 

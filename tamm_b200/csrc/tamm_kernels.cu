@@ -43,7 +43,7 @@ int fail(const char* fmt, const char* a = "", long b = 0) {
 #endif
 
 constexpr int TL = 16;     // layers per TMA sub-tile (16 * 80 B = 1280 B per profile)
-constexpr int CARRY_SLOTS = 36;   // 16-byte shared-memory slots per thread of stack_kernel (carry state + mode scratch)
+constexpr int CARRY_SLOTS = 34;   // 16-byte shared-memory slots per thread of stack_kernel (carry state + mode scratch)
 constexpr int NPMAX = 4;   // a CTA's lanes may span at most this many profiles (flattened lane mapping)
 
 // ---- mbarrier / bulk-copy (TMA) primitives -----------------------------------------------------
@@ -76,13 +76,14 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
 }
 
 __device__ __forceinline__ void st_cd(cd* p, cd v) { *reinterpret_cast<double2*>(p) = make_double2(v.re, v.im); }
+__device__ __forceinline__ void st_cd_stream(cd* p, cd v) { __stcs(reinterpret_cast<double2*>(p), make_double2(v.re, v.im)); }
 __device__ __forceinline__ cd ld_cd(const cd* p) {
     double2 v = *reinterpret_cast<const double2*>(p);
     return cd{v.x, v.y};
 }
 
 // Mode-solve scratch (tamm_core.cuh: ScratchArrays) in per-thread shared-memory slots: slot s of thread t sits at
-// base[s * stride + t], so any run-time slot index is bank-conflict free.  Slots 0-11: rv[k][j], 12-19: ms pairs.
+// base[s * stride + t], so any run-time slot index is bank-conflict free.  Slots 0-11: rv[k][j], 12-15: ms pairs.
 struct ScratchShared {
     double2* base;
     int stride;
@@ -91,13 +92,11 @@ struct ScratchShared {
         return cd{v.x, v.y};
     }
     __device__ __forceinline__ void set_rv(int k, int j, cd v) { base[(3 * k + j) * stride] = make_double2(v.re, v.im); }
-    __device__ __forceinline__ void ms_pair(int k, int h, double& a, double& b) const {
-        const double2 v = base[(12 + 2 * k + h) * stride];
+    __device__ __forceinline__ void ms_pair(int k, double& a, double& b) const {
+        const double2 v = base[(12 + k) * stride];
         a = v.x; b = v.y;
     }
-    __device__ __forceinline__ void set_ms_pair(int k, int h, double a, double b) {
-        base[(12 + 2 * k + h) * stride] = make_double2(a, b);
-    }
+    __device__ __forceinline__ void set_ms_pair(int k, double a, double b) { base[(12 + k) * stride] = make_double2(a, b); }
 };
 
 // ---- the hot kernel ------------------------------------------------------------------------------
@@ -159,18 +158,17 @@ stack_body(const double* __restrict__ layers, const double* __restrict__ lanes, 
         for (int q = 0; q < np; ++q) tma_bulk_g2s(&sbuf[0][q][0], src + (size_t)q * N * LAYER_STRIDE, bytes, &bar[0]);
     }
 
-    LaneParams ln;
+    // (2 pi f, 2 pi f eps0) stay in registers; the azimuth rotation (cos/sin of beta and 2 beta) is parked in shared memory
+    // below and re-read at the top of every layer (it would be spilled to local memory otherwise)
+    double ln_twopif, ln_w_eps0;
     {
-        const double2* lp2 = reinterpret_cast<const double2*>(lanes + (size_t)lc * LANE_STRIDE);
-        double2 a = __ldg(lp2), b = __ldg(lp2 + 1), c2 = __ldg(lp2 + 2);
-        ln.c1 = a.x; ln.s1 = a.y; ln.c2 = b.x; ln.s2 = b.y;
-        ln.twopif = c2.x; ln.w_eps0 = c2.y; ln.pad0 = 0; ln.pad1 = 0;
+        const double2 c2 = __ldg(reinterpret_cast<const double2*>(lanes + (size_t)lc * LANE_STRIDE) + 2);
+        ln_twopif = c2.x; ln_w_eps0 = c2.y;
     }
-
     // Per-thread state carried from layer to layer lives in shared memory (CARRY_SLOTS x 16 B per thread, conflict-free
     // [slot][thread] layout): slots 0-7 = Yt, Yr of the previous layer, 8-11 = D' (MODE_URD) or Er of the previous layer
-    // (MODE_U, which carries no D'), 12-15 = U' (field basis, see tamm_core.cuh: LayerF), 16-35 = scratch of the mode
-    // solve (ScratchShared).  Keeping all of it out of the register file and out of local memory matters twice: the
+    // (MODE_U, which carries no D'), 12-15 = U' (field basis, see tamm_core.cuh: LayerF), 16-31 = scratch of the mode
+    // solve (ScratchShared), 32-33 = (cos b, sin b), (cos 2b, sin 2b) of this lane.  Keeping all of it out of the register file and out of local memory matters twice: the
     // register-hungry layer solve stays (nearly) spill-free, and nothing competes for the small L1 that remains.
     extern __shared__ double2 carry[];
     double2* cs = carry + threadIdx.x;
@@ -180,6 +178,11 @@ stack_body(const double* __restrict__ layers, const double* __restrict__ lanes, 
     CS_ST(8, mk(1.0)); CS_ST(9, mk(0.0)); CS_ST(10, mk(0.0)); CS_ST(11, mk(1.0));
     CS_ST(12, mk(1.0)); CS_ST(13, mk(0.0)); CS_ST(14, mk(0.0)); CS_ST(15, mk(1.0));
     ScratchShared sc{cs + 16 * cstr, cstr};
+    {
+        const double2* lp2 = reinterpret_cast<const double2*>(lanes + (size_t)lc * LANE_STRIDE);
+        cs[32 * cstr] = __ldg(lp2);
+        cs[33 * cstr] = __ldg(lp2 + 1);
+    }
     int st = 0;
     cd* out = planes + ((size_t)p * NI * 4) * QF + lc;
 
@@ -207,6 +210,12 @@ stack_body(const double* __restrict__ layers, const double* __restrict__ lanes, 
                 double2 v0 = s2[0], v1 = s2[1], v2 = s2[2], v3 = s2[3], v4 = s2[4];
                 lp.t20 = v0.x; lp.n21r = v0.y; lp.n21i = v1.x; lp.n22r = v1.y; lp.n22i = v2.x;
                 lp.mono = v2.y; lp.deps = v3.x; lp.sigma = v3.y; lp.dz = v4.x; lp.pad = 0;
+            }
+            LaneParams ln;
+            {
+                const double2 a = cs[32 * cstr], b = cs[33 * cstr];
+                ln.c1 = a.x; ln.s1 = a.y; ln.c2 = b.x; ln.s2 = b.y;
+                ln.twopif = ln_twopif; ln.w_eps0 = ln_w_eps0; ln.pad0 = 0; ln.pad1 = 0;
             }
             LayerF cur;
 #ifdef TAMM_SYNC_PER_LAYER
@@ -252,10 +261,11 @@ stack_body(const double* __restrict__ layers, const double* __restrict__ lanes, 
                 }
                 if (live) {
                     cd* op = out + (size_t)n * 4 * QF;
-                    st_cd(op, o[0]);
-                    st_cd(op + QF, o[1]);
-                    st_cd(op + 2 * (size_t)QF, o[2]);
-                    st_cd(op + 3 * (size_t)QF, o[3]);
+                    // streaming stores: the planes are read back by another kernel, keep them out of the small L1
+                    st_cd_stream(op, o[0]);
+                    st_cd_stream(op + QF, o[1]);
+                    st_cd_stream(op + 2 * (size_t)QF, o[2]);
+                    st_cd_stream(op + 3 * (size_t)QF, o[3]);
                 }
 #pragma unroll
                 for (int k = 0; k < 4; ++k) { if (MODE == TAMM_MODE_URD) CS_ST(8 + k, D[k]); CS_ST(12 + k, U[k]); }
