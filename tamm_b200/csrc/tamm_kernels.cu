@@ -3,14 +3,17 @@
 // Kernels
 //   stack_kernel        FP64-pipe bound.  One thread = one (profile, lane, depth-chunk): it walks the chunk's
 //                       layers sequentially, solving each layer (tamm_core.cuh: rotation -> eps -> Berreman
-//                       eigenmodes -> sort -> gamma -> A, A^-1, phases), forming the interface matrices with
-//                       the previous layer carried in registers, and accumulating the chunk-local 2x2 products.
-//                       A and A^-1 never touch HBM.  A warp = 32 consecutive lanes of the same profile and
-//                       chunk, so the per-layer parameters are warp-uniform; they are streamed global->shared
-//                       by the TMA engine (cp.async.bulk + mbarrier, double buffered) and read as broadcasts.
+//                       eigenmodes -> sort -> gamma -> admittances / field-basis propagators, phases), forming the
+//                       interface with the previous layer and accumulating the chunk-local 2x2 products.  Everything
+//                       a thread carries between statements (previous layer, products, mode-solve scratch) sits in
+//                       per-thread shared-memory slots; A and A^-1 never exist, nothing but the result touches HBM.
+//                       A warp = 32 consecutive lanes of (mostly) one profile and one chunk, so the per-layer
+//                       parameters are warp-uniform; they are streamed global->shared by the TMA engine
+//                       (cp.async.bulk + mbarrier, double buffered) and read as broadcasts.
 //   chunk_scan_kernel   warp-shuffle (Kogge-Stone) scan over the chunk aggregates (D, U): exclusive prefixes.
-//   returns_kernel      HBM bound.  Applies the prefixes, Tx polarisation, |E|, HH-VV coherence.
-//   power_kernel        HBM bound.  Azimuth mean (warp reduction), dB, anomalies.
+//   returns_fused_kernel HBM / issue mix.  Prefix fix-up, Tx polarisation, |E|, HH-VV coherence and the azimuth mean,
+//                       dB and anomalies in one pass (32 <= F <= 1024).
+//   returns_kernel + power_kernel   the same in two passes for other F.
 //   export_kernel       HBM bound.  Prefix fix-up + transpose into the reference's (F, N-1, 2, 2) layout.
 //   layer_diag_kernel   per-(lane, layer) matrices for the `Layer` attribute API and the parity tests.
 #include <cuda_runtime.h>
