@@ -86,26 +86,27 @@ __device__ __forceinline__ cd ld_cd(const cd* p) {
 }
 
 // Mode-solve scratch (tamm_core.cuh: ScratchArrays) in per-thread shared-memory slots: slot s of thread t sits at
-// base[s * stride + t], so any run-time slot index is bank-conflict free.  Slots 0-11: rv[k][j], 12-15: ms pairs.
+// base[s * STRIDE + t] (STRIDE = the kernel's maximum CTA size, a compile-time constant: slot offsets fold into the
+// instructions), so any run-time slot index is bank-conflict free.  Slots 0-11: rv[k][j], 12-15: ms pairs.
+template <int STRIDE>
 struct ScratchShared {
     double2* base;
-    int stride;
     __device__ __forceinline__ cd rv(int k, int j) const {
-        const double2 v = base[(3 * k + j) * stride];
+        const double2 v = base[(3 * k + j) * STRIDE];
         return cd{v.x, v.y};
     }
-    __device__ __forceinline__ void set_rv(int k, int j, cd v) { base[(3 * k + j) * stride] = make_double2(v.re, v.im); }
+    __device__ __forceinline__ void set_rv(int k, int j, cd v) { base[(3 * k + j) * STRIDE] = make_double2(v.re, v.im); }
     __device__ __forceinline__ void ms_pair(int k, double& a, double& b) const {
-        const double2 v = base[(12 + k) * stride];
+        const double2 v = base[(12 + k) * STRIDE];
         a = v.x; b = v.y;
     }
-    __device__ __forceinline__ void set_ms_pair(int k, double a, double b) { base[(12 + k) * stride] = make_double2(a, b); }
+    __device__ __forceinline__ void set_ms_pair(int k, double a, double b) { base[(12 + k) * STRIDE] = make_double2(a, b); }
 };
 
 // ---- the hot kernel ------------------------------------------------------------------------------
 // grid = (lane blocks, chunks); block = TB threads (multiple of 32).
 // MU1: specialisation for mu == 1 (every multiplication by mu or 1/mu folds away)
-template <int MODE, bool MU1>
+template <int MODE, bool MU1, int CSTR>
 __device__ __forceinline__ void
 stack_body(const double* __restrict__ layers, const double* __restrict__ lanes, int P, int N, int QF, int flat, double zeta,
              double mu_arg, int chunk, int nchunks, cd* __restrict__ planes, cd* __restrict__ agg, int* __restrict__ status) {
@@ -175,12 +176,12 @@ stack_body(const double* __restrict__ layers, const double* __restrict__ lanes, 
     // register-hungry layer solve stays (nearly) spill-free, and nothing competes for the small L1 that remains.
     extern __shared__ double2 carry[];
     double2* cs = carry + threadIdx.x;
-    const int cstr = blockDim.x;
+    constexpr int cstr = CSTR;      // slot stride = maximum CTA size of this instantiation (>= blockDim.x)
 #define CS_LD(slot) ld_cd(reinterpret_cast<const cd*>(cs + (slot) * cstr))
 #define CS_ST(slot, v) st_cd(reinterpret_cast<cd*>(cs + (slot) * cstr), (v))
     CS_ST(8, mk(1.0)); CS_ST(9, mk(0.0)); CS_ST(10, mk(0.0)); CS_ST(11, mk(1.0));
     CS_ST(12, mk(1.0)); CS_ST(13, mk(0.0)); CS_ST(14, mk(0.0)); CS_ST(15, mk(1.0));
-    ScratchShared sc{cs + 16 * cstr, cstr};
+    ScratchShared<CSTR> sc{cs + 16 * cstr};
     {
         const double2* lp2 = reinterpret_cast<const double2*>(lanes + (size_t)lc * LANE_STRIDE);
         cs[32 * cstr] = __ldg(lp2);
@@ -296,7 +297,7 @@ stack_body(const double* __restrict__ layers, const double* __restrict__ lanes, 
 #define TAMM_STACK_PASS layers, lanes, P, N, QF, flat, zeta, mu, chunk, nchunks, planes, agg, status
 // MAXT / MINB: launch bounds (register budget): (256,1) -> 255 regs, (192,2) -> 168 regs, (256,2) -> 128 regs, ...
 template <int MODE, int MAXT, int MINB, bool MU1>
-__global__ void __launch_bounds__(MAXT, MINB) stack_kernel(TAMM_STACK_ARGS) { stack_body<MODE, MU1>(TAMM_STACK_PASS); }
+__global__ void __launch_bounds__(MAXT, MINB) stack_kernel(TAMM_STACK_ARGS) { stack_body<MODE, MU1, MAXT>(TAMM_STACK_PASS); }
 
 // ---- Fujita--Paren stack (modeltype 'FP'): thread = (profile, lane, chunk); same planes/aggregate layout as stack_kernel
 __global__ void __launch_bounds__(128)
@@ -863,7 +864,7 @@ int tamm_stack_urd(const double* layers, const double* lanes, int P, int N, int 
     dim3 grid((unsigned)gx, nch, 1);
     cd* agg = (cd*)workspace;
     cudaStream_t s = (cudaStream_t)stream;
-    const size_t dyn = (size_t)CARRY_SLOTS * sizeof(double2) * tb;   // per-thread carry state, see stack_kernel
+    const size_t dyn = (size_t)CARRY_SLOTS * sizeof(double2) * maxt;   // per-thread slots at the kernel's fixed stride
 #define TAMM_LAUNCH(MODE, MAXT, MINB)                                                                                   \
     do {                                                                                                                \
         static bool attr_set = false;                                                                                   \
