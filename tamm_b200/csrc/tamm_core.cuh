@@ -382,9 +382,8 @@ struct LayerDiag {   // optional diagnostics backing the `Layer` attributes of t
 };
 
 TAMM_HD cd clean_q(cd q) {  // layer_PPJ.py:199-203
-    if (fabs(q.im) > 0.0 && fabs(q.im) < ZERO_THR) q.im = 0.0;
-    if (fabs(q.re) > 0.0 && fabs(q.re) < ZERO_THR) q.re = 0.0;
-    return q;
+    // (|x| == 0 needs no test of its own: zeroing a zero changes nothing that is observed later)
+    return cd{fabs(q.re) < ZERO_THR ? 0.0 : q.re, fabs(q.im) < ZERO_THR ? 0.0 : q.im};
 }
 
 // 4x4 complex inverse via 2x2 minors (Laplace expansion); same adjugate/determinant as layer_PPJ.py:20-79
@@ -1002,8 +1001,10 @@ TAMM_HD bool eig4_fast(const WaveCoef& w, SC& sc) {
     const cd pwant = cmul_(det2(c00, c01, c01, c11), ikap);
     const cd rsum = ((-2.0 * w.zeta) * w.e02.re) * cmul_(w.k, ikap);      // -c3/c4 = sum of the four roots
     const double q2c = abs2(qc);
+    // both loops below are fully unrolled on the device: the selects and branches on `pair` / `r` fold away, which is
+    // worth more than the larger hot loop costs in instruction fetch (measured: -2.7 %)
 #if defined(__CUDA_ARCH__)
-#pragma unroll 1
+#pragma unroll
 #endif
     for (int pair = 0; pair < 2; ++pair) {
         cd centre, hb, hs;
@@ -1030,7 +1031,7 @@ TAMM_HD bool eig4_fast(const WaveCoef& w, SC& sc) {
         const double isep2 = frcp(sep2 + TINY);
         const cd seed = pair == 0 ? -qc : qc;
 #if defined(__CUDA_ARCH__)
-#pragma unroll 1
+#pragma unroll
 #endif
         for (int r = 0; r < 2; ++r) {
             const cd h0 = r ? hs : hb;
@@ -1254,7 +1255,7 @@ TAMM_HD int layer_modes(const LayerParams& lp, const LaneParams& ln, double zeta
     int im_mask = 0, re_mask = 0;
     bool has_im = false;
 #if defined(__CUDA_ARCH__)
-#pragma unroll 1
+#pragma unroll
 #endif
     for (int k = 0; k < 4; ++k) {
         const cd q = clean_q(sc.rv(k, 0));
