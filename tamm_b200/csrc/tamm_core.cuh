@@ -18,6 +18,7 @@
 //   D_mul, U_mul, accumulation  lib/layerstack.py:185-194
 #pragma once
 #include <math.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define TAMM_HD __host__ __device__ __forceinline__
@@ -149,6 +150,23 @@ TAMM_HD double n2n(double x) {
     return x;
 }
 TAMM_HD cd n2n(cd a) { return cd{n2n(a.re), n2n(a.im)}; }
+// Finite test on the integer pipe: the exponent field of x is all ones (inf / NaN) iff (high word << 1) >= 0xffe00000.
+// Several values are tested at once through the maximum of their keys.
+TAMM_HD unsigned nonfinite_key(double x) {
+#if defined(__CUDA_ARCH__)
+    return (unsigned)__double2hiint(x) << 1;
+#else
+    unsigned long long u;
+    memcpy(&u, &x, sizeof(u));
+    return (unsigned)(u >> 32) << 1;
+#endif
+}
+TAMM_HD unsigned nonfinite_key(cd a) {
+    const unsigned x = nonfinite_key(a.re), y = nonfinite_key(a.im);
+    return x > y ? x : y;
+}
+constexpr unsigned NONFINITE_KEY = 0xffe00000u;
+
 // Cold, out-of-line numpy.nan_to_num of three 2x2 blocks at once (values in, values out: taking the address of the
 // caller's arrays would move them to local memory on the hot path).
 struct Blocks3 { cd a[12]; };
@@ -1029,19 +1047,21 @@ TAMM_HD bool eig4_fast(const WaveCoef& w, SC& sc) {
         }
         const double sep2 = abs2(hb - hs);      // |distance between the two roots of the pair|^2 (estimate)
         const double isep2 = frcp(sep2 + TINY);
-        const cd seed = pair == 0 ? -qc : qc;
+        // how far the pair reaches from its seed -+qc (upper bound from the starting points: |a +- b|^2 <= 2|a|^2 + 2|b|^2)
+        const double ahb = abs2(hb), ahs = abs2(hs);
+        if (errv < 0.0) reach2 = fmax(reach2, fmax(ahb, ahs));
+        else reach2 = fmax(reach2, 2.0 * (abs2(centre - qc) + ahb));
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
         for (int r = 0; r < 2; ++r) {
             const cd h0 = r ? hs : hb;
             cd x = centre + h0;
-            double err2 = abs2(h0);
+            double err2 = r ? ahs : ahb;
             err2 = errv < 0.0 ? err2 * err2 * iq2c : errv * isep2;     // pair step: error ~ |h|^2/|q|
             TAMM_STAT(roots);
             WaveMat mm;
             refine_root(w, x, sep2, isep2, iq2c, tol2, err2, mm);
-            reach2 = fmax(reach2, abs2(x - seed));
             // null vector of N from the last evaluation (one step before x: accurate to the size of that step)
             bool use0 = abs2(mm.a) >= abs2(mm.d);
             const int idx = 2 * pair + r;
@@ -1519,12 +1539,16 @@ TAMM_HD void interface_fb(const cd pYt[4], const cd pYr[4], const LayerF& nx, cd
     mm22(U, X, V);
     mm22(V, nx.Q, W);                                     // U'_{n+1} = U'_n (M d3) Q'                layerstack.py:190
     // nan_to_num (layerstack.py:101-127) only matters for singular interfaces: one finite-check, rare slow path
-    double chk = 0.0;
+    unsigned chk = 0u;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    for (int k = 0; k < 4; ++k) chk += (W[k].re - W[k].re) + (W[k].im - W[k].im) + (D[k].re - D[k].re) + (D[k].im - D[k].im);
-    if (TAMM_RARE(chk != chk)) {
+    for (int k = 0; k < 4; ++k) {
+        const unsigned a = nonfinite_key(W[k]), b = nonfinite_key(D[k]);
+        chk = chk > a ? chk : a;
+        chk = chk > b ? chk : b;
+    }
+    if (TAMM_RARE(chk >= NONFINITE_KEY)) {
         Blocks3 b;
         for (int k = 0; k < 4; ++k) { b.a[k] = W[k]; b.a[4 + k] = D[k]; b.a[8 + k] = out[k]; }
         b = n2n_blocks(b);

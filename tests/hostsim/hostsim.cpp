@@ -133,6 +133,23 @@ int hostsim_phases(const double* q, const double* d, int n, double twopif, doubl
     return 0;
 }
 
+// One field-basis interface step (interface_fb<true>): every argument is a 2x2 complex block (row-major, 4 complex128).
+// D and U are updated in place, out receives URD_n.
+int hostsim_interface_fb(const double* pYt, const double* pYr, const double* nYt, const double* nYr, const double* P,
+                         const double* Q, double* D, double* U, double* out) {
+    LayerF nx;
+    cd a[4], b[4], d[4], u[4], o[4];
+    for (int k = 0; k < 4; ++k) {
+        a[k] = cd{pYt[2 * k], pYt[2 * k + 1]}; b[k] = cd{pYr[2 * k], pYr[2 * k + 1]};
+        nx.Yt[k] = cd{nYt[2 * k], nYt[2 * k + 1]}; nx.Yr[k] = cd{nYr[2 * k], nYr[2 * k + 1]};
+        nx.P[k] = cd{P[2 * k], P[2 * k + 1]}; nx.Q[k] = cd{Q[2 * k], Q[2 * k + 1]};
+        d[k] = cd{D[2 * k], D[2 * k + 1]}; u[k] = cd{U[2 * k], U[2 * k + 1]};
+    }
+    interface_fb<true>(a, b, nx, d, u, o);
+    for (int k = 0; k < 4; ++k) { put(D + 2 * k, d[k]); put(U + 2 * k, u[k]); put(out + 2 * k, o[k]); }
+    return 0;
+}
+
 // Eigen-solver path counters since the last reset: {roots, newton steps, quadratic-model steps, recentres, collapsed
 // pairs, Vieta checks, fallbacks}.
 int hostsim_solver_stats(long* out, int reset) {

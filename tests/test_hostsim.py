@@ -158,6 +158,34 @@ def test_hot_path_elementary_functions(sim):
     assert np.isfinite(out).all()
 
 
+def test_interface_step_and_nan_to_num(sim):
+    """interface_fb: the field-basis interface step against NumPy on random blocks, and its numpy.nan_to_num slow path
+    (layerstack.py:101-127) on a singular interface (Yt' = Yr: the matrix to invert is exactly zero) and on inf input."""
+    rng = np.random.default_rng(11)
+    blk = lambda: rng.standard_normal((2, 2)) + 1j * rng.standard_normal((2, 2))
+
+    def step(pYt, pYr, nYt, nYr, P, Q, D, U):
+        D = np.ascontiguousarray(D, dtype=np.complex128).copy(); U = np.ascontiguousarray(U, dtype=np.complex128).copy()
+        out = np.zeros((2, 2), dtype=np.complex128)
+        args = [np.ascontiguousarray(x, dtype=np.complex128) for x in (pYt, pYr, nYt, nYr, P, Q)]
+        assert sim.hostsim_interface_fb(*[_P(x) for x in args], _P(D), _P(U), _P(out)) == 0
+        return out, D, U
+
+    for _ in range(20):
+        pYt, pYr, nYt, nYr, P, Q, D, U = (blk() for _ in range(8))
+        M = np.linalg.inv(nYt - pYr)
+        V = M @ (pYt - nYt) @ D
+        want = (U @ V, P @ (D + V), U @ M @ (nYt - nYr) @ Q)
+        got = step(pYt, pYr, nYt, nYr, P, Q, D, U)
+        for g, w in zip(got, want):
+            assert np.abs(g - w).max() < 1e-12 * max(1.0, np.abs(w).max())
+    pYt, pYr, nYr, P, Q, D, U = (blk() for _ in range(7))
+    for bad in (step(pYt, pYr, pYr.copy(), nYr, P, Q, D, U),                       # singular: 1/0
+                step(pYt, pYr, blk(), nYr, P * np.inf, Q, D, U)):                   # inf in the propagator
+        for g in bad:
+            assert np.isfinite(g.view(np.float64)).all()
+
+
 def test_layer_phases_thin_and_thick_layers(sim):
     """layer_phases (one full exp(i k0 q0 d) + three small-argument corrections for thin layers, four full evaluations
     otherwise) against exp() in extended precision: K^-1 / K diagonals of layer.py:96-97."""
