@@ -250,11 +250,51 @@ def eig_factored(eps, mu, zeta, n_iter=3):
         roots = _mslp_step_pair(a, b, c, d, da, db, dc, dd)
         for r in range(2):
             q = qc + roots[r]
-            for _ in range(n_iter):
+            for it in range(40):
                 (a, b, c, d), (da, db, dc, dd) = wave_matrix(eps, mu, zeta, q)
-                q = q + _mslp_step_single(a, b, c, d, da, db, dc, dd)
+                h = _mslp_step_single(a, b, c, d, da, db, dc, dd)
+                q = q + h
+                # n_iter steps always (quadratic convergence from the pair step on ordinary media); more only while some
+                # element is still moving (grazing incidence, where the pair step is a poor start)
+                if it + 1 >= n_iter and not (np.abs(h) > 1e-17 * np.abs(q)).any():
+                    break
             out[..., 2 * pair + r] = q
-    return out
+    return _repair_unseparated_pairs(out, eps, mu, zeta)
+
+
+def _repair_unseparated_pairs(out, eps, mu, zeta):
+    """The pair seeding above assumes the transmitted and the reflected pair are far apart compared with their
+    splittings.  Near grazing incidence / for very strong anisotropy that fails (two starts end on one root).  Vieta's
+    relations expose it: det N(q) is a quartic c4 q^4 + ... + c0, so the roots must multiply to c0/c4 and sum to
+    -c3/c4.  Elements that violate them are recomputed from scratch: coefficients by interpolating det N at five points,
+    numpy.roots for starting values, then entry-wise MSLP polishing in the working precision (same accuracy argument as
+    above -- the coefficients only provide the starting points)."""
+    shp = out.shape[:-1]
+    flat = out.reshape(-1, 4)
+    epsf = np.broadcast_to(eps, shp + (3, 3)).reshape(-1, 3, 3)
+    xs = np.array([0.0, 1.0, -1.0, 2.0, -2.0])
+    vinv = np.linalg.inv(np.vander(xs, 5).astype(np.complex128))
+    ys = []
+    for x in xs:
+        (a, b, c, d), _ = wave_matrix(epsf, mu, zeta, np.full(epsf.shape[0], x, dtype=out.dtype))
+        ys.append((a * d - b * c).astype(np.complex128))
+    coef = np.einsum('ij,jn->ni', vinv, np.array(ys))              # (n, 5): c4 ... c0
+    prod_want = coef[:, 4] / coef[:, 0]
+    sum_want = -coef[:, 1] / coef[:, 0]
+    fl = flat.astype(np.complex128)
+    scale = np.abs(fl).max(axis=1) + 1e-300
+    bad = (np.abs(fl.prod(axis=1) - prod_want) > 1e-8 * scale ** 4) | (np.abs(fl.sum(axis=1) - sum_want) > 1e-8 * scale)
+    bad |= ~np.isfinite(fl).all(axis=1)
+    for i in np.nonzero(bad)[0]:
+        r0 = np.roots(coef[i])
+        e1 = epsf[i:i + 1]
+        for k in range(4):
+            q = np.array([r0[k]], dtype=out.dtype)
+            for _ in range(10):
+                (a, b, c, d), (da, db, dc, dd) = wave_matrix(e1, mu, zeta, q)
+                q = q + _mslp_step_single(a, b, c, d, da, db, dc, dd)
+            flat[i, k] = q[0]
+    return flat.reshape(out.shape)
 
 
 def _G(a, b, c, d, da, db, dc, dd):

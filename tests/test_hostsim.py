@@ -121,6 +121,35 @@ def _roots_fast(lib, os_, f, alpha):
     return out
 
 
+def _solver_stats(lib, reset=True):
+    a = (ctypes.c_long * 7)()
+    assert lib.hostsim_solver_stats(a, 1 if reset else 0) == 0
+    return dict(zip('roots newton quad recentre collapsed vieta fallback'.split(), list(a)))
+
+
+def test_eigen_solver_stays_on_its_straight_path_for_ice(sim):
+    """Path counters of the hot-path eigen-solver on ordinary ice (the benchmark regime): the second mode pair starts
+    from Vieta's relations, so a layer costs ~6 Newton steps (2 + 2 + 1 + 1), an MSLP step only for coincident roots, never a
+    Vieta product check or the Aberth fallback; at grazing incidence the product check (and, if needed, the fallback) takes over."""
+    from tamm_b200 import profiles
+    nlm, z = profiles.tilted(60, 400, seed=1)
+    os_ = orc.OracleStack(nlm, z, N_frames=19)
+    for alpha_deg in (5.0, 10.0, 30.0):
+        _solver_stats(sim)
+        _roots_fast(sim, os_, 179e6, np.deg2rad(alpha_deg))
+        st = _solver_stats(sim)
+        assert st['roots'] == 4 * 60 * 19
+        # (the isotropic top layer of the profile has coincident roots: those take MSLP steps by design)
+        assert st['quad'] <= 0.02 * st['roots'] and st['vieta'] == 0 and st['fallback'] == 0, st
+        assert 1.4 < st['newton'] / st['roots'] < 1.6, st
+    _solver_stats(sim)
+    got = _roots_fast(sim, os_, 179e6, np.deg2rad(88.0))
+    st = _solver_stats(sim)
+    assert st['vieta'] + st['fallback'] > 0, st
+    want = os_.layers(179e6, np.deg2rad(88.0))['qs_unsorted']
+    assert np.abs(np.sort_complex(got) - np.sort_complex(want)).max() < 5e-14
+
+
 @pytest.mark.parametrize('alpha_deg', [0.0, 10.0, 40.0])
 def test_eigen_solver_near_degenerate_and_strong_anisotropy(sim, alpha_deg):
     """Roots of the hot-path eigen-solver against the extended-precision roots for mode splittings |q_p - q_s| from
@@ -139,6 +168,32 @@ def test_eigen_solver_near_degenerate_and_strong_anisotropy(sim, alpha_deg):
             want = np.sort_complex(L['qs_unsorted'].astype(np.complex128))
             assert np.isfinite(got.view(np.float64)).all(), (deps, sc)
             assert np.abs(got - want).max() < tol, (deps, sc, np.abs(got - want).max())
+
+
+def test_eigen_solver_sweep_to_grazing_incidence(sim):
+    """Random tilted fabrics, ice-like and strongly anisotropic, from near-normal to grazing incidence: the roots of the
+    hot-path solver (pair solve, Vieta start, product check, Aberth fallback -- whichever applies) against the
+    extended-precision roots, matched as sets (sorting complex numbers is ambiguous for evanescent modes)."""
+    import itertools
+    from tamm_b200 import profiles
+    perms = np.array(list(itertools.permutations(range(4))))
+    worst = 0.0
+    for seed in (4, 5):
+        base, z = profiles.tilted(30, 200, seed=seed)
+        for deps in (0.034, 1.2):
+            for sc in (1.0, 0.1):
+                nlm = base.copy()
+                nlm[:, 1:] *= sc
+                os_ = orc.OracleStack(nlm, z, N_frames=5, epsa=[3.17 - deps], epsc=[3.17])
+                for a in (5.0, 45.0, 75.0, 84.0, 87.0, 89.5):
+                    alpha = np.deg2rad(a)
+                    got = _roots_fast(sim, os_, 179e6, alpha)
+                    want = os_.layers(179e6, alpha, eig='factored', precision='extended')['qs_unsorted']
+                    want = want.astype(np.complex128)
+                    err = np.abs(got[..., perms] - want[..., None, :]).max(-1).min(-1).max()
+                    assert err < 5e-14, (seed, deps, sc, a, err)
+                    worst = max(worst, err)
+    assert worst > 0.0
 
 
 def test_hot_path_elementary_functions(sim):
