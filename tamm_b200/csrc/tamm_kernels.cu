@@ -44,6 +44,9 @@ int fail(const char* fmt, const char* a = "", long b = 0) {
 #ifndef TAMM_DEFAULT_VARIANT
 #define TAMM_DEFAULT_VARIANT 5
 #endif
+#ifndef TAMM_RETURNS_TMA_DEFAULT
+#define TAMM_RETURNS_TMA_DEFAULT 0
+#endif
 
 constexpr int TL = 16;     // layers per TMA sub-tile (16 * 80 B = 1280 B per profile)
 constexpr int CARRY_SLOTS = 34;   // 16-byte shared-memory slots per thread of stack_kernel (carry state + mode scratch)
@@ -612,6 +615,139 @@ returns_fused_kernel(const cd* __restrict__ planes, const cd* __restrict__ pre, 
     }
 }
 
+// The same kernel fed by the TMA engine (F <= 256): the four plane rows of a depth (F x 16 B each, contiguous in the
+// planes layout) are bulk-copied global->shared into a ring of 2 * TNF depth stages, each with its own mbarrier, so the
+// loads in flight cost no registers and do not depend on how many warps are resident.  While group g (TNF depths) is
+// processed, group g+1 is already in flight; after the group's last CTA barrier thread 0 refills the stages it used
+// with group g+2.
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK, (BLOCK <= 128 ? 3 : (BLOCK <= 192 ? 2 : 1)))
+returns_tma_kernel(const cd* __restrict__ planes, const cd* __restrict__ pre, int N, int Q, int F, int mode, int chunk,
+                   int nchunks, cd e0, cd e1, int gtm_phase, cd* __restrict__ E_HH, cd* __restrict__ E_HV,
+                   cd* __restrict__ c_HHVV, double* __restrict__ dP_HH, double* __restrict__ dP_HV,
+                   double* __restrict__ Pm_HH, double* __restrict__ Pm_HV) {
+    static_assert(TNF == 4, "warp_sum8 reduces 2 * TNF = 8 values");
+    constexpr int NW = BLOCK / 32;
+    constexpr int NST = 2 * TNF;                        // depth stages in the ring
+    extern __shared__ double2 ring[];                   // [NST][4][BLOCK] complex128
+    __shared__ alignas(8) uint64_t bar[NST];
+    __shared__ double red[NW][2 * TNF];
+    __shared__ double tot[2 * TNF];
+    const int NI = N - 1, QF = Q * F;
+    const int p = blockIdx.z, iq = blockIdx.y;
+    const int ifr = threadIdx.x;
+    const bool live = ifr < F;
+    const int col = live ? ifr : F - 1;
+    const int l = iq * F + col;
+    const int nbeg = blockIdx.x * (TNF * TNG);
+    const int ne = min(NI, nbeg + TNF * TNG);
+    const uint32_t row_bytes = (uint32_t)F * (uint32_t)sizeof(cd);
+    const cd* src0 = planes + ((size_t)p * NI * 4) * QF + (size_t)iq * F;     // row (n, comp) starts at + (4 n + comp) QF
+    size_t o = (((size_t)p * Q + iq) * NI + nbeg) * F + col;                   // output element of depth nbeg
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < NST; ++s) mbar_init(&bar[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int n = nbeg; n < min(ne, nbeg + NST); ++n) {
+            const int s = n - nbeg;
+            mbar_expect_tx(&bar[s], 4 * row_bytes);
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                tma_bulk_g2s(ring + ((size_t)s * 4 + c) * BLOCK, src0 + ((size_t)n * 4 + c) * QF, row_bytes, &bar[s]);
+        }
+    }
+    cd Dp[4], Up[4];
+    int cc = -1;
+#pragma unroll 1
+    for (int nb = nbeg; nb < ne; nb += TNF) {
+        double amp[2 * TNF];
+        const int g = (nb - nbeg) / TNF;               // group index within the CTA
+        const int sbase = (g & 1) * TNF;               // its stages
+        const uint32_t parity = (uint32_t)((g >> 1) & 1);
+#pragma unroll
+        for (int k = 0; k < TNF; ++k) {
+            const int n = nb + k;
+            amp[2 * k] = 0.0; amp[2 * k + 1] = 0.0;
+            if (n < ne) {
+                mbar_wait(&bar[sbase + k], parity);
+                const double2* st = ring + (size_t)(sbase + k) * 4 * BLOCK + col;
+                cd m[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) { const double2 v = st[c * BLOCK]; m[c] = cd{v.x, v.y}; }
+                if (nchunks > 1) {
+                    const int c = n / chunk;
+                    if (c != cc) { load_prefix(pre, (size_t)p * QF + l, nchunks, c, Dp, Up); cc = c; }
+                    if (c > 0) {
+                        cd t[4];
+                        if (mode == TAMM_MODE_URD) { mm22(m, Dp, t); mm22(Up, t, m); }
+                        else { mm22(Up, m, t); m[0] = t[0]; m[1] = t[1]; m[2] = t[2]; m[3] = t[3]; }
+                    }
+                }
+                const cd hh = dot2(m[0], e0, m[1], e1);    // get_Rx_all (layerstack.py:298)
+                const cd hv = dot2(m[2], e0, m[3], e1);
+                const cd num = cmul_(m[0], conj(m[3]));    // c_HHVV (layerstack.py:271-278): num / (|m0| |m3|)
+                const double iden = tamm::frsqrt(abs2(m[0]) * abs2(m[3]));
+                cd c = cd{num.re * iden, num.im * iden};
+                if (gtm_phase) c = cd{-c.re, c.im};
+                if (live) {
+                    st_cd(E_HH + o, hh);
+                    st_cd(E_HV + o, hv);
+                    st_cd(c_HHVV + o, c);
+                    amp[2 * k] = tamm::fsqrt(abs2(hh));
+                    amp[2 * k + 1] = tamm::fsqrt(abs2(hv));
+                }
+            }
+            o += F;
+        }
+        {
+            const double r = warp_sum8(amp, lane);
+            if ((lane & 3) == 0) red[w][((lane >> 4) & 1) | (((lane >> 3) & 1) << 1) | (((lane >> 2) & 1) << 2)] = r;
+        }
+        __syncthreads();      // every thread has read this group's stages
+        if (threadIdx.x == 0) {
+            // refill them with the group after next
+            for (int k = 0; k < TNF; ++k) {
+                const int n = nb + k + NST;
+                if (n < ne) {
+                    mbar_expect_tx(&bar[sbase + k], 4 * row_bytes);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        tma_bulk_g2s(ring + ((size_t)(sbase + k) * 4 + c) * BLOCK, src0 + ((size_t)n * 4 + c) * QF, row_bytes,
+                                     &bar[sbase + k]);
+                }
+            }
+        }
+        if (threadIdx.x < 2 * TNF) {
+            double sum = 0.0;
+#pragma unroll
+            for (int i = 0; i < NW; ++i) sum += red[i][threadIdx.x];
+            const double pm = 20.0 * log10(sum / (double)F);
+            tot[threadIdx.x] = pm;
+            const int k = threadIdx.x >> 1, n = nb + k;
+            if (n < ne) {
+                const size_t row = ((size_t)p * Q + iq) * NI + n;
+                if (threadIdx.x & 1) Pm_HV[row] = pm; else Pm_HH[row] = pm;
+            }
+        }
+        __syncthreads();
+        if (live) {
+            size_t od = o - (size_t)TNF * F;
+#pragma unroll
+            for (int k = 0; k < TNF; ++k) {
+                if (nb + k < ne) {
+                    dP_HH[od] = 20.0 * log10_dev(amp[2 * k]) - tot[2 * k];      // layerstack.py:261-267
+                    dP_HV[od] = 20.0 * log10_dev(amp[2 * k + 1]) - tot[2 * k + 1];
+                }
+                od += F;
+            }
+        }
+    }
+}
+
 // one warp per (p, iq, n): azimuth mean of |E|, dB, anomaly (layerstack.py:257-267).  a* hold |E| on entry, dP on exit.
 __global__ void __launch_bounds__(256)
 power_kernel(double* __restrict__ aHH, double* __restrict__ aHV, double* __restrict__ Pm_HH, double* __restrict__ Pm_HV,
@@ -955,6 +1091,30 @@ int tamm_returns(const void* planes, const void* workspace, int P, int N, int Q,
 #define TAMM_RF(BLK)                                                                                                     \
     returns_fused_kernel<BLK><<<grid, BLK, 0, s>>>((const cd*)planes, pre, N, Q, F, mode, chunk, nch, e0, e1, gtm_phase, \
                                                    (cd*)E_HH, (cd*)E_HV, (cd*)c_HHVV, dP_HH, dP_HV, Pm_HH, Pm_HV)
+        // TMA-fed variant (rows must be 16-byte multiples: always true for complex128); TAMM_RETURNS_TMA=0 disables it
+        static int use_tma = -1;
+        if (use_tma < 0) { const char* ev = getenv("TAMM_RETURNS_TMA"); use_tma = ev ? atoi(ev) : TAMM_RETURNS_TMA_DEFAULT; }
+#define TAMM_RT(BLK)                                                                                                     \
+    do {                                                                                                                 \
+        const int dyn = 2 * TNF * 4 * BLK * (int)sizeof(double2);                                                        \
+        static bool attr_set = false;                                                                                    \
+        if (!attr_set) {                                                                                                 \
+            CUDA_OK(cudaFuncSetAttribute(returns_tma_kernel<BLK>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));    \
+            attr_set = true;                                                                                             \
+        }                                                                                                                \
+        returns_tma_kernel<BLK><<<grid, BLK, dyn, s>>>((const cd*)planes, pre, N, Q, F, mode, chunk, nch, e0, e1,        \
+                                                       gtm_phase, (cd*)E_HH, (cd*)E_HV, (cd*)c_HHVV, dP_HH, dP_HV,      \
+                                                       Pm_HH, Pm_HV);                                                    \
+    } while (0)
+        if (use_tma && F <= 256) {
+            if (F <= 64) TAMM_RT(64);
+            else if (F <= 128) TAMM_RT(128);
+            else if (F <= 192) TAMM_RT(192);
+            else TAMM_RT(256);
+            CUDA_OK(cudaGetLastError());
+            return 0;
+        }
+#undef TAMM_RT
         if (F <= 64) TAMM_RF(64);
         else if (F <= 128) TAMM_RF(128);
         else if (F <= 192) TAMM_RF(192);

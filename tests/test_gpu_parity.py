@@ -399,3 +399,24 @@ def test_unusual_regimes(eng, name, kw, alpha_deg):
     want = orc.OracleStack(nlm, z, N_frames=33, **kw).get_URD(179e6, alpha)
     assert np.isfinite(got.view(np.float64)).all()
     assert h.peak_rel_err(got, want, axis=(1, 2, 3)) < h.RTOL_COMPLEX
+
+
+def test_returns_tma_variant_matches_reference_fixture(built):
+    """The TMA-fed variant of the fused returns kernel (TAMM_RETURNS_TMA=1, read once per process -> own interpreter):
+    same returns as the default kernel, checked against the reference fixtures."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import sys, numpy as np\n"
+        "sys.path[:0] = %r\n"
+        "import helpers as h, layerstack as ls\n"
+        "for name in ('demo_a10', 'tilted_a10', 'rathmann_t4_a10'):\n"
+        "    g = h.load_golden(name)\n"
+        "    s = ls.LayerStack(g['nlm'], g['z'], N_frames=int(g['F']), VERBOSE=0, modeltype=h.modeltype(g), **h.stack_kwargs(g))\n"
+        "    got = s.get_returns(float(g['E0']), f=float(g['f']), alpha=float(g['alpha']), **h.returns_kwargs(g))\n"
+        "    h.assert_parity(got, [g['ret_' + n] for n in h.RET_NAMES], None, c_atol=1e-7)\n"
+        "print('tma variant ok')\n") % ([p for p in sys.path if p],)
+    env = dict(os.environ, TAMM_RETURNS_TMA='1')
+    r = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and 'tma variant ok' in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
