@@ -420,3 +420,35 @@ def test_returns_tma_variant_matches_reference_fixture(built):
     env = dict(os.environ, TAMM_RETURNS_TMA='1')
     r = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and 'tma variant ok' in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_config4_ensemble_launch_full_shape(eng):
+    """configs[4] at the shape bench.py launches (128 profiles x 5000 layers x 181 azimuths per launch, alpha = 10 deg)
+    through the public batched API: (1) first, middle and last profile of the launch against the oracle on a 12-azimuth
+    subset of the grid, all 4999 interfaces; (2) size-independent identities that tie the power returns to the fields for
+    EVERY profile of the launch: Pm = dB(mean_beta |E|), dP = dB|E| - Pm (layerstack.py:257-267), |c_HHVV| = 1
+    (layerstack.py:271-278)."""
+    from tamm_b200 import EnsembleStack
+    P, N, F = 128, 5000, 181
+    nlm, z = profiles.ensemble(P, N)
+    alpha = np.deg2rad(10.0)
+    ens = EnsembleStack(nlm, z, N_frames=F)
+    got = ens.get_returns(1e3, f=179e6, alpha=alpha, batch=P)
+    assert got['E_HH'].shape == (P, N - 1, F) and got['Pm_HH'].shape == (P, N - 1)
+    for n in h.RET_NAMES:
+        assert np.isfinite(got[n].view(np.float64)).all(), n
+    idx = np.linspace(0, F - 1, 12).round().astype(int)
+    for p in (0, P // 2 + 1, P - 1):
+        st = orc.OracleStack(nlm[p], z, N_frames=F)
+        want = orc.returns_from_URD(st.get_URD(179e6, alpha, beta=st.beta[idx]), 1e3)
+        for name, k in (('E_HH', 5), ('E_HV', 6)):
+            assert h.peak_rel_err(got[name][p][:, idx], want[k], axis=0) < h.RTOL_COMPLEX, (name, p)
+        # unit-modulus coherence = element-wise relative error of URD_hh, URD_vv; 5000 interfaces deep the weakest ones are
+        # 1e2 below the per-azimuth peak, so the bound is 10x the fixtures' (host simulator vs oracle: 1.4e-7)
+        assert np.abs(got['c_HHVV'][p][:, idx] - want[4]).max() < 10 * C_HHVV_ATOL, p
+    for name in ('HH', 'HV'):
+        amp = np.abs(got['E_' + name])
+        pm = 20 * np.log10(amp.mean(axis=2))
+        assert np.abs(got['Pm_' + name] - pm).max() < h.ATOL_DB, name
+        assert np.abs(got['dP_' + name] - (20 * np.log10(amp) - pm[:, :, None])).max() < h.ATOL_DB, name
+    assert np.abs(np.abs(got['c_HHVV']) - 1).max() < 1e-12
