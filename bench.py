@@ -359,8 +359,48 @@ def main():
             line['gather'] = dict(what=args.gather, arrays=names, bytes_per_rank=nbytes, ms=float(gm.item()),
                                   algbw_gbs=nbytes / (float(gm.item()) * 1e-3) / 1e9, included_in_value=False,
                                   value_with_gather=evals_job / ((ms_per_step + float(gm.item())) * 1e-3))
+            # the same gather cut into one collective per profile block and overlapped with the kernels of the next block
+            # (SURVEY.md 8e mitigation; tamm_b200.distributed.PipelinedGather): a whole step = compute + gather, timed
+            # with CUDA events on the compute stream after it has waited for the last collective, max over ranks
+            if Pl % B == 0 and P % (world * B) == 0:
+                pgs = {n: tdist.PipelinedGather(P, B, tuple(out[n].shape[1:]), out[n].dtype, dev) for n in names}
+
+                def step_gather():
+                    for bi, b0 in enumerate(range(0, Pl, B)):
+                        res = eng.stack(layers_d[b0:b0 + B], lanes_d, B, N, 1, F, zeta, 1.0, MODE_URD, planes=planes)
+                        eng.returns(res, etx, True, out={k: v[b0:b0 + B] for k, v in out.items()})
+                        for n in names:
+                            pgs[n].submit(bi, out[n][b0:b0 + B])
+                    for n in names:
+                        pgs[n].wait()
+                step_gather()
+                sync_all()
+                ksteps = max(1, min(args.steps, 3))
+                p0 = torch.cuda.Event(enable_timing=True); p1 = torch.cuda.Event(enable_timing=True)
+                p0.record()
+                for _ in range(ksteps):
+                    step_gather()
+                p1.record()
+                sync_all()
+                pm = torch.tensor([p0.elapsed_time(p1) / ksteps], dtype=torch.float64, device=dev)
+                dist.all_reduce(pm, op=dist.ReduceOp.MAX)
+                # check: every rank's block of round 0 must have arrived here (checksums exchanged by all-reduce)
+                asreal = lambda t: torch.view_as_real(t) if t.is_complex() else t
+                sums = torch.zeros(world, dtype=torch.float64, device=dev)
+                sums[rank] = asreal(out[names[0]][:B]).abs().sum()
+                dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+                full0 = pgs[names[0]].full
+                got_s = torch.stack([asreal(full0[r * B: (r + 1) * B]).abs().sum() for r in range(world)])
+                ok = ((got_s - sums).abs() <= 1e-12 * sums.abs()).all().to(torch.float64).reshape(1)
+                ok = ok * float(torch.equal(full0[rank * B: (rank + 1) * B], out[names[0]][:B]))
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+                line['gather'].update(pipelined_ms_per_step=float(pm.item()), pipelined_steps=ksteps,
+                                      value_pipelined=evals_job / (float(pm.item()) * 1e-3),
+                                      pipelined_check=bool(ok.item() == 1.0),
+                                      pipelined_layout='block-cyclic: round b of rank r = profiles (b*world + r)*%d ...' % B)
+                del pgs
         except Exception as e:
-            line['gather'] = dict(what=args.gather, error=repr(e)[:200])
+            line.setdefault('gather', {}).update(what=args.gather, error=repr(e)[:200])
 
     if rank == 0:
         line['clocks'] = sampler.summary()

@@ -62,6 +62,53 @@ def all_gather_profiles(local, P_total, group=None):
     return torch.view_as_complex(full.contiguous()) if cplx else full
 
 
+def block_cyclic_profiles(P_total, B, rank, ws):
+    """Profile indices held by `rank` when blocks of B profiles are dealt round-robin over the ranks: round b gives block
+    b*ws + rank to `rank`.  With this assignment the per-round all-gathers of `PipelinedGather` land in natural profile
+    order.  Requires P_total % (ws * B) == 0."""
+    if P_total % (ws * B):
+        raise ValueError('block-cyclic sharding needs P_total (=%d) divisible by world x block (=%d x %d)' % (P_total, ws, B))
+    rounds = P_total // (ws * B)
+    return np.concatenate([np.arange((b * ws + rank) * B, (b * ws + rank + 1) * B) for b in range(rounds)])
+
+
+class PipelinedGather:
+    """The final all-gather of SURVEY.md 8(e), cut into one collective per profile block and overlapped with the kernels
+    of the next block: `submit(b, block)` enqueues the all-gather of this rank's block of round b on the communication
+    stream (it starts when the producing kernels on the current stream have finished and does not block the current
+    stream), `wait()` makes the current stream wait for everything submitted.  `full` is the gathered tensor
+    (P_total, ...): round b of rank r is profiles (b*ws + r)*B ... (see `block_cyclic_profiles`)."""
+
+    def __init__(self, P_total, B, tail_shape, dtype, device, group=None):
+        import torch
+        import torch.distributed as dist
+        self.group = group
+        self.ws = dist.get_world_size(group) if dist.is_initialized() else 1
+        if P_total % (self.ws * B):
+            raise ValueError('PipelinedGather needs P_total (=%d) divisible by world x block (=%d x %d)' % (P_total, self.ws, B))
+        self.B, self.rounds = B, P_total // (self.ws * B)
+        self.full = torch.empty((P_total,) + tuple(tail_shape), dtype=dtype, device=device)
+        flat = torch.view_as_real(self.full) if self.full.is_complex() else self.full     # NCCL moves raw doubles
+        self._rounds = flat.view((self.rounds, self.ws * B) + tuple(flat.shape[1:]))
+        self._pending = []
+
+    def submit(self, b, block):
+        import torch
+        import torch.distributed as dist
+        assert block.shape[0] == self.B and 0 <= b < self.rounds
+        x = torch.view_as_real(block) if block.is_complex() else block
+        if self.ws == 1:
+            self._rounds[b].copy_(x)
+            return
+        self._pending.append(dist.all_gather_into_tensor(self._rounds[b], x.contiguous(), group=self.group, async_op=True))
+
+    def wait(self):
+        for w in self._pending:
+            w.wait()
+        self._pending = []
+        return self.full
+
+
 def all_reduce_azimuth_sums(sums, group=None):
     """For the alternative azimuth sharding of a single profile (configs[1], [3]): the per-depth sums of |E| over the
     local azimuths are summed over ranks before the dB step (layerstack.py:262).  Tiny: (N-1) x 2 doubles."""

@@ -1,6 +1,6 @@
 """The N > 1 path on CPU: two gloo ranks shard an ensemble by profile, each computes its shard with the (test-only) host
 simulator of the kernels, and the all-gather reassembles exactly what one rank computes alone.  Also covers the azimuth
-sharding + all-reduce alternative and the shard arithmetic."""
+sharding + all-reduce alternative, the block-cyclic pipelined gather and the shard arithmetic."""
 import os
 import socket
 import subprocess
@@ -70,6 +70,24 @@ WORKER = textwrap.dedent('''
     sums = all_reduce_azimuth_sums(torch.from_numpy(amp.sum(axis=0))).numpy()
     ref = np.abs(1e3 * urd_of(one, 0, 1, one.beta)[0][:, :, 0, 0])
     assert np.allclose(20 * np.log10(sums / F), 20 * np.log10(ref.mean(axis=0)), rtol=0, atol=1e-12)
+
+    # (3) block-cyclic sharding + pipelined (per-block, asynchronous) all-gather lands in natural profile order
+    from tamm_b200.distributed import PipelinedGather, block_cyclic_profiles
+    Pt, B = 8, 2
+    mine = block_cyclic_profiles(Pt, B, rank, ws)
+    assert list(mine) == ([0, 1, 4, 5] if rank == 0 else [2, 3, 6, 7])
+    table = (np.arange(Pt)[:, None, None] * 100 + np.arange(3)[None, :, None] * 10 + np.arange(4)[None, None, :]) * (1 + 0.5j)
+    for dtype, src in ((torch.complex128, table), (torch.float64, table.real.copy())):
+        loc = torch.from_numpy(src[mine])
+        pg = PipelinedGather(Pt, B, (3, 4), dtype, 'cpu')
+        for b in range(pg.rounds):
+            pg.submit(b, loc[b * B:(b + 1) * B])
+        assert np.array_equal(pg.wait().numpy(), src)
+    try:
+        PipelinedGather(7, B, (3, 4), torch.float64, 'cpu')
+        raise SystemExit('ragged ensemble accepted')
+    except ValueError:
+        pass
     dist.barrier()
     dist.destroy_process_group()
     open(os.path.join(%(out)r, 'rank%%d.ok' %% rank), 'w').write('ok')
