@@ -41,6 +41,9 @@ int fail(const char* fmt, const char* a = "", long b = 0) {
         if (e_ != cudaSuccess) return fail("%s (CUDA error %ld)", cudaGetErrorString(e_), (long)e_); \
     } while (0)
 
+// Q * F is an int everywhere below: refuse lane counts that do not fit
+inline bool lanes_fit(int Q, int F) { return (long)Q * (long)F <= 2147483647L; }
+
 #ifndef TAMM_DEFAULT_VARIANT
 #define TAMM_DEFAULT_VARIANT 5
 #endif
@@ -981,6 +984,7 @@ int tamm_stack_urd(const double* layers, const double* lanes, int P, int N, int 
     if (!aligned16(layers) || !aligned16(lanes) || !aligned16(planes) || !aligned16(workspace))
         return fail("tamm_stack_urd: buffers must be 16-byte aligned%s", "");
     if (!(mu != 0.0)) return fail("tamm_stack_urd: mu must be non-zero%s", "");
+    if (!lanes_fit(Q, F)) return fail("tamm_stack_urd: Q * F does not fit an int%s", "");
     const int QF = Q * F;
     const int nch = nchunks_of(N, chunk);
     if (nch > 65535) return fail("tamm_stack_urd: grid too large (chunks > 65535)%s", "");
@@ -1046,6 +1050,7 @@ int tamm_stack_urd_fp(const double* layers_fp, const double* lanes, int P, int N
     if (N < 2) return fail("tamm_stack_urd_fp: need at least 2 layers (N=%s%ld)", "", N);
     if (chunk < 1) return fail("tamm_stack_urd_fp: chunk must be >= 1%s", "");
     if (!aligned16(planes) || !aligned16(workspace)) return fail("tamm_stack_urd_fp: buffers must be 16-byte aligned%s", "");
+    if (!lanes_fit(Q, F)) return fail("tamm_stack_urd_fp: Q * F does not fit an int%s", "");
     const int QF = Q * F, nch = nchunks_of(N, chunk);
     if (nch > 65535) return fail("tamm_stack_urd_fp: grid too large (chunks > 65535)%s", "");
     if (nch > 1 && !workspace) return fail("tamm_stack_urd_fp: workspace required%s", "");
@@ -1066,7 +1071,7 @@ int tamm_stack_urd_fp(const double* layers_fp, const double* lanes, int P, int N
 int tamm_export_jones(const void* planes, const void* workspace, int P, int N, int Q, int F, int mode, int chunk, void* out,
                       void* stream) {
     if (!planes || !out) return fail("tamm_export_jones: null pointer%s", "");
-    if (P < 1 || N < 2 || Q < 1 || F < 1 || chunk < 1) return fail("tamm_export_jones: bad sizes%s", "");
+    if (P < 1 || N < 2 || Q < 1 || F < 1 || chunk < 1 || !lanes_fit(Q, F)) return fail("tamm_export_jones: bad sizes%s", "");
     const int QF = Q * F, NI = N - 1, nch = nchunks_of(N, chunk);
     const cd* pre = nch > 1 ? (const cd*)workspace + (size_t)P * QF * nch * 8 : nullptr;
     dim3 grid((QF + 127) / 128, (NI + TN - 1) / TN, P);
@@ -1080,7 +1085,7 @@ int tamm_returns(const void* planes, const void* workspace, int P, int N, int Q,
                  double* Pm_HV, void* stream) {
     if (!planes || !etx || !E_HH || !E_HV || !c_HHVV || !dP_HH || !dP_HV || !Pm_HH || !Pm_HV)
         return fail("tamm_returns: null pointer%s", "");
-    if (P < 1 || N < 2 || Q < 1 || F < 1 || chunk < 1) return fail("tamm_returns: bad sizes%s", "");
+    if (P < 1 || N < 2 || Q < 1 || F < 1 || chunk < 1 || !lanes_fit(Q, F)) return fail("tamm_returns: bad sizes%s", "");
     const int QF = Q * F, NI = N - 1, nch = nchunks_of(N, chunk);
     const cd* pre = nch > 1 ? (const cd*)workspace + (size_t)P * QF * nch * 8 : nullptr;
     cudaStream_t s = (cudaStream_t)stream;

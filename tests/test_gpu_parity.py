@@ -296,6 +296,8 @@ def test_two_layer_minimum_and_abi_errors(eng):
     assert lib.tamm_stack_urd(p, p, 1, 5, 1, 1, 0.0, 1.0, 7, 4, p, p, None, None) != 0       # bad mode
     assert lib.tamm_stack_urd(p, p, 1, 5, 1, 1, 0.0, 1.0, 0, 0, p, p, None, None) != 0       # bad chunk
     assert lib.tamm_stack_urd(p + 8, p, 1, 5, 1, 1, 0.0, 1.0, 0, 4, p, p, None, None) != 0   # misaligned
+    assert lib.tamm_stack_urd(p, p, 1, 5, 70000, 70000, 0.0, 1.0, 0, 4, p, p, None, None) != 0   # Q * F overflows int
+    assert b'Q * F' in lib.tamm_last_error()
     with pytest.raises(_lib.TammLibraryError):
         _lib.check(1, lib)
 
