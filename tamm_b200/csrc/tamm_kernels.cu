@@ -16,6 +16,7 @@
 //   returns_kernel + power_kernel   the same in two passes for other F.
 //   export_kernel       HBM bound.  Prefix fix-up + transpose into the reference's (F, N-1, 2, 2) layout.
 //   layer_diag_kernel   per-(lane, layer) matrices for the `Layer` attribute API and the parity tests.
+#include <atomic>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -990,11 +991,13 @@ int tamm_stack_urd(const double* layers, const double* lanes, int P, int N, int 
     if (nch > 65535) return fail("tamm_stack_urd: grid too large (chunks > 65535)%s", "");
     if (nch > 1 && !workspace) return fail("tamm_stack_urd: workspace required%s", "");
     // launch-bound variant (occupancy vs spills); TAMM_STACK_VARIANT overrides for experiments
-    static int variant = -1;
+    static std::atomic<int> variant_once{-1};
+    int variant = variant_once.load(std::memory_order_relaxed);
     if (variant < 0) {
         const char* ev = getenv("TAMM_STACK_VARIANT");
         variant = ev ? atoi(ev) : TAMM_DEFAULT_VARIANT;
         if (variant < 0 || variant > 5) variant = TAMM_DEFAULT_VARIANT;
+        variant_once.store(variant, std::memory_order_relaxed);
     }
     const int maxt = variant_threads(variant);
     int tb, flat;
@@ -1007,22 +1010,20 @@ int tamm_stack_urd(const double* layers, const double* lanes, int P, int N, int 
     const size_t dyn = (size_t)CARRY_SLOTS * sizeof(double2) * maxt;   // per-thread slots at the kernel's fixed stride
 #define TAMM_LAUNCH(MODE, MAXT, MINB)                                                                                   \
     do {                                                                                                                \
-        static bool attr_set = false;                                                                                   \
-        if (!attr_set) {                                                                                                \
+        /* the attribute is per device context: set it on every call (a few microseconds), not once per process */     \
+        if (mu == 1.0) {                                                                                                \
             CUDA_OK(cudaFuncSetAttribute(stack_kernel<MODE, MAXT, MINB, true>,                                          \
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,                                   \
                                          CARRY_SLOTS * (int)sizeof(double2) * MAXT));                                   \
+            stack_kernel<MODE, MAXT, MINB, true><<<grid, tb, dyn, s>>>(layers, lanes, P, N, QF, flat, zeta, mu, chunk,  \
+                                                                        nch, (cd*)planes, agg, status);                 \
+        } else {                                                                                                        \
             CUDA_OK(cudaFuncSetAttribute(stack_kernel<MODE, MAXT, MINB, false>,                                         \
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,                                   \
                                          CARRY_SLOTS * (int)sizeof(double2) * MAXT));                                   \
-            attr_set = true;                                                                                            \
-        }                                                                                                               \
-        if (mu == 1.0)                                                                                                  \
-            stack_kernel<MODE, MAXT, MINB, true><<<grid, tb, dyn, s>>>(layers, lanes, P, N, QF, flat, zeta, mu, chunk,  \
-                                                                        nch, (cd*)planes, agg, status);                 \
-        else                                                                                                            \
             stack_kernel<MODE, MAXT, MINB, false><<<grid, tb, dyn, s>>>(layers, lanes, P, N, QF, flat, zeta, mu, chunk, \
                                                                          nch, (cd*)planes, agg, status);                \
+        }                                                                                                               \
     } while (0)
     if (mode == TAMM_MODE_URD) {
         if (variant == 0) TAMM_LAUNCH(TAMM_MODE_URD, 256, 1);
@@ -1097,16 +1098,17 @@ int tamm_returns(const void* planes, const void* workspace, int P, int N, int Q,
     returns_fused_kernel<BLK><<<grid, BLK, 0, s>>>((const cd*)planes, pre, N, Q, F, mode, chunk, nch, e0, e1, gtm_phase, \
                                                    (cd*)E_HH, (cd*)E_HV, (cd*)c_HHVV, dP_HH, dP_HV, Pm_HH, Pm_HV)
         // TMA-fed variant (rows must be 16-byte multiples: always true for complex128); TAMM_RETURNS_TMA=0 disables it
-        static int use_tma = -1;
-        if (use_tma < 0) { const char* ev = getenv("TAMM_RETURNS_TMA"); use_tma = ev ? atoi(ev) : TAMM_RETURNS_TMA_DEFAULT; }
+        static std::atomic<int> use_tma_once{-1};
+        int use_tma = use_tma_once.load(std::memory_order_relaxed);
+        if (use_tma < 0) {
+            const char* ev = getenv("TAMM_RETURNS_TMA");
+            use_tma = (ev ? atoi(ev) : TAMM_RETURNS_TMA_DEFAULT) != 0;
+            use_tma_once.store(use_tma, std::memory_order_relaxed);
+        }
 #define TAMM_RT(BLK)                                                                                                     \
     do {                                                                                                                 \
         const int dyn = 2 * TNF * 4 * BLK * (int)sizeof(double2);                                                        \
-        static bool attr_set = false;                                                                                    \
-        if (!attr_set) {                                                                                                 \
-            CUDA_OK(cudaFuncSetAttribute(returns_tma_kernel<BLK>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));    \
-            attr_set = true;                                                                                             \
-        }                                                                                                                \
+        CUDA_OK(cudaFuncSetAttribute(returns_tma_kernel<BLK>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));        \
         returns_tma_kernel<BLK><<<grid, BLK, dyn, s>>>((const cd*)planes, pre, N, Q, F, mode, chunk, nch, e0, e1,        \
                                                        gtm_phase, (cd*)E_HH, (cd*)E_HV, (cd*)c_HHVV, dP_HH, dP_HV,      \
                                                        Pm_HH, Pm_HV);                                                    \
