@@ -248,6 +248,37 @@ class LayerStack:
         self.frm_layers = _LazyFrames(self, f if scalar_f else np.atleast_1d(f)[0], zeta)   # layerstack.py:286
         return returns
 
+    def get_returns_polarimetric(self, E0, f=179.0e6, alpha=0, URD='URD'):
+        """Extension: all four Tx/Rx pairs of layerstack.py:252-255 from ONE pass over the stack --
+        the reference computes E_VH, E_VV only when Tx_pol has a second entry and then drops them (254-255).
+        -> dict: E_xy, dP_xy, Pm_xy for xy in HH, HV (Tx = H = [1,0]) and VH, VV (Tx = V = [0,1]), plus c_HHVV; same
+        depth-major shapes as get_returns.  Equals get_returns(..., Tx_pol=([1,0],)) and get_returns(..., Tx_pol=([0,1],))."""
+        self.epsiso = (2 * self.epsa[0] + self.epsc[0]) / 3
+        zeta = np.sqrt(self.epsiso) * np.sin(alpha)
+        if URD == 'URD':
+            mode = MODE_URD
+        elif URD == 'U':
+            if self.modeltype != 'GTM':
+                raise ValueError('Only GTM model type supported')
+            mode = MODE_U
+        else:
+            raise ValueError('get_returns(): argument URD="%s" not understood' % (URD))
+        eng, res = self._run(self.beta, f, zeta, mode)
+        scalar_f = (np.ndim(f) == 0)
+        out = {}
+        for tx, pol in (('H', (1, 0)), ('V', (0, 1))):
+            E_Tx = np.array([E0 * pol[0], E0 * pol[1]], dtype=np.complex128)
+            dev = eng.returns(res, E_Tx, gtm_phase=(self.modeltype == 'GTM'))
+            for rx, col in (('H', 'HH'), ('V', 'HV')):        # the kernel's "HH"/"HV" are Rx = H / V of this Tx
+                for kind in ('E', 'dP', 'Pm'):
+                    a = dev['%s_%s' % (kind, col)].cpu().numpy()[0]
+                    out['%s_%s%s' % (kind, tx, rx)] = np.squeeze(a[0] if scalar_f else a)
+            if tx == 'H':
+                a = dev['c_HHVV'].cpu().numpy()[0]
+                out['c_HHVV'] = np.squeeze(a[0] if scalar_f else a)
+        self.frm_layers = _LazyFrames(self, f if scalar_f else np.atleast_1d(f)[0], zeta)
+        return out
+
     def get_Rx_all(self, E_Tx_list, URD, nn=None):
         """layerstack.py:291-301: received fields for each transmitted polarisation from caller-supplied URD."""
         Nl = self.N_layers - 1 if nn is None else 1

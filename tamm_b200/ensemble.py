@@ -89,7 +89,7 @@ class EnsembleStack:
         fa = np.atleast_1d(np.asarray(f, dtype=np.float64))
         Q, F, N, NI, Pl = fa.size, self.N_frames, self.N_layers, self.N_layers - 1, self.P_local
         zeta = self.zeta(alpha)
-        p = Tx_pol[0]
+        p = Tx_pol[0]                                                    # layerstack.py:249-252: only Tx_pol[0] is returned
         etx = np.array([E0 * p[0], E0 * p[1]], dtype=np.complex128)
         if batch is None:   # keep device buffers around 2 x 4 GiB
             batch = max(1, min(Pl, int(4 * 2 ** 30 // max(1, 64 * NI * Q * F))))
@@ -134,3 +134,17 @@ class EnsembleStack:
             res[n] = a[:, 0] if squeeze_q else a
         self._pinned = out
         return res
+
+    def get_returns_polarimetric(self, E0, f=179.0e6, alpha=0, URD='URD', batch=None):
+        """All four Tx/Rx pairs (layerstack.py:252-255; the reference drops E_VH, E_VV): two passes of `get_returns`
+        with Tx = H = [1, 0] and Tx = V = [0, 1].  -> dict E_xy, dP_xy, Pm_xy for xy in HH, HV, VH, VV and c_HHVV
+        (host arrays of the local shard; the stack is evaluated once per transmit polarisation)."""
+        out = {}
+        for tx, pol in (('H', [1, 0]), ('V', [0, 1])):
+            r = self.get_returns(E0, f=f, alpha=alpha, Tx_pol=(pol,), URD=URD, batch=batch)
+            for rx, col in (('H', 'HH'), ('V', 'HV')):
+                for kind in ('E', 'dP', 'Pm'):
+                    out['%s_%s%s' % (kind, tx, rx)] = r['%s_%s' % (kind, col)]
+            if tx == 'H':
+                out['c_HHVV'] = r['c_HHVV']
+        return out

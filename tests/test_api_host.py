@@ -119,3 +119,60 @@ def test_get_Rx_all_and_get_T_R_host_utilities():
     assert rx.shape == (4, 8, 4) and np.allclose(rx[:, :, 0], 1e3 * urd[:, :, 0, 0]) and np.allclose(rx[:, :, 3], 1e3 * urd[:, :, 1, 1])
     assert s.get_Rx_all(E, urd, nn=3).shape == (4, 1, 4)
     assert s.dB(10.0) == 20.0
+
+
+class _OracleEngine:
+    """Test double for tamm_b200.engine.Engine (CPU): the stack comes from the oracle, so that the HOST side of
+    lib/layerstack.py (argument handling, Tx/Rx naming, shapes, squeezing) is exercised without a GPU."""
+
+    def __init__(self, ostack, alpha):
+        self.o, self.alpha = ostack, alpha
+
+    def to_device(self, a):
+        return a
+
+    def stack(self, layers, lanes, P, N, Q, F, zeta, mu, mode):
+        import torch
+        from types import SimpleNamespace
+        fs = lanes[::F, 4] / (2 * np.pi)
+        urd = np.stack([self.o.get_URD(float(f), self.alpha, 'URD' if mode == 0 else 'U') for f in fs])   # (Q, F, NI, 2, 2)
+        return SimpleNamespace(urd=urd, P=1, Q=Q, F=F, N=N, status=torch.zeros(1, dtype=torch.int32))
+
+    def returns(self, res, etx, gtm_phase=True):
+        import torch
+        out = {k: [] for k in ('Pm_HH', 'Pm_HV', 'dP_HH', 'dP_HV', 'c_HHVV', 'E_HH', 'E_HV')}
+        for q in range(res.Q):
+            r = orc.returns_from_URD(res.urd[q], 1.0, Tx_pol=([etx[0], etx[1]],))
+            for k, a in zip(out, r):
+                out[k].append(a)
+        return {k: torch.from_numpy(np.stack(v)[None].copy()) for k, v in out.items()}     # (1, Q, NI[, F])
+
+
+def test_polarimetric_extension_host_side(monkeypatch):
+    """get_returns_polarimetric == two get_returns calls with Tx = H and Tx = V (layerstack.py:249-255), scalar and
+    vector f; host glue only (the device returns kernel is covered by the GPU suite)."""
+    ls, _, _ = _mods()
+    nlm, z = profiles.tilted(12, 60, seed=3)
+    alpha = 0.15
+    s = ls.LayerStack(nlm, z, N_frames=5, VERBOSE=0)
+    fake = _OracleEngine(orc.OracleStack(nlm, z, N_frames=5), alpha)
+    monkeypatch.setattr(ls, '_get_engine', lambda: fake)
+    for f in (179e6, np.array([150e6, 300e6])):
+        pol = s.get_returns_polarimetric(1e3, f=f, alpha=alpha)
+        h_ = s.get_returns(1e3, f=f, alpha=alpha, Tx_pol=([1, 0],))
+        v_ = s.get_returns(1e3, f=f, alpha=alpha, Tx_pol=([0, 1],))
+        names = ['Pm_%s', 'Pm_%s', 'dP_%s', 'dP_%s', 'c_HHVV', 'E_%s', 'E_%s']
+        rx = ['H', 'V', 'H', 'V', None, 'H', 'V']
+        for tx, ret in (('H', h_), ('V', v_)):
+            for n, r, a in zip(names, rx, ret):
+                if r is None:
+                    if tx == 'H':
+                        assert np.array_equal(pol['c_HHVV'], a)
+                    continue
+                got = pol[n % (tx + r)]
+                assert got.shape == a.shape and np.array_equal(got, a), (n, tx, r)
+    want = orc.OracleStack(nlm, z, N_frames=5).get_returns(1e3, f=179e6, alpha=alpha, Tx_pol=([0, 1],))
+    pol = s.get_returns_polarimetric(1e3, f=179e6, alpha=alpha)
+    assert np.allclose(pol['E_VH'], want[5], rtol=1e-12, atol=0) and np.allclose(pol['E_VV'], want[6], rtol=1e-12, atol=0)
+    with pytest.raises(ValueError):
+        s.get_returns_polarimetric(1e3, URD='nope')

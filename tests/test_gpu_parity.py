@@ -454,3 +454,19 @@ def test_config4_ensemble_launch_full_shape(eng):
         assert np.abs(got['Pm_' + name] - pm).max() < h.ATOL_DB, name
         assert np.abs(got['dP_' + name] - (20 * np.log10(amp) - pm[:, :, None])).max() < h.ATOL_DB, name
     assert np.abs(np.abs(got['c_HHVV']) - 1).max() < 1e-12
+
+
+def test_polarimetric_extension_matches_oracle(eng):
+    """All four Tx/Rx pairs from one pass (the reference drops E_VH, E_VV at layerstack.py:254-255):
+    H-transmit half == get_returns, V-transmit half == the oracle with Tx_pol = ([0, 1],)."""
+    import layerstack as ls
+    g = h.load_golden('tilted_a10')
+    s = ls.LayerStack(g['nlm'], g['z'], N_frames=int(g['F']), VERBOSE=0)
+    E0, f, alpha = float(g['E0']), float(g['f']), float(g['alpha'])
+    pol = s.get_returns_polarimetric(E0, f=f, alpha=alpha)
+    o = h.oracle_stack(g)
+    for tx, p in (('H', [1, 0]), ('V', [0, 1])):
+        want = o.get_returns(E0, f=f, alpha=alpha, Tx_pol=(p,))
+        got = [pol['Pm_%sH' % tx], pol['Pm_%sV' % tx], pol['dP_%sH' % tx], pol['dP_%sV' % tx], pol['c_HHVV'],
+               pol['E_%sH' % tx], pol['E_%sV' % tx]]
+        _check_returns(got, want)
