@@ -42,7 +42,14 @@ class Engine:
 
     # -- helpers -------------------------------------------------------------------------------
     def _stream(self):
-        return ctypes.c_void_p(_torch().cuda.current_stream(self.device).cuda_stream)
+        """Stream handle for the next C-ABI call.  The library launches on the CUDA context that is current in this thread
+        (one handle per device, include/tamm_b200.h), so the engine's device must be torch's current device."""
+        torch = _torch()
+        if torch.cuda.current_device() != self.device.index:
+            raise _lib.TammLibraryError('engine was created for cuda:%d but the current device is cuda:%d; use '
+                                        'torch.cuda.set_device / torch.cuda.device(...) around the call' % (
+                                            self.device.index, torch.cuda.current_device()))
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def to_device(self, arr):
         torch = _torch()
