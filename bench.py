@@ -321,12 +321,15 @@ def main():
     # end-to-end through the public API: host arrays in, host arrays out (all 7 returns of get_returns)
     if not args.no_e2e:
         try:
-            res = ens.get_returns(1e3, f=args.freq, alpha=alpha, batch=B)          # warm-up, allocates pinned outputs
+            # blocks of the e2e pipeline: the launch batch, or a quarter of the shard when the shard is a single launch
+            # batch (N = 8), so that the device->host copy of block b overlaps the kernels of block b+1
+            EB = B if Pl > B else max(1, (Pl + 3) // 4)
+            res = ens.get_returns(1e3, f=args.freq, alpha=alpha, batch=EB)         # warm-up, allocates pinned outputs
             pinned = ens._pinned
             sync_all()
             te = time.perf_counter()
             for _ in range(args.e2e_steps):
-                res = ens.get_returns(1e3, f=args.freq, alpha=alpha, batch=B, out=pinned)
+                res = ens.get_returns(1e3, f=args.freq, alpha=alpha, batch=EB, out=pinned)
             torch.cuda.synchronize()
             dt = torch.tensor([(time.perf_counter() - te) / args.e2e_steps], dtype=torch.float64, device=dev)
             if world > 1:
@@ -334,7 +337,7 @@ def main():
             d2h = sum(v.numel() * v.element_size() for v in pinned.values())
             h2d = Pl * N * packing.LAYER_STRIDE * 8 + F * packing.LANE_STRIDE * 8
             line['e2e'] = dict(value=evals_job / float(dt.item()), unit='layer*freq*azimuth evals/s', h2d_bytes_per_step=h2d,
-                               d2h_bytes_per_step=d2h, api='tamm_b200.EnsembleStack.get_returns (all 7 returns to pinned host arrays)',
+                               d2h_bytes_per_step=d2h, api='tamm_b200.EnsembleStack.get_returns (all 7 returns to pinned host arrays)', profiles_per_block=EB,
                                result_check=float(np.nanmax(res['Pm_HH'])))
         except Exception as e:  # e.g. not enough pinned host memory
             line['e2e'] = dict(value=None, error=repr(e)[:200])
