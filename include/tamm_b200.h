@@ -13,6 +13,9 @@
  *  - return value 0 = success; anything else is an error whose text is returned by tamm_last_error()
  *    (thread-local);
  *  - complex128 = interleaved (re, im) doubles;
+ *  - kernels run on the CUDA device that is current in the calling thread: make the device that owns the buffers
+ *    current before the call (one caller per device; calls for different devices are independent);
+ *  - sizes: N >= 2, P, Q, F >= 1 and Q*F must fit an int; all buffers 16-byte aligned;
  *  - there is NO CPU fallback: without a CUDA device every compute entry point fails.
  *
  * Input layouts (built by tamm_b200/packing.py with the reference's own NumPy expressions)
