@@ -250,6 +250,7 @@ def main():
                Pm_HV=eng.empty((Pl, 1, NI), r))
     planes = eng.empty((B, NI, 4, F), c)
     stack_events = []
+    returns_events = []
 
     def step(record=False):
         for b0 in range(0, Pl, B):
@@ -263,6 +264,10 @@ def main():
                 e1.record()
                 stack_events.append((e0, e1, (b1 - b0)))
             eng.returns(res, etx, True, out={k: v[b0:b1] for k, v in out.items()})
+            if record:
+                e2 = torch.cuda.Event(enable_timing=True)
+                e2.record()
+                returns_events.append((e1, e2, (b1 - b0)))
 
     def sync_all():
         if world > 1:
@@ -313,9 +318,28 @@ def main():
                     avg_launch_ms=stack_ms / max(1, len(stack_events)), share_of_step=stack_ms / ms if world == 1 else None,
                     hbm_alg_bytes_per_eval=64.5, hbm_achieved_gbs=stack_evals_per_s * 64.5 / 1e9)
 
+    # second kernel of the step (HBM-bound): fused returns, 64 B/eval of planes in + 64 B/eval of returns out
+    roofline_returns = None
+    try:
+        ret_ms = sum(a.elapsed_time(b) for a, b, _ in returns_events)
+        ret_evals = sum(n for _, _, n in returns_events) * float(NI) * F
+        try:
+            hbm_peak = float(json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs'])
+            hbm_src = 'MEASURED_PEAKS.json hbm_gbs (copy bandwidth, burst)'
+        except Exception:
+            hbm_peak, hbm_src = 6550.4, 'fallback: the copy bandwidth MEASURED_PEAKS.json held when the kernels were profiled'
+        ret_gbs = ret_evals * 128.0 / (ret_ms * 1e-3) / 1e9
+        roofline_returns = dict(bound='hbm', kernel='returns_fused_kernel', achieved=ret_gbs, peak=hbm_peak, unit='GB/s',
+                                frac=ret_gbs / hbm_peak, alg_bytes_per_eval=128.0, peak_source=hbm_src,
+                                avg_launch_ms=ret_ms / max(1, len(returns_events)),
+                                share_of_step=ret_ms / ms if world == 1 else None)
+    except Exception as e:
+        roofline_returns = dict(error=repr(e)[:200])
+
     line = dict(metric='layer*freq*azimuth evals/s (FP64)', value=value, unit='layer*freq*azimuth evals/s', n_gpus=world,
                 steps=args.steps, warmup=max(3, args.warmup), ms_per_step=ms_per_step, higher_is_better=True, scaling='strong',
                 vs_baseline=None, dtype='f64', data='synthetic', config=workload_config(args), roofline=roofline,
+                roofline_returns=roofline_returns,
                 gpu_launches=launches, fp64_tflops_alg=value * F_ALG / 1e12)
 
     # end-to-end through the public API: host arrays in, host arrays out (all 7 returns of get_returns)
