@@ -66,6 +66,13 @@ def main():
     run_case('rathmann_t2_a0', nlm, z, 24, 0.0, keep_layers=((6, 30),))
     nlm, z = profiles.rathmann_transition(61, 2000, fabric_type=4)
     run_case('rathmann_t4_a10', nlm, z, 24, np.deg2rad(10), keep_layers=((6, 30),))
+    main_ensemble()
+
+
+def main_ensemble():
+    """configs[4] recipe (profile 0 of the bench ensemble, seed 1000) at its layer spacing (0.5 m), 60 layers."""
+    nlm, z = profiles.ensemble(1, 60, H=29.5)
+    run_case('ensemble_a10', nlm[0], z, 16, np.deg2rad(10), keep_layers=((0, 0), (5, 17), (15, 59)))
 
 
 def main_fp():
@@ -83,5 +90,8 @@ def main_fp():
 if __name__ == '__main__':
     if len(sys.argv) > 1 and sys.argv[1] == 'fp':
         main_fp()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == 'ensemble':
+        main_ensemble()
         sys.exit(0)
     main()
