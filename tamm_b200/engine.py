@@ -51,6 +51,19 @@ class Engine:
                                             self.device.index, torch.cuda.current_device()))
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    # stream / event factories (the only torch.cuda objects the batched host API needs besides tensors)
+    def current_stream(self):
+        return _torch().cuda.current_stream(self.device)
+
+    def new_stream(self):
+        return _torch().cuda.Stream(self.device)
+
+    def new_event(self):
+        return _torch().cuda.Event()
+
+    def on_stream(self, stream):
+        return _torch().cuda.stream(stream)
+
     def to_device(self, arr):
         torch = _torch()
         t = torch.from_numpy(np.ascontiguousarray(arr))

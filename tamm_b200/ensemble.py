@@ -16,6 +16,16 @@ from .engine import MODE_U, MODE_URD, get_engine
 RETURN_NAMES = ('Pm_HH', 'Pm_HV', 'dP_HH', 'dP_HV', 'c_HHVV', 'E_HH', 'E_HV')
 
 
+def _pinned_empty(shape, dtype):
+    import torch
+    return torch.empty(shape, dtype=dtype, pin_memory=True)
+
+
+def _pinned_copy(arr):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(arr)).pin_memory()
+
+
 def shard_range(P, rank, world):
     """Contiguous, balanced split of P profiles over `world` ranks: [lo, hi) of `rank`."""
     base, rem = divmod(P, world)
@@ -81,11 +91,10 @@ class EnsembleStack:
         per-layer state LayerStack.__init__ keeps, layerstack.py:27-46), so they are packed once -- 0.15 s per 128 x 5000
         profiles on the host, which is as long as that block's results take to cross PCIe -- and every get_returns call
         copies them host -> device again.  Call `invalidate()` after changing nlm / epsa / epsc / sigma in place."""
-        import torch
         key = 'FP' if fp else 'GTM'
         t = self._packed.get(key)
         if t is None:
-            t = torch.from_numpy(np.ascontiguousarray(self.packed_layers(self.lo, self.hi, fp))).pin_memory()
+            t = _pinned_copy(self.packed_layers(self.lo, self.hi, fp))
             self._packed[key] = t
         return t
 
@@ -113,10 +122,10 @@ class EnsembleStack:
         shapes = {n: ((Pl, Q, NI) if n.startswith('Pm') else (Pl, Q, NI, F)) for n in RETURN_NAMES}
         dtypes = {n: (torch.complex128 if n in ('c_HHVV', 'E_HH', 'E_HV') else torch.float64) for n in RETURN_NAMES}
         if out is None:
-            out = {n: torch.empty(shapes[n], dtype=dtypes[n], pin_memory=True) for n in outputs}
+            out = {n: _pinned_empty(shapes[n], dtypes[n]) for n in outputs}
         lanes = eng.to_device(packing.pack_lanes(self.beta, fa))
         lay_all = self._packed_pinned(fp)
-        compute, copy = torch.cuda.current_stream(eng.device), torch.cuda.Stream(eng.device)
+        compute, copy = eng.current_stream(), eng.new_stream()
         dev = [None, None]
         done = [None, None]
         planes = [None, None]
@@ -134,13 +143,13 @@ class EnsembleStack:
             else:
                 res = eng.stack(lay, lanes, b1 - b0, N, Q, F, zeta, self.mu, mode, planes=planes[k])
             dev[k] = eng.returns(res, etx, gtm_phase=not fp, out=dev[k])
-            ready = torch.cuda.Event()
+            ready = eng.new_event()
             ready.record(compute)
-            with torch.cuda.stream(copy):
+            with eng.on_stream(copy):
                 copy.wait_event(ready)
                 for n in outputs:
                     out[n][b0:b1].copy_(dev[k][n], non_blocking=True)
-                done[k] = torch.cuda.Event()
+                done[k] = eng.new_event()
                 done[k].record(copy)
         copy.synchronize()
         compute.synchronize()
