@@ -40,6 +40,20 @@ int hostsim_layers(const double* layers, const double* lanes, int N, int F, doub
     return 0;
 }
 
+// Diagonal of K = diag(exp(-i k0 q d)) per (lane, layer) as layer_diag_kernel writes it (layer_PPJ.py:437).  (F, N, 4).
+int hostsim_layers_kd(const double* layers, const double* lanes, int N, int F, double zeta, double mu, double* Kd) {
+    for (int f = 0; f < F; ++f) {
+        LaneParams ln; std::memcpy(&ln, lanes + (size_t)f * LANE_STRIDE, sizeof(ln));
+        for (int n = 0; n < N; ++n) {
+            LayerParams lp; std::memcpy(&lp, layers + (size_t)n * LAYER_STRIDE, sizeof(lp));
+            LayerMats L; LayerDiag d;
+            layer_solve(lp, ln, zeta, mu, L, &d);
+            for (int k = 0; k < 4; ++k) put(Kd + (((size_t)f * N + n) * 4 + k) * 2, d.Kd[k]);
+        }
+    }
+    return 0;
+}
+
 // URD (mode 0) or U (mode 1) with the kernels' chunked accumulation: local products per chunk, exclusive
 // prefix over chunk aggregates, fix-up  URD_n = Upre_c * URDloc_n * Dpre_c.  Output (F, N-1, 2, 2) complex128.
 int hostsim_urd(const double* layers, const double* lanes, int N, int F, double zeta, double mu, int chunk, int mode,

@@ -2,11 +2,6 @@
 (double-buffered blocks, ragged last block, cached pinned layer records, output placement, sharding, `outputs=`, vector f,
 the polarimetric extension) runs against an engine double whose kernels are the host simulator of the device arithmetic
 (tests/hostsim, test-only); results are compared with the oracle per profile."""
-import contextlib
-import ctypes
-import os
-from types import SimpleNamespace
-
 import numpy as np
 import pytest
 import torch
@@ -15,71 +10,12 @@ import helpers as h
 import tamm_oracle as orc
 from tamm_b200 import EnsembleStack, ensemble, packing, profiles
 
-dp = ctypes.POINTER(ctypes.c_double)
-
-
-class _Stream:
-    def wait_event(self, ev):
-        pass
-
-    def synchronize(self):
-        pass
-
-
-class _Event:
-    def record(self, stream=None):
-        pass
-
-
-class HostSimEngine:
-    """Same surface as tamm_b200.engine.Engine for what EnsembleStack uses; the stack comes from hostsim_urd_fb (the
-    stack kernel's arithmetic compiled for the host), the returns from the oracle's returns_from_URD."""
-
-    def __init__(self, lib):
-        self.lib, self.device, self.launches = lib, torch.device('cpu'), 0
-        self.blocks = []                       # profiles per stack call, for the pipeline assertions
-
-    def current_stream(self): return _Stream()
-    def new_stream(self): return _Stream()
-    def new_event(self): return _Event()
-    def on_stream(self, s): return contextlib.nullcontext()
-    def to_device(self, a): return torch.from_numpy(np.ascontiguousarray(a))
-    def empty(self, shape, dtype): return torch.zeros(shape, dtype=dtype)
-
-    def stack(self, layers, lanes, P, N, Q, F, zeta, mu=1.0, mode=0, chunk=None, planes=None, workspace=None):
-        assert tuple(layers.shape) == (P, N, packing.LAYER_STRIDE) and layers.is_contiguous()
-        assert planes is not None and tuple(planes.shape) == (P, N - 1, 4, Q * F)
-        lay, lan = layers.numpy(), lanes.numpy()
-        urd = np.zeros((P, Q, F, N - 1, 2, 2), dtype=np.complex128)
-        for p in range(P):
-            for q in range(Q):
-                lq = np.ascontiguousarray(lan[q * F:(q + 1) * F])
-                rc = self.lib.hostsim_urd_fb(lay[p].ctypes.data_as(dp), lq.ctypes.data_as(dp), N, F, ctypes.c_double(float(zeta)),
-                                             ctypes.c_double(float(mu)), 7, mode, urd[p, q].ctypes.data_as(dp))
-                assert rc == 0
-        self.blocks.append(P)
-        return SimpleNamespace(urd=urd, P=P, Q=Q, F=F, N=N)
-
-    def returns(self, res, etx, gtm_phase=True, out=None):
-        names = ('Pm_HH', 'Pm_HV', 'dP_HH', 'dP_HV', 'c_HHVV', 'E_HH', 'E_HV')
-        acc = {k: [] for k in names}
-        for p in range(res.P):
-            per_q = [orc.returns_from_URD(res.urd[p, q], 1.0, Tx_pol=([etx[0], etx[1]],),
-                                          modeltype='GTM' if gtm_phase else 'FP') for q in range(res.Q)]
-            for i, k in enumerate(names):
-                acc[k].append(np.stack([r[i] for r in per_q]))
-        new = {k: torch.from_numpy(np.stack(v)) for k, v in acc.items()}      # (P, Q, NI[, F])
-        if out is None:
-            return new
-        for k in names:
-            out[k].copy_(new[k])
-        return out
+from hostsim_engine import HostSimEngine
 
 
 @pytest.fixture()
 def host_engine(built, monkeypatch):
-    lib = ctypes.CDLL(os.path.join(os.path.dirname(__file__), 'hostsim', '_hostsim.so'))
-    eng = HostSimEngine(lib)
+    eng = HostSimEngine()
     monkeypatch.setattr(ensemble, 'get_engine', lambda: eng)
     monkeypatch.setattr(ensemble, '_pinned_empty', lambda shape, dtype: torch.zeros(shape, dtype=dtype))
     monkeypatch.setattr(ensemble, '_pinned_copy', lambda a: torch.from_numpy(np.ascontiguousarray(a)))
