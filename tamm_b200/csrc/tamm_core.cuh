@@ -96,6 +96,50 @@ TAMM_HD double fsqrt(double a) {
 #endif
 }
 
+// Word access to a double (device: register moves; host simulator: memcpy)
+TAMM_HD int dbl_hi(double x) {
+#if defined(__CUDA_ARCH__)
+    return __double2hiint(x);
+#else
+    unsigned long long b; memcpy(&b, &x, 8); return (int)(b >> 32);
+#endif
+}
+TAMM_HD int dbl_lo(double x) {
+#if defined(__CUDA_ARCH__)
+    return __double2loint(x);
+#else
+    unsigned long long b; memcpy(&b, &x, 8); return (int)(b & 0xffffffffull);
+#endif
+}
+TAMM_HD double dbl_from(int hi, int lo) {
+#if defined(__CUDA_ARCH__)
+    return __hiloint2double(hi, lo);
+#else
+    unsigned long long b = ((unsigned long long)(unsigned)hi << 32) | (unsigned long long)(unsigned)lo;
+    double x; memcpy(&x, &b, 8); return x;
+#endif
+}
+
+// log10 for the dB conversions (layerstack.py:229): fdlibm's e_log kernel (x = 2^e m, m in [sqrt(1/2), sqrt 2),
+// s = f/(2+f), degree-14 minimax in s; < 1 ulp in ln m) with the reciprocal from frcp and none of libm's special-case
+// ladder on the fast path.  Zero, denormals, negatives, inf and NaN take the library routine.
+TAMM_HD double log10_fast(double x) {
+    int hi = dbl_hi(x);
+    if (TAMM_RARE((unsigned)(hi - 0x00100000) >= 0x7fe00000u)) return log10(x);
+    int e = (hi >> 20) - 1023;
+    double m = dbl_from((hi & 0x000fffff) | 0x3ff00000, dbl_lo(x));
+    if (m > 1.4142135623730951) { m *= 0.5; e += 1; }
+    const double f = m - 1.0;
+    const double s = f * frcp(2.0 + f);
+    const double z = s * s, w = z * z;
+    const double t1 = w * fma(w, fma(w, 1.531383769920937332e-01, 2.222219843214978396e-01), 3.999999999940941908e-01);
+    const double t2 = z * fma(w, fma(w, fma(w, 1.479819860511658591e-01, 1.818357216161805012e-01), 2.857142874366239149e-01),
+                              6.666666666666735130e-01);
+    const double hfsq = 0.5 * f * f;
+    const double lnm = f - (hfsq - s * (hfsq + (t1 + t2)));
+    return fma((double)e, 3.010299956639812e-01, lnm * 4.342944819032518e-01);
+}
+
 // 1/mu; folds to the constant 1 when the kernel is specialised for mu == 1 (the reference's default, layerstack.py:14)
 TAMM_HD double rcp_mu(double mu) { return mu == 1.0 ? 1.0 : frcp(mu); }
 

@@ -484,25 +484,8 @@ returns_kernel(const cd* __restrict__ planes, const cd* __restrict__ pre, int N,
 constexpr int TNF = 4;   // depths per reduction group of the fused returns kernel (keeps it at ~80 registers)
 constexpr int TNG = 4;   // groups per CTA
 
-// log10 for the dB conversions: fdlibm's e_log kernel (x = 2^e m, m in [sqrt(1/2), sqrt 2), s = f/(2+f), degree-14
-// minimax in s; < 1 ulp in ln m) with the reciprocal from frcp and none of libm's special-case ladder on the fast path.
-// Zero, denormals, negatives, inf and NaN take the library routine.
-__device__ __forceinline__ double log10_dev(double x) {
-    int hi = __double2hiint(x);
-    if (TAMM_RARE((unsigned)(hi - 0x00100000) >= 0x7fe00000u)) return log10(x);
-    int e = (hi >> 20) - 1023;
-    double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
-    if (m > 1.4142135623730951) { m *= 0.5; e += 1; }
-    const double f = m - 1.0;
-    const double s = f * tamm::frcp(2.0 + f);
-    const double z = s * s, w = z * z;
-    const double t1 = w * fma(w, fma(w, 1.531383769920937332e-01, 2.222219843214978396e-01), 3.999999999940941908e-01);
-    const double t2 = z * fma(w, fma(w, fma(w, 1.479819860511658591e-01, 1.818357216161805012e-01), 2.857142874366239149e-01),
-                              6.666666666666735130e-01);
-    const double hfsq = 0.5 * f * f;
-    const double lnm = f - (hfsq - s * (hfsq + (t1 + t2)));
-    return fma((double)e, 3.010299956639812e-01, lnm * 4.342944819032518e-01);
-}
+// log10 for the dB conversions: tamm::log10_fast (tamm_core.cuh)
+__device__ __forceinline__ double log10_dev(double x) { return tamm::log10_fast(x); }
 
 // Sum of 8 per-lane values over the warp in 9 shuffles: each butterfly step halves the number of values a lane carries
 // (lanes with the step's bit set keep the odd-indexed partial sums, the others the even-indexed ones).  On return lane L

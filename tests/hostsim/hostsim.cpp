@@ -126,6 +126,13 @@ int hostsim_urd_fp(const double* layers_fp, const double* lanes, int N, int F, d
     return 0;
 }
 
+// log10 of the dB conversions in the returns kernels (tamm::log10_fast; the reciprocal inside is the plain IEEE division
+// on the host instead of the device's MUFU seed + 2 Newton steps).
+int hostsim_log10(const double* x, int n, double* out) {
+    for (int i = 0; i < n; ++i) out[i] = log10_fast(x[i]);
+    return 0;
+}
+
 // Elementary functions of the hot path: out[i] = {sin, cos, exp} of x[i] through sincos_f / exp_f.
 int hostsim_elementary(const double* x, int n, double* out) {
     for (int i = 0; i < n; ++i) {

@@ -320,3 +320,29 @@ def test_unusual_regimes(sim, name, kw, alpha_deg):
     urd = sim_urd(sim, os_, 179e6, alpha, 16, field_basis=True)
     assert np.isfinite(urd.view(np.float64)).all()
     assert h.peak_rel_err(urd, orc.get_URD(L), axis=(1, 2, 3)) < h.RTOL_COMPLEX
+
+
+def test_returns_kernel_log10(sim):
+    """The dB conversion of the returns kernels (tamm::log10_fast, fdlibm e_log kernel with hand-typed coefficients)
+    against extended-precision log10: <= 2.5 ulp over the whole double range (ln m is < 1 ulp; the scaling by log10 e and
+    the e log10 2 term use single-double constants), i.e. ~1e-14 dB; special cases through libm."""
+    rng = np.random.default_rng(0)
+    x = np.concatenate([10.0 ** rng.uniform(-300, 300, 20000), 1 + rng.uniform(-1e-3, 1e-3, 5000),
+                        2.0 ** np.arange(-1000, 1000, 7.0), np.sqrt(2) * (1 + rng.uniform(-1e-12, 1e-12, 1000)),
+                        rng.uniform(0.5, 2.0, 20000), [1.0, 10.0, 1e-5, 1e3, np.nextafter(1.0, 2), np.nextafter(1.0, 0)]])
+    out = np.zeros_like(x)
+    assert sim.hostsim_log10(_P(x), len(x), _P(out)) == 0
+    want = np.log10(x.astype(np.longdouble))
+    ulp = np.spacing(np.abs(want.astype(np.float64)))
+    err = np.abs(out.astype(np.longdouble) - want).astype(np.float64)
+    near_one = np.abs(x - 1) < 1e-2             # log10 -> 0: the error is relative to the rounding of f = m - 1
+    assert (err[~near_one] / ulp[~near_one]).max() <= 2.5
+    assert (err[near_one] / np.maximum(ulp[near_one], 1e-19)).max() <= 2.5
+    assert out[-6] == 0.0                        # log10(1) exactly
+    sp = np.array([0.0, -1.0, np.inf, np.nan, 5e-324, 2.2250738585072014e-308])
+    o2 = np.zeros_like(sp)
+    with np.errstate(all='ignore'):
+        sim.hostsim_log10(_P(sp), len(sp), _P(o2))
+        w2 = np.log10(sp)
+    assert o2[0] == -np.inf and np.isnan(o2[1]) and o2[2] == np.inf and np.isnan(o2[3])
+    assert np.allclose(o2[4:], w2[4:], rtol=1e-15, atol=0)
