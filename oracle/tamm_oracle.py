@@ -248,8 +248,8 @@ def eig_factored(eps, mu, zeta, n_iter=3):
         # pair step
         (a, b, c, d), (da, db, dc, dd) = wave_matrix(eps, mu, zeta, qc)
         roots = _mslp_step_pair(a, b, c, d, da, db, dc, dd)
-        for r in range(2):
-            q = qc + roots[r]
+
+        def polish(q):
             for it in range(40):
                 (a, b, c, d), (da, db, dc, dd) = wave_matrix(eps, mu, zeta, q)
                 h = _mslp_step_single(a, b, c, d, da, db, dc, dd)
@@ -258,7 +258,20 @@ def eig_factored(eps, mu, zeta, n_iter=3):
                 # element is still moving (grazing incidence, where the pair step is a poor start)
                 if it + 1 >= n_iter and not (np.abs(h) > 1e-17 * np.abs(q)).any():
                     break
-            out[..., 2 * pair + r] = q
+            return q
+        qa, qb = polish(qc + roots[0]), polish(qc + roots[1])
+        # Near-degenerate pair (splitting comparable to the error of the pair step, ~1e-8 |q|): every MSLP step moves to
+        # the NEAREST root, so both starts can end on the same one.  Where the two results are much closer than the
+        # splitting the pair step predicted, the lost partner of qa is qa + (the other eigenvalue of -N'(qa)^-1 N(qa)),
+        # i.e. the second root of the local quadratic model of det N -- deflation without division by (q - qa).
+        split = np.abs(roots[0] - roots[1])
+        met = (np.abs(qa - qb) < 0.25 * split) & (split > 1e-14 * np.abs(qa))
+        if np.any(met):
+            (a, b, c, d), (da, db, dc, dd) = wave_matrix(eps, mu, zeta, qa)
+            big, _, _ = _eig2_small_large(*_G(a, b, c, d, da, db, dc, dd))
+            qb = np.where(met, polish(np.where(met, qa + big, qb)), qb)
+        out[..., 2 * pair] = qa
+        out[..., 2 * pair + 1] = qb
     return _repair_unseparated_pairs(out, eps, mu, zeta)
 
 

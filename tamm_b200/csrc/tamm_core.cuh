@@ -993,6 +993,28 @@ void eig4_fallback(double exx, double exy, double exz, double eyy, double eyz, d
         rv[k][1] = csel(use0, -mm.b, mm.d);
         rv[k][2] = csel(use0, mm.a, -mm.b);
     }
+    // Close pairs (splitting comparable to the accuracy of the starting values, ~1e-8 |q|): two starting points can be
+    // refined to the SAME root, leaving its partner unfound.  For every pair of coinciding results, the partner of the
+    // root is at x + h_big, h_big = the other eigenvalue of -N'(x)^-1 N(x) (the second root of the local quadratic model of
+    // det N, exact to O(h_big^2/|q|)); a truly degenerate pair has h_big = 0 and stays as it is.
+    for (int k = 0; k < 4; ++k)
+        for (int j = k + 1; j < 4; ++j) {
+            if (!(abs2(rv[k][0] - rv[j][0]) <= 1e-22 * abs2(rv[k][0]))) continue;
+            const WaveMat m = wave_matrix(w, rv[k][0]);
+            cd hb, hs;
+            mslp_eigs_f(m, w.db, hb, hs);
+            const double sep2 = abs2(hb);
+            cd x = rv[k][0] + hb;
+            if (!(sep2 > 1e-26 * abs2(x)) || !(sep2 < 1e-4 * abs2(x))) continue;
+            TAMM_STAT(recentre);
+            const double ix2 = frcp(abs2(x) + TINY);
+            WaveMat mm;
+            refine_root(w, x, sep2, frcp(sep2), ix2, 1e-31 * abs2(x), sep2 * sep2 * ix2, mm);
+            const bool use0 = abs2(mm.a) >= abs2(mm.d);
+            rv[j][0] = x;
+            rv[j][1] = csel(use0, -mm.b, mm.d);
+            rv[j][2] = csel(use0, mm.a, -mm.b);
+        }
 }
 
 // ---- per-thread scratch of the mode solve -------------------------------------------------------------------------
@@ -1095,6 +1117,20 @@ TAMM_HD bool eig4_fast(const WaveCoef& w, SC& sc) {
         const double ahb = abs2(hb), ahs = abs2(hs);
         if (errv < 0.0) reach2 = fmax(reach2, fmax(ahb, ahs));
         else reach2 = fmax(reach2, 2.0 * (abs2(centre - qc) + ahb));
+        // Near-degenerate pair (splitting down at the accuracy of the starting values, ~1e-8 |q| -- e.g. where the p and s
+        // branches of a smoothly rotating fabric cross at oblique incidence): every refinement step moves to the NEAREST
+        // root, so both starting values can end on the same one and its partner is lost.  When a starting value may be
+        // no closer to its own root than to the partner (error > splitting / 4) and the splitting is resolvable at all
+        // (below 1e-12 |q| the pair is degenerate for every later purpose, QSD_THR = 1e-10), the layer goes to the cold
+        // solver, which recovers lost partners by deflation.
+        {
+            const double emax = errv < 0.0 ? fmax(ahb, ahs) : 0.0;
+            const double e2 = errv < 0.0 ? emax * emax * iq2c : errv * isep2;
+            if (TAMM_RARE((e2 > 0.0625 * sep2) && (sep2 > 1e-24 * q2c))) {
+                TAMM_STAT(collapsed);
+                return false;
+            }
+        }
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif

@@ -509,6 +509,39 @@ __device__ __forceinline__ double warp_sum8(const double v[8], int lane) {
     return r;
 }
 
+// One (depth, azimuth) point of the returns tail (layerstack.py:249-278): received fields for the transmitted
+// polarisation, HH-VV coherence phase, field amplitudes.  Fast path: |.| through rsqrt of the squared modulus, the
+// coherence normaliser as ONE rsqrt of |m0|^2 |m3|^2.  That product / those squares leave the normal range once a
+// modulus is below ~1e-75 / ~1e-148 (strongly attenuating deep stacks) or the value is zero, inf or NaN: then the
+// arithmetic of the two-pass kernels is used (hypot like numpy.abs, true division), so the result does not depend on
+// which returns kernel F selects and stays finite exactly where the reference's is.
+__device__ __forceinline__ unsigned exp_field(double x) { return ((unsigned)__double2hiint(x) >> 20) & 0x7ffu; }
+__device__ __noinline__ void returns_point_slow(cd m0, cd m3, cd hh, cd hv, cd& c, double& ahh, double& ahv) {
+    const cd num = m0 * conj(m3);
+    const double den = cabs_(m0) * cabs_(m3);
+    c = cd{num.re / den, num.im / den};
+    ahh = cabs_(hh);
+    ahv = cabs_(hv);
+}
+__device__ __forceinline__ void returns_point(const cd m[4], cd e0, cd e1, int gtm_phase, cd& hh, cd& hv, cd& c, double& ahh,
+                                              double& ahv) {
+    hh = dot2(m[0], e0, m[1], e1);             // get_Rx_all (layerstack.py:298)
+    hv = dot2(m[2], e0, m[3], e1);
+    const double a0 = abs2(m[0]), a3 = abs2(m[3]), shh = abs2(hh), shv = abs2(hv);
+    // exponent fields: a0, a3 within 2^+-498 of 1 (their product stays normal), shh, shv normal with 40 bits to spare
+    const unsigned k0 = exp_field(a0) - 525u, k3 = exp_field(a3) - 525u, kh = exp_field(shh) - 40u, kv = exp_field(shv) - 40u;
+    if (TAMM_RARE(max(k0, k3) > 996u || max(kh, kv) > 2005u)) {
+        returns_point_slow(m[0], m[3], hh, hv, c, ahh, ahv);
+    } else {
+        const cd num = cmul_(m[0], conj(m[3]));    // c_HHVV (layerstack.py:271-278): num / (|m0| |m3|)
+        const double iden = tamm::frsqrt(a0 * a3);
+        c = cd{num.re * iden, num.im * iden};
+        ahh = tamm::fsqrt(shh);
+        ahv = tamm::fsqrt(shv);
+    }
+    if (gtm_phase) c = cd{-c.re, c.im};        // -|c| exp(-i angle c) = -conj(c)   (layerstack.py:276-278)
+}
+
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK, (BLOCK <= 256 ? 768 / BLOCK : 1))
 returns_fused_kernel(const cd* __restrict__ planes, const cd* __restrict__ pre, int N, int Q, int F, int mode, int chunk,
@@ -550,18 +583,15 @@ returns_fused_kernel(const cd* __restrict__ planes, const cd* __restrict__ pre, 
                         else { mm22(Up, m, t); m[0] = t[0]; m[1] = t[1]; m[2] = t[2]; m[3] = t[3]; }
                     }
                 }
-                const cd hh = dot2(m[0], e0, m[1], e1);    // get_Rx_all (layerstack.py:298)
-                const cd hv = dot2(m[2], e0, m[3], e1);
-                const cd num = cmul_(m[0], conj(m[3]));    // c_HHVV (layerstack.py:271-278): num / (|m0| |m3|)
-                const double iden = tamm::frsqrt(abs2(m[0]) * abs2(m[3]));
-                cd c = cd{num.re * iden, num.im * iden};
-                if (gtm_phase) c = cd{-c.re, c.im};
+                cd hh, hv, c;
+                double ahh, ahv;
+                returns_point(m, e0, e1, gtm_phase, hh, hv, c, ahh, ahv);
                 if (live) {
                     st_cd(E_HH + o, hh);
                     st_cd(E_HV + o, hv);
                     st_cd(c_HHVV + o, c);
-                    amp[2 * k] = tamm::fsqrt(abs2(hh));
-                    amp[2 * k + 1] = tamm::fsqrt(abs2(hv));
+                    amp[2 * k] = ahh;
+                    amp[2 * k + 1] = ahv;
                 }
             }
             ip += istride;
@@ -674,18 +704,15 @@ returns_tma_kernel(const cd* __restrict__ planes, const cd* __restrict__ pre, in
                         else { mm22(Up, m, t); m[0] = t[0]; m[1] = t[1]; m[2] = t[2]; m[3] = t[3]; }
                     }
                 }
-                const cd hh = dot2(m[0], e0, m[1], e1);    // get_Rx_all (layerstack.py:298)
-                const cd hv = dot2(m[2], e0, m[3], e1);
-                const cd num = cmul_(m[0], conj(m[3]));    // c_HHVV (layerstack.py:271-278): num / (|m0| |m3|)
-                const double iden = tamm::frsqrt(abs2(m[0]) * abs2(m[3]));
-                cd c = cd{num.re * iden, num.im * iden};
-                if (gtm_phase) c = cd{-c.re, c.im};
+                cd hh, hv, c;
+                double ahh, ahv;
+                returns_point(m, e0, e1, gtm_phase, hh, hv, c, ahh, ahv);
                 if (live) {
                     st_cd(E_HH + o, hh);
                     st_cd(E_HV + o, hv);
                     st_cd(c_HHVV + o, c);
-                    amp[2 * k] = tamm::fsqrt(abs2(hh));
-                    amp[2 * k + 1] = tamm::fsqrt(abs2(hv));
+                    amp[2 * k] = ahh;
+                    amp[2 * k + 1] = ahv;
                 }
             }
             o += F;

@@ -64,6 +64,8 @@ class EnsembleStack:
                 return np.full((self.P_total, self.N_layers), v[0])
             return np.broadcast_to(v, (self.P_total, self.N_layers))
         self.epsa, self.epsc, self.sigma = expand(epsa), expand(epsc), expand(sigma)
+        iso = (2 * self.epsa[:, 0] + self.epsc[:, 0]) / 3
+        self._uniform_top = bool(np.all(iso == iso[0]))
         self.nlm = nlm[:, :, :6]
         self._packed = {}          # model ('GTM'/'FP') -> pinned (P_local, N, 10) layer records, built on first use
         if VERBOSE:
@@ -75,6 +77,13 @@ class EnsembleStack:
         return self.hi - self.lo
 
     def zeta(self, alpha):
+        """In-plane wavevector component of the incident wave, sqrt(eps_iso) sin(alpha) (layerstack.py:236-237).  The
+        reference takes eps_iso from each stack's OWN top layer; one launch carries one zeta, so all profiles of the
+        ensemble must share the top-layer permittivity (checked in __init__ whenever alpha != 0 is requested)."""
+        if alpha != 0 and not self._uniform_top:
+            raise ValueError('EnsembleStack: (2*epsa[p,0] + epsc[p,0])/3 of the top layer differs between profiles; at '
+                             'oblique incidence every profile would need its own zeta (layerstack.py:236-237).  Group the '
+                             'profiles by top-layer permittivity into separate EnsembleStacks.')
         epsiso = (2 * self.epsa[0, 0] + self.epsc[0, 0]) / 3              # layerstack.py:236
         return np.sqrt(epsiso) * np.sin(alpha)
 
@@ -101,9 +110,11 @@ class EnsembleStack:
     def invalidate(self):
         self._packed = {}
 
-    def get_returns(self, E0, f=179.0e6, alpha=0, Tx_pol=([1, 0],), URD='URD', batch=None, out=None, outputs=RETURN_NAMES):
-        """-> dict name -> host array for the local shard, shapes (P_local, [Q,] N-1, F) / (P_local, [Q,] N-1).
-        Same numbers as LayerStack.get_returns per profile (layerstack.py:232-288)."""
+    def _solve(self, E0, f, alpha, pols, URD, batch, outs, outputs):
+        """The block pipeline behind get_returns / get_returns_polarimetric: per block of profiles ONE pass over the stack
+        (tamm_stack_urd) followed by one returns pass per transmit polarisation in `pols` on the same planes
+        (like LayerStack.get_returns_polarimetric, lib/layerstack.py), results copied into the pinned host arrays
+        `outs[i][name]` on a second stream while the next block computes.  -> list of dict name -> pinned tensor."""
         import torch
         if URD not in ('URD', 'U'):
             raise ValueError('get_returns(): argument URD="%s" not understood' % (URD))
@@ -114,21 +125,23 @@ class EnsembleStack:
         eng = get_engine()
         fa = np.atleast_1d(np.asarray(f, dtype=np.float64))
         Q, F, N, NI, Pl = fa.size, self.N_frames, self.N_layers, self.N_layers - 1, self.P_local
-        zeta = self.zeta(alpha)
-        p = Tx_pol[0]                                                    # layerstack.py:249-252: only Tx_pol[0] is returned
-        etx = np.array([E0 * p[0], E0 * p[1]], dtype=np.complex128)
+        zeta = 0.0 if fp else self.zeta(alpha)
+        etx = [np.array([E0 * p[0], E0 * p[1]], dtype=np.complex128) for p in pols]
         if batch is None:   # keep device buffers around 2 x 4 GiB
             batch = max(1, min(Pl, int(4 * 2 ** 30 // max(1, 64 * NI * Q * F))))
         shapes = {n: ((Pl, Q, NI) if n.startswith('Pm') else (Pl, Q, NI, F)) for n in RETURN_NAMES}
         dtypes = {n: (torch.complex128 if n in ('c_HHVV', 'E_HH', 'E_HV') else torch.float64) for n in RETURN_NAMES}
-        if out is None:
-            out = {n: _pinned_empty(shapes[n], dtypes[n]) for n in outputs}
+        outs = [None] * len(pols) if outs is None else list(outs)
+        for i in range(len(pols)):
+            if outs[i] is None:
+                outs[i] = {n: _pinned_empty(shapes[n], dtypes[n]) for n in outputs}
         lanes = eng.to_device(packing.pack_lanes(self.beta, fa))
         lay_all = self._packed_pinned(fp)
         compute, copy = eng.current_stream(), eng.new_stream()
-        dev = [None, None]
+        dev = [[None] * len(pols), [None] * len(pols)]
         done = [None, None]
         planes = [None, None]
+        status = []
         for bi, b0 in enumerate(range(0, Pl, batch)):
             b1 = min(Pl, b0 + batch)
             k = bi & 1
@@ -137,22 +150,49 @@ class EnsembleStack:
             lay = lay_all[b0:b1].to(eng.device, non_blocking=True)          # H2D of this block's inputs, every call
             if planes[k] is None or planes[k].shape[0] != b1 - b0:
                 planes[k] = eng.empty((b1 - b0, NI, 4, Q * F), torch.complex128)
-                dev[k] = None
+                dev[k] = [None] * len(pols)
             if fp:
                 res = eng.stack_fp(lay, lanes, b1 - b0, N, Q, F, planes=planes[k])
             else:
                 res = eng.stack(lay, lanes, b1 - b0, N, Q, F, zeta, self.mu, mode, planes=planes[k])
-            dev[k] = eng.returns(res, etx, gtm_phase=not fp, out=dev[k])
+                status.append((b0, res.status))
+            for i in range(len(pols)):
+                dev[k][i] = eng.returns(res, etx[i], gtm_phase=not fp, out=dev[k][i])
             ready = eng.new_event()
             ready.record(compute)
             with eng.on_stream(copy):
                 copy.wait_event(ready)
-                for n in outputs:
-                    out[n][b0:b1].copy_(dev[k][n], non_blocking=True)
+                for i in range(len(pols)):
+                    for n in outputs:
+                        outs[i][n][b0:b1].copy_(dev[k][i][n], non_blocking=True)
                 done[k] = eng.new_event()
                 done[k].record(copy)
         copy.synchronize()
         compute.synchronize()
+        self._warn_status(status)
+        return outs
+
+    def _warn_status(self, status):
+        """Per-profile status words of tamm_stack_urd (bit 0: a layer did not split into 2 transmitted + 2 reflected
+        modes, layer_PPJ.py:216-231, where the reference raises IndexError or mis-sorts silently): read once per call,
+        after the final synchronisation, and reported like LayerStack._run does."""
+        self.last_status = None
+        if not status:
+            return
+        import torch
+        st = torch.cat([t for _, t in status]).cpu().numpy()
+        self.last_status = st
+        bad = np.nonzero(st & 1)[0]
+        if bad.size:
+            import warnings
+            warnings.warn('tamm_b200: in %d profile(s) (local indices %s%s; global = local + %d) a layer did not have 2 '
+                          'transmitted + 2 reflected modes (layer_PPJ.py:216-231); results for these profiles are '
+                          'unreliable' % (bad.size, bad[:16].tolist(), ' ...' if bad.size > 16 else '', self.lo), UserWarning)
+
+    def get_returns(self, E0, f=179.0e6, alpha=0, Tx_pol=([1, 0],), URD='URD', batch=None, out=None, outputs=RETURN_NAMES):
+        """-> dict name -> host array for the local shard, shapes (P_local, [Q,] N-1, F) / (P_local, [Q,] N-1).
+        Same numbers as LayerStack.get_returns per profile (layerstack.py:232-288)."""
+        out = self._solve(E0, f, alpha, [Tx_pol[0]], URD, batch, [out], outputs)[0]   # layerstack.py:249-252: only Tx_pol[0]
         squeeze_q = (np.ndim(f) == 0)
         res = {}
         for n in outputs:
@@ -162,12 +202,14 @@ class EnsembleStack:
         return res
 
     def get_returns_polarimetric(self, E0, f=179.0e6, alpha=0, URD='URD', batch=None):
-        """All four Tx/Rx pairs (layerstack.py:252-255; the reference drops E_VH, E_VV): two passes of `get_returns`
-        with Tx = H = [1, 0] and Tx = V = [0, 1].  -> dict E_xy, dP_xy, Pm_xy for xy in HH, HV, VH, VV and c_HHVV
-        (host arrays of the local shard; the stack is evaluated once per transmit polarisation)."""
+        """All four Tx/Rx pairs (layerstack.py:252-255; the reference drops E_VH, E_VV) from ONE pass over the stack per
+        block: the returns kernel runs twice on the same planes, with Tx = H = [1, 0] and Tx = V = [0, 1].
+        -> dict E_xy, dP_xy, Pm_xy for xy in HH, HV, VH, VV and c_HHVV (host arrays of the local shard)."""
+        outs = self._solve(E0, f, alpha, [[1, 0], [0, 1]], URD, batch, None, RETURN_NAMES)
+        squeeze_q = (np.ndim(f) == 0)
         out = {}
-        for tx, pol in (('H', [1, 0]), ('V', [0, 1])):
-            r = self.get_returns(E0, f=f, alpha=alpha, Tx_pol=(pol,), URD=URD, batch=batch)
+        for tx, o in zip(('H', 'V'), outs):
+            r = {n: (o[n].numpy()[:, 0] if squeeze_q else o[n].numpy()) for n in RETURN_NAMES}
             for rx, col in (('H', 'HH'), ('V', 'HV')):
                 for kind in ('E', 'dP', 'Pm'):
                     out['%s_%s%s' % (kind, tx, rx)] = r['%s_%s' % (kind, col)]

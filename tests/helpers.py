@@ -80,6 +80,47 @@ def field_scale(ret):
     return np.where(s == 0, 1.0, s)
 
 
+def nonfinite_code(x):
+    """0 finite, 1 NaN, 2 +inf, 3 -inf (complex: either part NaN -> 1, else either part infinite -> 2 + sign of that part)."""
+    x = np.asarray(x)
+    if np.iscomplexobj(x):
+        c = np.zeros(x.shape, dtype=np.int8)
+        for part in (x.real, x.imag):
+            c = np.where((c == 0) & np.isposinf(part), 2, c)
+            c = np.where((c == 0) & np.isneginf(part), 3, c)
+        return np.where(np.isnan(x.real) | np.isnan(x.imag), 1, c).astype(np.int8)
+    return (np.isnan(x) * 1 + np.isposinf(x) * 2 + np.isneginf(x) * 3).astype(np.int8)
+
+
+def assert_same_nonfinite(a, b, name=''):
+    ca, cb = nonfinite_code(a), nonfinite_code(b)
+    if not np.array_equal(ca, cb):
+        bad = np.argwhere(ca != cb)
+        raise AssertionError('%s: non-finite pattern differs at %d entries, first %s: got code %d, want code %d' % (
+            name, len(bad), tuple(bad[0]), ca[tuple(bad[0])], cb[tuple(bad[0])]))
+
+
+def _urd_block(job):
+    nlm, z, F, kw, f, alpha, sel, opts = job
+    st = orc.OracleStack(nlm, z, N_frames=F, **kw)
+    return st.get_URD(f, alpha, beta=st.beta[sel], **opts)
+
+
+def oracle_urd_parallel(nlm, z, F, f, alpha, sel=None, nproc=None, stack_kw=None, **opts):
+    """OracleStack.get_URD over the azimuths `sel` (default: all F) split over a fork pool: lanes are independent, so
+    this is the same arithmetic per lane as one call, only faster on the test box's host cores.  -> (len(sel), N-1, 2, 2)."""
+    import multiprocessing as mp
+    sel = np.arange(F) if sel is None else np.asarray(sel)
+    nproc = min(nproc or (os.cpu_count() or 1), max(1, len(sel)))
+    parts = np.array_split(sel, nproc)
+    jobs = [(nlm, z, F, stack_kw or {}, f, alpha, s, opts) for s in parts if len(s)]
+    if len(jobs) == 1:
+        return _urd_block(jobs[0])
+    os.environ.setdefault('OMP_NUM_THREADS', '1')
+    with mp.get_context('fork').Pool(len(jobs)) as pool:
+        return np.concatenate(pool.map(_urd_block, jobs), axis=0)
+
+
 def assert_parity(got, want, arbiter=None, c_atol=1e-7, names=RET_NAMES):
     """The parity criterion of this repository for the 7-tuple of get_returns (layerstack.py:280-283).
 
@@ -105,6 +146,10 @@ def assert_parity(got, want, arbiter=None, c_atol=1e-7, names=RET_NAMES):
             assert a.shape == b.shape, (n, a.shape, b.shape)
             assert a.dtype == b.dtype, (n, a.dtype, b.dtype)
             ok = np.isfinite(a) & np.isfinite(b)
+            # non-finite entries must sit in the same places and be the same kind (NaN / +inf / -inf): the reference
+            # only produces them at exact nulls (dB of 0 = -inf, 0/0 coherence = NaN); a device NaN/inf where the
+            # reference is finite is a failure, not something to mask
+            assert_same_nonfinite(a, b, n)
             if n in ('E_HH', 'E_HV'):
                 tol = RTOL_COMPLEX * scale * np.ones(b.shape)
             elif n == 'c_HHVV':

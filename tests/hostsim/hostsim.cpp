@@ -295,4 +295,21 @@ int hostsim_urd_fast(const double* layers, const double* lanes, int N, int F, do
     return 0;
 }
 
+// Sorted roots of the hot path (layer_modes: eig4_fast + clean-up + partition + p/s sort) and the Poynting measures
+// {|Px|^2, |Px|^2+|Py|^2} of the four UNSORTED modes: qs complex128 (F, N, 4), ms double (F, N, 4, 2).
+int hostsim_modes(const double* layers, const double* lanes, int N, int F, double zeta, double mu, double* qs, double* ms) {
+    for (int f = 0; f < F; ++f) {
+        LaneParams ln; std::memcpy(&ln, lanes + (size_t)f * LANE_STRIDE, sizeof(ln));
+        for (int n = 0; n < N; ++n) {
+            LayerParams lp; std::memcpy(&lp, layers + (size_t)n * LAYER_STRIDE, sizeof(lp));
+            ModeSet m; ScratchArrays sc;
+            layer_modes(lp, ln, zeta, mu, m, sc);
+            const size_t i = (size_t)f * N + n;
+            put(qs + (i * 4 + 0) * 2, m.q0); put(qs + (i * 4 + 1) * 2, m.q1); put(qs + (i * 4 + 2) * 2, m.q2); put(qs + (i * 4 + 3) * 2, m.q3);
+            if (ms) for (int k = 0; k < 4; ++k) { ms[(i * 4 + k) * 2] = sc.ms_[k][0]; ms[(i * 4 + k) * 2 + 1] = sc.ms_[k][1]; }
+        }
+    }
+    return 0;
+}
+
 }  // extern "C"

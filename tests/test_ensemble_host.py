@@ -62,7 +62,9 @@ def test_shards_vector_frequency_and_polarimetric(host_engine):
         for q, f in enumerate(fs):
             h.assert_parity([full[n][p, q] for n in h.RET_NAMES], _want(nlm[p], z, F, float(f), alpha), None, c_atol=1e-7)
     ens = EnsembleStack(nlm, z, N_frames=F)
+    nblocks = len(host_engine.blocks)
     pol = ens.get_returns_polarimetric(1e3, f=179e6, alpha=alpha, batch=3)
+    assert host_engine.blocks[nblocks:] == [3, 1]          # ONE stack pass per block serves both transmit polarisations
     wv = _want(nlm[1], z, F, 179e6, alpha, Tx_pol=([0, 1],))
     wh = _want(nlm[1], z, F, 179e6, alpha)
     assert h.peak_rel_err(pol['E_VH'][1], wv[5], axis=0) < h.RTOL_COMPLEX
@@ -71,3 +73,44 @@ def test_shards_vector_frequency_and_polarimetric(host_engine):
     assert np.abs(pol['Pm_VV'][1] - wv[1]).max() < h.ATOL_DB and np.abs(pol['c_HHVV'][1] - wh[4]).max() < 1e-7
     with pytest.raises(ValueError):
         ens.get_returns(1e3, URD='nope')
+
+
+def test_per_profile_top_layer_permittivity(host_engine):
+    """one launch carries one zeta = sqrt(eps_iso) sin(alpha) (layerstack.py:236-237, per stack in the
+    reference).  Profiles whose top-layer permittivity differs must be refused at oblique incidence; at normal incidence
+    (zeta = 0 for every profile) they are fine and match per-profile oracle runs with their own epsa."""
+    P, N, F = 3, 20, 5
+    nlm, z = profiles.ensemble(P, N, H=9.5, first=3)
+    epsa = np.full((P, N), 3.17 - 0.034); epsa[1] = 3.10; epsa[2, 5:] = 3.12      # profile 2 differs only below the top
+    epsc = np.full((P, N), 3.17)
+    ens = EnsembleStack(nlm, z, N_frames=F, epsa=epsa, epsc=epsc)
+    with pytest.raises(ValueError, match='top layer differs between profiles'):
+        ens.get_returns(1e3, f=179e6, alpha=np.deg2rad(10))
+    got = ens.get_returns(1e3, f=179e6, alpha=0)
+    for p in range(P):
+        want = orc.OracleStack(nlm[p], z, N_frames=F, epsa=epsa[p], epsc=epsc[p]).get_returns(1e3, f=179e6, alpha=0)
+        h.assert_parity([got[n][p] for n in h.RET_NAMES], want, None, c_atol=1e-7)
+    # same top layer everywhere (differences deeper down only): oblique incidence is fine and equals P separate stacks
+    ens2 = EnsembleStack(nlm[[0, 2]], z, N_frames=F, epsa=epsa[[0, 2]], epsc=epsc[[0, 2]])
+    got2 = ens2.get_returns(1e3, f=179e6, alpha=np.deg2rad(10))
+    want = orc.OracleStack(nlm[2], z, N_frames=F, epsa=epsa[2], epsc=epsc[2]).get_returns(1e3, f=179e6, alpha=np.deg2rad(10))
+    h.assert_parity([got2[n][1] for n in h.RET_NAMES], want, None, c_atol=1e-7)
+
+
+def test_status_word_is_reported(host_engine, monkeypatch):
+    """the per-profile status of tamm_stack_urd (bit 0: no 2+2 mode partition) reaches the caller of the
+    batched API as a UserWarning naming the profiles, as LayerStack._run does for a single stack."""
+    P, N, F = 4, 12, 3
+    nlm, z = profiles.ensemble(P, N, H=5.5)
+    ens = EnsembleStack(nlm, z, N_frames=F)
+    real = host_engine.stack
+
+    def flagged(*a, **kw):
+        r = real(*a, **kw)
+        if r.P == 2 and len(host_engine.blocks) == 2:      # second block: flag its second profile (local index 3)
+            r.status[1] = 1
+        return r
+    monkeypatch.setattr(host_engine, 'stack', flagged)
+    with pytest.warns(UserWarning, match=r'local indices \[3\]'):
+        ens.get_returns(1e3, f=179e6, alpha=0.1, batch=2)
+    assert ens.last_status.tolist() == [0, 0, 0, 1]

@@ -346,3 +346,34 @@ def test_returns_kernel_log10(sim):
         w2 = np.log10(sp)
     assert o2[0] == -np.inf and np.isnan(o2[1]) and o2[2] == np.inf and np.isnan(o2[3])
     assert np.allclose(o2[4:], w2[4:], rtol=1e-15, atol=0)
+
+
+def test_near_degenerate_pair_crossing_at_oblique_incidence(sim):
+    from tamm_b200 import profiles
+    """Where the p and s branches of a smoothly rotating fabric cross at oblique incidence (configs[1], FABRIC_TYPE 3,
+    alpha = 10 deg, azimuth pi, layers 2662-2666 of the 3001-layer profile) the transmitted pair splits by only
+    1e-10 ... 2e-8.  Both refinements of the pair solver used to end on the SAME root there (round 1: q0 == q1, 0.8 % error
+    of the local reflection).  A fine sweep through the crossing: every root of the hot path within 1e-15 of the
+    extended-precision roots, no duplicated root, and the cold solver's deflation step was exercised."""
+    nlm, z = profiles.rathmann_transition(3001, 3000, fabric_type=3)
+    M = 801
+    t = np.linspace(0, 1, M)[:, None]
+    nl = np.concatenate([nlm[:1], nlm[2662][None] * (1 - t) + nlm[2666][None] * t])
+    os_ = orc.OracleStack(nl, np.linspace(0, -M, M + 1), N_frames=2)
+    beta, alpha = np.array([np.pi]), np.deg2rad(10)
+    qx = os_.layers(179e6, alpha, beta=beta, eig='factored', precision='extended')['qs'][0]
+    lay = packing.pack_layers(os_.nlm, os_.dz, os_.epsa, os_.epsc, os_.sigma)
+    lan = packing.pack_lanes(beta, 179e6)
+    N = os_.N_layers
+    qs = np.zeros((1, N, 4), np.complex128)
+    _solver_stats(sim)
+    assert sim.hostsim_modes(_P(lay), _P(lan), N, 1, ctypes.c_double(os_.zeta(alpha)), ctypes.c_double(1.0), _P(qs), None) == 0
+    st = _solver_stats(sim)
+    split = np.abs((qx[:, 0] - qx[:, 1]).astype(np.complex128))
+    assert 1e-10 < split[1:].min() < 1e-9 and split[1:].max() < 3e-8          # the regime under test
+    for n in range(1, N):
+        for sl in (slice(0, 2), slice(2, 4)):
+            got, want = np.sort_complex(qs[0, n, sl].astype(np.clongdouble)), np.sort_complex(qx[n, sl])
+            assert float(np.abs(got - want).max()) < 1e-15, (n, got, want)
+        assert abs(qs[0, n, 0] - qs[0, n, 1]) > 0.5 * split[n]
+    assert st['collapsed'] >= M and st['recentre'] > 0 and st['fallback'] >= M
