@@ -81,8 +81,8 @@ int tamm_suggest_chunk(int P, int N, int QF, int sm_count);
  *   planes    : out, complex128 [P][N-1][4][QF]; chunk-LOCAL products U_loc R D_loc (or U_loc)
  *   workspace : tamm_stack_workspace_bytes() bytes; receives per-chunk aggregates and exclusive prefixes
  * After this call `planes` + `workspace` together define the result; tamm_returns / tamm_export_jones apply the
- * prefixes (URD_n = Upre_c * planes_n * Dpre_c).  status (int32 [P], may be NULL) is OR-ed with per-layer
- * status bits.
+ * prefixes (URD_n = Upre_c * planes_n * Dpre_c).  status (int32 [P], may be NULL) is zeroed on `stream` and
+ * then receives the OR of the per-layer status bits of each profile.
  */
 int tamm_stack_urd(const double* layers, const double* lanes, int P, int N, int Q, int F, double zeta, double mu,
                    int mode, int chunk, void* planes, void* workspace, int* status, void* stream);
@@ -116,6 +116,22 @@ int tamm_export_jones(const void* planes, const void* workspace, int P, int N, i
 int tamm_returns(const void* planes, const void* workspace, int P, int N, int Q, int F, int mode, int chunk,
                  const double* etx, int gtm_phase, void* E_HH, void* E_HV, void* c_HHVV, double* dP_HH,
                  double* dP_HV, double* Pm_HH, double* Pm_HV, void* stream);
+
+/*
+ * The same returns with the azimuth mean split open, for a stack whose AZIMUTHS are sharded over several GPUs
+ * (the mean over azimuth in Pm / dP, layerstack.py:262,266, is the only cross-lane operation of the path).
+ *   tamm_returns_partial : E_HH, E_HV, c_HHVV as tamm_returns for the F local azimuths; amp_HH, amp_HV = |E| (double
+ *                          [P][Q][N-1][F]); sum_HH, sum_HV = sum over the LOCAL azimuths of |E| (double [P][Q][N-1]) -- no dB.
+ *   (caller: all-reduce(sum) of sum_HH, sum_HV over the ranks that share the stack -- (N-1) x 2 doubles per (P, Q))
+ *   tamm_returns_finish  : Pm = 20 log10(sum / F_total), dP = 20 log10|E| - Pm written over amp_* (layerstack.py:261-267).
+ *                          Pm_* may alias sum_*.  F_total = number of azimuths of the whole grid.
+ * With one rank (F_total = F) the pair equals tamm_returns' two-pass path.
+ */
+int tamm_returns_partial(const void* planes, const void* workspace, int P, int N, int Q, int F, int mode, int chunk,
+                         const double* etx, int gtm_phase, void* E_HH, void* E_HV, void* c_HHVV, double* amp_HH,
+                         double* amp_HV, double* sum_HH, double* sum_HV, void* stream);
+int tamm_returns_finish(double* amp_HH, double* amp_HV, const double* sum_HH, const double* sum_HV, int P, int N, int Q, int F,
+                        int F_total, double* Pm_HH, double* Pm_HV, void* stream);
 
 #ifdef __cplusplus
 }

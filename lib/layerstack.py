@@ -118,25 +118,41 @@ class LayerStack:
         return _packing.pack_layers(self.nlm, self.dz, self.epsa, self.epsc, self.sigma)
 
     def _run(self, betas, f, zeta, mode):
-        """Hot path on the device for this stack: returns (engine, StackResult)."""
+        """Hot path on the device for this stack: returns (engine, StackResult).  The packed layer records and the lane
+        table go host -> device through one pinned staging buffer and one asynchronous copy; nothing here waits for
+        the device (the status word is read together with the results, see _check_status)."""
         if self.N_layers < 2:
             raise ValueError('need at least two layers to form an interface')
         eng = _get_engine()
         fa = np.atleast_1d(np.asarray(f, dtype=np.float64))
-        lanes = eng.to_device(_packing.pack_lanes(betas, fa))
+        lanes_h = _packing.pack_lanes(betas, fa)
         if self.modeltype == 'FP':     # layer.py:100-128, layerstack.py:158-181
-            lay = _packing.pack_layers_fp(self.nlm, self.dz, self.epsa, self.epsc, self.sigma)
-            res = eng.stack_fp(eng.to_device(lay[None]), lanes, 1, self.N_layers, fa.size, len(betas))
+            lay_h = _packing.pack_layers_fp(self.nlm, self.dz, self.epsa, self.epsc, self.sigma)
+            lay, lanes = eng.stage_inputs(lay_h[None], lanes_h)
+            res = eng.stack_fp(lay, lanes, 1, self.N_layers, fa.size, len(betas))
         else:
-            layers = eng.to_device(self._packed_layers()[None])
-            res = eng.stack(layers, lanes, 1, self.N_layers, fa.size, len(betas), zeta, self.mu, mode)
-            if int(res.status.cpu()[0]) & 1:
-                # layer_PPJ.py:216-231 assumes two transmitted and two reflected modes; the reference indexes out of
-                # bounds (IndexError) or mis-sorts silently when that fails.  The device flags it instead.
-                import warnings
-                warnings.warn('tamm_b200: a layer did not have 2 transmitted + 2 reflected modes '
-                              '(layer_PPJ.py:216-231); results for this stack are unreliable', UserWarning)
+            lay, lanes = eng.stage_inputs(self._packed_layers()[None], lanes_h)
+            res = eng.stack(lay, lanes, 1, self.N_layers, fa.size, len(betas), zeta, self.mu, mode)
         return eng, res
+
+    @staticmethod
+    def _check_status(status):
+        if status is not None and int(np.asarray(status).reshape(-1)[0]) & 1:
+            # layer_PPJ.py:216-231 assumes two transmitted and two reflected modes; the reference indexes out of
+            # bounds (IndexError) or mis-sorts silently when that fails.  The device flags it instead.
+            import warnings
+            warnings.warn('tamm_b200: a layer did not have 2 transmitted + 2 reflected modes '
+                          '(layer_PPJ.py:216-231); results for this stack are unreliable', UserWarning)
+
+    def _jones(self, frm_layers, mode):
+        betas, f, zeta = self._frames_args(frm_layers)
+        eng, res = self._run(betas, f, zeta, mode)
+        dev = eng.export_jones(res)
+        if res.status is None:
+            return eng.to_host(dev)[0][0, 0]
+        out, status = eng.to_host(dev, res.status)
+        self._check_status(status)
+        return out[0, 0]
 
     # ------------------------------------------------------------------------------------------
     def get_eigenbasis(self):
@@ -193,44 +209,101 @@ class LayerStack:
 
     def get_URD(self, frm_layers):
         """layerstack.py:135-196: total downward-reflected-upward 2x2 transformation, shape (N_frames, N_layers-1, 2, 2)."""
-        betas, f, zeta = self._frames_args(frm_layers)
-        eng, res = self._run(betas, f, zeta, MODE_URD)
-        return eng.export_jones(res).cpu().numpy()[0, 0]
+        return self._jones(frm_layers, MODE_URD)
 
     def get_U(self, frm_layers):
         """layerstack.py:198-225: upward product only, shape (N_frames, N_layers-1, 2, 2)."""
         if self.modeltype != 'GTM':
             raise ValueError('Only GTM model type supported')
-        betas, f, zeta = self._frames_args(frm_layers)
-        eng, res = self._run(betas, f, zeta, MODE_U)
-        return eng.export_jones(res).cpu().numpy()[0, 0]
+        return self._jones(frm_layers, MODE_U)
 
     # ------------------------------------------------------------------------------------------
     def dB(self, amp):
         """layerstack.py:229."""
         return 20 * np.log10(amp)
 
-    def get_returns(self, E0, f=179.0e6, alpha=0, Tx_pol=([1, 0],), URD='URD', nn=None):
-        """layerstack.py:232-288 -> (Pm_HH, Pm_HV, dP_HH, dP_HV, c_HHVV, E_HH, E_HV), depth-major and squeezed
-        exactly like the reference.  `f` may be an array (extension): a leading frequency axis is added."""
-        self.epsiso = (2 * self.epsa[0] + self.epsc[0]) / 3
-        zeta = np.sqrt(self.epsiso) * np.sin(alpha)
-
+    def _mode(self, URD):
         if URD == 'URD':
-            mode = MODE_URD
-        elif URD == 'U':
+            return MODE_URD
+        if URD == 'U':
             if self.modeltype != 'GTM':
                 raise ValueError('Only GTM model type supported')
-            mode = MODE_U
+            return MODE_U
+        raise ValueError('get_returns(): argument URD="%s" not understood' % (URD))
+
+    def _solve_returns(self, E0, f, alpha, pols, URD, shard=None):
+        """Device part of get_returns / get_returns_polarimetric: ONE pass over the stack, one returns pass per transmit
+        polarisation in `pols`, one device->host copy per polarisation, one synchronisation.
+        -> (list of dict name -> host array (Q, N-1, F) / (Q, N-1), zeta).
+        shard: tamm_b200.distributed.AxisShard or None -- split the azimuth grid or the frequency vector over the ranks of
+        a process group."""
+        self.epsiso = (2 * self.epsa[0] + self.epsc[0]) / 3                       # layerstack.py:236
+        zeta = np.sqrt(self.epsiso) * np.sin(alpha)
+        mode = self._mode(URD)
+        betas, fa = self.beta, np.atleast_1d(np.asarray(f, dtype=np.float64))
+        if shard is not None and shard.world > 1:
+            if shard.axis == 'azimuth':
+                lo, hi = shard.range(len(betas))
+                betas = betas[lo:hi]
+            else:
+                lo, hi = shard.range(fa.size)
+                fa = fa[lo:hi]
+            if hi <= lo:
+                raise ValueError('AxisShard: rank %d of %d has no %s to evaluate' % (shard.rank, shard.world, shard.axis))
+        eng, res = self._run(betas, fa, zeta, mode)
+        gtm = (self.modeltype == 'GTM')
+        split_mean = shard is not None and shard.world > 1 and shard.axis == 'azimuth'
+        bufs, devs = [], []
+        for pol in pols:
+            E_Tx = np.array([E0 * pol[0], E0 * pol[1]], dtype=np.complex128)     # layerstack.py:249
+            buf, views = eng.new_returns(1, fa.size, self.N_layers - 1, len(betas))
+            if split_mean:
+                from tamm_b200 import distributed as tdist
+                eng.returns_partial(res, E_Tx, gtm_phase=gtm, out=views)
+                tdist.all_reduce_azimuth_sums(views['Pm_HH'], shard.group)       # the only exchange of the compute path
+                tdist.all_reduce_azimuth_sums(views['Pm_HV'], shard.group)
+                eng.returns_finish(views, self.N_frames)
+            else:
+                eng.returns(res, E_Tx, gtm_phase=gtm, out=views)
+            bufs.append(buf)
+            devs.append(views)
+        if shard is not None and shard.world > 1 and shard.gather:
+            # final all-gather along the sharded axis (north_star): every rank gets the whole result
+            from tamm_b200 import distributed as tdist
+            full = []
+            for views in devs:
+                g = {}
+                for name, v in views.items():
+                    if shard.axis == 'azimuth':
+                        g[name] = v if name.startswith('Pm') else tdist.all_gather_axis(v, 3, self.N_frames, shard.group)
+                    else:
+                        g[name] = tdist.all_gather_axis(v, 1, np.atleast_1d(f).size, shard.group)
+                full.append(g)
+            names = list(full[0])
+            flat = [g[n] for g in full for n in names]
+            fetched = eng.to_host(*(flat + ([res.status] if res.status is not None else [])))
+            hosts = [{n: fetched[i * len(names) + j][0] for j, n in enumerate(names)} for i in range(len(full))]
         else:
-            raise ValueError('get_returns(): argument URD="%s" not understood' % (URD))
+            fetched = eng.to_host(*(bufs + ([res.status] if res.status is not None else [])))
+            layout, _ = eng.returns_layout(1, fa.size, self.N_layers - 1, len(betas))
+            hosts = []
+            for i in range(len(bufs)):
+                hb = fetched[i]
+                host = {}
+                for name, (off, cnt, shape, cplx) in layout.items():
+                    a = hb[off:off + cnt]
+                    host[name] = (a.view(np.complex128) if cplx else a).reshape(shape)[0]
+                hosts.append(host)
+        if res.status is not None:
+            self._check_status(fetched[-1])
+        self.frm_layers = _LazyFrames(self, float(np.atleast_1d(f)[0]) if np.ndim(f) else f, zeta)   # layerstack.py:286
+        return hosts
 
-        eng, res = self._run(self.beta, f, zeta, mode)
-        p = Tx_pol[0]
-        E_Tx = np.array([E0 * p[0], E0 * p[1]], dtype=np.complex128)            # layerstack.py:249
-        out = eng.returns(res, E_Tx, gtm_phase=(self.modeltype == 'GTM'))
-        host = {k: v.cpu().numpy()[0] for k, v in out.items()}                   # (Q, N-1, F) / (Q, N-1)
-
+    def get_returns(self, E0, f=179.0e6, alpha=0, Tx_pol=([1, 0],), URD='URD', nn=None, shard=None):
+        """layerstack.py:232-288 -> (Pm_HH, Pm_HV, dP_HH, dP_HV, c_HHVV, E_HH, E_HV), depth-major and squeezed
+        exactly like the reference.  Extensions: `f` may be an array (a leading frequency axis is added); `shard` (a
+        tamm_b200.distributed.AxisShard) splits the azimuths or the frequencies over the GPUs of a process group."""
+        host = self._solve_returns(E0, f, alpha, [Tx_pol[0]], URD, shard)[0]      # layerstack.py:249-252: only Tx_pol[0]
         scalar_f = (np.ndim(f) == 0)
         I = slice(None) if nn is None else slice(nn, nn + 1) if nn != -1 else slice(nn, None)
 
@@ -242,41 +315,25 @@ class LayerStack:
                 a = a[0]
             return np.squeeze(a)
 
-        returns = (fmt('Pm_HH', 'Pm'), fmt('Pm_HV', 'Pm'), fmt('dP_HH', 'x'), fmt('dP_HV', 'x'),
-                   fmt('c_HHVV', 'x'), fmt('E_HH', 'x'), fmt('E_HV', 'x'))
+        return (fmt('Pm_HH', 'Pm'), fmt('Pm_HV', 'Pm'), fmt('dP_HH', 'x'), fmt('dP_HV', 'x'),
+                fmt('c_HHVV', 'x'), fmt('E_HH', 'x'), fmt('E_HV', 'x'))
 
-        self.frm_layers = _LazyFrames(self, f if scalar_f else np.atleast_1d(f)[0], zeta)   # layerstack.py:286
-        return returns
-
-    def get_returns_polarimetric(self, E0, f=179.0e6, alpha=0, URD='URD'):
+    def get_returns_polarimetric(self, E0, f=179.0e6, alpha=0, URD='URD', shard=None):
         """Extension: all four Tx/Rx pairs of layerstack.py:252-255 from ONE pass over the stack --
         the reference computes E_VH, E_VV only when Tx_pol has a second entry and then drops them (254-255).
         -> dict: E_xy, dP_xy, Pm_xy for xy in HH, HV (Tx = H = [1,0]) and VH, VV (Tx = V = [0,1]), plus c_HHVV; same
         depth-major shapes as get_returns.  Equals get_returns(..., Tx_pol=([1,0],)) and get_returns(..., Tx_pol=([0,1],))."""
-        self.epsiso = (2 * self.epsa[0] + self.epsc[0]) / 3
-        zeta = np.sqrt(self.epsiso) * np.sin(alpha)
-        if URD == 'URD':
-            mode = MODE_URD
-        elif URD == 'U':
-            if self.modeltype != 'GTM':
-                raise ValueError('Only GTM model type supported')
-            mode = MODE_U
-        else:
-            raise ValueError('get_returns(): argument URD="%s" not understood' % (URD))
-        eng, res = self._run(self.beta, f, zeta, mode)
+        hosts = self._solve_returns(E0, f, alpha, [(1, 0), (0, 1)], URD, shard)
         scalar_f = (np.ndim(f) == 0)
         out = {}
-        for tx, pol in (('H', (1, 0)), ('V', (0, 1))):
-            E_Tx = np.array([E0 * pol[0], E0 * pol[1]], dtype=np.complex128)
-            dev = eng.returns(res, E_Tx, gtm_phase=(self.modeltype == 'GTM'))
+        for (tx, host) in zip(('H', 'V'), hosts):
             for rx, col in (('H', 'HH'), ('V', 'HV')):        # the kernel's "HH"/"HV" are Rx = H / V of this Tx
                 for kind in ('E', 'dP', 'Pm'):
-                    a = dev['%s_%s' % (kind, col)].cpu().numpy()[0]
+                    a = host['%s_%s' % (kind, col)]
                     out['%s_%s%s' % (kind, tx, rx)] = np.squeeze(a[0] if scalar_f else a)
             if tx == 'H':
-                a = dev['c_HHVV'].cpu().numpy()[0]
+                a = host['c_HHVV']
                 out['c_HHVV'] = np.squeeze(a[0] if scalar_f else a)
-        self.frm_layers = _LazyFrames(self, f if scalar_f else np.atleast_1d(f)[0], zeta)
         return out
 
     def get_Rx_all(self, E_Tx_list, URD, nn=None):

@@ -3,7 +3,10 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libtamm_b200.so')
+DEFAULT_LIB_PATH = os.path.join(_HERE, 'libtamm_b200.so')
+# TAMM_B200_LIB selects another build of the SAME library (A/B experiments, tools/ab_variant.sh) without ever replacing
+# the in-tree file; `fingerprint()` says which file is loaded so that bench lines and test logs record it.
+LIB_PATH = os.environ.get('TAMM_B200_LIB') or DEFAULT_LIB_PATH
 
 _vp = ctypes.c_void_p
 _i = ctypes.c_int
@@ -22,6 +25,8 @@ SIGNATURES = {
     'tamm_stack_urd_fp': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     'tamm_export_jones': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     'tamm_returns': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, ctypes.POINTER(_d), _i] + [_vp] * 7 + [_vp]),
+    'tamm_returns_partial': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, ctypes.POINTER(_d), _i] + [_vp] * 7 + [_vp]),
+    'tamm_returns_finish': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
 }
 
 _lib = None
@@ -47,6 +52,13 @@ def load():
         fn.argtypes = args
     _lib = lib
     return lib
+
+
+def fingerprint():
+    """(path, md5 of the file) of the library in use -- recorded in the bench JSON line."""
+    import hashlib
+    with open(LIB_PATH, 'rb') as f:
+        return LIB_PATH, hashlib.md5(f.read()).hexdigest()
 
 
 def check(rc, lib=None):

@@ -516,7 +516,7 @@ __device__ __forceinline__ double warp_sum8(const double v[8], int lane) {
 // arithmetic of the two-pass kernels is used (hypot like numpy.abs, true division), so the result does not depend on
 // which returns kernel F selects and stays finite exactly where the reference's is.
 __device__ __forceinline__ unsigned exp_field(double x) { return ((unsigned)__double2hiint(x) >> 20) & 0x7ffu; }
-__device__ __noinline__ void returns_point_slow(cd m0, cd m3, cd hh, cd hv, cd& c, double& ahh, double& ahv) {
+__device__ __forceinline__ void returns_point_slow(cd m0, cd m3, cd hh, cd hv, cd& c, double& ahh, double& ahv) {
     const cd num = m0 * conj(m3);
     const double den = cabs_(m0) * cabs_(m3);
     c = cd{num.re / den, num.im / den};
@@ -763,14 +763,18 @@ returns_tma_kernel(const cd* __restrict__ planes, const cd* __restrict__ pre, in
 }
 
 // one warp per (p, iq, n): azimuth mean of |E|, dB, anomaly (layerstack.py:257-267).  a* hold |E| on entry, dP on exit.
+// Split in two so that a stack whose azimuths are sharded over several GPUs can sum the partial sums over ranks in
+// between (the azimuth mean is the only cross-lane operation of the whole path):
+//   azimuth_sum_kernel    sum over the LOCAL azimuths of |E_HH|, |E_HV| per depth   -> sHH, sHV
+//   power_finish_kernel   Pm = dB(sum / F_total), dP = dB|E| - Pm                   (F_total = azimuths of the whole grid)
 __global__ void __launch_bounds__(256)
-power_kernel(double* __restrict__ aHH, double* __restrict__ aHV, double* __restrict__ Pm_HH, double* __restrict__ Pm_HV,
-             long nrows, int F) {
+azimuth_sum_kernel(const double* __restrict__ aHH, const double* __restrict__ aHV, double* __restrict__ sHH,
+                   double* __restrict__ sHV, long nrows, int F) {
     const int lane = threadIdx.x & 31;
     const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= nrows) return;
-    double* h = aHH + (size_t)row * F;
-    double* v = aHV + (size_t)row * F;
+    const double* h = aHH + (size_t)row * F;
+    const double* v = aHV + (size_t)row * F;
     double sh = 0.0, sv = 0.0;
     for (int f = lane; f < F; f += 32) { sh += h[f]; sv += v[f]; }
 #pragma unroll
@@ -778,8 +782,21 @@ power_kernel(double* __restrict__ aHH, double* __restrict__ aHV, double* __restr
         sh += __shfl_xor_sync(0xffffffffu, sh, off);
         sv += __shfl_xor_sync(0xffffffffu, sv, off);
     }
-    const double pmh = 20.0 * log10(sh / (double)F);
-    const double pmv = 20.0 * log10(sv / (double)F);
+    if (lane == 0) { sHH[row] = sh; sHV[row] = sv; }
+}
+__global__ void __launch_bounds__(256)
+power_finish_kernel(double* __restrict__ aHH, double* __restrict__ aHV, const double* __restrict__ sHH,
+                    const double* __restrict__ sHV, double* __restrict__ Pm_HH, double* __restrict__ Pm_HV, long nrows, int F,
+                    int F_total) {
+    const int lane = threadIdx.x & 31;
+    const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= nrows) return;
+    double* h = aHH + (size_t)row * F;
+    double* v = aHV + (size_t)row * F;
+    const double pmh = 20.0 * log10(sHH[row] / (double)F_total);
+    const double pmv = 20.0 * log10(sHV[row] / (double)F_total);
+    // Pm may alias the sums (in-place finish): every lane has read its row's sums before lane 0 overwrites them
+    __syncwarp();
     if (lane == 0) { Pm_HH[row] = pmh; Pm_HV[row] = pmv; }
     for (int f = lane; f < F; f += 32) {
         h[f] = 20.0 * log10(h[f]) - pmh;
@@ -884,10 +901,27 @@ int pick_block(int QF, int maxt = 256) {
     return best;
 }
 
-// launch-bound variants of stack_kernel: threads per CTA (CTAs per SM, registers):
-//   0: 256 (1, 255)   5: 384 (1, 168, default).  One CTA per SM either way: the per-thread shared-memory state
-//   (CARRY_SLOTS x 16 B) of 384 threads fills the SM's 227 KB.
-int variant_threads(int v) { return v == 0 ? 256 : 384; }
+// launch-bound variants of stack_kernel: threads per CTA x CTAs per SM (registers):
+//   0: 256 x 1 (255)   5: 384 x 1 (168, default for batches)   6: 192 x 2 (168).
+// Either way the per-thread shared-memory state (CARRY_SLOTS x 16 B) of 384 threads fills the SM's 227 KB.  Variant 6
+// has the same threads, registers and shared memory per SM as variant 5 in two half-size CTAs: it is chosen when the
+// whole batch has at most 192 (profile, lane) pairs (a single profile on the reference's 181-azimuth grid), where
+// one CTA per SM would leave only 6 warps on an SM -- too few to keep the FP64 pipe issuing.
+int variant_threads(int v) { return v == 0 ? 256 : (v == 6 ? 192 : 384); }
+int variant_ctas_per_sm(int v) { return v == 6 ? 2 : 1; }
+
+int stack_variant(int P, int QF) {
+    static std::atomic<int> env_once{-2};
+    int env = env_once.load(std::memory_order_relaxed);
+    if (env == -2) {
+        const char* ev = getenv("TAMM_STACK_VARIANT");
+        env = ev ? atoi(ev) : -1;
+        if (env != 0 && env != 5 && env != 6) env = -1;
+        env_once.store(env, std::memory_order_relaxed);
+    }
+    if (env >= 0) return env;
+    return ((long)P * QF <= 192) ? 6 : TAMM_DEFAULT_VARIANT;
+}
 
 // CTA geometry of stack_kernel: flattened lanes whenever a CTA of `maxt` threads spans at most NPMAX profiles.
 void stack_geometry(int P, int QF, int maxt, int* tb, int* flat, long* gx) {
@@ -955,11 +989,9 @@ size_t tamm_stack_workspace_bytes(int P, int N, int QF, int chunk) {
 int tamm_suggest_chunk(int P, int N, int QF, int sm_count) {
     if (N < 2) return 1;
     const int NI = N - 1;
-    const char* ev = getenv("TAMM_STACK_VARIANT");
-    int variant = ev ? atoi(ev) : TAMM_DEFAULT_VARIANT;
-    if (variant < 0 || variant > 5) variant = TAMM_DEFAULT_VARIANT;
+    const int variant = stack_variant(P, QF);
     const int maxt = variant_threads(variant);
-    const int ctas_per_sm = 1;
+    const int ctas_per_sm = variant_ctas_per_sm(variant);
     int tb, flat;
     long bpc;                                                              // CTAs per chunk index
     stack_geometry(P, QF, maxt, &tb, &flat, &bpc);
@@ -1001,14 +1033,7 @@ int tamm_stack_urd(const double* layers, const double* lanes, int P, int N, int 
     if (nch > 65535) return fail("tamm_stack_urd: grid too large (chunks > 65535)%s", "");
     if (nch > 1 && !workspace) return fail("tamm_stack_urd: workspace required%s", "");
     // launch-bound variant (occupancy vs spills); TAMM_STACK_VARIANT overrides for experiments
-    static std::atomic<int> variant_once{-1};
-    int variant = variant_once.load(std::memory_order_relaxed);
-    if (variant < 0) {
-        const char* ev = getenv("TAMM_STACK_VARIANT");
-        variant = ev ? atoi(ev) : TAMM_DEFAULT_VARIANT;
-        if (variant < 0 || variant > 5) variant = TAMM_DEFAULT_VARIANT;
-        variant_once.store(variant, std::memory_order_relaxed);
-    }
+    const int variant = stack_variant(P, QF);
     const int maxt = variant_threads(variant);
     int tb, flat;
     long gx;
@@ -1017,6 +1042,7 @@ int tamm_stack_urd(const double* layers, const double* lanes, int P, int N, int 
     dim3 grid((unsigned)gx, nch, 1);
     cd* agg = (cd*)workspace;
     cudaStream_t s = (cudaStream_t)stream;
+    if (status) CUDA_OK(cudaMemsetAsync(status, 0, (size_t)P * sizeof(int), s));   // the kernels OR their bits into it
     const size_t dyn = (size_t)CARRY_SLOTS * sizeof(double2) * maxt;   // per-thread slots at the kernel's fixed stride
 #define TAMM_LAUNCH(MODE, MAXT, MINB)                                                                                   \
     do {                                                                                                                \
@@ -1037,9 +1063,11 @@ int tamm_stack_urd(const double* layers, const double* lanes, int P, int N, int 
     } while (0)
     if (mode == TAMM_MODE_URD) {
         if (variant == 0) TAMM_LAUNCH(TAMM_MODE_URD, 256, 1);
+        else if (variant == 6) TAMM_LAUNCH(TAMM_MODE_URD, 192, 2);
         else TAMM_LAUNCH(TAMM_MODE_URD, 384, 1);
     } else {
         if (variant == 0) TAMM_LAUNCH(TAMM_MODE_U, 256, 1);
+        else if (variant == 6) TAMM_LAUNCH(TAMM_MODE_U, 192, 2);
         else TAMM_LAUNCH(TAMM_MODE_U, 384, 1);
     }
 #undef TAMM_LAUNCH
@@ -1148,7 +1176,41 @@ int tamm_returns(const void* planes, const void* workspace, int P, int N, int Q,
     CUDA_OK(cudaGetLastError());
     long nrows = (long)P * Q * NI;
     int grid2 = (int)((nrows + 7) / 8);
-    power_kernel<<<grid2, 256, 0, s>>>(dP_HH, dP_HV, Pm_HH, Pm_HV, nrows, F);
+    // the sums go through the Pm arrays (finished in place)
+    azimuth_sum_kernel<<<grid2, 256, 0, s>>>(dP_HH, dP_HV, Pm_HH, Pm_HV, nrows, F);
+    CUDA_OK(cudaGetLastError());
+    power_finish_kernel<<<grid2, 256, 0, s>>>(dP_HH, dP_HV, Pm_HH, Pm_HV, Pm_HH, Pm_HV, nrows, F, F);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int tamm_returns_partial(const void* planes, const void* workspace, int P, int N, int Q, int F, int mode, int chunk,
+                         const double* etx, int gtm_phase, void* E_HH, void* E_HV, void* c_HHVV, double* amp_HH,
+                         double* amp_HV, double* sum_HH, double* sum_HV, void* stream) {
+    if (!planes || !etx || !E_HH || !E_HV || !c_HHVV || !amp_HH || !amp_HV || !sum_HH || !sum_HV)
+        return fail("tamm_returns_partial: null pointer%s", "");
+    if (P < 1 || N < 2 || Q < 1 || F < 1 || chunk < 1 || !lanes_fit(Q, F)) return fail("tamm_returns_partial: bad sizes%s", "");
+    if (P > 65535) return fail("tamm_returns_partial: P > 65535%s", "");
+    const int QF = Q * F, NI = N - 1, nch = nchunks_of(N, chunk);
+    const cd* pre = nch > 1 ? (const cd*)workspace + (size_t)P * QF * nch * 8 : nullptr;
+    cudaStream_t s = (cudaStream_t)stream;
+    dim3 grid((QF + 127) / 128, (NI + TN - 1) / TN, P);
+    returns_kernel<<<grid, 128, 0, s>>>((const cd*)planes, pre, N, Q, F, mode, chunk, nch, cd{etx[0], etx[1]},
+                                        cd{etx[2], etx[3]}, gtm_phase, (cd*)E_HH, (cd*)E_HV, (cd*)c_HHVV, amp_HH, amp_HV);
+    CUDA_OK(cudaGetLastError());
+    const long nrows = (long)P * Q * NI;
+    azimuth_sum_kernel<<<(int)((nrows + 7) / 8), 256, 0, s>>>(amp_HH, amp_HV, sum_HH, sum_HV, nrows, F);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int tamm_returns_finish(double* amp_HH, double* amp_HV, const double* sum_HH, const double* sum_HV, int P, int N, int Q, int F,
+                        int F_total, double* Pm_HH, double* Pm_HV, void* stream) {
+    if (!amp_HH || !amp_HV || !sum_HH || !sum_HV || !Pm_HH || !Pm_HV) return fail("tamm_returns_finish: null pointer%s", "");
+    if (P < 1 || N < 2 || Q < 1 || F < 1 || F_total < F) return fail("tamm_returns_finish: bad sizes%s", "");
+    const long nrows = (long)P * Q * (N - 1);
+    power_finish_kernel<<<(int)((nrows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(amp_HH, amp_HV, sum_HH, sum_HV, Pm_HH, Pm_HV,
+                                                                                  nrows, F, F_total);
     CUDA_OK(cudaGetLastError());
     return 0;
 }

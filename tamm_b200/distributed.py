@@ -109,13 +109,81 @@ class PipelinedGather:
         return self.full
 
 
-def all_reduce_azimuth_sums(sums, group=None):
-    """For the alternative azimuth sharding of a single profile (configs[1], [3]): the per-depth sums of |E| over the
-    local azimuths are summed over ranks before the dB step (layerstack.py:262).  Tiny: (N-1) x 2 doubles."""
+def _via_host(t, group):
+    """gloo moves host memory only: CUDA tensors are staged through the CPU for that backend (world-size-2 tests on ONE
+    GPU; NCCL refuses two ranks on one device)."""
     import torch.distributed as dist
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
-    return sums
+    return t.is_cuda and dist.get_backend(group) == 'gloo'
+
+
+def all_reduce_sum(t, group=None):
+    """In-place sum over the ranks of `group` (no-op without a process group)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return t
+    if _via_host(t, group):
+        h = t.cpu()
+        dist.all_reduce(h, op=dist.ReduceOp.SUM, group=group)
+        t.copy_(h)
+    else:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
+
+
+def all_reduce_azimuth_sums(sums, group=None):
+    """Azimuth sharding of a single stack (configs[1], [3]): the per-depth sums of |E| over the local azimuths
+    (tamm_returns_partial) are summed over the ranks before the dB step (layerstack.py:262) -- (N-1) x 2 doubles per
+    (profile, frequency), the only exchange on the compute path of any configuration."""
+    return all_reduce_sum(sums, group)
+
+
+def all_gather_axis(local, axis, n_total, group=None):
+    """All-gather tensors that are shards of one axis (balanced contiguous split, `shard_range`) into the full tensor on
+    every rank.  Uneven shards are padded to the largest one for the collective."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return local
+    ws = dist.get_world_size(group)
+    sizes = shard_sizes(n_total, ws)
+    assert local.shape[axis] == sizes[dist.get_rank(group)], (tuple(local.shape), axis, sizes)
+    m = max(sizes)
+    x = local.movedim(axis, 0)
+    cplx = x.is_complex()
+    x = torch.view_as_real(x.contiguous()) if cplx else x.contiguous()
+    if x.shape[0] < m:
+        x = torch.cat([x, torch.zeros((m - x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)], dim=0)
+    dev = x.device
+    if _via_host(x, group):
+        x = x.cpu()
+    out = torch.empty((ws * m,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    dist.all_gather_into_tensor(out, x.contiguous(), group=group)
+    full = torch.cat([out[r * m: r * m + sizes[r]] for r in range(ws)], dim=0) if len(set(sizes)) > 1 else out
+    full = full.to(dev)
+    if cplx:
+        full = torch.view_as_complex(full.contiguous())
+    return full.movedim(0, axis)
+
+
+class AxisShard:
+    """How ONE stack solve (LayerStack.get_returns) is split over the ranks of a process group:
+      axis='azimuth'   : rank r evaluates its contiguous share of the azimuth grid; the per-depth sums of |E| over azimuth
+                         are all-reduced (tiny) before the dB step -- configs[1], configs[3];
+      axis='frequency' : rank r evaluates its share of the frequency vector; no exchange at all -- configs[2].
+    With gather=True (default) every rank ends up with the full result (all-gather along the sharded axis: the final
+    NCCL all-gather of north_star); with gather=False each rank returns its own shard."""
+
+    def __init__(self, axis, group=None, gather=True):
+        import torch.distributed as dist
+        if axis not in ('azimuth', 'frequency'):
+            raise ValueError('AxisShard: axis must be "azimuth" or "frequency"')
+        self.axis, self.group, self.gather = axis, group, gather
+        on = dist.is_available() and dist.is_initialized()
+        self.rank = dist.get_rank(group) if on else 0
+        self.world = dist.get_world_size(group) if on else 1
+
+    def range(self, n):
+        return shard_range(n, self.rank, self.world)
 
 
 def gather_bytes(P_total, N, Q, F, what='jones'):

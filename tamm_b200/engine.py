@@ -72,6 +72,41 @@ class Engine:
     def empty(self, shape, dtype):
         return _torch().empty(shape, dtype=dtype, device=self.device)
 
+    def stage_inputs(self, *arrays):
+        """Host float64 arrays -> device tensors of the same shapes through ONE pinned staging buffer and ONE
+        asynchronous host->device copy on the current stream (every array's offset is a multiple of 16 bytes)."""
+        torch = _torch()
+        arrays = [np.ascontiguousarray(a, dtype=np.float64) for a in arrays]
+        offs, total = [], 0
+        for a in arrays:
+            offs.append(total)
+            total += (a.size + 1) // 2 * 2
+        pin = torch.empty((total,), dtype=torch.float64, pin_memory=True)
+        pn = pin.numpy()
+        for a, o in zip(arrays, offs):
+            pn[o:o + a.size] = a.reshape(-1)
+        dev = pin.to(self.device, non_blocking=True)
+        return [dev[o:o + a.size].view(a.shape) for a, o in zip(arrays, offs)]
+
+    def new_returns(self, P, Q, NI, F):
+        """(buffer, views): the seven return arrays of tamm_returns in one device buffer (see returns_layout)."""
+        layout, total = self.returns_layout(P, Q, NI, F)
+        buf = self.empty((total,), _torch().float64)
+        return buf, self.returns_views(buf, layout)
+
+    def to_host(self, *tensors):
+        """Device tensors -> NumPy arrays through pinned host memory: one asynchronous copy each on the current stream,
+        ONE synchronisation.  The pinned blocks come from torch's caching host allocator, so repeated calls reuse them
+        once the caller has dropped the previous results; the arrays returned are views that keep their block alive."""
+        torch = _torch()
+        host = []
+        for t in tensors:
+            h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            h.copy_(t, non_blocking=True)
+            host.append(h)
+        torch.cuda.current_stream(self.device).synchronize()
+        return [h.numpy() for h in host]
+
     def suggest_chunk(self, P, N, QF):
         return int(self.lib.tamm_suggest_chunk(P, N, QF, self.sm_count))
 
@@ -92,8 +127,10 @@ class Engine:
         return best
 
     # -- hot path ------------------------------------------------------------------------------
-    def stack(self, layers, lanes, P, N, Q, F, zeta, mu=1.0, mode=MODE_URD, chunk=None, planes=None, workspace=None):
-        """layers: float64 device tensor (P, N, 10); lanes: float64 device tensor (Q*F, 8)."""
+    def stack(self, layers, lanes, P, N, Q, F, zeta, mu=1.0, mode=MODE_URD, chunk=None, planes=None, workspace=None,
+              status=None):
+        """layers: float64 device tensor (P, N, 10); lanes: float64 device tensor (Q*F, 8).  `status` (int32 device tensor
+        (P,), optional) is zeroed by the library before the launch."""
         torch = _torch()
         if np.iscomplexobj(zeta) and np.imag(zeta) != 0:
             raise NotImplementedError('complex zeta is not supported')
@@ -109,7 +146,9 @@ class Engine:
         wsb = int(self.lib.tamm_stack_workspace_bytes(P, N, QF, chunk))
         if workspace is None or workspace.numel() * 8 < wsb:
             workspace = self.empty(((wsb + 7) // 8,), torch.float64)
-        status = torch.zeros((P,), dtype=torch.int32, device=self.device)
+        if status is None:
+            status = torch.empty((P,), dtype=torch.int32, device=self.device)
+        assert status.dtype == torch.int32 and status.numel() >= P
         rc = self.lib.tamm_stack_urd(layers.data_ptr(), lanes.data_ptr(), P, N, Q, F, zeta, mu, mode, chunk,
                                      planes.data_ptr(), workspace.data_ptr(), status.data_ptr(), self._stream())
         _lib.check(rc, self.lib)
@@ -146,22 +185,77 @@ class Engine:
         self.launches += 1
         return out
 
+    RETURN_NAMES = ('E_HH', 'E_HV', 'c_HHVV', 'dP_HH', 'dP_HV', 'Pm_HH', 'Pm_HV')
+
+    @staticmethod
+    def returns_layout(P, Q, NI, F):
+        """Offsets (in doubles) of the seven return arrays inside ONE buffer, so that a host caller moves them with a
+        single copy: name -> (offset, doubles, shape, is_complex); total doubles.  Complex arrays come first (16-byte
+        aligned offsets)."""
+        n, m = P * Q * NI * F, P * Q * NI
+        lay, off = {}, 0
+        for name, cnt, shape, cplx in (('E_HH', 2 * n, (P, Q, NI, F), True), ('E_HV', 2 * n, (P, Q, NI, F), True),
+                                       ('c_HHVV', 2 * n, (P, Q, NI, F), True), ('dP_HH', n, (P, Q, NI, F), False),
+                                       ('dP_HV', n, (P, Q, NI, F), False), ('Pm_HH', m, (P, Q, NI), False),
+                                       ('Pm_HV', m, (P, Q, NI), False)):
+            lay[name] = (off, cnt, shape, cplx)
+            off += cnt
+        return lay, off
+
+    @staticmethod
+    def returns_views(buf, layout):
+        """Typed views of the seven arrays on a float64 buffer (torch tensor on any device)."""
+        torch = _torch()
+        out = {}
+        for name, (off, cnt, shape, cplx) in layout.items():
+            v = buf[off:off + cnt]
+            out[name] = torch.view_as_complex(v.view(shape + (2,))) if cplx else v.view(shape)
+        return out
+
     def returns(self, res, etx, gtm_phase=True, out=None):
         """etx = (E0*p0, E0*p1) complex.  -> dict of device tensors, depth-major (P, Q, N-1, F)."""
         torch = _torch()
         P, Q, F, NI = res.P, res.Q, res.F, res.N - 1
         if out is None:
-            out = dict(E_HH=self.empty((P, Q, NI, F), torch.complex128), E_HV=self.empty((P, Q, NI, F), torch.complex128),
-                       c_HHVV=self.empty((P, Q, NI, F), torch.complex128), dP_HH=self.empty((P, Q, NI, F), torch.float64),
-                       dP_HV=self.empty((P, Q, NI, F), torch.float64), Pm_HH=self.empty((P, Q, NI), torch.float64),
-                       Pm_HV=self.empty((P, Q, NI), torch.float64))
+            layout, total = self.returns_layout(P, Q, NI, F)
+            out = self.returns_views(self.empty((total,), torch.float64), layout)
         e = (ctypes.c_double * 4)(float(np.real(etx[0])), float(np.imag(etx[0])), float(np.real(etx[1])), float(np.imag(etx[1])))
         rc = self.lib.tamm_returns(res.planes.data_ptr(), res.workspace.data_ptr(), P, res.N, Q, F, res.mode, res.chunk, e,
                                    1 if gtm_phase else 0, out['E_HH'].data_ptr(), out['E_HV'].data_ptr(),
                                    out['c_HHVV'].data_ptr(), out['dP_HH'].data_ptr(), out['dP_HV'].data_ptr(),
                                    out['Pm_HH'].data_ptr(), out['Pm_HV'].data_ptr(), self._stream())
         _lib.check(rc, self.lib)
-        self.launches += 1 if 32 <= F <= 1024 else 2      # fused returns+power kernel, or returns + power
+        # fused returns+power kernel, or returns + azimuth sums + finish
+        self.launches += 1 if (32 <= F <= 1024 and Q <= 65535 and P <= 65535) else 3
+        return out
+
+    def returns_partial(self, res, etx, gtm_phase=True, out=None):
+        """First half of the returns for a stack whose azimuths are sharded over ranks (include/tamm_b200.h:
+        tamm_returns_partial): fields and coherence of the F local azimuths, |E| parked in out['dP_*'], and the sums of |E|
+        over the local azimuths in out['Pm_*'] -- all-reduce those over the ranks, then call `returns_finish`."""
+        torch = _torch()
+        P, Q, F, NI = res.P, res.Q, res.F, res.N - 1
+        if out is None:
+            layout, total = self.returns_layout(P, Q, NI, F)
+            out = self.returns_views(self.empty((total,), torch.float64), layout)
+        e = (ctypes.c_double * 4)(float(np.real(etx[0])), float(np.imag(etx[0])), float(np.real(etx[1])), float(np.imag(etx[1])))
+        rc = self.lib.tamm_returns_partial(res.planes.data_ptr(), res.workspace.data_ptr(), P, res.N, Q, F, res.mode, res.chunk,
+                                           e, 1 if gtm_phase else 0, out['E_HH'].data_ptr(), out['E_HV'].data_ptr(),
+                                           out['c_HHVV'].data_ptr(), out['dP_HH'].data_ptr(), out['dP_HV'].data_ptr(),
+                                           out['Pm_HH'].data_ptr(), out['Pm_HV'].data_ptr(), self._stream())
+        _lib.check(rc, self.lib)
+        self.launches += 2
+        return out
+
+    def returns_finish(self, out, F_total):
+        """Second half: out['Pm_*'] hold the azimuth sums of |E| over ALL ranks on entry, Pm in dB on exit; out['dP_*']
+        hold |E| on entry, the anomalies on exit (layerstack.py:257-267)."""
+        P, Q, NI, F = out['dP_HH'].shape
+        rc = self.lib.tamm_returns_finish(out['dP_HH'].data_ptr(), out['dP_HV'].data_ptr(), out['Pm_HH'].data_ptr(),
+                                          out['Pm_HV'].data_ptr(), P, NI + 1, Q, F, int(F_total), out['Pm_HH'].data_ptr(),
+                                          out['Pm_HV'].data_ptr(), self._stream())
+        _lib.check(rc, self.lib)
+        self.launches += 1
         return out
 
     def layer_matrices(self, layers, lanes, N, QF, zeta, mu=1.0):

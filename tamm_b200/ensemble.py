@@ -36,17 +36,28 @@ def shard_range(P, rank, world):
 class EnsembleStack:
 
     def __init__(self, nlm, z, N_frames=100, epsa=(3.17 - 0.034,), epsc=(3.17,), sigma=(1e-5,), mu=1, modeltype='GTM',
-                 shard=(0, 1), VERBOSE=0):
-        """nlm: (P, N, >=6) complex; z: (N,) shared interface depths; epsa/epsc/sigma: length 1, (N,) or (P, N)."""
+                 shard=(0, 1), shard_axis='profile', group=None, VERBOSE=0):
+        """nlm: (P, N, >=6) complex; z: (N,) shared interface depths; epsa/epsc/sigma: length 1, (N,) or (P, N).
+        shard = (rank, world) and shard_axis say which part of the (profile x frequency x azimuth) batch this process
+        evaluates:
+          'profile'   : a contiguous block of profiles (default; no exchange at all, the azimuth mean stays local);
+          'frequency' : all profiles, a contiguous block of the frequency vector passed to get_returns (no exchange);
+          'azimuth'   : all profiles, a contiguous block of the azimuth grid; the per-depth sums of |E| over azimuth are
+                        all-reduced over `group` (torch.distributed) before the dB step -- the one exchange of this path.
+        Results are always those of the local shard (profiles / frequencies / azimuths); tamm_b200.distributed has the
+        all-gathers that assemble them."""
         if modeltype not in ('GTM', 'FP'):
             raise ValueError('Argument "modeltype" must be either "GTM" or "FP"')
+        if shard_axis not in ('profile', 'frequency', 'azimuth'):
+            raise ValueError('shard_axis must be "profile", "frequency" or "azimuth"')
+        self.shard_axis, self.group = shard_axis, group
         nlm = np.asarray(nlm)
         if nlm.ndim != 3:
             raise ValueError('nlm must have shape (P, N, >=6)')
         self.modeltype = modeltype
         self.P_total, self.N_layers = nlm.shape[:2]
         self.rank, self.world = shard
-        self.lo, self.hi = shard_range(self.P_total, self.rank, self.world)
+        self.lo, self.hi = shard_range(self.P_total, self.rank, self.world) if shard_axis == 'profile' else (0, self.P_total)
         self.N_frames = N_frames
         self.beta = np.linspace(0, np.pi, N_frames)                       # layerstack.py:25
         z = np.asarray(z)
@@ -124,7 +135,17 @@ class EnsembleStack:
         fp = (self.modeltype == 'FP')
         eng = get_engine()
         fa = np.atleast_1d(np.asarray(f, dtype=np.float64))
-        Q, F, N, NI, Pl = fa.size, self.N_frames, self.N_layers, self.N_layers - 1, self.P_local
+        beta = self.beta
+        if self.world > 1 and self.shard_axis == 'frequency':
+            qlo, qhi = shard_range(fa.size, self.rank, self.world)
+            fa = fa[qlo:qhi]
+        elif self.world > 1 and self.shard_axis == 'azimuth':
+            flo, fhi = shard_range(self.N_frames, self.rank, self.world)
+            beta = beta[flo:fhi]
+        if fa.size == 0 or beta.size == 0:
+            raise ValueError('rank %d of %d has nothing to evaluate along the %s axis' % (self.rank, self.world, self.shard_axis))
+        split_mean = self.world > 1 and self.shard_axis == 'azimuth'
+        Q, F, N, NI, Pl = fa.size, beta.size, self.N_layers, self.N_layers - 1, self.P_local
         zeta = 0.0 if fp else self.zeta(alpha)
         etx = [np.array([E0 * p[0], E0 * p[1]], dtype=np.complex128) for p in pols]
         if batch is None:   # keep device buffers around 2 x 4 GiB
@@ -135,7 +156,7 @@ class EnsembleStack:
         for i in range(len(pols)):
             if outs[i] is None:
                 outs[i] = {n: _pinned_empty(shapes[n], dtypes[n]) for n in outputs}
-        lanes = eng.to_device(packing.pack_lanes(self.beta, fa))
+        lanes = eng.to_device(packing.pack_lanes(beta, fa))
         lay_all = self._packed_pinned(fp)
         compute, copy = eng.current_stream(), eng.new_stream()
         dev = [[None] * len(pols), [None] * len(pols)]
@@ -157,7 +178,15 @@ class EnsembleStack:
                 res = eng.stack(lay, lanes, b1 - b0, N, Q, F, zeta, self.mu, mode, planes=planes[k])
                 status.append((b0, res.status))
             for i in range(len(pols)):
-                dev[k][i] = eng.returns(res, etx[i], gtm_phase=not fp, out=dev[k][i])
+                if split_mean:
+                    # azimuths sharded over ranks: local sums of |E| -> all-reduce over the group -> dB (layerstack.py:262)
+                    from . import distributed as tdist
+                    dev[k][i] = eng.returns_partial(res, etx[i], gtm_phase=not fp, out=dev[k][i])
+                    tdist.all_reduce_azimuth_sums(dev[k][i]['Pm_HH'], self.group)
+                    tdist.all_reduce_azimuth_sums(dev[k][i]['Pm_HV'], self.group)
+                    eng.returns_finish(dev[k][i], self.N_frames)
+                else:
+                    dev[k][i] = eng.returns(res, etx[i], gtm_phase=not fp, out=dev[k][i])
             ready = eng.new_event()
             ready.record(compute)
             with eng.on_stream(copy):

@@ -12,6 +12,7 @@ import torch
 
 import tamm_oracle as orc
 from tamm_b200 import packing
+from tamm_b200.engine import Engine
 
 dp = ctypes.POINTER(ctypes.c_double)
 RET = ('Pm_HH', 'Pm_HV', 'dP_HH', 'dP_HV', 'c_HHVV', 'E_HH', 'E_HV')
@@ -48,9 +49,18 @@ class HostSimEngine:
     def on_stream(self, s): return contextlib.nullcontext()
     def to_device(self, a): return torch.from_numpy(np.ascontiguousarray(a))
     def empty(self, shape, dtype): return torch.zeros(shape, dtype=dtype)
+    def stage_inputs(self, *arrays): return [torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)) for a in arrays]
+    def to_host(self, *tensors): return [t.numpy() for t in tensors]
+    returns_layout = staticmethod(Engine.returns_layout)
+    returns_views = staticmethod(Engine.returns_views)
+
+    def new_returns(self, P, Q, NI, F):
+        layout, total = self.returns_layout(P, Q, NI, F)
+        buf = torch.zeros((total,), dtype=torch.float64)
+        return buf, self.returns_views(buf, layout)
 
     # kernels
-    def stack(self, layers, lanes, P, N, Q, F, zeta, mu=1.0, mode=0, chunk=None, planes=None, workspace=None):
+    def stack(self, layers, lanes, P, N, Q, F, zeta, mu=1.0, mode=0, chunk=None, planes=None, workspace=None, status=None):
         assert tuple(layers.shape)[-2:] == (N, packing.LAYER_STRIDE) and layers.numel() == P * N * packing.LAYER_STRIDE
         assert layers.is_contiguous() and lanes.numel() == Q * F * packing.LANE_STRIDE
         if planes is not None:
@@ -78,6 +88,24 @@ class HostSimEngine:
 
     def export_jones(self, res, out=None):
         return torch.from_numpy(res.urd.copy())
+
+    def returns_partial(self, res, etx, gtm_phase=True, out=None):
+        """As Engine.returns_partial: |E| parked in dP_*, sums of |E| over the local azimuths in Pm_*."""
+        new = self.returns(res, etx, gtm_phase)
+        new['dP_HH'], new['dP_HV'] = new['E_HH'].abs(), new['E_HV'].abs()
+        new['Pm_HH'], new['Pm_HV'] = new['dP_HH'].sum(dim=-1), new['dP_HV'].sum(dim=-1)
+        if out is None:
+            return new
+        for k in RET:
+            out[k].copy_(new[k])
+        return out
+
+    def returns_finish(self, out, F_total):
+        for n in ('HH', 'HV'):
+            pm = 20 * torch.log10(out['Pm_' + n] / F_total)
+            out['dP_' + n].copy_(20 * torch.log10(out['dP_' + n]) - pm[..., None])
+            out['Pm_' + n].copy_(pm)
+        return out
 
     def returns(self, res, etx, gtm_phase=True, out=None):
         acc = {k: [] for k in RET}

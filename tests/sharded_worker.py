@@ -1,0 +1,70 @@
+"""Worker of tests/test_gpu_sharded.py (one process per rank under torchrun): ONE stack solved with its azimuths or its
+frequencies sharded over the ranks, on the real CUDA kernels, against the same solve on one rank.
+backend 'nccl': rank r uses GPU r.  backend 'gloo': every rank uses cuda:0 and the two collectives are staged through the
+host (tamm_b200.distributed._via_host) -- the device kernels of the sharded path (tamm_returns_partial / _finish) are the
+same, so a one-GPU box exercises them too."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, 'lib')):
+    sys.path.insert(0, p)
+
+backend, outdir = sys.argv[1], sys.argv[2]
+from tamm_b200 import EnsembleStack, profiles                                   # noqa: E402
+from tamm_b200 import distributed as tdist                                       # noqa: E402
+rank, ws, local = tdist.world()
+torch.cuda.set_device(local if backend == 'nccl' else 0)
+tdist.init(backend)
+import layerstack as ls                                                          # noqa: E402
+
+TOL = 1e-12
+
+
+def close(a, b, what):
+    fin = np.isfinite(b)
+    assert np.array_equal(np.isfinite(a), fin), what
+    scale = max(1.0, float(np.abs(b[fin]).max())) if fin.any() else 1.0
+    err = float(np.abs(a - b)[fin].max()) if fin.any() else 0.0
+    assert err <= TOL * scale, (what, err, scale)
+
+
+names = ['Pm_HH', 'Pm_HV', 'dP_HH', 'dP_HV', 'c_HHVV', 'E_HH', 'E_HV']
+# configs[1]: 3001 layers x 181 azimuths, azimuths sharded; all-reduce of the |E| sums, all-gather along azimuth
+nlm, z = profiles.rathmann_transition(3001, 3000, fabric_type=2)
+st = ls.LayerStack(nlm, z, N_frames=181, VERBOSE=0)
+for alpha in (0.0, np.deg2rad(10)):
+    whole = st.get_returns(1e3, f=179e6, alpha=alpha)
+    got = st.get_returns(1e3, f=179e6, alpha=alpha, shard=tdist.AxisShard('azimuth'))
+    for n, a, b in zip(names, got, whole):
+        assert a.shape == b.shape, n
+        close(a, b, ('azimuth', alpha, n))
+    lo, hi = tdist.shard_range(181, rank, ws)
+    part = st.get_returns(1e3, f=179e6, alpha=alpha, shard=tdist.AxisShard('azimuth', gather=False))
+    assert part[5].shape == (3000, hi - lo)
+    close(part[5], whole[5][:, lo:hi], 'local azimuths')
+    close(part[0], whole[0], 'Pm is global on every rank')
+# configs[2]: frequency vector sharded (no exchange), both transmit polarisations from one pass
+nlm, z = profiles.rathmann_transition(3000, 3000, fabric_type=4)
+st = ls.LayerStack(nlm, z, N_frames=3, VERBOSE=0)
+fs = np.linspace(150e6, 450e6, 257)
+whole = st.get_returns_polarimetric(1e3, f=fs, alpha=np.deg2rad(10))
+got = st.get_returns_polarimetric(1e3, f=fs, alpha=np.deg2rad(10), shard=tdist.AxisShard('frequency'))
+for k in whole:
+    assert got[k].shape == whole[k].shape, k
+    close(got[k], whole[k], ('frequency', k))
+# batched API: all profiles everywhere, azimuths split
+nlm, z = profiles.ensemble(3, 400, 200)
+w = EnsembleStack(nlm, z, N_frames=181).get_returns(1e3, f=179e6, alpha=np.deg2rad(10))
+e = EnsembleStack(nlm, z, N_frames=181, shard=(rank, ws), shard_axis='azimuth').get_returns(1e3, f=179e6, alpha=np.deg2rad(10))
+lo, hi = tdist.shard_range(181, rank, ws)
+close(e['E_HV'], w['E_HV'][..., lo:hi], 'ensemble azimuth shard E_HV')
+close(e['dP_HH'], w['dP_HH'][..., lo:hi], 'ensemble azimuth shard dP_HH')
+close(e['Pm_HV'], w['Pm_HV'], 'ensemble azimuth shard Pm_HV')
+dist.barrier()
+dist.destroy_process_group()
+open(os.path.join(outdir, 'rank%d.ok' % rank), 'w').write('ok')

@@ -131,6 +131,23 @@ class _OracleEngine:
     def to_device(self, a):
         return a
 
+    def stage_inputs(self, *arrays):
+        return list(arrays)
+
+    def to_host(self, *tensors):
+        return [t.numpy() for t in tensors]
+
+    def returns_layout(self, *a):
+        from tamm_b200.engine import Engine
+        return Engine.returns_layout(*a)
+
+    def new_returns(self, P, Q, NI, F):
+        import torch
+        from tamm_b200.engine import Engine
+        layout, total = Engine.returns_layout(P, Q, NI, F)
+        buf = torch.zeros((total,), dtype=torch.float64)
+        return buf, Engine.returns_views(buf, layout)
+
     def stack(self, layers, lanes, P, N, Q, F, zeta, mu, mode):
         import torch
         from types import SimpleNamespace
@@ -138,14 +155,16 @@ class _OracleEngine:
         urd = np.stack([self.o.get_URD(float(f), self.alpha, 'URD' if mode == 0 else 'U') for f in fs])   # (Q, F, NI, 2, 2)
         return SimpleNamespace(urd=urd, P=1, Q=Q, F=F, N=N, status=torch.zeros(1, dtype=torch.int32))
 
-    def returns(self, res, etx, gtm_phase=True):
+    def returns(self, res, etx, gtm_phase=True, out=None):
         import torch
-        out = {k: [] for k in ('Pm_HH', 'Pm_HV', 'dP_HH', 'dP_HV', 'c_HHVV', 'E_HH', 'E_HV')}
+        new = {k: [] for k in ('Pm_HH', 'Pm_HV', 'dP_HH', 'dP_HV', 'c_HHVV', 'E_HH', 'E_HV')}
         for q in range(res.Q):
             r = orc.returns_from_URD(res.urd[q], 1.0, Tx_pol=([etx[0], etx[1]],))
-            for k, a in zip(out, r):
-                out[k].append(a)
-        return {k: torch.from_numpy(np.stack(v)[None].copy()) for k, v in out.items()}     # (1, Q, NI[, F])
+            for k, a in zip(new, r):
+                new[k].append(a)
+        for k, v in new.items():
+            out[k].copy_(torch.from_numpy(np.stack(v)[None].copy()))                      # (1, Q, NI[, F])
+        return out
 
 
 def test_polarimetric_extension_host_side(monkeypatch):

@@ -62,14 +62,48 @@ WORKER = textwrap.dedent('''
     want = urd_of(whole, 0, P, whole.beta)
     assert full.shape == want.shape and np.array_equal(full, want)
 
-    # (2) azimuth sharding of one profile + all-reduce of the |E| sums before the dB step (layerstack.py:262)
-    one = EnsembleStack(nlm[:1], z, N_frames=F)
-    lo, hi = (0, 4) if rank == 0 else (4, F)
-    u = urd_of(one, 0, 1, one.beta[lo:hi])[0]                 # (F_local, N-1, 2, 2)
-    amp = np.abs(1e3 * u[:, :, 0, 0])
-    sums = all_reduce_azimuth_sums(torch.from_numpy(amp.sum(axis=0))).numpy()
-    ref = np.abs(1e3 * urd_of(one, 0, 1, one.beta)[0][:, :, 0, 0])
-    assert np.allclose(20 * np.log10(sums / F), 20 * np.log10(ref.mean(axis=0)), rtol=0, atol=1e-12)
+    # (2) azimuth / frequency sharding of ONE stack through the real host path (lib/layerstack.py + tamm_b200/distributed.py,
+    #     kernels replaced by the host simulator): local azimuths -> sums of |E| -> all-reduce -> dB -> all-gather
+    sys.path.insert(0, os.path.join(%(root)r, 'lib')); sys.path.insert(0, os.path.join(%(root)r, 'oracle'))
+    import layer, layerstack
+    from hostsim_engine import HostSimEngine
+    from tamm_b200 import ensemble as ens_mod
+    from tamm_b200.distributed import AxisShard, all_gather_axis
+    eng = HostSimEngine()
+    layer._get_engine = layerstack._get_engine = lambda: eng
+    ens_mod.get_engine = lambda: eng
+    ens_mod._pinned_empty = lambda shape, dtype: torch.zeros(shape, dtype=dtype)
+    ens_mod._pinned_copy = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    st = layerstack.LayerStack(nlm[0], z, N_frames=F, VERBOSE=0)
+    fs = np.array([150e6, 179e6, 300e6])
+    whole = st.get_returns(1e3, f=fs, alpha=alpha)
+    for axis in ('azimuth', 'frequency'):
+        got = st.get_returns(1e3, f=fs, alpha=alpha, shard=AxisShard(axis))
+        for a, b in zip(got, whole):
+            assert a.shape == b.shape and a.dtype == b.dtype
+            assert np.allclose(a, b, rtol=0, atol=1e-12 * max(1.0, np.abs(b).max())), axis
+        part = st.get_returns(1e3, f=fs, alpha=alpha, shard=AxisShard(axis, gather=False))
+        if axis == 'azimuth':
+            lo, hi = (0, 4) if rank == 0 else (4, F)
+            assert part[5].shape == (3, N - 1, hi - lo) and np.allclose(part[2], whole[2][..., lo:hi], rtol=0, atol=1e-12)
+            assert np.allclose(part[0], whole[0], rtol=0, atol=1e-12)            # Pm: mean over ALL azimuths on every rank
+        else:
+            lo, hi = (0, 2) if rank == 0 else (2, 3)
+            assert part[5].shape == np.squeeze(whole[5][lo:hi]).shape
+    pol = st.get_returns_polarimetric(1e3, f=179e6, alpha=alpha, shard=AxisShard('azimuth'))
+    polw = st.get_returns_polarimetric(1e3, f=179e6, alpha=alpha)
+    for k in polw:
+        assert np.allclose(pol[k], polw[k], rtol=0, atol=1e-12 * max(1.0, np.abs(polw[k]).max())), k
+    #     the same for the batched API: all profiles on every rank, azimuths (or frequencies) split
+    whole_e = EnsembleStack(nlm[:3], z, N_frames=F).get_returns(1e3, f=fs, alpha=alpha, batch=2)
+    for axis, ax in (('azimuth', 3), ('frequency', 1)):
+        e = EnsembleStack(nlm[:3], z, N_frames=F, shard=(rank, ws), shard_axis=axis)
+        loc = e.get_returns(1e3, f=fs, alpha=alpha, batch=2)
+        for n in ('E_HH', 'dP_HV', 'c_HHVV'):
+            full = all_gather_axis(torch.from_numpy(np.ascontiguousarray(loc[n])), ax, F if axis == 'azimuth' else 3).numpy()
+            assert np.allclose(full, whole_e[n], rtol=0, atol=1e-12 * max(1.0, np.abs(whole_e[n]).max())), (axis, n)
+        pm = loc['Pm_HH'] if axis == 'azimuth' else all_gather_axis(torch.from_numpy(np.ascontiguousarray(loc['Pm_HH'])), 1, 3).numpy()
+        assert np.allclose(pm, whole_e['Pm_HH'], rtol=0, atol=1e-12)
 
     # (3) block-cyclic sharding + pipelined (per-block, asynchronous) all-gather lands in natural profile order
     from tamm_b200.distributed import PipelinedGather, block_cyclic_profiles
