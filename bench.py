@@ -1,19 +1,24 @@
 #!/usr/bin/env python
 """
-Benchmark of the hot path on BASELINE.json's headline configuration.
+Benchmark of the hot path (LayerStack.get_returns and everything under it) on the configurations BASELINE.json names.
 
-Workload (configs[4], the one the metric is quoted on): ensemble of 1024 random fabric profiles x 181 azimuths x
-5000 layers, f = 179 MHz, oblique incidence alpha = 10 deg (general anisotropic eigen path), synthetic profiles
-(tamm_b200/profiles.py: ensemble).  A "step" is one pass of the hot path over the whole ensemble:
-stack kernel (+ chunk scan) -> returns kernel -> power kernel, inputs resident in HBM.  The ensemble is split by
-profile over the ranks (strong scaling, no data-path collective: profiles are independent and the azimuth mean is
-local to a profile).  Metric: layer*freq*azimuth evaluations per second, whole job.
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config {0,1,2,3,4}] [--impl reference]
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--profiles P --layers N --frames F]
+--config 4 (default; the configuration the metric is quoted on): ensemble of 1024 random fabric profiles x 181 azimuths x
+  5000 layers, f = 179 MHz, alpha = 10 deg (general anisotropic eigen path).  A step = stack kernel (+ chunk scan) ->
+  fused returns kernel over the whole ensemble, inputs resident in HBM.  Profiles are split over the ranks (strong scaling,
+  no data-path collective: profiles are independent, the azimuth mean is local to a profile).  For N > 1 the line also
+  carries the final NCCL all-gather of north_star in three sizes (jones / fields / power), back to back and pipelined
+  against the kernels in sub-batch blocks: `gather.*.value_with_gather`.
+--config 0..3: the single-stack shapes (demo 500 x 181; Rathmann-2021 transition 3001 x 181; wideband 4096 bins x 3000
+  layers x 2 polarisations; oblique tilted 10000 x 361).  A step = one stack solve + returns with inputs resident in HBM
+  (L2 flushed between steps: these outputs fit the 126 MB L2); e2e = the drop-in `lib/` call LayerStack.get_returns from
+  host arrays to host arrays.  For N > 1 the stack is sharded by azimuth (0, 1, 3: one all-reduce of (N-1) x 2 sums on
+  the compute path) or by frequency (2: no exchange).
 
-Under torchrun every rank runs its shard; rank 0 prints ONE JSON line.
-`--impl reference` times the CPU restatement of the reference's algorithm (oracle/, all host cores) on a bounded
-sample of the same workload; the Python reference itself cannot travel to the GPU box.
+Metric: layer*freq*azimuth evaluations per second, whole job.  Under torchrun every rank runs its shard; rank 0 prints ONE
+JSON line.  `--impl reference` times the reference's own CPU implementation on the host cores: the UNMODIFIED reference
+modules staged in oracle/_ref (oracle/stage_ref.py; kind "reference") when present, else the oracle port (kind "port").
 """
 import argparse
 import json
@@ -31,6 +36,10 @@ sys.path.insert(0, ROOT)
 F_ALG = 4000.0            # algorithmic FP64 flop per (layer, frequency, azimuth) evaluation, SURVEY.md 8(d)
 F_ALG_STACK = 3960.0      # of which stages A-G run in the stack kernel (H = 40 flop runs in the returns kernels)
 FP64_PEAK_FALLBACK = 34.2  # TFLOP/s, tools/dfma_peak.cu measured on this pool's B200 (profiles/r01_dfma_peak.log)
+FP64_NOMINAL = 148 * 64 * 2 * 1.965e9 / 1e12   # 148 SMs x 64 DFMA/clk x 2 flop x 1965 MHz = 37.2 TFLOP/s
+NVLINK_PEER_GBS = 770.0   # measured all-gather bandwidth per rank on this pool's NVSwitch boxes (round 1, N = 8)
+METRIC = 'layer*freq*azimuth evals/s (FP64)'
+UNIT = 'layer*freq*azimuth evals/s'
 
 
 def parse():
@@ -39,89 +48,186 @@ def parse():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='tamm_b200', choices=['tamm_b200', 'reference'])
-    ap.add_argument('--profiles', type=int, default=1024)
-    ap.add_argument('--layers', type=int, default=5000)
-    ap.add_argument('--frames', type=int, default=181)
-    ap.add_argument('--alpha-deg', type=float, default=10.0)
+    ap.add_argument('--config', type=int, default=4, choices=[0, 1, 2, 3, 4])
+    ap.add_argument('--profiles', type=int, default=None, help='config 4: profiles in the ensemble (default 1024)')
+    ap.add_argument('--layers', type=int, default=None)
+    ap.add_argument('--frames', type=int, default=None)
+    ap.add_argument('--bins', type=int, default=None, help='config 2: frequency bins (default 4096)')
+    ap.add_argument('--alpha-deg', type=float, default=None)
     ap.add_argument('--freq', type=float, default=179e6)
-    ap.add_argument('--batch', type=int, default=128, help='profiles per kernel launch')
-    ap.add_argument('--e2e-steps', type=int, default=2)
+    ap.add_argument('--batch', type=int, default=128, help='config 4: profiles per kernel launch')
+    ap.add_argument('--e2e-steps', type=int, default=5)
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
-    ap.add_argument('--cpu-seconds', type=float, default=15.0)
-    ap.add_argument('--gather', default='fields', choices=['none', 'power', 'fields', 'jones'],
-                    help='N>1 only: additionally time the final NCCL all-gather of results (reported separately)')
+    ap.add_argument('--cpu-seconds', type=float, default=12.0)
+    ap.add_argument('--gather', default='all', choices=['none', 'power', 'fields', 'jones', 'all'],
+                    help='config 4, N > 1: also time the final NCCL all-gather of results (reported separately)')
+    ap.add_argument('--gather-block', type=int, default=0, help='profiles per pipelined all-gather block (0: shard / 4)')
     return ap.parse_args()
 
 
 # ---------------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port on the host cores (the one place bench.py may execute oracle/)
+# Workloads
 # ---------------------------------------------------------------------------------------------------------
+def workload(args):
+    """Resolved description of the configuration: sizes, incidence, generator, how it shards."""
+    c = args.config
+    if c == 0:
+        w = dict(name='configs[0] demo.ipynb stack', layers=500, frames=181, bins=1, alpha_deg=0.0, profiles=1, axis='azimuth')
+    elif c == 1:
+        w = dict(name='configs[1] Rathmann-2021 fabric transition (FABRIC_TYPE 2)', layers=3001, frames=181, bins=1,
+                 alpha_deg=10.0, profiles=1, axis='azimuth')
+    elif c == 2:
+        w = dict(name='configs[2] wideband sweep 150-450 MHz, both transmit polarisations', layers=3000, frames=1, bins=4096,
+                 alpha_deg=10.0, profiles=1, axis='frequency')
+    elif c == 3:
+        w = dict(name='configs[3] oblique incidence, tilted non-symmetric fabrics', layers=10000, frames=361, bins=1,
+                 alpha_deg=10.0, profiles=1, axis='azimuth')
+    else:
+        w = dict(name='configs[4] ensemble', layers=5000, frames=181, bins=1, alpha_deg=10.0, profiles=1024, axis='profile')
+    for k, a in (('layers', args.layers), ('frames', args.frames), ('bins', args.bins), ('alpha_deg', args.alpha_deg),
+                 ('profiles', args.profiles if c == 4 else None)):
+        if a is not None:
+            w[k] = a
+    w['config'] = c
+    w['pols'] = 2 if c == 2 else 1
+    w['freqs'] = np.linspace(150e6, 450e6, w['bins']) if c == 2 else np.array([args.freq])
+    w['evals'] = float(w['profiles']) * w['layers'] * w['bins'] * w['frames']
+    return w
+
+
+def make_profile(w, first=0, count=1):
+    """Synthetic inputs of the configuration (tamm_b200/profiles.py): nlm (count, N, 6) for config 4, else (N, 6); z."""
+    from tamm_b200 import profiles
+    c, N = w['config'], w['layers']
+    if c == 0:
+        return profiles.demo(N, 1500)
+    if c == 1:
+        return profiles.rathmann_transition(N, 3000, fabric_type=2)
+    if c == 2:
+        return profiles.rathmann_transition(N, 3000, fabric_type=4)
+    if c == 3:
+        return profiles.tilted(N, 3000, seed=4)
+    return profiles.ensemble(count, N, first=first)
+
+
+def workload_config(w, extra=None):
+    d = dict(workload='%s: %d profile(s) x %d frequency bin(s) x %d azimuths x %d layers, alpha=%g deg, GTM%s' % (
+        w['name'], w['profiles'], w['bins'], w['frames'], w['layers'], w['alpha_deg'],
+        ', both Tx polarisations' if w['pols'] == 2 else ''),
+        config_index=w['config'], profiles=w['profiles'], layers=w['layers'], azimuths=w['frames'], frequencies=w['bins'],
+        alpha_deg=w['alpha_deg'], tx_polarisations=w['pols'])
+    if w['config'] == 4:
+        d.update(partition='profiles over ranks, no data-path collective', l2='inputs+outputs >> L2 (no flush needed)')
+    else:
+        d.update(partition='%s over ranks%s' % (w['axis'], ' (one all-reduce of (N-1) x 2 |E| sums per solve)' if w['axis'] == 'azimuth' else ', no exchange'),
+                 l2='L2 flushed between timed steps (256 MiB write); each step timed with its own CUDA event pair')
+    if extra:
+        d.update(extra)
+    return d
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's implementation on the host cores (the one place bench.py may execute oracle/)
+# ---------------------------------------------------------------------------------------------------------
+def _cpu_job_inputs(w, seed_first):
+    nlm, z = make_profile(w, first=seed_first, count=1)
+    return (nlm[0] if w['config'] == 4 else nlm), z
+
+
 def _cpu_worker(job):
-    seed_first, n_layers, n_frames, alpha, f = job
+    """One process: `frames` azimuths (an evenly spaced subset of the workload's grid) x all layers x `nf` frequencies of one
+    profile.  kind 'port' = oracle/tamm_oracle.py (vectorised restatement); 'reference' = the unmodified modules in
+    oracle/_ref through their public entry point LayerStack.get_returns (beta grid = linspace(0, pi, frames))."""
+    kind, w, seed_first, frames, nf = job
     os.environ.setdefault('OMP_NUM_THREADS', '1')
     sys.path.insert(0, os.path.join(ROOT, 'oracle'))
-    import tamm_oracle as orc
-    from tamm_b200 import profiles
-    nlm, z = profiles.ensemble(1, n_layers, first=seed_first)
+    alpha = np.deg2rad(w['alpha_deg'])
+    nlm, z = _cpu_job_inputs(w, seed_first)
+    fs = w['freqs'][np.linspace(0, len(w['freqs']) - 1, nf).round().astype(int)]
+    chk = 0.0
     t = time.perf_counter()
-    st = orc.OracleStack(nlm[0], z, N_frames=181)
-    idx = np.linspace(0, 180, n_frames).round().astype(int)
-    urd = st.get_URD(f, alpha, beta=st.beta[idx])
-    r = orc.returns_from_URD(urd, 1e3)
-    return time.perf_counter() - t, n_layers * n_frames, float(np.abs(r[5]).sum())
+    if kind == 'reference':
+        import stage_ref
+        ls = stage_ref.load()
+        st = ls.LayerStack(nlm, z, N_frames=frames, VERBOSE=0)
+        for f in fs:
+            r = st.get_returns(1e3, f=float(f), alpha=alpha)
+            chk += float(np.abs(np.atleast_1d(r[5])).sum())
+    else:
+        import tamm_oracle as orc
+        st = orc.OracleStack(nlm, z, N_frames=w['frames'])
+        idx = np.linspace(0, w['frames'] - 1, frames).round().astype(int)
+        for f in fs:
+            r = orc.returns_from_URD(st.get_URD(float(f), alpha, beta=st.beta[idx]), 1e3)
+            chk += float(np.abs(r[5]).sum())
+    return time.perf_counter() - t, w['layers'] * frames * nf, chk
 
 
-def cpu_baseline(args, seconds):
+def cpu_sample(w, kind, seconds, cores=None):
+    """Time `kind` on all host cores over a bounded sample of the workload sized for ~`seconds` of wall time.
+    -> (cpu_baseline dict, wall seconds)."""
     import multiprocessing as mp
-    cores = os.cpu_count() or 1
-    alpha = np.deg2rad(args.alpha_deg)
-    # calibrate one small job, then size the sample for ~`seconds` of wall time on all cores
-    t0, ev0, _ = _cpu_worker((0, min(args.layers, 500), 8, alpha, args.freq))
+    cores = cores or (os.cpu_count() or 1)
+    small = dict(w, layers=min(w['layers'], 400))
+    t0, ev0, _ = _cpu_worker((kind, small, 0, 2, 1))                 # calibration (also imports)
+    t0, ev0, _ = _cpu_worker((kind, small, 0, 2, 1))
     rate = ev0 / t0
-    frames = int(max(4, min(args.frames, rate * seconds / args.layers)))
-    jobs = [(i, args.layers, frames, alpha, args.freq) for i in range(cores)]
+    lanes = max(2, int(rate * seconds / w['layers']))
+    if w['config'] == 2:
+        frames, nf = 1, min(w['bins'], lanes)
+    else:
+        frames, nf = min(w['frames'], lanes), 1
+    jobs = [(kind, w, i, frames, nf) for i in range(cores)]
     ctx = mp.get_context('fork')
     t = time.perf_counter()
     with ctx.Pool(cores) as pool:
         res = pool.map(_cpu_worker, jobs)
     wall = time.perf_counter() - t
     evals = sum(r[1] for r in res)
-    return dict(value=evals / wall, unit='layer*freq*azimuth evals/s', cores=cores, kind='port',
-                sample='%d profiles x %d layers x %d of %d azimuths (%.3g evals, %.1f s wall), vectorised NumPy+LAPACK '
-                       'restatement of the reference (oracle/tamm_oracle.py), one process per core; the unmodified '
-                       'Python reference measured 1.15e3 evals/s/core in the build container (BASELINE.md)' % (
-                           cores, args.layers, frames, args.frames, evals, wall)), wall
+    what = ('UNMODIFIED reference modules (oracle/_ref, staged by oracle/stage_ref.py) through LayerStack.get_returns'
+            if kind == 'reference' else
+            'vectorised NumPy+LAPACK restatement of the reference (oracle/tamm_oracle.py)')
+    return dict(value=evals / wall, unit=UNIT, cores=cores, kind=kind,
+                sample='%d processes x (1 profile x %d layers x %d azimuth(s) x %d frequency bin(s)) = %.3g evals in %.1f s wall; %s' % (
+                    cores, w['layers'], frames, nf, evals, wall, what)), wall
+
+
+def reference_kind():
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    try:
+        import stage_ref
+        return 'reference' if stage_ref.staged() else 'port'
+    except Exception:
+        return 'port'
 
 
 def run_reference(args, emit):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    t = time.perf_counter()
-    vals = []
-    base = None
-    for _ in range(max(1, min(args.steps, 3)) + (1 if args.warmup > 0 else 0)):
-        base, wall = cpu_baseline(args, args.cpu_seconds)
-        vals.append(base['value'])
-    vals = vals[1:] if args.warmup > 0 and len(vals) > 1 else vals
+    w = workload(args)
+    kind = reference_kind()
+    nwarm = 1 if args.warmup > 0 else 0
+    nsteps = max(1, min(args.steps, 3))
+    vals, walls, base = [], [], None
+    for i in range(nwarm + nsteps):
+        base, wall = cpu_sample(w, kind, args.cpu_seconds)
+        if i >= nwarm:
+            vals.append(base['value'])
+            walls.append(wall)
     v = float(np.mean(vals))
     base['value'] = v
-    evals_job = float(args.profiles) * args.layers * args.frames
-    line = dict(metric='layer*freq*azimuth evals/s (FP64)', value=v, unit='layer*freq*azimuth evals/s', impl='reference',
-                n_gpus=args.gpus, steps=len(vals), warmup=1 if args.warmup > 0 else 0, ms_per_step=1e3 * evals_job / v,
-                higher_is_better=True, scaling='strong', vs_baseline=None, dtype='f64', data='synthetic',
-                config=workload_config(args), cpu_baseline=base,
-                e2e=dict(value=v, unit='layer*freq*azimuth evals/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0),
-                gpu_launches=0, note='CPU arm: ms_per_step is the whole workload extrapolated from the bounded sample rate')
+    line = dict(metric=METRIC, value=v, unit=UNIT, impl='reference', n_gpus=args.gpus, steps=nsteps, warmup=nwarm,
+                ms_per_step=1e3 * float(np.mean(walls)), higher_is_better=True, scaling='strong', vs_baseline=None, dtype='f64',
+                data='synthetic', config=workload_config(w), cpu_baseline=base,
+                e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0,
+                note='CPU arm: a step is ONE bounded sample of the workload (cpu_baseline.sample); ms_per_step is its '
+                     'measured wall time, value = evals of the sample / that time')
+    if kind == 'reference':     # the faster restatement beside it, for scale
+        port, _ = cpu_sample(w, 'port', min(args.cpu_seconds, 8.0))
+        line['cpu_baseline_port'] = port
     emit(json.dumps(line))
-
-
-def workload_config(args):
-    return dict(workload='configs[4] ensemble: %d profiles x %d azimuths x %d layers, f=%.0f MHz, alpha=%g deg, GTM' % (
-        args.profiles, args.frames, args.layers, args.freq / 1e6, args.alpha_deg),
-        profiles=args.profiles, layers=args.layers, azimuths=args.frames, frequencies=1, alpha_deg=args.alpha_deg,
-        partition='profiles over ranks, no data-path collective', l2='inputs+outputs >> L2 (no flush needed)')
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -210,33 +316,239 @@ def _claim_stdout():
     return emit
 
 
-def main():
-    args = parse()
-    emit = _claim_stdout()
-    if args.impl == 'reference':
-        return run_reference(args, emit)
+# ---------------------------------------------------------------------------------------------------------
+# Shared pieces of the GPU arms
+# ---------------------------------------------------------------------------------------------------------
+class Ctx:
+    pass
 
+
+def setup():
     import torch
     import torch.distributed as dist
     from tamm_b200 import distributed as tdist
-    rank, world, local = tdist.world()
-    torch.cuda.set_device(local)
+    c = Ctx()
+    c.torch, c.dist, c.tdist = torch, dist, tdist
+    c.rank, c.world, c.local = tdist.world()
+    torch.cuda.set_device(c.local)
     tdist.init('nccl')
     import __graft_entry__ as g
-    if rank == 0:
+    if c.rank == 0:
         g.build()
-    if world > 1:
+    if c.world > 1:
         dist.barrier()
-    from tamm_b200 import EnsembleStack, packing, profiles, shard_range
-    from tamm_b200.engine import MODE_URD, get_engine
-    eng = get_engine()
-    dev = eng.device
+    from tamm_b200 import _lib
+    from tamm_b200.engine import get_engine
+    c.eng = get_engine()
+    c.dev = c.eng.device
+    c.lib_path, c.lib_md5 = _lib.fingerprint()
+    return c
 
-    P, N, F = args.profiles, args.layers, args.frames
+
+def sync_all(c):
+    if c.world > 1:
+        c.dist.barrier()
+    c.torch.cuda.synchronize()
+
+
+def max_over_ranks(c, x):
+    t = c.torch.tensor([float(x)], dtype=c.torch.float64, device=c.dev)
+    if c.world > 1:
+        c.dist.all_reduce(t, op=c.dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def fp64_peak(c):
+    try:
+        return c.eng.fp64_peak_tflops(), ('DFMA probe kernel (tamm_fp64_probe) timed with CUDA events in this run; '
+                                          'MEASURED_PEAKS.json has no FP64 entry')
+    except Exception:
+        return FP64_PEAK_FALLBACK, 'fallback: tools/dfma_peak.cu on this pool (profiles/r01_dfma_peak.log)'
+
+
+def hbm_peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs']), 'MEASURED_PEAKS.json hbm_gbs (copy bandwidth, burst)'
+    except Exception:
+        return 6550.4, 'fallback: the copy bandwidth MEASURED_PEAKS.json held when the kernels were profiled'
+
+
+def stack_traffic(c, evals_per_launch):
+    """DRAM bytes of one stack-kernel launch from the committed `ncu --set full` capture -- only when that capture was
+    taken on the very library file this run loaded (md5); otherwise null: a stale figure must not outlive a kernel change."""
+    try:
+        tj = json.load(open(os.path.join(ROOT, 'profiles', 'r02_stack_traffic.json')))
+        if tj.get('library_md5') != c.lib_md5:
+            return None, 'none: profiles/r02_stack_traffic.json was captured on another build (md5 %s)' % tj.get('library_md5')
+        return tj['dram_bytes_per_eval'] * evals_per_launch, ('committed ncu capture of this same library build: '
+                                                               'profiles/r02_stack_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum per eval x evals per launch)')
+    except Exception as e:
+        return None, 'none: %s' % repr(e)[:80]
+
+
+def stack_roofline(c, stack_ms, stack_evals, launches, step_ms_total, evals_per_launch, kernel):
+    peak, src = fp64_peak(c)
+    rate = stack_evals / (stack_ms * 1e-3)
+    achieved = rate * F_ALG_STACK / 1e12
+    traffic, tsrc = stack_traffic(c, evals_per_launch)
+    return dict(bound='fp64', kernel=kernel, achieved=achieved, peak=peak, unit='TFLOP/s', frac=achieved / peak,
+                frac_of_nominal=achieved / FP64_NOMINAL, nominal_peak=FP64_NOMINAL,
+                nominal_peak_source='148 SMs x 64 DFMA/clk/SM x 2 flop x 1.965 GHz', traffic=traffic, traffic_source=tsrc,
+                peak_source=src, flop_per_eval=F_ALG_STACK, evals_per_launch=evals_per_launch,
+                avg_launch_ms=stack_ms / max(1, launches), share_of_step=(stack_ms / step_ms_total) if c.world == 1 else None,
+                hbm_alg_bytes_per_eval=64.5, hbm_achieved_gbs=rate * 64.5 / 1e9)
+
+
+def base_line(c, args, w, value, ms_per_step, launches, extra_cfg=None):
+    return dict(metric=METRIC, value=value, unit=UNIT, n_gpus=c.world, steps=args.steps, warmup=max(3, args.warmup),
+                ms_per_step=ms_per_step, higher_is_better=True, scaling='strong', vs_baseline=None, dtype='f64',
+                data='synthetic', config=workload_config(w, extra_cfg), gpu_launches=launches,
+                fp64_tflops_alg=value * F_ALG / 1e12, library=dict(path=os.path.relpath(c.lib_path, ROOT), md5=c.lib_md5))
+
+
+def finish(c, args, w, line, sampler, emit):
+    if c.rank == 0:
+        line['clocks'] = sampler.summary()
+        if c.world == 1 and not args.no_cpu:
+            kind = reference_kind()
+            line['cpu_baseline'], _ = cpu_sample(w, kind, args.cpu_seconds)
+            if kind == 'reference':
+                line['cpu_baseline_port'], _ = cpu_sample(w, 'port', min(args.cpu_seconds, 8.0))
+        emit(json.dumps(line))
+    if c.world > 1:
+        c.dist.barrier()
+        c.dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# configs[0..3]: one stack
+# ---------------------------------------------------------------------------------------------------------
+def bench_single(c, args, w, emit):
+    torch, eng = c.torch, c.eng
+    from tamm_b200 import packing, shard_range
+    from tamm_b200.engine import MODE_URD
+    sys.path.insert(0, os.path.join(ROOT, 'lib'))
+    import layerstack as ls
+    nlm, z = make_profile(w)
+    N, F, Q = w['layers'], w['frames'], w['bins']
+    NI = N - 1
+    alpha = np.deg2rad(w['alpha_deg'])
+    st = ls.LayerStack(nlm, z, N_frames=F, VERBOSE=0)
+    zeta = np.sqrt((2 * st.epsa[0] + st.epsc[0]) / 3) * np.sin(alpha)
+    betas, fa = st.beta, w['freqs']
+    shard = None
+    if c.world > 1:
+        shard = c.tdist.AxisShard(w['axis'])
+        if w['axis'] == 'azimuth':
+            lo, hi = shard_range(F, c.rank, c.world)
+            betas = betas[lo:hi]
+        else:
+            lo, hi = shard_range(Q, c.rank, c.world)
+            fa = fa[lo:hi]
+    Fl, Ql = len(betas), len(fa)
+    split_mean = c.world > 1 and w['axis'] == 'azimuth'
+    pols = [(1, 0), (0, 1)][:w['pols']]
+    etxs = [np.array([1e3 * p[0], 1e3 * p[1]], dtype=np.complex128) for p in pols]
+
+    # inputs resident in HBM
+    layers_d = eng.to_device(st._packed_layers()[None])
+    lanes_d = eng.to_device(packing.pack_lanes(betas, fa))
+    chunk = eng.suggest_chunk(1, N, Ql * Fl)
+    planes = eng.empty((1, NI, 4, Ql * Fl), torch.complex128)
+    wsb = int(eng.lib.tamm_stack_workspace_bytes(1, N, Ql * Fl, chunk))
+    workspace = eng.empty(((wsb + 7) // 8,), torch.float64)
+    status = eng.empty((1,), torch.int32)
+    outs = [eng.new_returns(1, Ql, NI, Fl)[1] for _ in pols]
+    flush = eng.empty((256 * 2 ** 20 // 8,), torch.float64)
+    stack_ev, step_ev = [], []
+
+    def step(record=False):
+        if record:
+            flush.zero_()      # evict the previous step's planes / returns from the 126 MB L2 (outside the event pairs)
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            e0.record()
+        res = eng.stack(layers_d, lanes_d, 1, N, Ql, Fl, zeta, 1.0, MODE_URD, chunk, planes=planes, workspace=workspace, status=status)
+        if record:
+            e1.record()
+        for etx, out in zip(etxs, outs):
+            if split_mean:
+                eng.returns_partial(res, etx, True, out=out)
+                c.tdist.all_reduce_azimuth_sums(out['Pm_HH'])
+                c.tdist.all_reduce_azimuth_sums(out['Pm_HV'])
+                eng.returns_finish(out, F)
+            else:
+                eng.returns(res, etx, True, out=out)
+        if record:
+            e2.record()
+            stack_ev.append((e0, e1))
+            step_ev.append((e0, e2))
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    sync_all(c)
+    sampler = ClockSampler(c.local)
+    if c.rank == 0:
+        sampler.start()
+    l0 = eng.launches
+    for _ in range(args.steps):
+        step(record=True)
+    sync_all(c)
+    launches = eng.launches - l0
+    sampler.stop_flag = True
+    ms_total = max_over_ranks(c, sum(a.elapsed_time(b) for a, b in step_ev))
+    ms_per_step = ms_total / args.steps
+    value = w['evals'] / (ms_per_step * 1e-3)
+    stack_ms = sum(a.elapsed_time(b) for a, b in stack_ev)
+    evals_local = float(N) * Ql * Fl
+    line = base_line(c, args, w, value, ms_per_step, launches,
+                     dict(chunk=chunk, chunks=(NI + chunk - 1) // chunk, lanes_per_rank=Ql * Fl))
+    line['roofline'] = stack_roofline(c, stack_ms, evals_local * args.steps, args.steps, ms_total, evals_local,
+                                      'stack_kernel<URD> (+ chunk_scan_kernel)')
+    line['returns_ms_per_step'] = (ms_total - stack_ms) / args.steps
+    if int(status.cpu()[0]) != 0:
+        line['status_word'] = int(status.cpu()[0])
+
+    # end to end through the drop-in API: host arrays in, the reference's 7-tuple (host arrays) out
+    if not args.no_e2e:
+        try:
+            call = (lambda: st.get_returns_polarimetric(1e3, f=(w['freqs'] if Q > 1 else float(w['freqs'][0])), alpha=alpha, shard=shard)) \
+                if w['pols'] == 2 else \
+                (lambda: st.get_returns(1e3, f=(w['freqs'] if Q > 1 else float(w['freqs'][0])), alpha=alpha, shard=shard))
+            r = call(); r = call()
+            sync_all(c)
+            te = time.perf_counter()
+            for _ in range(args.e2e_steps):
+                r = call()
+            torch.cuda.synchronize()
+            dt = max_over_ranks(c, (time.perf_counter() - te) / args.e2e_steps)
+            arrs = list(r.values()) if isinstance(r, dict) else list(r)
+            d2h = int(sum(np.asarray(a).nbytes for a in arrs)) if c.world == 1 else None
+            h2d = (N * packing.LAYER_STRIDE + Ql * Fl * packing.LANE_STRIDE) * 8
+            chk = np.asarray(r['Pm_HH'] if isinstance(r, dict) else r[0])
+            line['e2e'] = dict(value=w['evals'] / dt, unit=UNIT, ms_per_call=1e3 * dt, steps=args.e2e_steps, h2d_bytes_per_step=h2d,
+                               d2h_bytes_per_step=d2h if d2h is not None else int(64 * evals_local * w['pols']),
+                               api='lib/layerstack.py LayerStack.%s (host arrays in, host arrays out%s)' % (
+                                   'get_returns_polarimetric' if w['pols'] == 2 else 'get_returns',
+                                   ', sharded by %s with the final all-gather' % w['axis'] if shard is not None else ''),
+                               result_check=float(np.nanmax(chk)))
+        except Exception as e:
+            line['e2e'] = dict(value=None, error=repr(e)[:300])
+    finish(c, args, w, line, sampler, emit)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# configs[4]: the ensemble
+# ---------------------------------------------------------------------------------------------------------
+def bench_ensemble(c, args, w, emit):
+    torch, dist, tdist, eng, dev = c.torch, c.dist, c.tdist, c.eng, c.dev
+    from tamm_b200 import EnsembleStack, packing, profiles, shard_range
+    from tamm_b200.engine import MODE_URD
+    rank, world = c.rank, c.world
+    P, N, F = w['profiles'], w['layers'], w['frames']
     NI = N - 1
     lo, hi = shard_range(P, rank, world)
     Pl = hi - lo
-    alpha = np.deg2rad(args.alpha_deg)
+    alpha = np.deg2rad(w['alpha_deg'])
     nlm, z = profiles.ensemble(Pl, N, first=lo)
     ens = EnsembleStack(nlm, z, N_frames=F)
     zeta = ens.zeta(alpha)
@@ -244,22 +556,23 @@ def main():
     lanes_d = eng.to_device(packing.pack_lanes(ens.beta, args.freq))
     etx = np.array([1e3, 0.0], dtype=np.complex128)
     B = max(1, min(args.batch, Pl))
-    c, r = torch.complex128, torch.float64
-    out = dict(E_HH=eng.empty((Pl, 1, NI, F), c), E_HV=eng.empty((Pl, 1, NI, F), c), c_HHVV=eng.empty((Pl, 1, NI, F), c),
-               dP_HH=eng.empty((Pl, 1, NI, F), r), dP_HV=eng.empty((Pl, 1, NI, F), r), Pm_HH=eng.empty((Pl, 1, NI), r),
-               Pm_HV=eng.empty((Pl, 1, NI), r))
-    planes = eng.empty((B, NI, 4, F), c)
-    stack_events = []
-    returns_events = []
+    cdt, rdt = torch.complex128, torch.float64
+    out = dict(E_HH=eng.empty((Pl, 1, NI, F), cdt), E_HV=eng.empty((Pl, 1, NI, F), cdt), c_HHVV=eng.empty((Pl, 1, NI, F), cdt),
+               dP_HH=eng.empty((Pl, 1, NI, F), rdt), dP_HV=eng.empty((Pl, 1, NI, F), rdt), Pm_HH=eng.empty((Pl, 1, NI), rdt),
+               Pm_HV=eng.empty((Pl, 1, NI), rdt))
+    planes = eng.empty((B, NI, 4, F), cdt)
+    status = eng.empty((Pl,), torch.int32)
+    stack_events, returns_events = [], []
 
-    def step(record=False):
-        for b0 in range(0, Pl, B):
-            b1 = min(Pl, b0 + B)
-            pl = planes[: b1 - b0]
+    def step(record=False, blk=B, pl=None, after_block=None):
+        pl = planes if pl is None else pl
+        for bi, b0 in enumerate(range(0, Pl, blk)):
+            b1 = min(Pl, b0 + blk)
             if record:
                 e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
                 e0.record()
-            res = eng.stack(layers_d[b0:b1], lanes_d, b1 - b0, N, 1, F, zeta, 1.0, MODE_URD, planes=pl)
+            res = eng.stack(layers_d[b0:b1], lanes_d, b1 - b0, N, 1, F, zeta, 1.0, MODE_URD, planes=pl[: b1 - b0],
+                            status=status[b0:b1])
             if record:
                 e1.record()
                 stack_events.append((e0, e1, (b1 - b0)))
@@ -268,16 +581,13 @@ def main():
                 e2 = torch.cuda.Event(enable_timing=True)
                 e2.record()
                 returns_events.append((e1, e2, (b1 - b0)))
-
-    def sync_all():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+            if after_block is not None:
+                after_block(bi, b0, b1)
 
     for _ in range(max(3, args.warmup)):
         step()
-    sync_all()
-    sampler = ClockSampler(local)
+    sync_all(c)
+    sampler = ClockSampler(c.local)
     if rank == 0:
         sampler.start()
     launches0 = eng.launches
@@ -286,157 +596,173 @@ def main():
     for _ in range(args.steps):
         step(record=True)
     t1.record()
-    sync_all()
-    ms = t0.elapsed_time(t1)
+    sync_all(c)
+    ms_local = t0.elapsed_time(t1)
     launches = eng.launches - launches0
     sampler.stop_flag = True
-    tm = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-    ms = float(tm.item())
+    ms = max_over_ranks(c, ms_local)
     ms_per_step = ms / args.steps
-    evals_job = float(P) * N * F
+    evals_job = w['evals']
     value = evals_job / (ms_per_step * 1e-3)
 
-    # roofline of the dominant kernel (stack_kernel incl. the tiny chunk scan when chunked): CUDA events around its launches
     stack_ms = sum(a.elapsed_time(b) for a, b, _ in stack_events)
     stack_evals = sum(n for _, _, n in stack_events) * float(N) * F
-    stack_evals_per_s = stack_evals / (stack_ms * 1e-3)
-    try:
-        peak, peak_src = eng.fp64_peak_tflops(), 'DFMA probe kernel (tamm_fp64_probe) timed with CUDA events in this run; MEASURED_PEAKS.json has no FP64 entry'
-    except Exception:
-        peak, peak_src = FP64_PEAK_FALLBACK, 'fallback: tools/dfma_peak.cu on this pool (profiles/r01_dfma_peak.log)'
-    achieved = stack_evals_per_s * F_ALG_STACK / 1e12
-    traffic = None
-    try:   # DRAM bytes per eval of this kernel from the committed ncu capture, scaled to this run's launch size
-        tj = json.load(open(os.path.join(ROOT, 'profiles', 'r01_stack_traffic.json')))
-        traffic = tj['dram_bytes_per_eval'] * float(B) * N * F
-    except Exception:
-        pass
-    roofline = dict(bound='fp64', kernel='stack_kernel<URD>', achieved=achieved, peak=peak, unit='TFLOP/s', frac=achieved / peak,
-                    traffic=traffic, traffic_source='profiles/r01_stack_traffic.json (ncu dram__bytes_read+write per eval x evals per launch)', peak_source=peak_src, flop_per_eval=F_ALG_STACK, evals_per_launch=float(B) * N * F,
-                    avg_launch_ms=stack_ms / max(1, len(stack_events)), share_of_step=stack_ms / ms if world == 1 else None,
-                    hbm_alg_bytes_per_eval=64.5, hbm_achieved_gbs=stack_evals_per_s * 64.5 / 1e9)
-
-    # second kernel of the step (HBM-bound): fused returns, 64 B/eval of planes in + 64 B/eval of returns out
-    roofline_returns = None
-    try:
+    line = base_line(c, args, w, value, ms_per_step, launches, dict(profiles_per_launch=B))
+    line['roofline'] = stack_roofline(c, stack_ms, stack_evals, len(stack_events), ms_local, float(B) * N * F,
+                                      'stack_kernel<URD> (+ chunk_scan_kernel)')
+    try:   # second kernel of the step (HBM-bound): fused returns, 64 B/eval of planes in + 64 B/eval of returns out
         ret_ms = sum(a.elapsed_time(b) for a, b, _ in returns_events)
         ret_evals = sum(n for _, _, n in returns_events) * float(NI) * F
-        try:
-            hbm_peak = float(json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs'])
-            hbm_src = 'MEASURED_PEAKS.json hbm_gbs (copy bandwidth, burst)'
-        except Exception:
-            hbm_peak, hbm_src = 6550.4, 'fallback: the copy bandwidth MEASURED_PEAKS.json held when the kernels were profiled'
+        hp, hsrc = hbm_peak()
         ret_gbs = ret_evals * 128.0 / (ret_ms * 1e-3) / 1e9
-        roofline_returns = dict(bound='hbm', kernel='returns_fused_kernel', achieved=ret_gbs, peak=hbm_peak, unit='GB/s',
-                                frac=ret_gbs / hbm_peak, alg_bytes_per_eval=128.0, peak_source=hbm_src,
-                                avg_launch_ms=ret_ms / max(1, len(returns_events)),
-                                share_of_step=ret_ms / ms if world == 1 else None)
+        line['roofline_returns'] = dict(bound='hbm', kernel='returns_fused_kernel', achieved=ret_gbs, peak=hp, unit='GB/s',
+                                        frac=ret_gbs / hp, alg_bytes_per_eval=128.0, peak_source=hsrc,
+                                        avg_launch_ms=ret_ms / max(1, len(returns_events)),
+                                        share_of_step=ret_ms / ms_local if world == 1 else None)
     except Exception as e:
-        roofline_returns = dict(error=repr(e)[:200])
+        line['roofline_returns'] = dict(error=repr(e)[:200])
+    st_host = status.cpu().numpy()
+    if st_host.any():
+        line['status_profiles_flagged'] = int((st_host != 0).sum())
 
-    line = dict(metric='layer*freq*azimuth evals/s (FP64)', value=value, unit='layer*freq*azimuth evals/s', n_gpus=world,
-                steps=args.steps, warmup=max(3, args.warmup), ms_per_step=ms_per_step, higher_is_better=True, scaling='strong',
-                vs_baseline=None, dtype='f64', data='synthetic', config=workload_config(args), roofline=roofline,
-                roofline_returns=roofline_returns,
-                gpu_launches=launches, fp64_tflops_alg=value * F_ALG / 1e12)
-
-    # end-to-end through the public API: host arrays in, host arrays out (all 7 returns of get_returns)
+    # ---- end to end through the public batched API: host arrays in, pinned host arrays out
     if not args.no_e2e:
         try:
             # blocks of the e2e pipeline: the launch batch, or a quarter of the shard when the shard is a single launch
             # batch (N = 8), so that the device->host copy of block b overlaps the kernels of block b+1
             EB = B if Pl > B else max(1, (Pl + 3) // 4)
-            res = ens.get_returns(1e3, f=args.freq, alpha=alpha, batch=EB)         # warm-up, allocates pinned outputs
-            pinned = ens._pinned
-            sync_all()
-            te = time.perf_counter()
-            for _ in range(args.e2e_steps):
-                res = ens.get_returns(1e3, f=args.freq, alpha=alpha, batch=EB, out=pinned)
-            torch.cuda.synchronize()
-            dt = torch.tensor([(time.perf_counter() - te) / args.e2e_steps], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-            d2h = sum(v.numel() * v.element_size() for v in pinned.values())
             h2d = Pl * N * packing.LAYER_STRIDE * 8 + F * packing.LANE_STRIDE * 8
-            line['e2e'] = dict(value=evals_job / float(dt.item()), unit='layer*freq*azimuth evals/s', h2d_bytes_per_step=h2d,
-                               d2h_bytes_per_step=d2h, api='tamm_b200.EnsembleStack.get_returns (all 7 returns to pinned host arrays)', profiles_per_block=EB,
-                               result_check=float(np.nanmax(res['Pm_HH'])))
-        except Exception as e:  # e.g. not enough pinned host memory
-            line['e2e'] = dict(value=None, error=repr(e)[:200])
 
-    # final all-gather of results over NVLink (north_star) -- NOT part of `value`: profiles are independent, the
-    # compute path has no exchange step; this is what a caller pays when every rank needs the whole ensemble.
+            def e2e_run(outputs, steps):
+                res = ens.get_returns(1e3, f=args.freq, alpha=alpha, batch=EB, outputs=outputs)   # warm-up, allocates pinned outputs
+                pinned = ens._pinned
+                sync_all(c)
+                te = time.perf_counter()
+                for _ in range(steps):
+                    res = ens.get_returns(1e3, f=args.freq, alpha=alpha, batch=EB, out=pinned, outputs=outputs)
+                torch.cuda.synchronize()
+                dt = max_over_ranks(c, (time.perf_counter() - te) / steps)
+                d2h = sum(v.numel() * v.element_size() for v in pinned.values())
+                return dt, d2h, pinned, res
+
+            from tamm_b200.ensemble import RETURN_NAMES
+            dt, d2h, pinned, res = e2e_run(RETURN_NAMES, args.e2e_steps)
+            line['e2e'] = dict(value=evals_job / dt, unit=UNIT, steps=args.e2e_steps, ms_per_call=1e3 * dt, h2d_bytes_per_step=h2d,
+                               d2h_bytes_per_step=d2h, d2h_gbs_per_rank=d2h / dt / 1e9,
+                               api='tamm_b200.EnsembleStack.get_returns (all 7 returns to pinned host arrays)',
+                               profiles_per_block=EB, result_check=float(np.nanmax(res['Pm_HH'])))
+            # the e2e roofline: the same device->host copies with nothing else running (all ranks at once)
+            devs = {n: out[n] for n in pinned}
+            sync_all(c)
+            tb = time.perf_counter()
+            for _ in range(2):
+                for n, hbuf in pinned.items():
+                    hbuf.copy_(devs[n].view(hbuf.shape), non_blocking=True)
+            torch.cuda.synchronize()
+            bare = max_over_ranks(c, (time.perf_counter() - tb) / 2)
+            line['e2e'].update(bare_d2h_s=bare, bare_d2h_gbs_per_rank=d2h / bare / 1e9, bare_d2h_gbs_all_ranks=world * d2h / bare / 1e9,
+                               frac_of_bare_d2h=bare / dt,
+                               note='bare_d2h = the same pinned device->host copies alone, all ranks concurrently: the host-side ceiling of e2e')
+            del pinned, res
+            ens._pinned = None
+            dtp, d2hp, pinned, res = e2e_run(('Pm_HH', 'Pm_HV', 'dP_HH', 'dP_HV'), args.e2e_steps)
+            line['e2e_power'] = dict(value=evals_job / dtp, unit=UNIT, steps=args.e2e_steps, ms_per_call=1e3 * dtp, h2d_bytes_per_step=h2d,
+                                     d2h_bytes_per_step=d2hp, d2h_gbs_per_rank=d2hp / dtp / 1e9,
+                                     api="tamm_b200.EnsembleStack.get_returns(outputs=('Pm_HH','Pm_HV','dP_HH','dP_HV')): the power returns only (16 B/eval)",
+                                     result_check=float(np.nanmax(res['Pm_HH'])))
+            del pinned, res
+            ens._pinned = None
+        except Exception as e:  # e.g. not enough pinned host memory
+            line.setdefault('e2e', dict(value=None))['error'] = repr(e)[:300]
+
+    # ---- the final all-gather of results over NVLink (north_star) -- NOT part of `value` (profiles are independent, the
+    # compute path has no exchange step): what a caller pays when every rank needs the whole ensemble, in three sizes.
     if world > 1 and args.gather != 'none':
-        names = dict(power=['dP_HH', 'dP_HV'], fields=['E_HH', 'E_HV'], jones=['E_HH', 'E_HV', 'c_HHVV', 'dP_HH', 'dP_HV'])[args.gather]
-        try:
-            g0 = torch.cuda.Event(enable_timing=True); g1 = torch.cuda.Event(enable_timing=True)
-            got = [tdist.all_gather_profiles(out[n], P) for n in names[:1]]    # warm-up (NCCL channel setup)
-            del got
-            sync_all()
-            g0.record()
-            got = [tdist.all_gather_profiles(out[n], P) for n in names]
-            g1.record()
-            sync_all()
-            gm = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
-            dist.all_reduce(gm, op=dist.ReduceOp.MAX)
-            nbytes = sum(t.numel() * t.element_size() for t in got)
-            del got
-            line['gather'] = dict(what=args.gather, arrays=names, bytes_per_rank=nbytes, ms=float(gm.item()),
-                                  algbw_gbs=nbytes / (float(gm.item()) * 1e-3) / 1e9, included_in_value=False,
-                                  value_with_gather=evals_job / ((ms_per_step + float(gm.item())) * 1e-3))
-            # the same gather cut into one collective per profile block and overlapped with the kernels of the next block
-            # (SURVEY.md 8e mitigation; tamm_b200.distributed.PipelinedGather): a whole step = compute + gather, timed
-            # with CUDA events on the compute stream after it has waited for the last collective, max over ranks
-            if Pl % B == 0 and P % (world * B) == 0:
-                pgs = {n: tdist.PipelinedGather(P, B, tuple(out[n].shape[1:]), out[n].dtype, dev) for n in names}
+        variants = dict(power=['dP_HH', 'dP_HV'], fields=['E_HH', 'E_HV'], jones=['E_HH', 'E_HV', 'c_HHVV', 'dP_HH', 'dP_HV'])
+        todo = ['power', 'fields', 'jones'] if args.gather == 'all' else [args.gather]
+        GB = args.gather_block or max(1, Pl // 4)
+        while Pl % GB or P % (world * GB):
+            GB -= 1
+        planes_g = planes[:GB] if GB <= B else eng.empty((GB, NI, 4, F), cdt)
+        line['gather'] = dict(included_in_value=False, block_profiles=GB, blocks_per_rank=Pl // GB,
+                              peer_bandwidth_gbs=NVLINK_PEER_GBS,
+                              peer_bandwidth_source='ncclAllGather algbw per rank measured on this pool at N = 8 (round 1)',
+                              layout='block-cyclic: round b of rank r = profiles (b*world + r)*%d ... (natural profile order after the gather)' % GB)
+        for what in todo:
+            names = variants[what]
+            g = dict(arrays=names, bytes_per_eval=sum(16 if n[0] in 'Ec' else 8 for n in names))
+            try:
+                # (1) back to back: kernels, then one all-gather per array
+                got = [tdist.all_gather_profiles(out[n], P) for n in names[:1]]    # warm-up (NCCL channel setup)
+                del got
+                sync_all(c)
+                g0 = torch.cuda.Event(enable_timing=True); g1 = torch.cuda.Event(enable_timing=True)
+                g0.record()
+                got = [tdist.all_gather_profiles(out[n], P) for n in names]
+                g1.record()
+                sync_all(c)
+                gm = max_over_ranks(c, g0.elapsed_time(g1))
+                nbytes = sum(t.numel() * t.element_size() for t in got)
+                recv = nbytes * (world - 1) // world
+                del got
+                g.update(bytes_gathered_per_rank=nbytes, bytes_received_per_rank=recv, ms=gm, algbw_gbs=nbytes / (gm * 1e-3) / 1e9,
+                         link_floor_ms=recv / NVLINK_PEER_GBS / 1e6,
+                         value_with_gather_back_to_back=evals_job / ((ms_per_step + gm) * 1e-3))
+                # (2) pipelined: one asynchronous all-gather per sub-batch block on NCCL's stream while the compute stream
+                # goes on with the next block; a whole step = kernels + gather, CUDA events on the compute stream after it
+                # has waited for the last collective, max over ranks
+                pgs = {n: tdist.PipelinedGather(P, GB, tuple(out[n].shape[1:]), out[n].dtype, dev) for n in names}
+
+                def submit(bi, b0, b1):
+                    for n in names:
+                        pgs[n].submit(bi, out[n][b0:b1])
 
                 def step_gather():
-                    for bi, b0 in enumerate(range(0, Pl, B)):
-                        res = eng.stack(layers_d[b0:b0 + B], lanes_d, B, N, 1, F, zeta, 1.0, MODE_URD, planes=planes)
-                        eng.returns(res, etx, True, out={k: v[b0:b0 + B] for k, v in out.items()})
-                        for n in names:
-                            pgs[n].submit(bi, out[n][b0:b0 + B])
+                    step(blk=GB, pl=planes_g, after_block=submit)
                     for n in names:
                         pgs[n].wait()
                 step_gather()
-                sync_all()
+                sync_all(c)
                 ksteps = max(1, min(args.steps, 3))
                 p0 = torch.cuda.Event(enable_timing=True); p1 = torch.cuda.Event(enable_timing=True)
                 p0.record()
                 for _ in range(ksteps):
                     step_gather()
                 p1.record()
-                sync_all()
-                pm = torch.tensor([p0.elapsed_time(p1) / ksteps], dtype=torch.float64, device=dev)
-                dist.all_reduce(pm, op=dist.ReduceOp.MAX)
+                sync_all(c)
+                pm = max_over_ranks(c, p0.elapsed_time(p1) / ksteps)
                 # check: every rank's block of round 0 must have arrived here (checksums exchanged by all-reduce)
                 asreal = lambda t: torch.view_as_real(t) if t.is_complex() else t
                 sums = torch.zeros(world, dtype=torch.float64, device=dev)
-                sums[rank] = asreal(out[names[0]][:B]).abs().sum()
+                sums[rank] = asreal(out[names[0]][:GB]).abs().sum()
                 dist.all_reduce(sums, op=dist.ReduceOp.SUM)
                 full0 = pgs[names[0]].full
-                got_s = torch.stack([asreal(full0[r * B: (r + 1) * B]).abs().sum() for r in range(world)])
+                got_s = torch.stack([asreal(full0[r * GB: (r + 1) * GB]).abs().sum() for r in range(world)])
                 ok = ((got_s - sums).abs() <= 1e-12 * sums.abs()).all().to(torch.float64).reshape(1)
-                ok = ok * float(torch.equal(full0[rank * B: (rank + 1) * B], out[names[0]][:B]))
+                ok = ok * float(torch.equal(full0[rank * GB: (rank + 1) * GB], out[names[0]][:GB]))
                 dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-                line['gather'].update(pipelined_ms_per_step=float(pm.item()), pipelined_steps=ksteps,
-                                      value_pipelined=evals_job / (float(pm.item()) * 1e-3),
-                                      pipelined_check=bool(ok.item() == 1.0),
-                                      pipelined_layout='block-cyclic: round b of rank r = profiles (b*world + r)*%d ...' % B)
+                g.update(pipelined_ms_per_step=pm, pipelined_steps=ksteps, value_with_gather=evals_job / (pm * 1e-3),
+                         scaling_vs_1gpu_needs='value_with_gather / the N = 1 value of this bench',
+                         nvlink_roofline_frac=(recv / NVLINK_PEER_GBS / 1e6) / pm, pipelined_check=bool(ok.item() == 1.0))
                 del pgs
-        except Exception as e:
-            line.setdefault('gather', {}).update(what=args.gather, error=repr(e)[:200])
+                torch.cuda.empty_cache()
+            except Exception as e:
+                g['error'] = repr(e)[:300]
+            line['gather'][what] = g
+    finish(c, args, w, line, sampler, emit)
 
-    if rank == 0:
-        line['clocks'] = sampler.summary()
-        if world == 1 and not args.no_cpu:
-            line['cpu_baseline'], _ = cpu_baseline(args, args.cpu_seconds)
-        emit(json.dumps(line))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+
+def main():
+    args = parse()
+    emit = _claim_stdout()
+    if args.impl == 'reference':
+        return run_reference(args, emit)
+    c = setup()
+    w = workload(args)
+    if w['config'] == 4:
+        bench_ensemble(c, args, w, emit)
+    else:
+        bench_single(c, args, w, emit)
 
 
 if __name__ == '__main__':

@@ -19,7 +19,14 @@ def test_reference_arm_prints_one_json_line():
               'vs_baseline', 'dtype', 'data', 'config', 'impl', 'cpu_baseline', 'e2e'):
         assert k in d, k
     assert d['impl'] == 'reference' and d['dtype'] == 'f64' and d['vs_baseline'] is None and d['value'] > 0
-    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1 and 'sample' in d['cpu_baseline']
+    # the unmodified reference modules when oracle/_ref is staged (build container, GPU box), else the oracle port
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import stage_ref
+    kind = 'reference' if stage_ref.staged() else 'port'
+    assert d['cpu_baseline']['kind'] == kind and d['cpu_baseline']['cores'] >= 1 and 'sample' in d['cpu_baseline']
+    assert (kind == 'port') or d['cpu_baseline_port']['kind'] == 'port'
+    # a step of the CPU arm is one bounded sample: ms_per_step is its measured wall time, never an extrapolation
+    assert d['steps'] == 1 and d['ms_per_step'] < 60e3
     assert d['e2e']['h2d_bytes_per_step'] == 0 and d['e2e']['d2h_bytes_per_step'] == 0
     assert 'workload' in d['config'] and 'model' not in d['config']
 
