@@ -66,6 +66,15 @@ int tamm_layer_matrices(const double* layers, const double* lanes, int N, int QF
                         void* Delta, void* Py, void* Kd, int* status, void* stream);
 
 /*
+ * Sorted propagation constants qs [QF][N][4] (complex128) of one profile from the HOT-PATH mode solve -- the pair solver
+ * that tamm_stack_urd runs per (lane, layer), with its clean-up, transmitted/reflected partition and p/s sort
+ * (layer_PPJ.py:197-293); tamm_layer_matrices uses the plainer diagnostic solver.  Backs the parity tests of that solver on
+ * the device (near-degenerate mode pairs); status int32 [QF][N] may be NULL.
+ */
+int tamm_layer_modes(const double* layers, const double* lanes, int N, int QF, double zeta, double mu, void* qs, int* status,
+                     void* stream);
+
+/*
  * Workspace (bytes) needed by tamm_stack_urd for the chunk aggregates and their prefixes.
  * chunk = number of interfaces one thread walks sequentially (>= 1).
  */

@@ -988,33 +988,64 @@ void eig4_fallback(double exx, double exy, double exz, double eyy, double eyz, d
         WaveMat mm;
         // coefficient-form roots are good to ~sqrt(eps) at worst (double roots): start the refinement from there
         refine_root(w, x, sep2, frcp(sep2 + TINY), frcp(abs2(x) + TINY), 1e-31 * abs2(x), 1e-16 * (abs2(x) + 1e-300) + 1e-20, mm);
+        mm = wave_matrix(w, x);      // null vector at the final root (the cold path can afford the extra evaluation)
         bool use0 = abs2(mm.a) >= abs2(mm.d);
         rv[k][0] = x;
         rv[k][1] = csel(use0, -mm.b, mm.d);
         rv[k][2] = csel(use0, mm.a, -mm.b);
     }
     // Close pairs (splitting comparable to the accuracy of the starting values, ~1e-8 |q|): two starting points can be
-    // refined to the SAME root, leaving its partner unfound.  For every pair of coinciding results, the partner of the
-    // root is at x + h_big, h_big = the other eigenvalue of -N'(x)^-1 N(x) (the second root of the local quadratic model of
-    // det N, exact to O(h_big^2/|q|)); a truly degenerate pair has h_big = 0 and stays as it is.
-    for (int k = 0; k < 4; ++k)
-        for (int j = k + 1; j < 4; ++j) {
-            if (!(abs2(rv[k][0] - rv[j][0]) <= 1e-22 * abs2(rv[k][0]))) continue;
-            const WaveMat m = wave_matrix(w, rv[k][0]);
-            cd hb, hs;
-            mslp_eigs_f(m, w.db, hb, hs);
-            const double sep2 = abs2(hb);
-            cd x = rv[k][0] + hb;
-            if (!(sep2 > 1e-26 * abs2(x)) || !(sep2 < 1e-4 * abs2(x))) continue;
-            TAMM_STAT(recentre);
-            const double ix2 = frcp(abs2(x) + TINY);
-            WaveMat mm;
-            refine_root(w, x, sep2, frcp(sep2), ix2, 1e-31 * abs2(x), sep2 * sep2 * ix2, mm);
-            const bool use0 = abs2(mm.a) >= abs2(mm.d);
-            rv[j][0] = x;
-            rv[j][1] = csel(use0, -mm.b, mm.d);
-            rv[j][2] = csel(use0, mm.a, -mm.b);
+    // refined to the SAME root, leaving its partner unfound.  At a root x the other eigenvalue h_big of -N'(x)^-1 N(x) is
+    // the second root of the local quadratic model of det N: for a close pair it is the distance to the partner, exact to
+    // O(h_big^2/|q|).  Two results much closer to each other than that predicted distance are one root found twice; the
+    // second is replaced by x + h_big and refined.  A truly degenerate pair has h_big = 0 and stays as it is; for
+    // well-separated roots h_big is O(|q|) and is not used.
+    for (int k = 0; k < 4; ++k) {
+        const WaveMat m = wave_matrix(w, rv[k][0]);
+        cd hb, hs;
+        mslp_eigs_f(m, w.db, hb, hs);
+        const double sep2 = abs2(hb), x2 = abs2(rv[k][0]);
+        if (!(sep2 > 1e-26 * x2) || !(sep2 < 1e-4 * x2)) continue;
+        bool have_partner = false;
+        int dup = -1;
+        for (int j = 0; j < 4; ++j) {
+            if (j == k) continue;
+            if (abs2(rv[k][0] + hb - rv[j][0]) < 0.0625 * sep2) have_partner = true;
+            else if (abs2(rv[k][0] - rv[j][0]) < 0.0625 * sep2 && dup < 0) dup = j;
         }
+        if (have_partner || dup < 0) continue;
+        TAMM_STAT(recentre);
+        cd x = rv[k][0] + hb;
+        const double ix2 = frcp(abs2(x) + TINY);
+        WaveMat mm;
+        refine_root(w, x, sep2, frcp(sep2), ix2, 1e-31 * abs2(x), sep2 * sep2 * ix2, mm);
+        mm = wave_matrix(w, x);
+        const bool use0 = abs2(mm.a) >= abs2(mm.d);
+        rv[dup][0] = x;
+        rv[dup][1] = csel(use0, -mm.b, mm.d);
+        rv[dup][2] = csel(use0, mm.a, -mm.b);
+    }
+}
+
+// Cold helper of layer_modes: two roots of the hot-path solver coincide (to QSD_THR).  Either the pair is truly degenerate
+// -- N vanishes at the root and so do both eigenvalues of -N'^-1 N -- or both refinements of a near-degenerate pair
+// (splitting down at the accuracy of the starting values, ~1e-8 |q|, e.g. where the p and s branches of a smoothly
+// rotating fabric cross at oblique incidence) ended on the SAME root, because every refinement step moves to the nearest
+// one; then the other eigenvalue of -N'(x)^-1 N(x), the distance to the partner root, is resolvably non-zero.
+#if defined(__CUDA_ARCH__)
+__device__ __noinline__
+#else
+inline
+#endif
+bool partner_lost(double exx, double exy, double exz, double eyy, double eyz, double ezz, double eim, double mu, double zeta,
+                  cd x) {
+    Sym3 e;
+    e.xx = exx; e.xy = exy; e.xz = exz; e.yy = eyy; e.yz = eyz; e.zz = ezz; e.im = eim;
+    const WaveCoef w = wave_coef(e, mu, zeta);
+    const WaveMat m = wave_matrix(w, x);
+    cd hb, hs;
+    mslp_eigs_f(m, w.db, hb, hs);
+    return abs2(hb) >= QSD_THR * QSD_THR;
 }
 
 // ---- per-thread scratch of the mode solve -------------------------------------------------------------------------
@@ -1117,20 +1148,6 @@ TAMM_HD bool eig4_fast(const WaveCoef& w, SC& sc) {
         const double ahb = abs2(hb), ahs = abs2(hs);
         if (errv < 0.0) reach2 = fmax(reach2, fmax(ahb, ahs));
         else reach2 = fmax(reach2, 2.0 * (abs2(centre - qc) + ahb));
-        // Near-degenerate pair (splitting down at the accuracy of the starting values, ~1e-8 |q| -- e.g. where the p and s
-        // branches of a smoothly rotating fabric cross at oblique incidence): every refinement step moves to the NEAREST
-        // root, so both starting values can end on the same one and its partner is lost.  When a starting value may be
-        // no closer to its own root than to the partner (error > splitting / 4) and the splitting is resolvable at all
-        // (below 1e-12 |q| the pair is degenerate for every later purpose, QSD_THR = 1e-10), the layer goes to the cold
-        // solver, which recovers lost partners by deflation.
-        {
-            const double emax = errv < 0.0 ? fmax(ahb, ahs) : 0.0;
-            const double e2 = errv < 0.0 ? emax * emax * iq2c : errv * isep2;
-            if (TAMM_RARE((e2 > 0.0625 * sep2) && (sep2 > 1e-24 * q2c))) {
-                TAMM_STAT(collapsed);
-                return false;
-            }
-        }
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -1335,7 +1352,19 @@ TAMM_HD int layer_modes(const LayerParams& lp, const LaneParams& ln, double zeta
     int status = 0;
     const Sym3 e = permittivity(lp, ln);
     const WaveCoef w = wave_coef(e, mu, zeta);
-    if (TAMM_RARE(!eig4_fast(w, sc))) {
+    bool solved = eig4_fast(w, sc);
+    if (TAMM_USUAL(solved)) {
+        // a coinciding pair is either a true degeneracy or a lost partner root (see partner_lost): the latter is re-solved
+        const cd r0 = sc.rv(0, 0), r2 = sc.rv(2, 0);
+        const bool c01 = abs2(r0 - sc.rv(1, 0)) < QSD_THR * QSD_THR, c23 = abs2(r2 - sc.rv(3, 0)) < QSD_THR * QSD_THR;
+        if (TAMM_RARE(c01 || c23)) {
+            if (partner_lost(e.xx, e.xy, e.xz, e.yy, e.yz, e.zz, e.im, mu, zeta, c01 ? r0 : r2)) {
+                TAMM_STAT(collapsed);
+                solved = false;
+            }
+        }
+    }
+    if (TAMM_RARE(!solved)) {
         TAMM_STAT(fallback);
         cd rv[4][3];
         eig4_fallback(e.xx, e.xy, e.xz, e.yy, e.yz, e.zz, e.im, mu, zeta, rv);

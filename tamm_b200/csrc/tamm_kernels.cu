@@ -51,6 +51,9 @@ inline bool lanes_fit(int Q, int F) { return (long)Q * (long)F <= 2147483647L; }
 #ifndef TAMM_RETURNS_TMA_DEFAULT
 #define TAMM_RETURNS_TMA_DEFAULT 0
 #endif
+#ifndef TAMM_RETURNS_V16_DEFAULT
+#define TAMM_RETURNS_V16_DEFAULT 0
+#endif
 
 constexpr int TL = 16;     // layers per TMA sub-tile (16 * 80 B = 1280 B per profile)
 constexpr int CARRY_SLOTS = 34;   // 16-byte shared-memory slots per thread of stack_kernel (carry state + mode scratch)
@@ -632,6 +635,100 @@ returns_fused_kernel(const cd* __restrict__ planes, const cd* __restrict__ pre, 
     }
 }
 
+// Variant with ONE reduction per CTA instead of one per depth group: the |E| of all TNF * TNG = 16 depths of the CTA are
+// parked in shared memory ([depth][pol][thread], conflict-free), the warps stream through their 16 depths without meeting
+// (no CTA barrier between the loads of consecutive groups), and only then the 32 azimuth sums are formed (fixed order ->
+// deterministic), turned into Pm, and the anomalies written.  Two CTA barriers per 16 depths instead of eight.
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK, (BLOCK <= 256 ? 768 / BLOCK : 1))
+returns_fused16_kernel(const cd* __restrict__ planes, const cd* __restrict__ pre, int N, int Q, int F, int mode, int chunk,
+                       int nchunks, cd e0, cd e1, int gtm_phase, cd* __restrict__ E_HH, cd* __restrict__ E_HV,
+                       cd* __restrict__ c_HHVV, double* __restrict__ dP_HH, double* __restrict__ dP_HV,
+                       double* __restrict__ Pm_HH, double* __restrict__ Pm_HV) {
+    static_assert(TNF == 4, "warp_sum8 reduces 2 * TNF = 8 values");
+    constexpr int NW = BLOCK / 32, ND = TNF * TNG;
+    extern __shared__ double sm16[];
+    double* amp_s = sm16;                       // [ND][2][BLOCK]
+    double* red = sm16 + ND * 2 * BLOCK;        // [NW][ND * 2]
+    double* tot = red + NW * ND * 2;            // [ND * 2]
+    const int NI = N - 1, QF = Q * F;
+    const int p = blockIdx.z, iq = blockIdx.y;
+    const int ifr = threadIdx.x;
+    const bool live = ifr < F;
+    const int l = iq * F + (live ? ifr : F - 1);
+    const int nbeg = blockIdx.x * ND;
+    const int ne = min(NI, nbeg + ND);
+    const size_t istride = (size_t)4 * QF;
+    const cd* ip = planes + ((size_t)p * NI + (size_t)nbeg) * istride + l;
+    const size_t o0 = (((size_t)p * Q + iq) * NI + (size_t)nbeg) * F + (live ? ifr : F - 1);
+    size_t o = o0;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    cd Dp[4], Up[4];
+    int cc = -1;
+#pragma unroll 1
+    for (int g = 0; g < TNG; ++g) {
+        double amp[2 * TNF];
+#pragma unroll
+        for (int k = 0; k < TNF; ++k) {
+            const int n = nbeg + g * TNF + k;
+            amp[2 * k] = 0.0; amp[2 * k + 1] = 0.0;
+            if (n < ne) {
+                cd m[4] = {ld_cd(ip), ld_cd(ip + QF), ld_cd(ip + 2 * (size_t)QF), ld_cd(ip + 3 * (size_t)QF)};
+                if (nchunks > 1) {
+                    const int c = n / chunk;
+                    if (c != cc) { load_prefix(pre, (size_t)p * QF + l, nchunks, c, Dp, Up); cc = c; }
+                    if (c > 0) {
+                        cd t[4];
+                        if (mode == TAMM_MODE_URD) { mm22(m, Dp, t); mm22(Up, t, m); }
+                        else { mm22(Up, m, t); m[0] = t[0]; m[1] = t[1]; m[2] = t[2]; m[3] = t[3]; }
+                    }
+                }
+                cd hh, hv, c;
+                double ahh, ahv;
+                returns_point(m, e0, e1, gtm_phase, hh, hv, c, ahh, ahv);
+                if (live) {
+                    st_cd(E_HH + o, hh);
+                    st_cd(E_HV + o, hv);
+                    st_cd(c_HHVV + o, c);
+                    amp[2 * k] = ahh;
+                    amp[2 * k + 1] = ahv;
+                }
+            }
+            amp_s[((g * TNF + k) * 2) * BLOCK + threadIdx.x] = amp[2 * k];
+            amp_s[((g * TNF + k) * 2 + 1) * BLOCK + threadIdx.x] = amp[2 * k + 1];
+            ip += istride;
+            o += F;
+        }
+        const double r = warp_sum8(amp, lane);
+        if ((lane & 3) == 0) red[w * (ND * 2) + g * 8 + (((lane >> 4) & 1) | (((lane >> 3) & 1) << 1) | (((lane >> 2) & 1) << 2))] = r;
+    }
+    __syncthreads();
+    if (threadIdx.x < ND * 2) {
+        double sum = 0.0;
+#pragma unroll
+        for (int i = 0; i < NW; ++i) sum += red[i * (ND * 2) + threadIdx.x];
+        const double pm = 20.0 * log10(sum / (double)F);
+        tot[threadIdx.x] = pm;
+        const int n = nbeg + (threadIdx.x >> 1);
+        if (n < ne) {
+            const size_t row = ((size_t)p * Q + iq) * NI + n;
+            if (threadIdx.x & 1) Pm_HV[row] = pm; else Pm_HH[row] = pm;
+        }
+    }
+    __syncthreads();
+    if (live) {
+        size_t od = o0;
+#pragma unroll 4
+        for (int d = 0; d < ND; ++d) {
+            if (nbeg + d < ne) {
+                dP_HH[od] = 20.0 * log10_dev(amp_s[(d * 2) * BLOCK + threadIdx.x]) - tot[2 * d];       // layerstack.py:261-267
+                dP_HV[od] = 20.0 * log10_dev(amp_s[(d * 2 + 1) * BLOCK + threadIdx.x]) - tot[2 * d + 1];
+            }
+            od += F;
+        }
+    }
+}
+
 // The same kernel fed by the TMA engine (F <= 256): the four plane rows of a depth (F x 16 B each, contiguous in the
 // planes layout) are bulk-copied global->shared into a ring of 2 * TNF depth stages, each with its own mbarrier, so the
 // loads in flight cost no registers and do not depend on how many warps are resident.  While group g (TNF depths) is
@@ -804,6 +901,32 @@ power_finish_kernel(double* __restrict__ aHH, double* __restrict__ aHV, const do
     }
 }
 
+// The same two steps with ONE THREAD per (p, iq, n) row, for F < 32 (wideband sweeps: many frequencies, one or a few
+// azimuths -- a warp per row would idle 31 lanes): do_sum forms the local sums, do_finish the dB step.
+__global__ void __launch_bounds__(256)
+power_rows_kernel(double* __restrict__ aHH, double* __restrict__ aHV, double* sHH, double* sHV, double* Pm_HH, double* Pm_HV,
+                  long nrows, int F, int F_total, int do_sum, int do_finish) {
+    const long row = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= nrows) return;
+    double* h = aHH + (size_t)row * F;
+    double* v = aHV + (size_t)row * F;
+    double sh, sv;
+    if (do_sum) {
+        sh = 0.0; sv = 0.0;
+        for (int f = 0; f < F; ++f) { sh += h[f]; sv += v[f]; }
+        if (!do_finish) { sHH[row] = sh; sHV[row] = sv; return; }
+    } else {
+        sh = sHH[row]; sv = sHV[row];
+    }
+    const double pmh = 20.0 * log10(sh / (double)F_total);
+    const double pmv = 20.0 * log10(sv / (double)F_total);
+    Pm_HH[row] = pmh; Pm_HV[row] = pmv;
+    for (int f = 0; f < F; ++f) {
+        h[f] = 20.0 * log10(h[f]) - pmh;
+        v[f] = 20.0 * log10(v[f]) - pmv;
+    }
+}
+
 // planes (+prefix) -> reference layout [P][Q][F][N-1][2][2]
 __global__ void __launch_bounds__(128)
 export_kernel(const cd* __restrict__ planes, const cd* __restrict__ pre, int N, int QF, int mode, int chunk, int nchunks,
@@ -868,6 +991,28 @@ layer_diag_kernel(const double* __restrict__ layers, const double* __restrict__ 
     if (eps)
         for (int r = 0; r < 3; ++r)
             for (int c = 0; c < 3; ++c) eps[i * 9 + r * 3 + c] = d.eps[r][c];
+}
+
+// Sorted roots of the HOT-PATH mode solve (tamm::layer_modes: the pair solver of stack_kernel with its cold fallbacks, clean-up,
+// partition and p/s sort) per (lane, layer) -- diagnostics / parity tests of the device arithmetic of that solver.
+__global__ void __launch_bounds__(128)
+layer_modes_kernel(const double* __restrict__ layers, const double* __restrict__ lanes, int N, int QF, double zeta, double mu,
+                   cd* __restrict__ qs, int* __restrict__ status) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;  // i = l*N + n
+    if (i >= (long)QF * N) return;
+    const int l = (int)(i / N), n = (int)(i - (long)l * N);
+    LayerParams lp;
+    LaneParams ln;
+    const double* a = layers + (size_t)n * LAYER_STRIDE;
+    lp.t20 = a[0]; lp.n21r = a[1]; lp.n21i = a[2]; lp.n22r = a[3]; lp.n22i = a[4];
+    lp.mono = a[5]; lp.deps = a[6]; lp.sigma = a[7]; lp.dz = a[8]; lp.pad = 0;
+    const double* b = lanes + (size_t)l * LANE_STRIDE;
+    ln.c1 = b[0]; ln.s1 = b[1]; ln.c2 = b[2]; ln.s2 = b[3]; ln.twopif = b[4]; ln.w_eps0 = b[5]; ln.pad0 = 0; ln.pad1 = 0;
+    ModeSet m;
+    ScratchArrays sc;
+    const int st = layer_modes(lp, ln, zeta, mu, m, sc);
+    qs[i * 4] = m.q0; qs[i * 4 + 1] = m.q1; qs[i * 4 + 2] = m.q2; qs[i * 4 + 3] = m.q3;
+    if (status) status[i] = st;
 }
 
 __global__ void __launch_bounds__(256) fp64_probe_kernel(double* out, int iters, double a, double b) {
@@ -979,6 +1124,16 @@ int tamm_layer_matrices(const double* layers, const double* lanes, int N, int QF
     return 0;
 }
 
+int tamm_layer_modes(const double* layers, const double* lanes, int N, int QF, double zeta, double mu, void* qs, int* status,
+                     void* stream) {
+    if (!layers || !lanes || !qs) return fail("tamm_layer_modes: null pointer%s", "");
+    if (N < 1 || QF < 1) return fail("tamm_layer_modes: empty problem%s", "");
+    const long tot = (long)N * QF;
+    layer_modes_kernel<<<(int)((tot + 127) / 128), 128, 0, (cudaStream_t)stream>>>(layers, lanes, N, QF, zeta, mu, (cd*)qs, status);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 size_t tamm_stack_workspace_bytes(int P, int N, int QF, int chunk) {
     if (P < 1 || N < 2 || QF < 1 || chunk < 1) return 0;
     int nch = nchunks_of(N, chunk);
@@ -996,20 +1151,27 @@ int tamm_suggest_chunk(int P, int N, int QF, int sm_count) {
     long bpc;                                                              // CTAs per chunk index
     stack_geometry(P, QF, maxt, &tb, &flat, &bpc);
     const long slots = (long)(sm_count > 0 ? sm_count : 148) * ctas_per_sm;  // resident CTAs per wave
-    // Every CTA walks `chunk` interfaces (+1 halo layer).  Choose the number of chunks that maximises
-    //   (CTAs / (waves * slots))  x  chunk / (chunk + 1)      wave-quantisation x halo efficiency,
-    // preferring fewer chunks on ties; chunk >= 8 bounds the halo overhead at 12.5 %.
+    // Every CTA walks `chunk` interfaces (+1 halo layer), all CTAs of a launch in lock step.  Cost model of a launch with n
+    // chunks, in units of "one layer on a fully occupied SM" (12 warps):
+    //     T(n) = (chunk + 1) x [ R t(k wc) + t(ceil(r / SMs) wc) ],     ctas = R (SMs k) + r,
+    // k = CTAs per SM, wc = warps per CTA, and t(w) = time of one layer on an SM holding w warps: 1 at 12 warps, 0.7 at 6
+    // (measured on configs[1]: 6 warps keep the FP64 pipe about 70 % as busy as 12, the dependent chains of a layer bound
+    // the rest), 0.4 for one or two warps.  The minimum over n (ties -> fewer chunks) balances wave quantisation, halo and
+    // -- for single small stacks, which cannot fill the machine -- the serial depth per CTA.  chunk >= 2 bounds the halo.
+    const long sms = sm_count > 0 ? sm_count : 148;
+    const double wc = (double)tb / 32.0;
+    auto t_of = [](double w) { return w <= 2.0 ? 0.4 : (w <= 6.0 ? 0.4 + 0.075 * (w - 2.0) : (w < 12.0 ? 0.7 + 0.05 * (w - 6.0) : 1.0)); };
     long best_n = 1;
-    double best = -1.0;
-    const long max_n = NI / 8 > 0 ? NI / 8 : 1;
+    double best = 1e300;
+    const long max_n = (NI + 1) / 2 > 0 ? (NI + 1) / 2 : 1;
     for (long n = 1; n <= max_n && n <= 65535; ++n) {
         long chunk = (NI + n - 1) / n;
         long nch = (NI + chunk - 1) / chunk;        // actual number of chunks for this chunk length
         long ctas = bpc * nch;
-        long waves = (ctas + slots - 1) / slots;
-        double eff = (double)ctas / (double)(waves * slots) * (double)chunk / (double)(chunk + 1);
-        if (ctas < slots) eff *= 0.5;                // not even one CTA per slot: heavily penalised
-        if (eff > best + 1e-9) { best = eff; best_n = n; }
+        long full = ctas / slots, r = ctas - full * slots;
+        double waves = (double)full * t_of((double)ctas_per_sm * wc) + (r > 0 ? t_of((double)((r + sms - 1) / sms) * wc) : 0.0);
+        double t = (double)(chunk + 1) * waves;
+        if (t < best * (1.0 - 1e-9)) { best = t; best_n = n; }
         if (ctas > 64 * slots) break;
     }
     long chunk = (NI + best_n - 1) / best_n;
@@ -1160,6 +1322,31 @@ int tamm_returns(const void* planes, const void* workspace, int P, int N, int Q,
             return 0;
         }
 #undef TAMM_RT
+        static std::atomic<int> use_v16_once{-1};
+        int use_v16 = use_v16_once.load(std::memory_order_relaxed);
+        if (use_v16 < 0) {
+            const char* ev = getenv("TAMM_RETURNS_V16");
+            use_v16 = (ev ? atoi(ev) : TAMM_RETURNS_V16_DEFAULT) != 0;
+            use_v16_once.store(use_v16, std::memory_order_relaxed);
+        }
+#define TAMM_R16(BLK)                                                                                                    \
+    do {                                                                                                                 \
+        const int dyn = (TNF * TNG * 2 * BLK + (BLK / 32) * TNF * TNG * 2 + TNF * TNG * 2) * (int)sizeof(double);        \
+        CUDA_OK(cudaFuncSetAttribute(returns_fused16_kernel<BLK>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));    \
+        returns_fused16_kernel<BLK><<<grid, BLK, dyn, s>>>((const cd*)planes, pre, N, Q, F, mode, chunk, nch, e0, e1,    \
+                                                           gtm_phase, (cd*)E_HH, (cd*)E_HV, (cd*)c_HHVV, dP_HH, dP_HV,  \
+                                                           Pm_HH, Pm_HV);                                                \
+    } while (0)
+        if (use_v16 && F <= 512) {
+            if (F <= 64) TAMM_R16(64);
+            else if (F <= 128) TAMM_R16(128);
+            else if (F <= 192) TAMM_R16(192);
+            else if (F <= 256) TAMM_R16(256);
+            else TAMM_R16(512);
+            CUDA_OK(cudaGetLastError());
+            return 0;
+        }
+#undef TAMM_R16
         if (F <= 64) TAMM_RF(64);
         else if (F <= 128) TAMM_RF(128);
         else if (F <= 192) TAMM_RF(192);
@@ -1175,6 +1362,11 @@ int tamm_returns(const void* planes, const void* workspace, int P, int N, int Q,
                                         cd{etx[2], etx[3]}, gtm_phase, (cd*)E_HH, (cd*)E_HV, (cd*)c_HHVV, dP_HH, dP_HV);
     CUDA_OK(cudaGetLastError());
     long nrows = (long)P * Q * NI;
+    if (F < 32) {   // one thread per row: sums and dB step in one launch
+        power_rows_kernel<<<(int)((nrows + 255) / 256), 256, 0, s>>>(dP_HH, dP_HV, Pm_HH, Pm_HV, Pm_HH, Pm_HV, nrows, F, F, 1, 1);
+        CUDA_OK(cudaGetLastError());
+        return 0;
+    }
     int grid2 = (int)((nrows + 7) / 8);
     // the sums go through the Pm arrays (finished in place)
     azimuth_sum_kernel<<<grid2, 256, 0, s>>>(dP_HH, dP_HV, Pm_HH, Pm_HV, nrows, F);
@@ -1199,7 +1391,10 @@ int tamm_returns_partial(const void* planes, const void* workspace, int P, int N
                                         cd{etx[2], etx[3]}, gtm_phase, (cd*)E_HH, (cd*)E_HV, (cd*)c_HHVV, amp_HH, amp_HV);
     CUDA_OK(cudaGetLastError());
     const long nrows = (long)P * Q * NI;
-    azimuth_sum_kernel<<<(int)((nrows + 7) / 8), 256, 0, s>>>(amp_HH, amp_HV, sum_HH, sum_HV, nrows, F);
+    if (F < 32)
+        power_rows_kernel<<<(int)((nrows + 255) / 256), 256, 0, s>>>(amp_HH, amp_HV, sum_HH, sum_HV, nullptr, nullptr, nrows, F, F, 1, 0);
+    else
+        azimuth_sum_kernel<<<(int)((nrows + 7) / 8), 256, 0, s>>>(amp_HH, amp_HV, sum_HH, sum_HV, nrows, F);
     CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -1209,8 +1404,12 @@ int tamm_returns_finish(double* amp_HH, double* amp_HV, const double* sum_HH, co
     if (!amp_HH || !amp_HV || !sum_HH || !sum_HV || !Pm_HH || !Pm_HV) return fail("tamm_returns_finish: null pointer%s", "");
     if (P < 1 || N < 2 || Q < 1 || F < 1 || F_total < F) return fail("tamm_returns_finish: bad sizes%s", "");
     const long nrows = (long)P * Q * (N - 1);
-    power_finish_kernel<<<(int)((nrows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(amp_HH, amp_HV, sum_HH, sum_HV, Pm_HH, Pm_HV,
-                                                                                  nrows, F, F_total);
+    if (F < 32)
+        power_rows_kernel<<<(int)((nrows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+            amp_HH, amp_HV, const_cast<double*>(sum_HH), const_cast<double*>(sum_HV), Pm_HH, Pm_HV, nrows, F, F_total, 0, 1);
+    else
+        power_finish_kernel<<<(int)((nrows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(amp_HH, amp_HV, sum_HH, sum_HV, Pm_HH,
+                                                                                      Pm_HV, nrows, F, F_total);
     CUDA_OK(cudaGetLastError());
     return 0;
 }

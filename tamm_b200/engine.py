@@ -226,7 +226,7 @@ class Engine:
                                    out['Pm_HH'].data_ptr(), out['Pm_HV'].data_ptr(), self._stream())
         _lib.check(rc, self.lib)
         # fused returns+power kernel, or returns + azimuth sums + finish
-        self.launches += 1 if (32 <= F <= 1024 and Q <= 65535 and P <= 65535) else 3
+        self.launches += 1 if (32 <= F <= 1024 and Q <= 65535 and P <= 65535) else (2 if F < 32 else 3)
         return out
 
     def returns_partial(self, res, etx, gtm_phase=True, out=None):
@@ -274,6 +274,18 @@ class Engine:
         _lib.check(rc, self.lib)
         self.launches += 1
         return o
+
+
+    def layer_modes(self, layers, lanes, N, QF, zeta, mu=1.0):
+        """Sorted qs (QF, N, 4) and status (QF, N) of one profile from the hot-path mode solve (tamm_layer_modes)."""
+        torch = _torch()
+        qs = self.empty((QF, N, 4), torch.complex128)
+        st = self.empty((QF, N), torch.int32)
+        rc = self.lib.tamm_layer_modes(layers.data_ptr(), lanes.data_ptr(), N, QF, float(np.real(zeta)), float(mu),
+                                       qs.data_ptr(), st.data_ptr(), self._stream())
+        _lib.check(rc, self.lib)
+        self.launches += 1
+        return qs, st
 
 
 _engine = None

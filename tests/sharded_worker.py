@@ -25,12 +25,18 @@ import layerstack as ls                                                         
 TOL = 1e-12
 
 
-def close(a, b, what):
+def close(a, b, what, tol=TOL):
     fin = np.isfinite(b)
     assert np.array_equal(np.isfinite(a), fin), what
     scale = max(1.0, float(np.abs(b[fin]).max())) if fin.any() else 1.0
     err = float(np.abs(a - b)[fin].max()) if fin.any() else 0.0
-    assert err <= TOL * scale, (what, err, scale)
+    assert err <= tol * scale, (what, err, scale)
+
+
+# A shard has fewer lanes than the whole solve, so the depth scan is cut into different chunks and the products are rounded
+# in a different order.  Fields, powers: 1e-12 of the array's peak.  c_HHVV has unit modulus at every depth, i.e. it carries
+# the ELEMENT-WISE relative rounding of URD_hh, URD_vv including the weakest returns (1e2 ... 1e4 below the peak): 1e-10.
+C_TOL = 1e-10
 
 
 names = ['Pm_HH', 'Pm_HV', 'dP_HH', 'dP_HV', 'c_HHVV', 'E_HH', 'E_HV']
@@ -42,7 +48,7 @@ for alpha in (0.0, np.deg2rad(10)):
     got = st.get_returns(1e3, f=179e6, alpha=alpha, shard=tdist.AxisShard('azimuth'))
     for n, a, b in zip(names, got, whole):
         assert a.shape == b.shape, n
-        close(a, b, ('azimuth', alpha, n))
+        close(a, b, ('azimuth', alpha, n), C_TOL if n == 'c_HHVV' else TOL)
     lo, hi = tdist.shard_range(181, rank, ws)
     part = st.get_returns(1e3, f=179e6, alpha=alpha, shard=tdist.AxisShard('azimuth', gather=False))
     assert part[5].shape == (3000, hi - lo)
@@ -56,7 +62,7 @@ whole = st.get_returns_polarimetric(1e3, f=fs, alpha=np.deg2rad(10))
 got = st.get_returns_polarimetric(1e3, f=fs, alpha=np.deg2rad(10), shard=tdist.AxisShard('frequency'))
 for k in whole:
     assert got[k].shape == whole[k].shape, k
-    close(got[k], whole[k], ('frequency', k))
+    close(got[k], whole[k], ('frequency', k), C_TOL if k == 'c_HHVV' else TOL)
 # batched API: all profiles everywhere, azimuths split
 nlm, z = profiles.ensemble(3, 400, 200)
 w = EnsembleStack(nlm, z, N_frames=181).get_returns(1e3, f=179e6, alpha=np.deg2rad(10))

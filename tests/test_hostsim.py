@@ -376,4 +376,5 @@ def test_near_degenerate_pair_crossing_at_oblique_incidence(sim):
             got, want = np.sort_complex(qs[0, n, sl].astype(np.clongdouble)), np.sort_complex(qx[n, sl])
             assert float(np.abs(got - want).max()) < 1e-15, (n, got, want)
         assert abs(qs[0, n, 0] - qs[0, n, 1]) > 0.5 * split[n]
-    assert st['collapsed'] >= M and st['recentre'] > 0 and st['fallback'] >= M
+    # only pairs whose two refinements actually met go to the cold solver; there the deflation step finds the partner
+    assert 0 < st['collapsed'] <= M and st['fallback'] == st['collapsed'] and st['recentre'] > 0
