@@ -55,10 +55,13 @@ def parse():
     ap.add_argument('--bins', type=int, default=None, help='config 2: frequency bins (default 4096)')
     ap.add_argument('--alpha-deg', type=float, default=None)
     ap.add_argument('--freq', type=float, default=179e6)
-    ap.add_argument('--batch', type=int, default=128, help='config 4: profiles per kernel launch')
+    ap.add_argument('--batch', type=int, default=0,
+                    help='config 4: profiles per kernel launch (0: as many as fill the machine exactly once without cutting the '
+                         'depth into chunks -- 148 SMs x 384 lanes / 181 azimuths = 313 -- or the whole shard if smaller)')
     ap.add_argument('--e2e-steps', type=int, default=5)
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='configs 0-3: time plain launches instead of a CUDA graph replay')
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
     ap.add_argument('--gather', default='all', choices=['none', 'power', 'fields', 'jones', 'all'],
                     help='config 4, N > 1: also time the final NCCL all-gather of results (reported separately)')
@@ -486,25 +489,52 @@ def bench_single(c, args, w, emit):
     for _ in range(max(3, args.warmup)):
         step()
     sync_all(c)
+    # One small stack is launch-bound when its kernels are enqueued one by one from Python (3-4 launches of 10-30 us): the
+    # step is captured ONCE into a CUDA graph and replayed (single rank only: the sharded step has a collective in it).
+    graph = None
+    if c.world == 1 and not args.no_graph:
+        try:
+            graph = eng.capture(step)
+        except Exception as e:
+            print('CUDA graph capture failed, timing plain launches: %r' % (e,), file=sys.stderr)
+            graph = None
+    graph_ev = []
+    if graph is not None:
+        for _ in range(3):
+            graph.replay()
+        sync_all(c)
     sampler = ClockSampler(c.local)
     if c.rank == 0:
         sampler.start()
     l0 = eng.launches
     for _ in range(args.steps):
-        step(record=True)
+        step(record=True)                 # plain launches with per-kernel events: the stack kernel's own duration
+        if graph is not None:
+            flush.zero_()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            graph.replay()
+            g1.record()
+            graph_ev.append((g0, g1))
     sync_all(c)
     launches = eng.launches - l0
     sampler.stop_flag = True
-    ms_total = max_over_ranks(c, sum(a.elapsed_time(b) for a, b in step_ev))
+    plain_ms_total = max_over_ranks(c, sum(a.elapsed_time(b) for a, b in step_ev))
+    ms_total = plain_ms_total if graph is None else sum(a.elapsed_time(b) for a, b in graph_ev)
+    if graph is not None:
+        launches += graph.kernels_per_replay * args.steps
     ms_per_step = ms_total / args.steps
     value = w['evals'] / (ms_per_step * 1e-3)
     stack_ms = sum(a.elapsed_time(b) for a, b in stack_ev)
     evals_local = float(N) * Ql * Fl
     line = base_line(c, args, w, value, ms_per_step, launches,
                      dict(chunk=chunk, chunks=(NI + chunk - 1) // chunk, lanes_per_rank=Ql * Fl))
-    line['roofline'] = stack_roofline(c, stack_ms, evals_local * args.steps, args.steps, ms_total, evals_local,
+    line['roofline'] = stack_roofline(c, stack_ms, evals_local * args.steps, args.steps, plain_ms_total, evals_local,
                                       'stack_kernel<URD> (+ chunk_scan_kernel)')
-    line['returns_ms_per_step'] = (ms_total - stack_ms) / args.steps
+    line['returns_ms_per_step'] = (plain_ms_total - stack_ms) / args.steps
+    line['launch_mode'] = dict(timed='CUDA graph replay of the step (tamm_b200.Engine.capture)' if graph is not None else 'plain launches',
+                               plain_launch_ms_per_step=plain_ms_total / args.steps,
+                               note='the roofline entry times the stack kernel in the plain-launch steps, which alternate with the graph replays')
     if int(status.cpu()[0]) != 0:
         line['status_word'] = int(status.cpu()[0])
 
@@ -555,7 +585,8 @@ def bench_ensemble(c, args, w, emit):
     layers_d = eng.to_device(ens.packed_layers())                       # (Pl, N, 10) resident in HBM
     lanes_d = eng.to_device(packing.pack_lanes(ens.beta, args.freq))
     etx = np.array([1e3, 0.0], dtype=np.complex128)
-    B = max(1, min(args.batch, Pl))
+    auto_batch = (eng.sm_count * 384) // F            # one full wave of 384-lane CTAs: every thread walks the WHOLE depth
+    B = max(1, min(args.batch or auto_batch, Pl))
     cdt, rdt = torch.complex128, torch.float64
     out = dict(E_HH=eng.empty((Pl, 1, NI, F), cdt), E_HV=eng.empty((Pl, 1, NI, F), cdt), c_HHVV=eng.empty((Pl, 1, NI, F), cdt),
                dP_HH=eng.empty((Pl, 1, NI, F), rdt), dP_HV=eng.empty((Pl, 1, NI, F), rdt), Pm_HH=eng.empty((Pl, 1, NI), rdt),
@@ -630,7 +661,7 @@ def bench_ensemble(c, args, w, emit):
         try:
             # blocks of the e2e pipeline: the launch batch, or a quarter of the shard when the shard is a single launch
             # batch (N = 8), so that the device->host copy of block b overlaps the kernels of block b+1
-            EB = B if Pl > B else max(1, (Pl + 3) // 4)
+            EB = min(B, 128) if Pl > min(B, 128) else max(1, (Pl + 3) // 4)
             h2d = Pl * N * packing.LAYER_STRIDE * 8 + F * packing.LANE_STRIDE * 8
 
             def e2e_run(outputs, steps):

@@ -1347,24 +1347,20 @@ struct ModeSet {          // sorted roots and unnormalised gamma entries of one 
 };
 
 // Everything up to the unnormalised field vectors: permittivity, roots, clean-up, partition, p/s sort, gamma.
-template <class SC>
-TAMM_HD int layer_modes(const LayerParams& lp, const LaneParams& ln, double zeta, double mu, ModeSet& ms_out, SC& sc) {
+// COLD = true: the out-of-line repeat of a layer whose pair solve lost a root (cold solver from the start, no further retry).
+#if defined(__CUDA_ARCH__)
+__device__ __noinline__
+#else
+inline
+#endif
+int layer_modes_cold(LayerParams lp, LaneParams ln, double zeta, double mu, ModeSet* out);
+
+template <bool COLD, class SC>
+TAMM_HD int layer_modes_impl(const LayerParams& lp, const LaneParams& ln, double zeta, double mu, ModeSet& ms_out, SC& sc) {
     int status = 0;
     const Sym3 e = permittivity(lp, ln);
     const WaveCoef w = wave_coef(e, mu, zeta);
-    bool solved = eig4_fast(w, sc);
-    if (TAMM_USUAL(solved)) {
-        // a coinciding pair is either a true degeneracy or a lost partner root (see partner_lost): the latter is re-solved
-        const cd r0 = sc.rv(0, 0), r2 = sc.rv(2, 0);
-        const bool c01 = abs2(r0 - sc.rv(1, 0)) < QSD_THR * QSD_THR, c23 = abs2(r2 - sc.rv(3, 0)) < QSD_THR * QSD_THR;
-        if (TAMM_RARE(c01 || c23)) {
-            if (partner_lost(e.xx, e.xy, e.xz, e.yy, e.yz, e.zz, e.im, mu, zeta, c01 ? r0 : r2)) {
-                TAMM_STAT(collapsed);
-                solved = false;
-            }
-        }
-    }
-    if (TAMM_RARE(!solved)) {
+    if (TAMM_RARE(COLD || !eig4_fast(w, sc))) {
         TAMM_STAT(fallback);
         cd rv[4][3];
         eig4_fallback(e.xx, e.xy, e.xz, e.yy, e.yz, e.zz, e.im, mu, zeta, rv);
@@ -1450,6 +1446,24 @@ TAMM_HD int layer_modes(const LayerParams& lp, const LaneParams& ln, double zeta
     }
     const int o0 = flip_t ? t1 : t0, o1 = flip_t ? t0 : t1, o2 = flip_r ? r1 : r0, o3 = flip_r ? r0 : r1;
     const cd q0 = sc.rv(o0, 0), q1 = sc.rv(o1, 0), q2 = sc.rv(o2, 0), q3 = sc.rv(o3, 0);
+    const bool deg01 = abs2(q0 - q1) < QSD_THR * QSD_THR, deg23 = abs2(q2 - q3) < QSD_THR * QSD_THR;   // |q_a - q_b| < qsd_thr
+    // Two coinciding roots are either a true degeneracy or a lost partner root (see partner_lost): then the whole mode
+    // solve of this layer is redone by the cold solver, out of line.  Costs the hot path nothing beyond the two
+    // |q_a - q_b| < QSD_THR tests the gamma stage needs anyway; the result comes back through a temporary so that the hot
+    // path's values stay in registers.
+    if (!COLD) {
+        if (TAMM_RARE(deg01 || deg23)) {
+            if (partner_lost(e.xx, e.xy, e.xz, e.yy, e.yz, e.zz, e.im, mu, zeta, deg01 ? q0 : q2)) {
+                TAMM_STAT(collapsed);
+                ModeSet t;
+                const int st = layer_modes_cold(lp, ln, zeta, mu, &t);
+                ms_out.q0 = t.q0; ms_out.q1 = t.q1; ms_out.q2 = t.q2; ms_out.q3 = t.q3;
+                ms_out.g12 = t.g12; ms_out.g13 = t.g13; ms_out.g21 = t.g21; ms_out.g23 = t.g23;
+                ms_out.g32 = t.g32; ms_out.g33 = t.g33; ms_out.g41 = t.g41; ms_out.g43 = t.g43;
+                return st;
+            }
+        }
+    }
 
     // ---- gamma (layer_PPJ.py:309-389), unnormalised; see layer_solve for the line-by-line citations
     const cd e00 = mk(e.xx, e.im), e11 = mk(e.yy, e.im);
@@ -1474,7 +1488,7 @@ TAMM_HD int layer_modes(const LayerParams& lp, const LaneParams& ln, double zeta
         cfma(den1, -u1, u1);
         g21 = cmul_(m12 * u1 - c01m, crecip_s(den1));
         g23 = cmul_(cmul_(-u1, g21) - m12, imez);
-        if (abs2(q0 - q1) < QSD_THR * QSD_THR) { g12 = mk(0.0); g13 = g13p; g21 = mk(0.0); g23 = g23p; }   // |q0-q1| < qsd_thr
+        if (deg01) { g12 = mk(0.0); g13 = g13p; g21 = mk(0.0); g23 = g23p; }   // layer_PPJ.py:317-324
         cd den2 = cmul_(mez, mzz - csq(q2)) - m12sq;
         g32 = cmul_(c01m - m12 * u2, crecip_s(den2));
         g33 = cmul_(u2 + m12 * g32, imez);
@@ -1482,12 +1496,26 @@ TAMM_HD int layer_modes(const LayerParams& lp, const LaneParams& ln, double zeta
         cfma(den3, -u3, u3);
         g41 = cmul_(m12 * u3 - c01m, crecip_s(den3));
         g43 = cmul_(cmul_(-u3, g41) - m12, imez);
-        if (abs2(q2 - q3) < QSD_THR * QSD_THR) { g32 = mk(0.0); g33 = g33p; g41 = mk(0.0); g43 = g23p; }
+        if (deg23) { g32 = mk(0.0); g33 = g33p; g41 = mk(0.0); g43 = g23p; }    // layer_PPJ.py:356-360
     }
     ms_out.q0 = q0; ms_out.q1 = q1; ms_out.q2 = q2; ms_out.q3 = q3;
     ms_out.g12 = g12; ms_out.g13 = g13; ms_out.g21 = g21; ms_out.g23 = g23;
     ms_out.g32 = g32; ms_out.g33 = g33; ms_out.g41 = g41; ms_out.g43 = g43;
     return status;
+}
+
+template <class SC>
+TAMM_HD int layer_modes(const LayerParams& lp, const LaneParams& ln, double zeta, double mu, ModeSet& ms_out, SC& sc) {
+    return layer_modes_impl<false>(lp, ln, zeta, mu, ms_out, sc);
+}
+#if defined(__CUDA_ARCH__)
+__device__ __noinline__
+#else
+inline
+#endif
+int layer_modes_cold(LayerParams lp, LaneParams ln, double zeta, double mu, ModeSet* out) {
+    ScratchArrays sc;
+    return layer_modes_impl<true>(lp, ln, zeta, mu, *out, sc);
 }
 
 // Amplitude-basis layer record (normalised E blocks, their inverses, admittances, phases).

@@ -51,9 +51,6 @@ inline bool lanes_fit(int Q, int F) { return (long)Q * (long)F <= 2147483647L; }
 #ifndef TAMM_RETURNS_TMA_DEFAULT
 #define TAMM_RETURNS_TMA_DEFAULT 0
 #endif
-#ifndef TAMM_RETURNS_V16_DEFAULT
-#define TAMM_RETURNS_V16_DEFAULT 0
-#endif
 
 constexpr int TL = 16;     // layers per TMA sub-tile (16 * 80 B = 1280 B per profile)
 constexpr int CARRY_SLOTS = 34;   // 16-byte shared-memory slots per thread of stack_kernel (carry state + mode scratch)
@@ -519,25 +516,27 @@ __device__ __forceinline__ double warp_sum8(const double v[8], int lane) {
 // arithmetic of the two-pass kernels is used (hypot like numpy.abs, true division), so the result does not depend on
 // which returns kernel F selects and stays finite exactly where the reference's is.
 __device__ __forceinline__ unsigned exp_field(double x) { return ((unsigned)__double2hiint(x) >> 20) & 0x7ffu; }
-__device__ __forceinline__ void returns_point_slow(cd m0, cd m3, cd hh, cd hv, cd& c, double& ahh, double& ahv) {
+// returns {c.re, c.im, |hh|, |hv|} in registers (a by-reference result would go through local memory on BOTH paths)
+__device__ __noinline__ double4 returns_point_slow(cd m0, cd m3, cd hh, cd hv) {
     const cd num = m0 * conj(m3);
     const double den = cabs_(m0) * cabs_(m3);
-    c = cd{num.re / den, num.im / den};
-    ahh = cabs_(hh);
-    ahv = cabs_(hv);
+    return make_double4(num.re / den, num.im / den, cabs_(hh), cabs_(hv));
 }
 __device__ __forceinline__ void returns_point(const cd m[4], cd e0, cd e1, int gtm_phase, cd& hh, cd& hv, cd& c, double& ahh,
                                               double& ahv) {
     hh = dot2(m[0], e0, m[1], e1);             // get_Rx_all (layerstack.py:298)
     hv = dot2(m[2], e0, m[3], e1);
-    const double a0 = abs2(m[0]), a3 = abs2(m[3]), shh = abs2(hh), shv = abs2(hv);
-    // exponent fields: a0, a3 within 2^+-498 of 1 (their product stays normal), shh, shv normal with 40 bits to spare
-    const unsigned k0 = exp_field(a0) - 525u, k3 = exp_field(a3) - 525u, kh = exp_field(shh) - 40u, kv = exp_field(shv) - 40u;
-    if (TAMM_RARE(max(k0, k3) > 996u || max(kh, kv) > 2005u)) {
-        returns_point_slow(m[0], m[3], hh, hv, c, ahh, ahv);
+    const double prod = abs2(m[0]) * abs2(m[3]), shh = abs2(hh), shv = abs2(hv);
+    // exponent fields: all three normal with 40 binades to spare below and not inf / NaN (prod = 0 when a modulus is 0)
+    const unsigned kp = exp_field(prod) - 40u, kh = exp_field(shh) - 40u, kv = exp_field(shv) - 40u;
+    if (TAMM_RARE(max(kp, max(kh, kv)) > 2005u)) {
+        const double4 r = returns_point_slow(m[0], m[3], hh, hv);
+        c = cd{r.x, r.y};
+        ahh = r.z;
+        ahv = r.w;
     } else {
         const cd num = cmul_(m[0], conj(m[3]));    // c_HHVV (layerstack.py:271-278): num / (|m0| |m3|)
-        const double iden = tamm::frsqrt(a0 * a3);
+        const double iden = tamm::frsqrt(prod);
         c = cd{num.re * iden, num.im * iden};
         ahh = tamm::fsqrt(shh);
         ahv = tamm::fsqrt(shv);
@@ -632,100 +631,6 @@ returns_fused_kernel(const cd* __restrict__ planes, const cd* __restrict__ pre, 
         }
         // red / tot are rewritten by the next group only after its own barrier on red; tot is read above before the next
         // group's first barrier, and written after it -> no extra barrier needed
-    }
-}
-
-// Variant with ONE reduction per CTA instead of one per depth group: the |E| of all TNF * TNG = 16 depths of the CTA are
-// parked in shared memory ([depth][pol][thread], conflict-free), the warps stream through their 16 depths without meeting
-// (no CTA barrier between the loads of consecutive groups), and only then the 32 azimuth sums are formed (fixed order ->
-// deterministic), turned into Pm, and the anomalies written.  Two CTA barriers per 16 depths instead of eight.
-template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK, (BLOCK <= 256 ? 768 / BLOCK : 1))
-returns_fused16_kernel(const cd* __restrict__ planes, const cd* __restrict__ pre, int N, int Q, int F, int mode, int chunk,
-                       int nchunks, cd e0, cd e1, int gtm_phase, cd* __restrict__ E_HH, cd* __restrict__ E_HV,
-                       cd* __restrict__ c_HHVV, double* __restrict__ dP_HH, double* __restrict__ dP_HV,
-                       double* __restrict__ Pm_HH, double* __restrict__ Pm_HV) {
-    static_assert(TNF == 4, "warp_sum8 reduces 2 * TNF = 8 values");
-    constexpr int NW = BLOCK / 32, ND = TNF * TNG;
-    extern __shared__ double sm16[];
-    double* amp_s = sm16;                       // [ND][2][BLOCK]
-    double* red = sm16 + ND * 2 * BLOCK;        // [NW][ND * 2]
-    double* tot = red + NW * ND * 2;            // [ND * 2]
-    const int NI = N - 1, QF = Q * F;
-    const int p = blockIdx.z, iq = blockIdx.y;
-    const int ifr = threadIdx.x;
-    const bool live = ifr < F;
-    const int l = iq * F + (live ? ifr : F - 1);
-    const int nbeg = blockIdx.x * ND;
-    const int ne = min(NI, nbeg + ND);
-    const size_t istride = (size_t)4 * QF;
-    const cd* ip = planes + ((size_t)p * NI + (size_t)nbeg) * istride + l;
-    const size_t o0 = (((size_t)p * Q + iq) * NI + (size_t)nbeg) * F + (live ? ifr : F - 1);
-    size_t o = o0;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    cd Dp[4], Up[4];
-    int cc = -1;
-#pragma unroll 1
-    for (int g = 0; g < TNG; ++g) {
-        double amp[2 * TNF];
-#pragma unroll
-        for (int k = 0; k < TNF; ++k) {
-            const int n = nbeg + g * TNF + k;
-            amp[2 * k] = 0.0; amp[2 * k + 1] = 0.0;
-            if (n < ne) {
-                cd m[4] = {ld_cd(ip), ld_cd(ip + QF), ld_cd(ip + 2 * (size_t)QF), ld_cd(ip + 3 * (size_t)QF)};
-                if (nchunks > 1) {
-                    const int c = n / chunk;
-                    if (c != cc) { load_prefix(pre, (size_t)p * QF + l, nchunks, c, Dp, Up); cc = c; }
-                    if (c > 0) {
-                        cd t[4];
-                        if (mode == TAMM_MODE_URD) { mm22(m, Dp, t); mm22(Up, t, m); }
-                        else { mm22(Up, m, t); m[0] = t[0]; m[1] = t[1]; m[2] = t[2]; m[3] = t[3]; }
-                    }
-                }
-                cd hh, hv, c;
-                double ahh, ahv;
-                returns_point(m, e0, e1, gtm_phase, hh, hv, c, ahh, ahv);
-                if (live) {
-                    st_cd(E_HH + o, hh);
-                    st_cd(E_HV + o, hv);
-                    st_cd(c_HHVV + o, c);
-                    amp[2 * k] = ahh;
-                    amp[2 * k + 1] = ahv;
-                }
-            }
-            amp_s[((g * TNF + k) * 2) * BLOCK + threadIdx.x] = amp[2 * k];
-            amp_s[((g * TNF + k) * 2 + 1) * BLOCK + threadIdx.x] = amp[2 * k + 1];
-            ip += istride;
-            o += F;
-        }
-        const double r = warp_sum8(amp, lane);
-        if ((lane & 3) == 0) red[w * (ND * 2) + g * 8 + (((lane >> 4) & 1) | (((lane >> 3) & 1) << 1) | (((lane >> 2) & 1) << 2))] = r;
-    }
-    __syncthreads();
-    if (threadIdx.x < ND * 2) {
-        double sum = 0.0;
-#pragma unroll
-        for (int i = 0; i < NW; ++i) sum += red[i * (ND * 2) + threadIdx.x];
-        const double pm = 20.0 * log10(sum / (double)F);
-        tot[threadIdx.x] = pm;
-        const int n = nbeg + (threadIdx.x >> 1);
-        if (n < ne) {
-            const size_t row = ((size_t)p * Q + iq) * NI + n;
-            if (threadIdx.x & 1) Pm_HV[row] = pm; else Pm_HH[row] = pm;
-        }
-    }
-    __syncthreads();
-    if (live) {
-        size_t od = o0;
-#pragma unroll 4
-        for (int d = 0; d < ND; ++d) {
-            if (nbeg + d < ne) {
-                dP_HH[od] = 20.0 * log10_dev(amp_s[(d * 2) * BLOCK + threadIdx.x]) - tot[2 * d];       // layerstack.py:261-267
-                dP_HV[od] = 20.0 * log10_dev(amp_s[(d * 2 + 1) * BLOCK + threadIdx.x]) - tot[2 * d + 1];
-            }
-            od += F;
-        }
     }
 }
 
@@ -1171,7 +1076,7 @@ int tamm_suggest_chunk(int P, int N, int QF, int sm_count) {
         long full = ctas / slots, r = ctas - full * slots;
         double waves = (double)full * t_of((double)ctas_per_sm * wc) + (r > 0 ? t_of((double)((r + sms - 1) / sms) * wc) : 0.0);
         double t = (double)(chunk + 1) * waves;
-        if (t < best * (1.0 - 1e-9)) { best = t; best_n = n; }
+        if (t < best * (1.0 - 5e-3)) { best = t; best_n = n; }     // more chunks only for a gain above 0.5 %
         if (ctas > 64 * slots) break;
     }
     long chunk = (NI + best_n - 1) / best_n;
@@ -1322,31 +1227,6 @@ int tamm_returns(const void* planes, const void* workspace, int P, int N, int Q,
             return 0;
         }
 #undef TAMM_RT
-        static std::atomic<int> use_v16_once{-1};
-        int use_v16 = use_v16_once.load(std::memory_order_relaxed);
-        if (use_v16 < 0) {
-            const char* ev = getenv("TAMM_RETURNS_V16");
-            use_v16 = (ev ? atoi(ev) : TAMM_RETURNS_V16_DEFAULT) != 0;
-            use_v16_once.store(use_v16, std::memory_order_relaxed);
-        }
-#define TAMM_R16(BLK)                                                                                                    \
-    do {                                                                                                                 \
-        const int dyn = (TNF * TNG * 2 * BLK + (BLK / 32) * TNF * TNG * 2 + TNF * TNG * 2) * (int)sizeof(double);        \
-        CUDA_OK(cudaFuncSetAttribute(returns_fused16_kernel<BLK>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));    \
-        returns_fused16_kernel<BLK><<<grid, BLK, dyn, s>>>((const cd*)planes, pre, N, Q, F, mode, chunk, nch, e0, e1,    \
-                                                           gtm_phase, (cd*)E_HH, (cd*)E_HV, (cd*)c_HHVV, dP_HH, dP_HV,  \
-                                                           Pm_HH, Pm_HV);                                                \
-    } while (0)
-        if (use_v16 && F <= 512) {
-            if (F <= 64) TAMM_R16(64);
-            else if (F <= 128) TAMM_R16(128);
-            else if (F <= 192) TAMM_R16(192);
-            else if (F <= 256) TAMM_R16(256);
-            else TAMM_R16(512);
-            CUDA_OK(cudaGetLastError());
-            return 0;
-        }
-#undef TAMM_R16
         if (F <= 64) TAMM_RF(64);
         else if (F <= 128) TAMM_RF(128);
         else if (F <= 192) TAMM_RF(192);

@@ -107,6 +107,26 @@ class Engine:
         torch.cuda.current_stream(self.device).synchronize()
         return [h.numpy() for h in host]
 
+    def capture(self, fn):
+        """Record the launches `fn()` enqueues (C-ABI calls on preallocated buffers, nothing that allocates or synchronises)
+        into a CUDA graph and return it; `graph.replay()` then re-issues the whole sequence with one driver call.  For
+        launch-bound sequences: a single small stack is three or four kernels of 10-30 us each, less than the host needs to
+        enqueue them one by one through ctypes."""
+        torch = _torch()
+        cur = torch.cuda.current_stream(self.device)
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            fn()                                   # warm-up outside the capture (lazy module loading, attribute calls)
+        cur.wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        n0 = self.launches
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            fn()
+        g.kernels_per_replay = self.launches - n0
+        return g
+
     def suggest_chunk(self, P, N, QF):
         return int(self.lib.tamm_suggest_chunk(P, N, QF, self.sm_count))
 

@@ -21,11 +21,9 @@ PY
 CMD2="python bench.py --profiles 128 --steps 2 --warmup 3 --no-e2e --no-cpu"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${T}_launches.csv $CMD2 > gpurun_out/${T}_ncu_list.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:stack_kernel -s 3 -c 1 -o gpurun_out/${T}_stack $CMD2 > gpurun_out/${T}_ncu_stack.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:returns_fused -s 3 -c 1 -o gpurun_out/${T}_returns $CMD2 > gpurun_out/${T}_ncu_returns.log 2>&1
-TAMM_RETURNS_V16=1 ncu --set full --clock-control none --import-source on -k regex:returns_fused16 -s 3 -c 1 -o gpurun_out/${T}_returns16 $CMD2 > gpurun_out/${T}_ncu_returns16.log 2>&1
+ncu --set full --clock-control none -k regex:returns_fused -s 3 -c 1 -o gpurun_out/${T}_returns $CMD2 > gpurun_out/${T}_ncu_returns.log 2>&1
+TAMM_RETURNS_V16=1 ncu --set full --clock-control none -k regex:returns_fused16 -s 3 -c 1 -o gpurun_out/${T}_returns16 $CMD2 > gpurun_out/${T}_ncu_returns16.log 2>&1
 # alpha = 0: the closed-form eigen path (configs[0], configs[1] at normal incidence)
 CMD3="python bench.py --config 1 --alpha-deg 0 --steps 3 --warmup 3 --no-e2e --no-cpu"
-ncu --set full --clock-control none --import-source on -k regex:stack_kernel -s 3 -c 1 -o gpurun_out/${T}_stack_cfg1_a0 $CMD3 > gpurun_out/${T}_ncu_stack_a0.log 2>&1
-CMD4="python bench.py --config 1 --steps 3 --warmup 3 --no-e2e --no-cpu"
-ncu --set full --clock-control none --import-source on -k regex:stack_kernel -s 3 -c 1 -o gpurun_out/${T}_stack_cfg1_a10 $CMD4 > gpurun_out/${T}_ncu_stack_a10.log 2>&1
+ncu --set full --clock-control none -k regex:stack_kernel -s 3 -c 1 -o gpurun_out/${T}_stack_cfg1_a0 $CMD3 > gpurun_out/${T}_ncu_stack_a0.log 2>&1
 ls -la gpurun_out/*.ncu-rep | tail -8
