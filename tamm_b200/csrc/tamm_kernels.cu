@@ -233,7 +233,32 @@ stack_body(const double* __restrict__ layers, const double* __restrict__ lanes, 
             __syncthreads();
 #endif
             // normalised E blocks are only needed for MODE_U here; the start of a stack uses the cold helper below
-            st |= layer_solve_field<MODE == TAMM_MODE_U>(lp, ln, zeta, mu, cur, sc);
+            int lst = layer_solve_field<MODE == TAMM_MODE_U>(lp, ln, zeta, mu, cur, sc);
+            if (TAMM_RARE(lst & ST_COINCIDE)) {
+                // two roots of a pair coincide: a degenerate pair (e.g. the isotropic top layer) or a lost partner root
+                // (tamm_core.cuh: partner_lost) -- the layer is repeated out of line, from fresh copies of its parameters
+                // (taking the address of lp / ln themselves would put them in local memory for every layer)
+                LayerParams lp0;
+                {
+                    const volatile double* r = tile + jj * LAYER_STRIDE;
+                    lp0.t20 = r[0]; lp0.n21r = r[1]; lp0.n21i = r[2]; lp0.n22r = r[3]; lp0.n22i = r[4];
+                    lp0.mono = r[5]; lp0.deps = r[6]; lp0.sigma = r[7]; lp0.dz = r[8]; lp0.pad = 0;
+                }
+                LaneParams ln0;
+                {
+                    const volatile double* r = lanes + (size_t)lc * LANE_STRIDE;
+                    ln0.c1 = r[0]; ln0.s1 = r[1]; ln0.c2 = r[2]; ln0.s2 = r[3]; ln0.twopif = r[4]; ln0.w_eps0 = r[5];
+                    ln0.pad0 = 0; ln0.pad1 = 0;
+                }
+                LayerF redo;
+                lst = layer_redo_cold(&lp0, &ln0, zeta, mu, &redo);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    cur.Yt[k] = redo.Yt[k]; cur.Yr[k] = redo.Yr[k]; cur.P[k] = redo.P[k]; cur.Q[k] = redo.Q[k];
+                    if (MODE == TAMM_MODE_U) cur.Er[k] = redo.Er[k];
+                }
+            }
+            st |= lst;
 #ifdef TAMM_SYNC_PER_LAYER
             __syncthreads();
 #endif
@@ -515,7 +540,6 @@ __device__ __forceinline__ double warp_sum8(const double v[8], int lane) {
 // modulus is below ~1e-75 / ~1e-148 (strongly attenuating deep stacks) or the value is zero, inf or NaN: then the
 // arithmetic of the two-pass kernels is used (hypot like numpy.abs, true division), so the result does not depend on
 // which returns kernel F selects and stays finite exactly where the reference's is.
-__device__ __forceinline__ unsigned exp_field(double x) { return ((unsigned)__double2hiint(x) >> 20) & 0x7ffu; }
 // returns {c.re, c.im, |hh|, |hv|} in registers (a by-reference result would go through local memory on BOTH paths)
 __device__ __noinline__ double4 returns_point_slow(cd m0, cd m3, cd hh, cd hv) {
     const cd num = m0 * conj(m3);
@@ -527,9 +551,10 @@ __device__ __forceinline__ void returns_point(const cd m[4], cd e0, cd e1, int g
     hh = dot2(m[0], e0, m[1], e1);             // get_Rx_all (layerstack.py:298)
     hv = dot2(m[2], e0, m[3], e1);
     const double prod = abs2(m[0]) * abs2(m[3]), shh = abs2(hh), shv = abs2(hv);
-    // exponent fields: all three normal with 40 binades to spare below and not inf / NaN (prod = 0 when a modulus is 0)
-    const unsigned kp = exp_field(prod) - 40u, kh = exp_field(shh) - 40u, kv = exp_field(shv) - 40u;
-    if (TAMM_RARE(max(kp, max(kh, kv)) > 2005u)) {
+    // all three within 2^-980 ... 2^+980 (normal, with room to spare, not inf / NaN; prod = 0 when a modulus is 0): the high
+    // words of non-negative doubles order like the values, so this is two 3-way integer min/max and two compares
+    const unsigned hp = (unsigned)__double2hiint(prod), hh_ = (unsigned)__double2hiint(shh), hv_ = (unsigned)__double2hiint(shv);
+    if (TAMM_RARE(min(hp, min(hh_, hv_)) < 0x02B00000u || max(hp, max(hh_, hv_)) > 0x7D300000u)) {
         const double4 r = returns_point_slow(m[0], m[3], hh, hv);
         c = cd{r.x, r.y};
         ahh = r.z;

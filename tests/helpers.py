@@ -80,6 +80,16 @@ def field_scale(ret):
     return np.where(s == 0, 1.0, s)
 
 
+def record(name, report):
+    """Append one measured parity report (errors in units of the tolerance) to the JSON-lines file named by
+    TAMM_PARITY_REPORT -- how the per-configuration worst cases quoted in DESIGN.md are collected on the GPU box."""
+    path = os.environ.get('TAMM_PARITY_REPORT')
+    if path:
+        import json
+        with open(path, 'a') as f:
+            f.write(json.dumps(dict(test=name, report=report)) + '\n')
+
+
 def nonfinite_code(x):
     """0 finite, 1 NaN, 2 +inf, 3 -inf (complex: either part NaN -> 1, else either part infinite -> 2 + sign of that part)."""
     x = np.asarray(x)
