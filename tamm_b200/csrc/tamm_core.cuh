@@ -1027,18 +1027,6 @@ void eig4_fallback(double exx, double exy, double exz, double eyy, double eyz, d
     }
 }
 
-// Two roots of the pair solver coincide (to QSD_THR).  Either the pair is truly degenerate -- N vanishes at the root and so
-// do both eigenvalues of -N'^-1 N -- or both refinements of a near-degenerate pair (splitting down at the accuracy of the
-// starting values, ~1e-8 |q|, e.g. where the p and s branches of a smoothly rotating fabric cross at oblique incidence)
-// ended on the SAME root, because every refinement step moves to the nearest one; then the other eigenvalue of
-// -N'(x)^-1 N(x), the distance to the partner root, is resolvably non-zero.  Only called from cold code.
-TAMM_HD bool partner_lost(const WaveCoef& w, cd x) {
-    const WaveMat m = wave_matrix(w, x);
-    cd hb, hs;
-    mslp_eigs_f(m, w.db, hb, hs);
-    return abs2(hb) >= QSD_THR * QSD_THR;
-}
-
 // ---- per-thread scratch of the mode solve -------------------------------------------------------------------------
 // rv[k] = {q_k, Ex_k, Ey_k} (roots + null vectors) and ms[k] = four sort measures are indexed with RUN-TIME indices (the
 // p/s sort is a permutation), which a register-resident array can only serve with long select/move chains.  They live
@@ -1156,6 +1144,16 @@ TAMM_HD bool eig4_fast(const WaveCoef& w, SC& sc) {
             sc.set_rv(idx, 0, x);
             sc.set_rv(idx, 1, csel(use0, -mm.b, mm.d));
             sc.set_rv(idx, 2, csel(use0, mm.a, -mm.b));
+        }
+        // Near-degenerate pair (splitting down at the accuracy of the starting values, ~1e-8 |q| -- e.g. where the p and s
+        // branches of a smoothly rotating fabric cross at oblique incidence): every refinement step moves to the NEAREST
+        // root, so both starting values can end on the same one and its partner is lost.  If the two results are much
+        // closer than the splitting the pair step predicted (and that is resolvable at all: below 1e-12 |q| the pair is
+        // degenerate for every later purpose, QSD_THR = 1e-10), the layer goes to the cold solver, which recovers lost
+        // partners by deflation (eig4_fallback).  tol2 = 0.8e-31 |qc|^2.
+        if (TAMM_RARE((abs2(sc.rv(2 * pair, 0) - sc.rv(2 * pair + 1, 0)) < 0.0625 * sep2) && (sep2 > 1.25e7 * tol2))) {
+            TAMM_STAT(collapsed);
+            return false;
         }
     }
     // The pair-based solve is only at risk when the roots of a pair are not close to their centre compared with the
@@ -1338,18 +1336,12 @@ struct ModeSet {          // sorted roots and unnormalised gamma entries of one 
 };
 
 // Everything up to the unnormalised field vectors: permittivity, roots, clean-up, partition, p/s sort, gamma.
-// Status bits of the mode solve
-constexpr int ST_PARTITION = 1;   // the transmitted / reflected partition of layer_PPJ.py:216-231 was not 2 + 2
-constexpr int ST_COINCIDE = 2;    // internal: two roots of a pair coincide (degenerate pair OR a lost partner root, see
-                                  // partner_lost); the caller then repeats the layer with layer_redo_cold().  Never
-                                  // reported to the user.
-// COLD = true: the cold solver from the start (the out-of-line repeat of a layer whose pair solve lost a root).
-template <bool COLD, class SC>
-TAMM_HD int layer_modes_impl(const LayerParams& lp, const LaneParams& ln, double zeta, double mu, ModeSet& ms_out, SC& sc) {
+template <class SC>
+TAMM_HD int layer_modes(const LayerParams& lp, const LaneParams& ln, double zeta, double mu, ModeSet& ms_out, SC& sc) {
     int status = 0;
     const Sym3 e = permittivity(lp, ln);
     const WaveCoef w = wave_coef(e, mu, zeta);
-    if (TAMM_RARE(COLD || !eig4_fast(w, sc))) {
+    if (TAMM_RARE(!eig4_fast(w, sc))) {
         TAMM_STAT(fallback);
         cd rv[4][3];
         eig4_fallback(e.xx, e.xy, e.xz, e.yy, e.yz, e.zz, e.im, mu, zeta, rv);
@@ -1405,7 +1397,7 @@ TAMM_HD int layer_modes_impl(const LayerParams& lp, const LaneParams& ln, double
             case 0xA: t0 = 1; t1 = 3; r0 = 0; r1 = 2; break;
             case 0x6: t0 = 1; t1 = 2; r0 = 0; r1 = 3; break;
             case 0x9: t0 = 0; t1 = 3; r0 = 1; r1 = 2; break;
-            default:  t0 = 0; t1 = 1; r0 = 2; r1 = 3; status |= ST_PARTITION; break;
+            default:  t0 = 0; t1 = 1; r0 = 2; r1 = 3; status |= 1; break;
         }
     }
     // C_a > C_b  <=>  n_a s_b > n_b s_a  for ratios C = n/s with s > 0; NaN (s = 0) compares false like the reference
@@ -1436,12 +1428,6 @@ TAMM_HD int layer_modes_impl(const LayerParams& lp, const LaneParams& ln, double
     const int o0 = flip_t ? t1 : t0, o1 = flip_t ? t0 : t1, o2 = flip_r ? r1 : r0, o3 = flip_r ? r0 : r1;
     const cd q0 = sc.rv(o0, 0), q1 = sc.rv(o1, 0), q2 = sc.rv(o2, 0), q3 = sc.rv(o3, 0);
     const bool deg01 = abs2(q0 - q1) < QSD_THR * QSD_THR, deg23 = abs2(q2 - q3) < QSD_THR * QSD_THR;   // |q_a - q_b| < qsd_thr
-    // coinciding roots: the caller checks out of line whether a partner root was lost (costs the hot path only this flag;
-    // the two tests are the ones the gamma stage needs anyway)
-    if (!COLD) {
-        if (TAMM_RARE(deg01 || deg23)) status |= ST_COINCIDE;
-    }
-
     // ---- gamma (layer_PPJ.py:309-389), unnormalised; see layer_solve for the line-by-line citations
     const cd e00 = mk(e.xx, e.im), e11 = mk(e.yy, e.im);
     const double m01 = mu * e.xy, m02 = mu * e.xz, m12 = mu * e.yz;
@@ -1479,22 +1465,6 @@ TAMM_HD int layer_modes_impl(const LayerParams& lp, const LaneParams& ln, double
     ms_out.g12 = g12; ms_out.g13 = g13; ms_out.g21 = g21; ms_out.g23 = g23;
     ms_out.g32 = g32; ms_out.g33 = g33; ms_out.g41 = g41; ms_out.g43 = g43;
     return status;
-}
-
-// Mode solve with the lost-partner check and repeat done in place (diagnostics, host simulator, cold callers).
-template <class SC>
-TAMM_HD int layer_modes(const LayerParams& lp, const LaneParams& ln, double zeta, double mu, ModeSet& ms_out, SC& sc) {
-    int st = layer_modes_impl<false>(lp, ln, zeta, mu, ms_out, sc);
-    if (st & ST_COINCIDE) {
-        st &= ~ST_COINCIDE;
-        const WaveCoef w = wave_coef(permittivity(lp, ln), mu, zeta);
-        const bool d01 = abs2(ms_out.q0 - ms_out.q1) < QSD_THR * QSD_THR, d23 = abs2(ms_out.q2 - ms_out.q3) < QSD_THR * QSD_THR;
-        if ((d01 && partner_lost(w, ms_out.q0)) || (d23 && partner_lost(w, ms_out.q2))) {
-            TAMM_STAT(collapsed);
-            st = layer_modes_impl<true>(lp, ln, zeta, mu, ms_out, sc);
-        }
-    }
-    return st;
 }
 
 // Amplitude-basis layer record (normalised E blocks, their inverses, admittances, phases).
@@ -1535,12 +1505,10 @@ TAMM_HD int layer_solve_fast(const LayerParams& lp, const LaneParams& ln, double
 // Field-basis layer record straight from the unnormalised field vectors: P = Et diag(Mfwd) Et^-1, Q = Er diag(Mrev) Er^-1
 // and the admittances are invariant under the row normalisation of gamma (layer_PPJ.py:399-402), so the norms are only
 // evaluated when the normalised blocks themselves are needed (first layer of a stack, MODE_U).
-// CHECKED = false: raw pair solve; the returned status may carry ST_COINCIDE and the caller repeats such a layer out of line
-// (stack_kernel -> layer_redo_cold).  CHECKED = true: the lost-partner check and repeat happen in place (layer_modes).
-template <bool WANT_E, bool CHECKED, class SC>
-TAMM_HD int layer_solve_field_impl(const LayerParams& lp, const LaneParams& ln, double zeta, double mu, LayerF& F, SC& sc) {
+template <bool WANT_E, class SC>
+TAMM_HD int layer_solve_field(const LayerParams& lp, const LaneParams& ln, double zeta, double mu, LayerF& F, SC& sc) {
     ModeSet m;
-    int status = CHECKED ? layer_modes(lp, ln, zeta, mu, m, sc) : layer_modes_impl<false>(lp, ln, zeta, mu, m, sc);
+    int status = layer_modes(lp, ln, zeta, mu, m, sc);
     const double imu = rcp_mu(mu);
     cd Mf0, Mf1, Mr0, Mr1;
     layer_phases(m.q0, m.q1, m.q2, m.q3, ln.twopif, lp.dz, Mf0, Mf1, Mr0, Mr1);
@@ -1571,26 +1539,10 @@ TAMM_HD int layer_solve_field_impl(const LayerParams& lp, const LaneParams& ln, 
     return status;
 }
 
-template <bool WANT_E, class SC>
-TAMM_HD int layer_solve_field(const LayerParams& lp, const LaneParams& ln, double zeta, double mu, LayerF& F, SC& sc) {
-    return layer_solve_field_impl<WANT_E, false>(lp, ln, zeta, mu, F, sc);
-}
 template <bool WANT_E>
 TAMM_HD int layer_solve_field(const LayerParams& lp, const LaneParams& ln, double zeta, double mu, LayerF& F) {
     ScratchArrays sc;
-    return layer_solve_field_impl<WANT_E, true>(lp, ln, zeta, mu, F, sc);
-}
-
-// Cold path of stack_kernel: the layer again, with the lost-partner check and -- if a root was lost -- the cold solver; all
-// blocks of the record are filled.  Never inlined: the hot loop only carries the ST_COINCIDE test.
-#if defined(__CUDA_ARCH__)
-__device__ __noinline__
-#else
-inline
-#endif
-int layer_redo_cold(const LayerParams* lp, const LaneParams* ln, double zeta, double mu, LayerF* out) {
-    ScratchArrays sc;
-    return layer_solve_field_impl<true, true>(*lp, *ln, zeta, mu, *out, sc);
+    return layer_solve_field<WANT_E>(lp, ln, zeta, mu, F, sc);
 }
 
 // Cold path: the normalised E blocks of one layer (start of a stack: D'_0 = Et_0, U'_0 = Er_0^-1).  Never inlined, so the

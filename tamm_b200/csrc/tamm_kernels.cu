@@ -233,32 +233,7 @@ stack_body(const double* __restrict__ layers, const double* __restrict__ lanes, 
             __syncthreads();
 #endif
             // normalised E blocks are only needed for MODE_U here; the start of a stack uses the cold helper below
-            int lst = layer_solve_field<MODE == TAMM_MODE_U>(lp, ln, zeta, mu, cur, sc);
-            if (TAMM_RARE(lst & ST_COINCIDE)) {
-                // two roots of a pair coincide: a degenerate pair (e.g. the isotropic top layer) or a lost partner root
-                // (tamm_core.cuh: partner_lost) -- the layer is repeated out of line, from fresh copies of its parameters
-                // (taking the address of lp / ln themselves would put them in local memory for every layer)
-                LayerParams lp0;
-                {
-                    const volatile double* r = tile + jj * LAYER_STRIDE;
-                    lp0.t20 = r[0]; lp0.n21r = r[1]; lp0.n21i = r[2]; lp0.n22r = r[3]; lp0.n22i = r[4];
-                    lp0.mono = r[5]; lp0.deps = r[6]; lp0.sigma = r[7]; lp0.dz = r[8]; lp0.pad = 0;
-                }
-                LaneParams ln0;
-                {
-                    const volatile double* r = lanes + (size_t)lc * LANE_STRIDE;
-                    ln0.c1 = r[0]; ln0.s1 = r[1]; ln0.c2 = r[2]; ln0.s2 = r[3]; ln0.twopif = r[4]; ln0.w_eps0 = r[5];
-                    ln0.pad0 = 0; ln0.pad1 = 0;
-                }
-                LayerF redo;
-                lst = layer_redo_cold(&lp0, &ln0, zeta, mu, &redo);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    cur.Yt[k] = redo.Yt[k]; cur.Yr[k] = redo.Yr[k]; cur.P[k] = redo.P[k]; cur.Q[k] = redo.Q[k];
-                    if (MODE == TAMM_MODE_U) cur.Er[k] = redo.Er[k];
-                }
-            }
-            st |= lst;
+            st |= layer_solve_field<MODE == TAMM_MODE_U>(lp, ln, zeta, mu, cur, sc);
 #ifdef TAMM_SYNC_PER_LAYER
             __syncthreads();
 #endif
