@@ -180,6 +180,7 @@ def assert_parity(got, want, arbiter=None, c_atol=1e-7, names=RET_NAMES):
                 ref_x = float((np.abs(b - x) / tol)[okx].max()) if okx.any() else 0.0
                 assert dev_x <= max(1.0, ref_x), (n, 'vs arbiter', dev_x, ref_x)
                 slack = 2 * ref_x
+                report.setdefault('vs_exact(device, reference)', {})[n] = (dev_x, ref_x)
             assert dev_ref <= 1.0 + slack, (n, 'vs reference', dev_ref, slack)
             report[n] = float((err / tol)[ok].max()) if ok.any() else 0.0
     return report
