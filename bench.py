@@ -66,6 +66,8 @@ def parse():
     ap.add_argument('--gather', default='all', choices=['none', 'power', 'fields', 'jones', 'all'],
                     help='config 4, N > 1: also time the final NCCL all-gather of results (reported separately)')
     ap.add_argument('--gather-block', type=int, default=0, help='profiles per pipelined all-gather block (0: shard / 4)')
+    ap.add_argument('--gather-mode', default='both', choices=['nccl', 'ce', 'both'],
+                    help='transport of the pipelined gather: NCCL collectives, copy-engine peer writes, or time both')
     return ap.parse_args()
 
 
@@ -739,44 +741,61 @@ def bench_ensemble(c, args, w, emit):
                 g.update(bytes_gathered_per_rank=nbytes, bytes_received_per_rank=recv, ms=gm, algbw_gbs=nbytes / (gm * 1e-3) / 1e9,
                          link_floor_ms=recv / NVLINK_PEER_GBS / 1e6,
                          value_with_gather_back_to_back=evals_job / ((ms_per_step + gm) * 1e-3))
-                # (2) pipelined: one asynchronous all-gather per sub-batch block on NCCL's stream while the compute stream
-                # goes on with the next block; a whole step = kernels + gather, CUDA events on the compute stream after it
-                # has waited for the last collective, max over ranks
-                pgs = {n: tdist.PipelinedGather(P, GB, tuple(out[n].shape[1:]), out[n].dtype, dev) for n in names}
-
-                def submit(bi, b0, b1):
-                    for n in names:
-                        pgs[n].submit(bi, out[n][b0:b1])
-
-                def step_gather():
-                    step(blk=GB, pl=planes_g, after_block=submit)
-                    for n in names:
-                        pgs[n].wait()
-                step_gather()
-                sync_all(c)
-                ksteps = max(1, min(args.steps, 3))
-                p0 = torch.cuda.Event(enable_timing=True); p1 = torch.cuda.Event(enable_timing=True)
-                p0.record()
-                for _ in range(ksteps):
-                    step_gather()
-                p1.record()
-                sync_all(c)
-                pm = max_over_ranks(c, p0.elapsed_time(p1) / ksteps)
-                # check: every rank's block of round 0 must have arrived here (checksums exchanged by all-reduce)
+                # (2) pipelined: the gather of sub-batch block b runs while the compute stream goes on with block b+1; a whole
+                # step = kernels + gather, CUDA events on the compute stream after it has waited for the last transfer, max
+                # over ranks.  Two transports: 'nccl' = one asynchronous all_gather_into_tensor per block on NCCL's
+                # (high-priority) stream; 'ce' = copy-engine writes into the peers' symmetric memory (tdist.PeerGather).
                 asreal = lambda t: torch.view_as_real(t) if t.is_complex() else t
-                sums = torch.zeros(world, dtype=torch.float64, device=dev)
-                sums[rank] = asreal(out[names[0]][:GB]).abs().sum()
-                dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-                full0 = pgs[names[0]].full
-                got_s = torch.stack([asreal(full0[r * GB: (r + 1) * GB]).abs().sum() for r in range(world)])
-                ok = ((got_s - sums).abs() <= 1e-12 * sums.abs()).all().to(torch.float64).reshape(1)
-                ok = ok * float(torch.equal(full0[rank * GB: (rank + 1) * GB], out[names[0]][:GB]))
-                dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-                g.update(pipelined_ms_per_step=pm, pipelined_steps=ksteps, value_with_gather=evals_job / (pm * 1e-3),
+
+                def time_pipelined(make):
+                    pgs = {n: make(n) for n in names}
+
+                    def submit(bi, b0, b1):
+                        for n in names:
+                            pgs[n].submit(bi, out[n][b0:b1])
+
+                    def step_gather():
+                        step(blk=GB, pl=planes_g, after_block=submit)
+                        for n in names:
+                            pgs[n].wait()
+                    step_gather()
+                    sync_all(c)
+                    ksteps = max(1, min(args.steps, 3))
+                    p0 = torch.cuda.Event(enable_timing=True); p1 = torch.cuda.Event(enable_timing=True)
+                    p0.record()
+                    for _ in range(ksteps):
+                        step_gather()
+                    p1.record()
+                    sync_all(c)
+                    pm = max_over_ranks(c, p0.elapsed_time(p1) / ksteps)
+                    # check: every rank's block of round 0 must have arrived here (checksums exchanged by all-reduce)
+                    sums = torch.zeros(world, dtype=torch.float64, device=dev)
+                    sums[rank] = asreal(out[names[0]][:GB]).abs().sum()
+                    dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+                    full0 = pgs[names[0]].full
+                    got_s = torch.stack([asreal(full0[r * GB: (r + 1) * GB]).abs().sum() for r in range(world)])
+                    ok = ((got_s - sums).abs() <= 1e-12 * sums.abs()).all().to(torch.float64).reshape(1)
+                    ok = ok * float(torch.equal(full0[rank * GB: (rank + 1) * GB], out[names[0]][:GB]))
+                    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+                    del pgs
+                    torch.cuda.empty_cache()
+                    return pm, ksteps, bool(ok.item() == 1.0)
+
+                pm, ksteps, ok = time_pipelined(lambda n: tdist.PipelinedGather(P, GB, tuple(out[n].shape[1:]), out[n].dtype, dev))
+                g.update(pipelined_ms_per_step=pm, pipelined_steps=ksteps, pipelined_check=ok, pipelined_transport='nccl')
+                best = pm
+                if args.gather_mode in ('ce', 'both'):
+                    try:
+                        pc, _, okc = time_pipelined(lambda n: tdist.PeerGather(P, GB, tuple(out[n].shape[1:]), out[n].dtype, dev))
+                        g.update(pipelined_ce_ms_per_step=pc, pipelined_ce_check=okc)
+                        if okc and pc < best:
+                            best = pc
+                            g['pipelined_transport'] = 'copy engines into symmetric memory (tdist.PeerGather)'
+                    except Exception as e:
+                        g['pipelined_ce_error'] = repr(e)[:300]
+                g.update(best_pipelined_ms_per_step=best, value_with_gather=evals_job / (best * 1e-3),
                          scaling_vs_1gpu_needs='value_with_gather / the N = 1 value of this bench',
-                         nvlink_roofline_frac=(recv / NVLINK_PEER_GBS / 1e6) / pm, pipelined_check=bool(ok.item() == 1.0))
-                del pgs
-                torch.cuda.empty_cache()
+                         nvlink_roofline_frac=(recv / NVLINK_PEER_GBS / 1e6) / best)
             except Exception as e:
                 g['error'] = repr(e)[:300]
             line['gather'][what] = g

@@ -123,6 +123,61 @@ class PipelinedGather:
         return self.full
 
 
+class PeerGather:
+    """The same final all-gather as `PipelinedGather`, but written straight into the peers' memory by the COPY ENGINES
+    instead of by an NCCL kernel: the gathered array lives in symmetric memory (torch.distributed._symmetric_memory: every
+    rank maps every rank's buffer over NVLink / NVSwitch), and `submit(b, block)` enqueues one asynchronous device-to-device
+    copy per rank -- this rank's block of round b into slot (b, rank) of each peer's array -- on per-peer side streams that
+    wait for the producing kernels.  Copy engines need no SM, so the transfer neither waits for the stack kernel (which
+    keeps every SM full) to free SMs nor takes any away from it; `wait()` joins the side streams and runs a device-side
+    barrier over the group, after which every rank's `full` holds the whole ensemble.  Layout and arguments as
+    PipelinedGather (block-cyclic rounds)."""
+
+    def __init__(self, P_total, B, tail_shape, dtype, device, group=None):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.ws, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        if P_total % (self.ws * B):
+            raise ValueError('PeerGather needs P_total (=%d) divisible by world x block (=%d x %d)' % (P_total, self.ws, B))
+        self.B, self.rounds = B, P_total // (self.ws * B)
+        real = torch.float64 if dtype in (torch.complex128, torch.float64) else None
+        if real is None:
+            raise ValueError('PeerGather moves float64 / complex128 arrays')
+        self._tail = tuple(tail_shape) + ((2,) if dtype == torch.complex128 else ())
+        shape = (P_total,) + self._tail
+        self._flat = symm_mem.empty(shape, dtype=torch.float64, device=device)
+        self._hdl = symm_mem.rendezvous(self._flat, self.group)
+        self.full = torch.view_as_complex(self._flat) if dtype == torch.complex128 else self._flat
+        rshape = (self.rounds, self.ws * B) + self._tail
+        self._peers = [self._hdl.get_buffer(r, shape, torch.float64).view(rshape) for r in range(self.ws)]
+        self._streams = [torch.cuda.Stream(device) for _ in range(self.ws)]
+        self._torch = torch
+
+    def submit(self, b, block):
+        torch = self._torch
+        assert block.shape[0] == self.B and 0 <= b < self.rounds
+        x = torch.view_as_real(block) if block.is_complex() else block
+        ready = torch.cuda.Event()
+        ready.record()
+        lo = self.rank * self.B
+        for k in range(self.ws):
+            r = (self.rank + k) % self.ws          # own copy first, then the peers in ring order (spreads the link load)
+            st = self._streams[r]
+            st.wait_event(ready)
+            with torch.cuda.stream(st):
+                self._peers[r][b, lo:lo + self.B].copy_(x, non_blocking=True)
+
+    def wait(self):
+        torch = self._torch
+        cur = torch.cuda.current_stream()
+        for st in self._streams:
+            cur.wait_stream(st)
+        self._hdl.barrier()        # every peer's copies into THIS rank's array have been enqueued before and are complete after
+        return self.full
+
+
 def _via_host(t, group):
     """gloo moves host memory only: CUDA tensors are staged through the CPU for that backend (world-size-2 tests on ONE
     GPU; NCCL refuses two ranks on one device)."""
