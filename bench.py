@@ -63,8 +63,9 @@ def parse():
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='configs 0-3: time plain launches instead of a CUDA graph replay')
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
-    ap.add_argument('--gather', default='all', choices=['none', 'power', 'fields', 'jones', 'all'],
-                    help='config 4, N > 1: also time the final NCCL all-gather of results (reported separately)')
+    ap.add_argument('--gather', default='all',
+                    help='config 4, N > 1: also time the final all-gather of results (reported separately): none, all, or a '
+                         'comma list of power, fields, jones')
     ap.add_argument('--gather-block', type=int, default=0, help='profiles per pipelined all-gather block (0: shard / 4)')
     ap.add_argument('--gather-mode', default='both', choices=['nccl', 'ce', 'both'],
                     help='transport of the pipelined gather: NCCL collectives, copy-engine peer writes, or time both')
@@ -712,12 +713,13 @@ def bench_ensemble(c, args, w, emit):
     # compute path has no exchange step): what a caller pays when every rank needs the whole ensemble, in three sizes.
     if world > 1 and args.gather != 'none':
         variants = dict(power=['dP_HH', 'dP_HV'], fields=['E_HH', 'E_HV'], jones=['E_HH', 'E_HV', 'c_HHVV', 'dP_HH', 'dP_HV'])
-        todo = ['power', 'fields', 'jones'] if args.gather == 'all' else [args.gather]
+        todo = ['power', 'fields', 'jones'] if args.gather == 'all' else [t for t in args.gather.split(',') if t in variants]
         GB = args.gather_block or max(1, Pl // 4)
         while Pl % GB or P % (world * GB):
             GB -= 1
         planes_g = planes[:GB] if GB <= B else eng.empty((GB, NI, 4, F), cdt)
         line['gather'] = dict(included_in_value=False, block_profiles=GB, blocks_per_rank=Pl // GB,
+                              nccl_env={k: v for k, v in os.environ.items() if k.startswith('NCCL_') or k.startswith('TAMM_NCCL')},
                               peer_bandwidth_gbs=NVLINK_PEER_GBS,
                               peer_bandwidth_source='ncclAllGather algbw per rank measured on this pool at N = 8 (round 1)',
                               layout='block-cyclic: round b of rank r = profiles (b*world + r)*%d ... (natural profile order after the gather)' % GB)

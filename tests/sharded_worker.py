@@ -71,6 +71,22 @@ lo, hi = tdist.shard_range(181, rank, ws)
 close(e['E_HV'], w['E_HV'][..., lo:hi], 'ensemble azimuth shard E_HV')
 close(e['dP_HH'], w['dP_HH'][..., lo:hi], 'ensemble azimuth shard dP_HH')
 close(e['Pm_HV'], w['Pm_HV'], 'ensemble azimuth shard Pm_HV')
+# the two transports of the pipelined final all-gather (block-cyclic rounds land in natural profile order)
+if backend == 'nccl':
+    Pt, B = 4 * ws, 2
+    mine = tdist.block_cyclic_profiles(Pt, B, rank, ws)
+    table = (np.arange(Pt)[:, None, None] * 100 + np.arange(3)[None, :, None] * 10 + np.arange(5)[None, None, :]) * (1 + 0.5j)
+    for dtype, src in ((torch.complex128, table), (torch.float64, table.real.copy())):
+        loc = torch.from_numpy(src[mine]).cuda()
+        for cls in (tdist.PipelinedGather, tdist.PeerGather):       # NCCL collectives / copy engines into symmetric memory
+            pg = cls(Pt, B, (3, 5), dtype, loc.device)
+            for rep in range(2):                                      # reuse of the same gather object
+                for b in range(pg.rounds):
+                    pg.submit(b, loc[b * B:(b + 1) * B])
+                full = pg.wait()
+                torch.cuda.synchronize()
+                assert np.array_equal(full.cpu().numpy(), src), (cls.__name__, str(dtype), rep)
+            del pg
 dist.barrier()
 dist.destroy_process_group()
 open(os.path.join(outdir, 'rank%d.ok' % rank), 'w').write('ok')

@@ -24,8 +24,8 @@ try:
     for k in ('power', 'fields', 'jones'):
         if k in g:
             x = g[k]
-            print('  gather %-6s: back-to-back %.2f ms (algbw %.0f GB/s), pipelined step %.2f ms -> %.4g evals/s, link floor %.2f ms, check %s %s' % (
-                k, x.get('ms', 0), x.get('algbw_gbs', 0), x.get('pipelined_ms_per_step', 0), x.get('value_with_gather', 0), x.get('link_floor_ms', 0), x.get('pipelined_check'), x.get('error', '')))
+            print('  gather %-6s: back-to-back %.2f ms (algbw %.0f GB/s), pipelined step nccl %.2f ms / ce %s ms -> %.4g evals/s, link floor %.2f ms, checks %s %s %s %s' % (
+                k, x.get('ms', 0), x.get('algbw_gbs', 0), x.get('pipelined_ms_per_step', 0), x.get('pipelined_ce_ms_per_step'), x.get('value_with_gather', 0), x.get('link_floor_ms', 0), x.get('pipelined_check'), x.get('pipelined_ce_check'), x.get('pipelined_ce_error', ''), x.get('error', '')))
 except Exception as ex:
     print('cfg4 failed:', ex)
 for c in (1, 2, 3):
