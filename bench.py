@@ -67,8 +67,10 @@ def parse():
                     help='config 4, N > 1: also time the final all-gather of results (reported separately): none, all, or a '
                          'comma list of power, fields, jones')
     ap.add_argument('--gather-block', type=int, default=0, help='profiles per pipelined all-gather block (0: shard / 4)')
-    ap.add_argument('--gather-mode', default='both', choices=['nccl', 'ce', 'both'],
-                    help='transport of the pipelined gather: NCCL collectives, copy-engine peer writes, or time both')
+    ap.add_argument('--gather-mode', default='both', choices=['nccl', 'peer', 'mc', 'uc', 'ce', 'both'],
+                    help='transport of the pipelined gather: NCCL collectives only, peer stores into symmetric memory (multicast '
+                         'if available, else unicast), copy engines, or (both) NCCL + peer stores + copy engines')
+    ap.add_argument('--push-ctas', type=int, default=8, help='CTAs of the peer-push kernel (tamm_peer_push)')
     return ap.parse_args()
 
 
@@ -786,15 +788,27 @@ def bench_ensemble(c, args, w, emit):
                 pm, ksteps, ok = time_pipelined(lambda n: tdist.PipelinedGather(P, GB, tuple(out[n].shape[1:]), out[n].dtype, dev))
                 g.update(pipelined_ms_per_step=pm, pipelined_steps=ksteps, pipelined_check=ok, pipelined_transport='nccl')
                 best = pm
-                if args.gather_mode in ('ce', 'both'):
-                    try:
-                        pc, _, okc = time_pipelined(lambda n: tdist.PeerGather(P, GB, tuple(out[n].shape[1:]), out[n].dtype, dev))
-                        g.update(pipelined_ce_ms_per_step=pc, pipelined_ce_check=okc)
-                        if okc and pc < best:
-                            best = pc
-                            g['pipelined_transport'] = 'copy engines into symmetric memory (tdist.PeerGather)'
-                    except Exception as e:
-                        g['pipelined_ce_error'] = repr(e)[:300]
+                if args.gather_mode != 'nccl':
+                    modes = ['auto', 'ce'] if args.gather_mode == 'both' else [dict(peer='auto').get(args.gather_mode, args.gather_mode)]
+                    for mode in modes:
+                        try:
+                            used = []
+
+                            def make(n, mode=mode):
+                                pgx = tdist.PeerGather(P, GB, tuple(out[n].shape[1:]), out[n].dtype, dev, mode=mode, ctas=args.push_ctas)
+                                used.append(pgx.mode)
+                                return pgx
+                            pc, _, okc = time_pipelined(make)
+                            tag = used[0]
+                            g['pipelined_%s_ms_per_step' % tag] = pc
+                            g['pipelined_%s_check' % tag] = okc
+                            if okc and pc < best:
+                                best = pc
+                                g['pipelined_transport'] = {'mc': 'multicast stores into symmetric memory (tamm_peer_push, tdist.PeerGather)',
+                                                            'uc': 'unicast peer stores into symmetric memory (tamm_peer_push, tdist.PeerGather)',
+                                                            'ce': 'copy engines into symmetric memory (tdist.PeerGather)'}[tag]
+                        except Exception as e:
+                            g['pipelined_%s_error' % mode] = repr(e)[:300]
                 g.update(best_pipelined_ms_per_step=best, value_with_gather=evals_job / (best * 1e-3),
                          scaling_vs_1gpu_needs='value_with_gather / the N = 1 value of this bench',
                          nvlink_roofline_frac=(recv / NVLINK_PEER_GBS / 1e6) / best)

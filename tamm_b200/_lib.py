@@ -20,6 +20,7 @@ SIGNATURES = {
     'tamm_fp64_probe': (_i, [_vp, _i, _i, _vp]),
     'tamm_layer_matrices': (_i, [_vp, _vp, _i, _i, _d, _d] + [_vp] * 10 + [_vp, _vp]),
     'tamm_layer_modes': (_i, [_vp, _vp, _i, _i, _d, _d, _vp, _vp, _vp]),
+    'tamm_peer_push': (_i, [_vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_ulonglong), _i, _i, _i, _vp]),
     'tamm_stack_workspace_bytes': (ctypes.c_size_t, [_i, _i, _i, _i]),
     'tamm_suggest_chunk': (_i, [_i, _i, _i, _i]),
     'tamm_stack_urd': (_i, [_vp, _vp, _i, _i, _i, _i, _d, _d, _i, _i, _vp, _vp, _vp, _vp]),

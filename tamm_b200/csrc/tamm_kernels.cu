@@ -920,6 +920,34 @@ layer_modes_kernel(const double* __restrict__ layers, const double* __restrict__
     if (status) status[i] = st;
 }
 
+// ---- the final all-gather as plain stores into peer memory -----------------------------------------------------------------
+// One rank's finished block of results is pushed into the same slot of EVERY rank's gathered array.  The destination is
+// symmetric memory (every rank maps every rank's buffer over NVLink / NVSwitch):
+//   multicast: ONE multimem.st per 16 bytes to the multicast address of the group -- the NVSwitch replicates it into all
+//              replicas (this GPU's own included), so the sender's link carries the block once, not once per peer;
+//   unicast  : one st.global per destination buffer (fallback without multicast support).
+// A handful of CTAs saturate the sender side (the block is 1/N of what each GPU receives), so the push is launched on a
+// high-priority side stream next to the stack kernel of the NEXT block and costs it a few SMs for about a millisecond.
+__device__ __forceinline__ void multimem_st16(void* mc, uint4 v) {
+    asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(__uint_as_float(v.x)),
+                 "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w))
+                 : "memory");
+}
+struct PeerPtrs {
+    uint4* p[16];
+};
+__global__ void __launch_bounds__(1024) peer_push_mc_kernel(const uint4* __restrict__ src, uint4* mc, size_t n16) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) multimem_st16(mc + i, __ldcs(src + i));
+}
+__global__ void __launch_bounds__(1024) peer_push_uc_kernel(const uint4* __restrict__ src, PeerPtrs dst, int ndst, size_t n16) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+        const uint4 v = __ldcs(src + i);
+        for (int d = 0; d < ndst; ++d) __stcs(dst.p[d] + i, v);
+    }
+}
+
 __global__ void __launch_bounds__(256) fp64_probe_kernel(double* out, int iters, double a, double b) {
     double x[8];
 #pragma unroll
@@ -1035,6 +1063,26 @@ int tamm_layer_modes(const double* layers, const double* lanes, int N, int QF, d
     if (N < 1 || QF < 1) return fail("tamm_layer_modes: empty problem%s", "");
     const long tot = (long)N * QF;
     layer_modes_kernel<<<(int)((tot + 127) / 128), 128, 0, (cudaStream_t)stream>>>(layers, lanes, N, QF, zeta, mu, (cd*)qs, status);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int tamm_peer_push(const void* src, size_t bytes, const unsigned long long* dst, int ndst, int multicast, int ctas, void* stream) {
+    if (!src || !dst || ndst < 1 || ndst > 16) return fail("tamm_peer_push: bad arguments%s", "");
+    if ((bytes & 15) || !aligned16(src)) return fail("tamm_peer_push: source must be 16-byte aligned and a multiple of 16 bytes%s", "");
+    for (int d = 0; d < ndst; ++d)
+        if (!dst[d] || (dst[d] & 15)) return fail("tamm_peer_push: destination %s(%ld) is null or misaligned", "", d);
+    if (bytes == 0) return 0;
+    if (ctas < 1) ctas = 8;
+    const size_t n16 = bytes / 16;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (multicast) {
+        peer_push_mc_kernel<<<ctas, 1024, 0, s>>>((const uint4*)src, (uint4*)dst[0], n16);
+    } else {
+        PeerPtrs pp;
+        for (int d = 0; d < 16; ++d) pp.p[d] = (uint4*)(d < ndst ? dst[d] : 0ull);
+        peer_push_uc_kernel<<<ctas, 1024, 0, s>>>((const uint4*)src, pp, ndst, n16);
+    }
     CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -124,57 +124,89 @@ class PipelinedGather:
 
 
 class PeerGather:
-    """The same final all-gather as `PipelinedGather`, but written straight into the peers' memory by the COPY ENGINES
-    instead of by an NCCL kernel: the gathered array lives in symmetric memory (torch.distributed._symmetric_memory: every
-    rank maps every rank's buffer over NVLink / NVSwitch), and `submit(b, block)` enqueues one asynchronous device-to-device
-    copy per rank -- this rank's block of round b into slot (b, rank) of each peer's array -- on per-peer side streams that
-    wait for the producing kernels.  Copy engines need no SM, so the transfer neither waits for the stack kernel (which
-    keeps every SM full) to free SMs nor takes any away from it; `wait()` joins the side streams and runs a device-side
-    barrier over the group, after which every rank's `full` holds the whole ensemble.  Layout and arguments as
-    PipelinedGather (block-cyclic rounds)."""
+    """The final all-gather of north_star without NCCL: the gathered array lives in SYMMETRIC MEMORY
+    (torch.distributed._symmetric_memory: every rank maps every rank's buffer over NVLink / NVSwitch) and each rank
+    writes its finished block straight into slot (round b, rank) of every rank's array.  `submit(b, block)` enqueues that
+    write on a high-priority side stream which waits for the producing kernels, so it runs under the kernels of the next
+    block; `wait()` joins the side stream(s) and runs a device-side barrier over the group, after which `full` holds the
+    whole ensemble on every rank.  Layout and arguments as PipelinedGather (block-cyclic rounds).  Transports:
+      'mc'  one store per 16 bytes to the group's MULTICAST address (tamm_peer_push, include/tamm_b200.h): the NVSwitch
+            replicates it into all replicas, the sender's link carries the block once -- a few CTAs for about a
+            millisecond per block, against the ~32 SMs an NCCL all-gather kernel holds for the whole transfer;
+      'uc'  the same kernel with one store per destination rank (no multicast support);
+      'ce'  copy engines: one cudaMemcpyAsync per destination rank on per-peer streams (no SM at all, ~450 GB/s).
+    mode='auto' picks 'mc' when the symmetric allocation has a multicast mapping, else 'uc'."""
 
-    def __init__(self, P_total, B, tail_shape, dtype, device, group=None):
+    def __init__(self, P_total, B, tail_shape, dtype, device, group=None, mode='auto', ctas=8):
+        import ctypes
         import torch
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
         self.group = group if group is not None else dist.group.WORLD
         self.ws, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
         if P_total % (self.ws * B):
             raise ValueError('PeerGather needs P_total (=%d) divisible by world x block (=%d x %d)' % (P_total, self.ws, B))
-        self.B, self.rounds = B, P_total // (self.ws * B)
-        real = torch.float64 if dtype in (torch.complex128, torch.float64) else None
-        if real is None:
+        if dtype not in (torch.complex128, torch.float64):
             raise ValueError('PeerGather moves float64 / complex128 arrays')
+        self.B, self.rounds, self.ctas = B, P_total // (self.ws * B), int(ctas)
         self._tail = tuple(tail_shape) + ((2,) if dtype == torch.complex128 else ())
         shape = (P_total,) + self._tail
         self._flat = symm_mem.empty(shape, dtype=torch.float64, device=device)
         self._hdl = symm_mem.rendezvous(self._flat, self.group)
         self.full = torch.view_as_complex(self._flat) if dtype == torch.complex128 else self._flat
-        rshape = (self.rounds, self.ws * B) + self._tail
-        self._peers = [self._hdl.get_buffer(r, shape, torch.float64).view(rshape) for r in range(self.ws)]
-        self._streams = [torch.cuda.Stream(device) for _ in range(self.ws)]
-        self._torch = torch
+        mc = int(getattr(self._hdl, 'multicast_ptr', 0) or 0)
+        if mode == 'auto':
+            mode = 'mc' if mc else 'uc'
+        if mode == 'mc' and not mc:
+            raise RuntimeError('PeerGather: this symmetric allocation has no multicast mapping')
+        self.mode = mode
+        self._block_bytes = B * int(np.prod(self._tail)) * 8
+        off = int(getattr(self._hdl, 'offset', 0) or 0)
+        if mode == 'mc':
+            self._dst_base = [mc + off]
+        elif mode == 'uc':
+            self._dst_base = [int(p) + off for p in self._hdl.buffer_ptrs]
+        else:
+            rshape = (self.rounds, self.ws * B) + self._tail
+            self._peers = [self._hdl.get_buffer(r, shape, torch.float64).view(rshape) for r in range(self.ws)]
+        lo, hi = torch.cuda.Stream.priority_range() if hasattr(torch.cuda.Stream, 'priority_range') else (0, -1)
+        nstreams = self.ws if mode == 'ce' else 1
+        self._streams = [torch.cuda.Stream(device, priority=-1) for _ in range(nstreams)]
+        self._lib, self._ctypes, self._torch = _lib.load(), ctypes, torch
+        self._check = _lib.check
 
     def submit(self, b, block):
-        torch = self._torch
+        torch, ct = self._torch, self._ctypes
         assert block.shape[0] == self.B and 0 <= b < self.rounds
         x = torch.view_as_real(block) if block.is_complex() else block
+        assert x.is_contiguous() and x.numel() * 8 == self._block_bytes
         ready = torch.cuda.Event()
         ready.record()
-        lo = self.rank * self.B
-        for k in range(self.ws):
-            r = (self.rank + k) % self.ws          # own copy first, then the peers in ring order (spreads the link load)
-            st = self._streams[r]
-            st.wait_event(ready)
-            with torch.cuda.stream(st):
-                self._peers[r][b, lo:lo + self.B].copy_(x, non_blocking=True)
+        slot = (b * self.ws + self.rank) * self._block_bytes                   # byte offset of (round b, this rank)
+        if self.mode == 'ce':
+            lo = self.rank * self.B
+            for k in range(self.ws):
+                r = (self.rank + k) % self.ws      # own copy first, then the peers in ring order (spreads the link load)
+                st = self._streams[r]
+                st.wait_event(ready)
+                with torch.cuda.stream(st):
+                    self._peers[r][b, lo:lo + self.B].copy_(x, non_blocking=True)
+            return
+        st = self._streams[0]
+        st.wait_event(ready)
+        dst = (ct.c_ulonglong * len(self._dst_base))(*[p + slot for p in self._dst_base])
+        rc = self._lib.tamm_peer_push(x.data_ptr(), self._block_bytes, dst, len(self._dst_base), 1 if self.mode == 'mc' else 0,
+                                      self.ctas, ct.c_void_p(st.cuda_stream))
+        self._check(rc, self._lib)
+        x.record_stream(st)
 
     def wait(self):
         torch = self._torch
         cur = torch.cuda.current_stream()
         for st in self._streams:
             cur.wait_stream(st)
-        self._hdl.barrier()        # every peer's copies into THIS rank's array have been enqueued before and are complete after
+        self._hdl.barrier()        # every rank's writes into THIS rank's array were enqueued before and are complete after
         return self.full
 
 

@@ -78,14 +78,17 @@ if backend == 'nccl':
     table = (np.arange(Pt)[:, None, None] * 100 + np.arange(3)[None, :, None] * 10 + np.arange(5)[None, None, :]) * (1 + 0.5j)
     for dtype, src in ((torch.complex128, table), (torch.float64, table.real.copy())):
         loc = torch.from_numpy(src[mine]).cuda()
-        for cls in (tdist.PipelinedGather, tdist.PeerGather):       # NCCL collectives / copy engines into symmetric memory
-            pg = cls(Pt, B, (3, 5), dtype, loc.device)
+        makers = [('nccl', lambda: tdist.PipelinedGather(Pt, B, (3, 5), dtype, loc.device))]
+        for mode in ('auto', 'uc', 'ce'):       # peer stores (multicast if the allocation has it), unicast stores, copy engines
+            makers.append((mode, lambda mode=mode: tdist.PeerGather(Pt, B, (3, 5), dtype, loc.device, mode=mode, ctas=2)))
+        for label, make in makers:
+            pg = make()
             for rep in range(2):                                      # reuse of the same gather object
                 for b in range(pg.rounds):
                     pg.submit(b, loc[b * B:(b + 1) * B])
                 full = pg.wait()
                 torch.cuda.synchronize()
-                assert np.array_equal(full.cpu().numpy(), src), (cls.__name__, str(dtype), rep)
+                assert np.array_equal(full.cpu().numpy(), src), (label, getattr(pg, 'mode', ''), str(dtype), rep)
             del pg
 dist.barrier()
 dist.destroy_process_group()

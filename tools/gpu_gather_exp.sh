@@ -2,7 +2,8 @@
 # gather-overlap experiment on N GPUs: high-priority NCCL stream on / off, block count
 N=${1:?ranks}; T=${2:?tag}; mkdir -p gpurun_out
 RUN="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29519"
-$RUN bench.py --gpus $N --steps 5 --warmup 3 --no-e2e --no-cpu > gpurun_out/${T}_hp1_n$N.json 2> gpurun_out/${T}_hp1_n$N.err
+if [ "$3" = "tests" ]; then python -m pytest tests/test_gpu_sharded.py -q -k nccl > gpurun_out/${T}_sharded_tests.log 2>&1; echo "sharded tests rc=$?"; tail -5 gpurun_out/${T}_sharded_tests.log; fi
+$RUN bench.py --gpus $N --steps 5 --warmup 3 --no-e2e --no-cpu $EXTRA > gpurun_out/${T}_hp1_n$N.json 2> gpurun_out/${T}_hp1_n$N.err
 python - "$N" "$T" <<'PY'
 import json, sys
 n, t = sys.argv[1], sys.argv[2]
@@ -13,7 +14,9 @@ for tag in ('hp1',):
         print(tag, 'compute %.2f ms/step; block %d x %d' % (d['ms_per_step'], g['block_profiles'], g['blocks_per_rank']))
         for k in ('power', 'fields', 'jones'):
             x = g[k]
-            print('   %-6s back-to-back %.2f ms, pipelined step nccl %.2f ms / ce %s ms (floor %.2f) check %s %s %s %s' % (k, x.get('ms', 0), x.get('pipelined_ms_per_step', 0), x.get('pipelined_ce_ms_per_step'), x.get('link_floor_ms', 0), x.get('pipelined_check'), x.get('pipelined_ce_check'), x.get('pipelined_ce_error', ''), x.get('error', '')))
+            pip = {kk.replace('pipelined_', '').replace('_ms_per_step', ''): round(v, 2) for kk, v in x.items() if kk.endswith('_ms_per_step') and kk.startswith('pipelined')}
+            chk = {kk: v for kk, v in x.items() if kk.endswith('_check') or kk.endswith('_error')}
+            print('   %-6s back-to-back %.2f ms, floor %.2f; pipelined step (ms): %s  %s -> %s' % (k, x.get('ms', 0), x.get('link_floor_ms', 0), pip, chk, x.get('pipelined_transport')))
     except Exception as e:
         print(tag, 'failed', e)
 PY
