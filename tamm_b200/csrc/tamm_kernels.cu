@@ -936,13 +936,34 @@ __device__ __forceinline__ void multimem_st16(void* mc, uint4 v) {
 struct PeerPtrs {
     uint4* p[16];
 };
+// Each thread keeps PUSH_ILP independent 16-byte loads in flight before it stores them (one load per thread and iteration
+// moves only ~15 GB/s per CTA: 1024 x 16 B per memory latency); consecutive threads touch consecutive 16-byte words.
+constexpr int PUSH_ILP = 8;
 __global__ void __launch_bounds__(1024) peer_push_mc_kernel(const uint4* __restrict__ src, uint4* mc, size_t n16) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) multimem_st16(mc + i, __ldcs(src + i));
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + (PUSH_ILP - 1) * stride < n16; i += PUSH_ILP * stride) {
+        uint4 v[PUSH_ILP];
+#pragma unroll
+        for (int k = 0; k < PUSH_ILP; ++k) v[k] = __ldcs(src + i + k * stride);
+#pragma unroll
+        for (int k = 0; k < PUSH_ILP; ++k) multimem_st16(mc + i + k * stride, v[k]);
+    }
+    for (; i < n16; i += stride) multimem_st16(mc + i, __ldcs(src + i));
 }
 __global__ void __launch_bounds__(1024) peer_push_uc_kernel(const uint4* __restrict__ src, PeerPtrs dst, int ndst, size_t n16) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + (PUSH_ILP - 1) * stride < n16; i += PUSH_ILP * stride) {
+        uint4 v[PUSH_ILP];
+#pragma unroll
+        for (int k = 0; k < PUSH_ILP; ++k) v[k] = __ldcs(src + i + k * stride);
+        for (int d = 0; d < ndst; ++d) {
+#pragma unroll
+            for (int k = 0; k < PUSH_ILP; ++k) __stcs(dst.p[d] + i + k * stride, v[k]);
+        }
+    }
+    for (; i < n16; i += stride) {
         const uint4 v = __ldcs(src + i);
         for (int d = 0; d < ndst; ++d) __stcs(dst.p[d] + i, v);
     }
