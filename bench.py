@@ -66,7 +66,7 @@ def parse():
     ap.add_argument('--gather', default='all',
                     help='config 4, N > 1: also time the final all-gather of results (reported separately): none, all, or a '
                          'comma list of power, fields, jones')
-    ap.add_argument('--gather-block', type=int, default=0, help='profiles per pipelined all-gather block (0: shard / 4)')
+    ap.add_argument('--gather-block', type=int, default=0, help='profiles per pipelined all-gather block (0: tdist.gather_schedule -- small first and last block)')
     ap.add_argument('--gather-mode', default='both', choices=['nccl', 'peer', 'mc', 'uc', 'ce', 'both'],
                     help='transport of the pipelined gather: NCCL collectives only, peer stores into symmetric memory (multicast '
                          'if available, else unicast), copy engines, or (both) NCCL + peer stores + copy engines')
@@ -601,9 +601,14 @@ def bench_ensemble(c, args, w, emit):
     stack_events, returns_events = [], []
 
     def step(record=False, blk=B, pl=None, after_block=None):
+        """One pass over the shard in launches of `blk` profiles (an int, or the list of block sizes of a gather schedule)."""
         pl = planes if pl is None else pl
-        for bi, b0 in enumerate(range(0, Pl, blk)):
-            b1 = min(Pl, b0 + blk)
+        if np.ndim(blk) == 0:
+            edges = list(range(0, Pl, blk)) + [Pl]
+        else:
+            edges = [0] + list(np.cumsum(blk))
+        for bi in range(len(edges) - 1):
+            b0, b1 = int(edges[bi]), int(edges[bi + 1])
             if record:
                 e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
                 e0.record()
@@ -716,15 +721,23 @@ def bench_ensemble(c, args, w, emit):
     if world > 1 and args.gather != 'none':
         variants = dict(power=['dP_HH', 'dP_HV'], fields=['E_HH', 'E_HV'], jones=['E_HH', 'E_HV', 'c_HHVV', 'dP_HH', 'dP_HV'])
         todo = ['power', 'fields', 'jones'] if args.gather == 'all' else [t for t in args.gather.split(',') if t in variants]
-        GB = args.gather_block or max(1, Pl // 4)
-        while Pl % GB or P % (world * GB):
-            GB -= 1
-        planes_g = planes[:GB] if GB <= B else eng.empty((GB, NI, 4, F), cdt)
-        line['gather'] = dict(included_in_value=False, block_profiles=GB, blocks_per_rank=Pl // GB,
+        # blocks of the pipelined gather: --gather-block B (uniform) or the default schedule with a small first and last block
+        if args.gather_block:
+            GB = args.gather_block
+            while Pl % GB or P % (world * GB):
+                GB -= 1
+            sched = [GB] * (Pl // GB)
+        else:
+            sched = tdist.gather_schedule(Pl)
+        GB0 = sched[0]
+        GBmax = max(sched)
+        planes_g = planes[:GBmax] if GBmax <= B else eng.empty((GBmax, NI, 4, F), cdt)
+        line['gather'] = dict(included_in_value=False, block_schedule=sched, blocks_per_rank=len(sched),
                               nccl_env={k: v for k, v in os.environ.items() if k.startswith('NCCL_') or k.startswith('TAMM_NCCL')},
                               peer_bandwidth_gbs=NVLINK_PEER_GBS,
                               peer_bandwidth_source='ncclAllGather algbw per rank measured on this pool at N = 8 (round 1)',
-                              layout='block-cyclic: round b of rank r = profiles (b*world + r)*%d ... (natural profile order after the gather)' % GB)
+                              layout='rounds of world x block profiles: round b of rank r = the b-th block of rank r (block-cyclic; natural '
+                                     'profile order when the profiles are dealt with tdist.block_cyclic_profiles)')
         for what in todo:
             names = variants[what]
             g = dict(arrays=names, bytes_per_eval=sum(16 if n[0] in 'Ec' else 8 for n in names))
@@ -759,7 +772,7 @@ def bench_ensemble(c, args, w, emit):
                             pgs[n].submit(bi, out[n][b0:b1])
 
                     def step_gather():
-                        step(blk=GB, pl=planes_g, after_block=submit)
+                        step(blk=sched, pl=planes_g, after_block=submit)
                         for n in names:
                             pgs[n].wait()
                     step_gather()
@@ -774,18 +787,18 @@ def bench_ensemble(c, args, w, emit):
                     pm = max_over_ranks(c, p0.elapsed_time(p1) / ksteps)
                     # check: every rank's block of round 0 must have arrived here (checksums exchanged by all-reduce)
                     sums = torch.zeros(world, dtype=torch.float64, device=dev)
-                    sums[rank] = asreal(out[names[0]][:GB]).abs().sum()
+                    sums[rank] = asreal(out[names[0]][:GB0]).abs().sum()
                     dist.all_reduce(sums, op=dist.ReduceOp.SUM)
                     full0 = pgs[names[0]].full
-                    got_s = torch.stack([asreal(full0[r * GB: (r + 1) * GB]).abs().sum() for r in range(world)])
+                    got_s = torch.stack([asreal(full0[r * GB0: (r + 1) * GB0]).abs().sum() for r in range(world)])
                     ok = ((got_s - sums).abs() <= 1e-12 * sums.abs()).all().to(torch.float64).reshape(1)
-                    ok = ok * float(torch.equal(full0[rank * GB: (rank + 1) * GB], out[names[0]][:GB]))
+                    ok = ok * float(torch.equal(full0[rank * GB0: (rank + 1) * GB0], out[names[0]][:GB0]))
                     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
                     del pgs
                     torch.cuda.empty_cache()
                     return pm, ksteps, bool(ok.item() == 1.0)
 
-                pm, ksteps, ok = time_pipelined(lambda n: tdist.PipelinedGather(P, GB, tuple(out[n].shape[1:]), out[n].dtype, dev))
+                pm, ksteps, ok = time_pipelined(lambda n: tdist.PipelinedGather(P, sched, tuple(out[n].shape[1:]), out[n].dtype, dev))
                 g.update(pipelined_ms_per_step=pm, pipelined_steps=ksteps, pipelined_check=ok, pipelined_transport='nccl')
                 best = pm
                 if args.gather_mode != 'nccl':
@@ -795,7 +808,7 @@ def bench_ensemble(c, args, w, emit):
                             used = []
 
                             def make(n, mode=mode):
-                                pgx = tdist.PeerGather(P, GB, tuple(out[n].shape[1:]), out[n].dtype, dev, mode=mode, ctas=args.push_ctas)
+                                pgx = tdist.PeerGather(P, sched, tuple(out[n].shape[1:]), out[n].dtype, dev, mode=mode, ctas=args.push_ctas)
                                 used.append(pgx.mode)
                                 return pgx
                             pc, _, okc = time_pipelined(make)

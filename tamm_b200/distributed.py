@@ -76,14 +76,36 @@ def all_gather_profiles(local, P_total, group=None):
     return torch.view_as_complex(full.contiguous()) if cplx else full
 
 
+def _round_sizes(P_total, B, ws):
+    """Block sizes of the rounds: B may be one size (uniform rounds) or a sequence of per-round sizes; every rank
+    contributes a block of B[r] profiles to round r, so sum(B) * ws == P_total."""
+    sizes = [int(B)] * (P_total // (ws * int(B))) if np.ndim(B) == 0 else [int(b) for b in B]
+    if not sizes or min(sizes) < 1 or sum(sizes) * ws != P_total:
+        raise ValueError('gather rounds %s x world %d do not tile P_total = %d' % (B, ws, P_total))
+    return sizes
+
+
+def gather_schedule(P_local, inner=3):
+    """Block sizes for a pipelined gather of a shard of P_local profiles: a SMALL first block (nothing can be sent while the
+    first block is being computed), a small last block (its transfer is the exposed tail), `inner` equal blocks between."""
+    edge = max(1, P_local // 16)
+    if P_local < 4 * edge + inner:
+        return [P_local]
+    rest = P_local - 2 * edge
+    mid = [rest // inner + (1 if i < rest % inner else 0) for i in range(inner)]
+    return [edge] + mid + [edge]
+
+
 def block_cyclic_profiles(P_total, B, rank, ws):
     """Profile indices held by `rank` when blocks of B profiles are dealt round-robin over the ranks: round b gives block
     b*ws + rank to `rank`.  With this assignment the per-round all-gathers of `PipelinedGather` land in natural profile
     order.  Requires P_total % (ws * B) == 0."""
-    if P_total % (ws * B):
-        raise ValueError('block-cyclic sharding needs P_total (=%d) divisible by world x block (=%d x %d)' % (P_total, ws, B))
-    rounds = P_total // (ws * B)
-    return np.concatenate([np.arange((b * ws + rank) * B, (b * ws + rank + 1) * B) for b in range(rounds)])
+    sizes = _round_sizes(P_total, B, ws)
+    out, base = [], 0
+    for b in sizes:
+        out.append(np.arange(base + rank * b, base + (rank + 1) * b))
+        base += ws * b
+    return np.concatenate(out)
 
 
 class PipelinedGather:
@@ -98,18 +120,20 @@ class PipelinedGather:
         import torch.distributed as dist
         self.group = group
         self.ws = dist.get_world_size(group) if dist.is_initialized() else 1
-        if P_total % (self.ws * B):
-            raise ValueError('PipelinedGather needs P_total (=%d) divisible by world x block (=%d x %d)' % (P_total, self.ws, B))
-        self.B, self.rounds = B, P_total // (self.ws * B)
+        self.sizes = _round_sizes(P_total, B, self.ws)        # B: one block size or a list of per-round sizes
+        self.rounds = len(self.sizes)
         self.full = torch.empty((P_total,) + tuple(tail_shape), dtype=dtype, device=device)
         flat = torch.view_as_real(self.full) if self.full.is_complex() else self.full     # NCCL moves raw doubles
-        self._rounds = flat.view((self.rounds, self.ws * B) + tuple(flat.shape[1:]))
+        self._rounds, base = [], 0
+        for b in self.sizes:
+            self._rounds.append(flat[base:base + self.ws * b])
+            base += self.ws * b
         self._pending = []
 
     def submit(self, b, block):
         import torch
         import torch.distributed as dist
-        assert block.shape[0] == self.B and 0 <= b < self.rounds
+        assert 0 <= b < self.rounds and block.shape[0] == self.sizes[b]
         x = torch.view_as_real(block) if block.is_complex() else block
         if self.ws == 1:
             self._rounds[b].copy_(x)
@@ -145,11 +169,13 @@ class PeerGather:
         from . import _lib
         self.group = group if group is not None else dist.group.WORLD
         self.ws, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
-        if P_total % (self.ws * B):
-            raise ValueError('PeerGather needs P_total (=%d) divisible by world x block (=%d x %d)' % (P_total, self.ws, B))
         if dtype not in (torch.complex128, torch.float64):
             raise ValueError('PeerGather moves float64 / complex128 arrays')
-        self.B, self.rounds, self.ctas = B, P_total // (self.ws * B), int(ctas)
+        self.sizes = _round_sizes(P_total, B, self.ws)        # B: one block size or a list of per-round sizes
+        self.rounds, self.ctas = len(self.sizes), int(ctas)
+        self._base = [0]
+        for b in self.sizes:
+            self._base.append(self._base[-1] + self.ws * b)   # first profile of each round
         self._tail = tuple(tail_shape) + ((2,) if dtype == torch.complex128 else ())
         shape = (P_total,) + self._tail
         self._flat = symm_mem.empty(shape, dtype=torch.float64, device=device)
@@ -161,15 +187,14 @@ class PeerGather:
         if mode == 'mc' and not mc:
             raise RuntimeError('PeerGather: this symmetric allocation has no multicast mapping')
         self.mode = mode
-        self._block_bytes = B * int(np.prod(self._tail)) * 8
+        self._row_bytes = int(np.prod(self._tail)) * 8
         off = int(getattr(self._hdl, 'offset', 0) or 0)
         if mode == 'mc':
             self._dst_base = [mc + off]
         elif mode == 'uc':
             self._dst_base = [int(p) + off for p in self._hdl.buffer_ptrs]
         else:
-            rshape = (self.rounds, self.ws * B) + self._tail
-            self._peers = [self._hdl.get_buffer(r, shape, torch.float64).view(rshape) for r in range(self.ws)]
+            self._peers = [self._hdl.get_buffer(r, shape, torch.float64) for r in range(self.ws)]
         lo, hi = torch.cuda.Stream.priority_range() if hasattr(torch.cuda.Stream, 'priority_range') else (0, -1)
         nstreams = self.ws if mode == 'ce' else 1
         self._streams = [torch.cuda.Stream(device, priority=-1) for _ in range(nstreams)]
@@ -178,25 +203,25 @@ class PeerGather:
 
     def submit(self, b, block):
         torch, ct = self._torch, self._ctypes
-        assert block.shape[0] == self.B and 0 <= b < self.rounds
+        assert 0 <= b < self.rounds and block.shape[0] == self.sizes[b]
         x = torch.view_as_real(block) if block.is_complex() else block
-        assert x.is_contiguous() and x.numel() * 8 == self._block_bytes
+        nbytes = self.sizes[b] * self._row_bytes
+        assert x.is_contiguous() and x.numel() * 8 == nbytes
         ready = torch.cuda.Event()
         ready.record()
-        slot = (b * self.ws + self.rank) * self._block_bytes                   # byte offset of (round b, this rank)
+        first = self._base[b] + self.rank * self.sizes[b]                       # first profile of (round b, this rank)
         if self.mode == 'ce':
-            lo = self.rank * self.B
             for k in range(self.ws):
                 r = (self.rank + k) % self.ws      # own copy first, then the peers in ring order (spreads the link load)
                 st = self._streams[r]
                 st.wait_event(ready)
                 with torch.cuda.stream(st):
-                    self._peers[r][b, lo:lo + self.B].copy_(x, non_blocking=True)
+                    self._peers[r][first:first + self.sizes[b]].copy_(x, non_blocking=True)
             return
         st = self._streams[0]
         st.wait_event(ready)
-        dst = (ct.c_ulonglong * len(self._dst_base))(*[p + slot for p in self._dst_base])
-        rc = self._lib.tamm_peer_push(x.data_ptr(), self._block_bytes, dst, len(self._dst_base), 1 if self.mode == 'mc' else 0,
+        dst = (ct.c_ulonglong * len(self._dst_base))(*[p + first * self._row_bytes for p in self._dst_base])
+        rc = self._lib.tamm_peer_push(x.data_ptr(), nbytes, dst, len(self._dst_base), 1 if self.mode == 'mc' else 0,
                                       self.ctas, ct.c_void_p(st.cuda_stream))
         self._check(rc, self._lib)
         x.record_stream(st)

@@ -81,11 +81,19 @@ if backend == 'nccl':
         makers = [('nccl', lambda: tdist.PipelinedGather(Pt, B, (3, 5), dtype, loc.device))]
         for mode in ('auto', 'uc', 'ce'):       # peer stores (multicast if the allocation has it), unicast stores, copy engines
             makers.append((mode, lambda mode=mode: tdist.PeerGather(Pt, B, (3, 5), dtype, loc.device, mode=mode, ctas=2)))
+        sched = [1, 2, 1]                                              # non-uniform rounds (tdist.gather_schedule)
+        mine_s = tdist.block_cyclic_profiles(Pt, sched, rank, ws)
+        loc_s = torch.from_numpy(src[mine_s]).cuda()
+        makers.append(('nccl-sched', lambda: tdist.PipelinedGather(Pt, sched, (3, 5), dtype, loc.device)))
+        makers.append(('peer-sched', lambda: tdist.PeerGather(Pt, sched, (3, 5), dtype, loc.device, ctas=2)))
         for label, make in makers:
             pg = make()
             for rep in range(2):                                      # reuse of the same gather object
+                o = 0
                 for b in range(pg.rounds):
-                    pg.submit(b, loc[b * B:(b + 1) * B])
+                    n = pg.sizes[b]
+                    pg.submit(b, (loc_s if label.endswith('sched') else loc)[o:o + n])
+                    o += n
                 full = pg.wait()
                 torch.cuda.synchronize()
                 assert np.array_equal(full.cpu().numpy(), src), (label, getattr(pg, 'mode', ''), str(dtype), rep)

@@ -117,6 +117,18 @@ WORKER = textwrap.dedent('''
         for b in range(pg.rounds):
             pg.submit(b, loc[b * B:(b + 1) * B])
         assert np.array_equal(pg.wait().numpy(), src)
+    # non-uniform rounds (gather_schedule: small first and last block)
+    from tamm_b200.distributed import gather_schedule
+    assert gather_schedule(128) == [8, 38, 37, 37, 8] and sum(gather_schedule(512)) == 512 and gather_schedule(3) == [3]
+    sched = [1, 2, 1]
+    mine = block_cyclic_profiles(Pt, sched, rank, ws)
+    assert list(mine) == ([0, 2, 3, 6] if rank == 0 else [1, 4, 5, 7])
+    loc = torch.from_numpy(table[mine])
+    pg = PipelinedGather(Pt, sched, (3, 4), torch.complex128, 'cpu')
+    o = 0
+    for b, n in enumerate(sched):
+        pg.submit(b, loc[o:o + n]); o += n
+    assert np.array_equal(pg.wait().numpy(), table)
     try:
         PipelinedGather(7, B, (3, 4), torch.float64, 'cpu')
         raise SystemExit('ragged ensemble accepted')

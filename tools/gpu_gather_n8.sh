@@ -1,18 +1,16 @@
 #!/bin/bash
 N=${1:?ranks}; T=${2:?tag}; mkdir -p gpurun_out
 RUN="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29523"
-$RUN tools/peer_push_bench.py 2>&1 | grep -v "OMP_NUM\|^\*\*\*" > gpurun_out/${T}_pushbench_n$N.txt; cat gpurun_out/${T}_pushbench_n$N.txt
-$RUN bench.py --gpus $N --steps 5 --warmup 3 --no-e2e --no-cpu --gather-mode peer > gpurun_out/${T}_a_n$N.json 2> gpurun_out/${T}_a_n$N.err
+$RUN bench.py --gpus $N --steps 5 --warmup 3 --no-e2e --no-cpu --gather-mode both > gpurun_out/${T}_a_n$N.json 2> gpurun_out/${T}_a_n$N.err
 $RUN bench.py --gpus $N --steps 5 --warmup 3 --no-e2e --no-cpu --gather power,fields --gather-mode peer --push-ctas 4 > gpurun_out/${T}_b_n$N.json 2> gpurun_out/${T}_b_n$N.err
-$RUN bench.py --gpus $N --steps 5 --warmup 3 --no-e2e --no-cpu --gather power,fields --gather-mode peer --gather-block 16 > gpurun_out/${T}_c_n$N.json 2> gpurun_out/${T}_c_n$N.err
 python - "$N" "$T" <<'PY'
 import json, sys
 n, t = sys.argv[1], sys.argv[2]
-for tag in ('a', 'b', 'c'):
+for tag in ('a', 'b'):
     try:
         d = json.loads(open('gpurun_out/%s_%s_n%s.json' % (t, tag, n)).read().strip().splitlines()[-1])
         g = d['gather']
-        print(tag, 'compute %.2f ms/step; block %d x %d' % (d['ms_per_step'], g['block_profiles'], g['blocks_per_rank']))
+        print(tag, 'compute %.2f ms/step; schedule %s' % (d['ms_per_step'], g.get('block_schedule')))
         for k in ('power', 'fields', 'jones'):
             if k not in g: continue
             x = g[k]
