@@ -66,10 +66,12 @@ def parse():
     ap.add_argument('--gather', default='all',
                     help='config 4, N > 1: also time the final all-gather of results (reported separately): none, all, or a '
                          'comma list of power, fields, jones')
-    ap.add_argument('--gather-block', type=int, default=0, help='profiles per pipelined all-gather block (0: tdist.gather_schedule -- small first and last block)')
-    ap.add_argument('--gather-mode', default='both', choices=['nccl', 'peer', 'mc', 'uc', 'ce', 'both'],
-                    help='transport of the pipelined gather: NCCL collectives only, peer stores into symmetric memory (multicast '
-                         'if available, else unicast), copy engines, or (both) NCCL + peer stores + copy engines')
+    ap.add_argument('--gather-block', type=int, default=0, help='profiles per pipelined gather block (0: a quarter of the shard)')
+    ap.add_argument('--gather-blocks', default='', help='explicit comma list of gather block sizes per rank (e.g. from tdist.gather_schedule)')
+    ap.add_argument('--gather-mode', default='peer', choices=['nccl', 'peer', 'mc', 'uc', 'ce', 'both'],
+                    help='transports of the pipelined gather timed besides NCCL collectives: peer = stores into symmetric memory '
+                         '(multicast if available, else unicast); mc / uc / ce = that one only (ce: copy engines); both = peer + ce; '
+                         'nccl = none')
     ap.add_argument('--push-ctas', type=int, default=8, help='CTAs of the peer-push kernel (tamm_peer_push)')
     return ap.parse_args()
 
@@ -727,8 +729,15 @@ def bench_ensemble(c, args, w, emit):
             while Pl % GB or P % (world * GB):
                 GB -= 1
             sched = [GB] * (Pl // GB)
-        else:
-            sched = tdist.gather_schedule(Pl)
+        elif args.gather_blocks:
+            sched = [int(t) for t in args.gather_blocks.split(',')]
+            assert sum(sched) == Pl, 'gather block list must sum to the profiles of one rank'
+        else:   # a quarter of the shard per block: measured best at N = 2 and N = 8 (finer or graded schedules lose more to
+                # small launches than they gain at the ends of the pipeline)
+            GB = max(1, Pl // 4)
+            while Pl % GB:
+                GB -= 1
+            sched = [GB] * (Pl // GB)
         GB0 = sched[0]
         GBmax = max(sched)
         planes_g = planes[:GBmax] if GBmax <= B else eng.empty((GBmax, NI, 4, F), cdt)

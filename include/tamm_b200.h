@@ -146,7 +146,8 @@ int tamm_returns_finish(double* amp_HH, double* amp_HV, const double* sum_HH, co
  * The final all-gather of north_star ("a final NCCL all-gather over NVLink of the per-depth Jones matrices") as stores into
  * peer memory: pushes `bytes` bytes at `src` (this GPU) to the same offset of every rank's gathered array, which must live in
  * symmetric memory (mapped on all GPUs of the group over NVLink / NVSwitch, e.g. torch.distributed._symmetric_memory).
- *   multicast != 0 : dst[0] is the MULTICAST address of the destination (one multimem.st per 16 bytes; the NVSwitch
+ *   multicast != 0 : dst[0] is the MULTICAST address of the destination (one multimem.st per 16 bytes -- per 8 bytes when a
+ *                    pointer or the size is only 8-byte aligned, e.g. odd rows of a float64 array; the NVSwitch
  *                    replicates into every rank's copy, the sender's link carries the block once);
  *   multicast == 0 : dst[0..ndst-1] are the ndst (<= 16) per-rank unicast addresses.
  * `ctas` CTAs of 1024 threads do the copy (<= 0: 8).  The caller orders it after the producing kernels (stream / event) and

@@ -928,34 +928,42 @@ layer_modes_kernel(const double* __restrict__ layers, const double* __restrict__
 //   unicast  : one st.global per destination buffer (fallback without multicast support).
 // A handful of CTAs saturate the sender side (the block is 1/N of what each GPU receives), so the push is launched on a
 // high-priority side stream next to the stack kernel of the NEXT block and costs it a few SMs for about a millisecond.
-__device__ __forceinline__ void multimem_st16(void* mc, uint4 v) {
+__device__ __forceinline__ void multimem_st(uint4* mc, uint4 v) {
     asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(__uint_as_float(v.x)),
                  "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w))
                  : "memory");
 }
+__device__ __forceinline__ void multimem_st(uint2* mc, uint2 v) {
+    asm volatile("multimem.st.weak.global.v2.f32 [%0], {%1, %2};" ::"l"(mc), "f"(__uint_as_float(v.x)), "f"(__uint_as_float(v.y))
+                 : "memory");
+}
+template <class V>
 struct PeerPtrs {
-    uint4* p[16];
+    V* p[16];
 };
-// Each thread keeps PUSH_ILP independent 16-byte loads in flight before it stores them (one load per thread and iteration
-// moves only ~15 GB/s per CTA: 1024 x 16 B per memory latency); consecutive threads touch consecutive 16-byte words.
+// Each thread keeps PUSH_ILP independent loads in flight before it stores them (one load per thread and iteration moves
+// only ~15 GB/s per CTA: 1024 x 16 B per memory latency); consecutive threads touch consecutive words.  V = uint4 (16-byte
+// words) when source, destination and size allow it, else uint2 (a float64 array cut at an odd row is only 8-byte aligned).
 constexpr int PUSH_ILP = 8;
-__global__ void __launch_bounds__(1024) peer_push_mc_kernel(const uint4* __restrict__ src, uint4* mc, size_t n16) {
+template <class V>
+__global__ void __launch_bounds__(1024) peer_push_mc_kernel(const V* __restrict__ src, V* mc, size_t n) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    for (; i + (PUSH_ILP - 1) * stride < n16; i += PUSH_ILP * stride) {
-        uint4 v[PUSH_ILP];
+    for (; i + (PUSH_ILP - 1) * stride < n; i += PUSH_ILP * stride) {
+        V v[PUSH_ILP];
 #pragma unroll
         for (int k = 0; k < PUSH_ILP; ++k) v[k] = __ldcs(src + i + k * stride);
 #pragma unroll
-        for (int k = 0; k < PUSH_ILP; ++k) multimem_st16(mc + i + k * stride, v[k]);
+        for (int k = 0; k < PUSH_ILP; ++k) multimem_st(mc + i + k * stride, v[k]);
     }
-    for (; i < n16; i += stride) multimem_st16(mc + i, __ldcs(src + i));
+    for (; i < n; i += stride) multimem_st(mc + i, __ldcs(src + i));
 }
-__global__ void __launch_bounds__(1024) peer_push_uc_kernel(const uint4* __restrict__ src, PeerPtrs dst, int ndst, size_t n16) {
+template <class V>
+__global__ void __launch_bounds__(1024) peer_push_uc_kernel(const V* __restrict__ src, PeerPtrs<V> dst, int ndst, size_t n) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    for (; i + (PUSH_ILP - 1) * stride < n16; i += PUSH_ILP * stride) {
-        uint4 v[PUSH_ILP];
+    for (; i + (PUSH_ILP - 1) * stride < n; i += PUSH_ILP * stride) {
+        V v[PUSH_ILP];
 #pragma unroll
         for (int k = 0; k < PUSH_ILP; ++k) v[k] = __ldcs(src + i + k * stride);
         for (int d = 0; d < ndst; ++d) {
@@ -963,8 +971,8 @@ __global__ void __launch_bounds__(1024) peer_push_uc_kernel(const uint4* __restr
             for (int k = 0; k < PUSH_ILP; ++k) __stcs(dst.p[d] + i + k * stride, v[k]);
         }
     }
-    for (; i < n16; i += stride) {
-        const uint4 v = __ldcs(src + i);
+    for (; i < n; i += stride) {
+        const V v = __ldcs(src + i);
         for (int d = 0; d < ndst; ++d) __stcs(dst.p[d] + i, v);
     }
 }
@@ -1037,6 +1045,20 @@ void stack_geometry(int P, int QF, int maxt, int* tb, int* flat, long* gx) {
     }
 }
 
+template <class V>
+int peer_push_launch(const void* src, size_t bytes, const unsigned long long* dst, int ndst, int multicast, int ctas, cudaStream_t s) {
+    const size_t n = bytes / sizeof(V);
+    if (multicast) {
+        peer_push_mc_kernel<V><<<ctas, 1024, 0, s>>>((const V*)src, (V*)dst[0], n);
+    } else {
+        PeerPtrs<V> pp;
+        for (int d = 0; d < 16; ++d) pp.p[d] = (V*)(d < ndst ? dst[d] : 0ull);
+        peer_push_uc_kernel<V><<<ctas, 1024, 0, s>>>((const V*)src, pp, ndst, n);
+    }
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
 }  // namespace
@@ -1090,22 +1112,18 @@ int tamm_layer_modes(const double* layers, const double* lanes, int N, int QF, d
 
 int tamm_peer_push(const void* src, size_t bytes, const unsigned long long* dst, int ndst, int multicast, int ctas, void* stream) {
     if (!src || !dst || ndst < 1 || ndst > 16) return fail("tamm_peer_push: bad arguments%s", "");
-    if ((bytes & 15) || !aligned16(src)) return fail("tamm_peer_push: source must be 16-byte aligned and a multiple of 16 bytes%s", "");
-    for (int d = 0; d < ndst; ++d)
-        if (!dst[d] || (dst[d] & 15)) return fail("tamm_peer_push: destination %s(%ld) is null or misaligned", "", d);
+    uintptr_t all = (uintptr_t)src | (uintptr_t)bytes;
+    for (int d = 0; d < ndst; ++d) {
+        if (!dst[d]) return fail("tamm_peer_push: destination %s(%ld) is null", "", d);
+        all |= (uintptr_t)dst[d];
+    }
+    if (all & 7) return fail("tamm_peer_push: source, destinations and size must be multiples of 8 bytes%s", "");
     if (bytes == 0) return 0;
     if (ctas < 1) ctas = 8;
-    const size_t n16 = bytes / 16;
     cudaStream_t s = (cudaStream_t)stream;
-    if (multicast) {
-        peer_push_mc_kernel<<<ctas, 1024, 0, s>>>((const uint4*)src, (uint4*)dst[0], n16);
-    } else {
-        PeerPtrs pp;
-        for (int d = 0; d < 16; ++d) pp.p[d] = (uint4*)(d < ndst ? dst[d] : 0ull);
-        peer_push_uc_kernel<<<ctas, 1024, 0, s>>>((const uint4*)src, pp, ndst, n16);
-    }
-    CUDA_OK(cudaGetLastError());
-    return 0;
+    // 16-byte words when everything is 16-byte aligned, else 8-byte words (rows of a float64 array)
+    return (all & 15) ? peer_push_launch<uint2>(src, bytes, dst, ndst, multicast, ctas, s)
+                      : peer_push_launch<uint4>(src, bytes, dst, ndst, multicast, ctas, s);
 }
 
 size_t tamm_stack_workspace_bytes(int P, int N, int QF, int chunk) {
