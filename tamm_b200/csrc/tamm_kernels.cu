@@ -510,18 +510,13 @@ __device__ __forceinline__ double warp_sum8(const double v[8], int lane) {
 }
 
 // One (depth, azimuth) point of the returns tail (layerstack.py:249-278): received fields for the transmitted
-// polarisation, HH-VV coherence phase, field amplitudes.  Fast path: |.| through rsqrt of the squared modulus, the
-// coherence normaliser as ONE rsqrt of |m0|^2 |m3|^2.  That product / those squares leave the normal range once a
-// modulus is below ~1e-75 / ~1e-148 (strongly attenuating deep stacks) or the value is zero, inf or NaN: then the
-// arithmetic of the two-pass kernels is used (hypot like numpy.abs, true division), so the result does not depend on
-// which returns kernel F selects and stays finite exactly where the reference's is.
-// returns {c.re, c.im, |hh|, |hv|} in registers (a by-reference result would go through local memory on BOTH paths)
-__device__ __noinline__ double4 returns_point_slow(cd m0, cd m3, cd hh, cd hv) {
-    const cd num = m0 * conj(m3);
-    const double den = cabs_(m0) * cabs_(m3);
-    return make_double4(num.re / den, num.im / den, cabs_(hh), cabs_(hv));
-}
-__device__ __forceinline__ void returns_point(const cd m[4], cd e0, cd e1, int gtm_phase, cd& hh, cd& hv, cd& c, double& ahh,
+// polarisation, HH-VV coherence phase, field amplitudes.  Fast arithmetic: |.| through rsqrt of the squared modulus, the
+// coherence normaliser as ONE rsqrt of |m0|^2 |m3|^2.  That product / those squares leave the normal range once a modulus
+// is below ~1e-75 / ~1e-148 (strongly attenuating deep stacks) or a value is zero, inf or NaN.  The point then only
+// raises `bad`; the CTA repeats its whole depth tile afterwards with the arithmetic of the two-pass kernels (hypot like
+// numpy.abs, true division: returns_tile_slow), so the result does not depend on which returns kernel F selects and
+// is finite exactly where the reference's is -- and the hot loop carries no call and no extra live state.
+__device__ __forceinline__ bool returns_point(const cd m[4], cd e0, cd e1, int gtm_phase, cd& hh, cd& hv, cd& c, double& ahh,
                                               double& ahv) {
     hh = dot2(m[0], e0, m[1], e1);             // get_Rx_all (layerstack.py:298)
     hv = dot2(m[2], e0, m[3], e1);
@@ -529,19 +524,65 @@ __device__ __forceinline__ void returns_point(const cd m[4], cd e0, cd e1, int g
     // all three within 2^-980 ... 2^+980 (normal, with room to spare, not inf / NaN; prod = 0 when a modulus is 0): the high
     // words of non-negative doubles order like the values, so this is two 3-way integer min/max and two compares
     const unsigned hp = (unsigned)__double2hiint(prod), hh_ = (unsigned)__double2hiint(shh), hv_ = (unsigned)__double2hiint(shv);
-    if (TAMM_RARE(min(hp, min(hh_, hv_)) < 0x02B00000u || max(hp, max(hh_, hv_)) > 0x7D300000u)) {
-        const double4 r = returns_point_slow(m[0], m[3], hh, hv);
-        c = cd{r.x, r.y};
-        ahh = r.z;
-        ahv = r.w;
-    } else {
-        const cd num = cmul_(m[0], conj(m[3]));    // c_HHVV (layerstack.py:271-278): num / (|m0| |m3|)
-        const double iden = tamm::frsqrt(prod);
-        c = cd{num.re * iden, num.im * iden};
-        ahh = tamm::fsqrt(shh);
-        ahv = tamm::fsqrt(shv);
-    }
+    const bool bad = min(hp, min(hh_, hv_)) < 0x02B00000u || max(hp, max(hh_, hv_)) > 0x7D300000u;
+    const cd num = cmul_(m[0], conj(m[3]));    // c_HHVV (layerstack.py:271-278): num / (|m0| |m3|)
+    const double iden = tamm::frsqrt(prod);
+    c = cd{num.re * iden, num.im * iden};
     if (gtm_phase) c = cd{-c.re, c.im};        // -|c| exp(-i angle c) = -conj(c)   (layerstack.py:276-278)
+    ahh = tamm::fsqrt(shh);
+    ahv = tamm::fsqrt(shv);
+    return bad;
+}
+
+// Cold repeat of one CTA's depth tile [nbeg, ne) of (profile p, frequency iq) with the reference-like arithmetic of
+// returns_kernel + the azimuth sums + the dB step; thread = azimuth, called by ALL threads of the CTA (it synchronises).
+__device__ __noinline__ void returns_tile_slow(const cd* __restrict__ planes, const cd* __restrict__ pre, int N, int Q, int F,
+                                               int mode, int chunk, int nchunks, cd e0, cd e1, int gtm_phase, cd* E_HH, cd* E_HV,
+                                               cd* c_HHVV, double* dP_HH, double* dP_HV, double* Pm_HH, double* Pm_HV, int p,
+                                               int iq, int nbeg, int ne, double* red) {
+    const int NI = N - 1, QF = Q * F, NW = blockDim.x >> 5;
+    const int ifr = threadIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const bool live = ifr < F;
+    const int l = iq * F + (live ? ifr : F - 1);
+    for (int n = nbeg; n < ne; ++n) {
+        const cd* ip = planes + ((size_t)p * NI + n) * 4 * (size_t)QF + l;
+        cd m[4] = {ld_cd(ip), ld_cd(ip + QF), ld_cd(ip + 2 * (size_t)QF), ld_cd(ip + 3 * (size_t)QF)};
+        if (nchunks > 1 && n / chunk > 0) {
+            cd Dp[4], Up[4];
+            load_prefix(pre, (size_t)p * QF + l, nchunks, n / chunk, Dp, Up);
+            cd t[4];
+            if (mode == TAMM_MODE_URD) { mm22(m, Dp, t); mm22(Up, t, m); }
+            else { mm22(Up, m, t); m[0] = t[0]; m[1] = t[1]; m[2] = t[2]; m[3] = t[3]; }
+        }
+        const cd hh = dot2(m[0], e0, m[1], e1), hv = dot2(m[2], e0, m[3], e1);
+        const cd num = m[0] * conj(m[3]);
+        const double den = cabs_(m[0]) * cabs_(m[3]);
+        cd c = cd{num.re / den, num.im / den};
+        if (gtm_phase) c = cd{-c.re, c.im};
+        const double ahh = live ? cabs_(hh) : 0.0, ahv = live ? cabs_(hv) : 0.0;
+        const size_t o = (((size_t)p * Q + iq) * NI + n) * F + (live ? ifr : F - 1);
+        if (live) { st_cd(E_HH + o, hh); st_cd(E_HV + o, hv); st_cd(c_HHVV + o, c); }
+        double sh = ahh, sv = ahv;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            sh += __shfl_xor_sync(0xffffffffu, sh, off);
+            sv += __shfl_xor_sync(0xffffffffu, sv, off);
+        }
+        __syncthreads();
+        if (lane == 0) { red[2 * w] = sh; red[2 * w + 1] = sv; }
+        __syncthreads();
+        double th = 0.0, tv = 0.0;
+        for (int i = 0; i < NW; ++i) { th += red[2 * i]; tv += red[2 * i + 1]; }
+        const double pmh = 20.0 * log10(th / (double)F), pmv = 20.0 * log10(tv / (double)F);
+        if (threadIdx.x == 0) {
+            const size_t row = ((size_t)p * Q + iq) * NI + n;
+            Pm_HH[row] = pmh; Pm_HV[row] = pmv;
+        }
+        if (live) {
+            dP_HH[o] = 20.0 * log10(ahh) - pmh;
+            dP_HV[o] = 20.0 * log10(ahv) - pmv;
+        }
+    }
 }
 
 template <int BLOCK>
@@ -554,6 +595,9 @@ returns_fused_kernel(const cd* __restrict__ planes, const cd* __restrict__ pre, 
     constexpr int NW = BLOCK / 32;
     __shared__ double red[NW][2 * TNF];
     __shared__ double tot[2 * TNF];
+    __shared__ int s_bad;         // a point of this tile left the range of the fast arithmetic (returns_point)
+    if (threadIdx.x == 0) s_bad = 0;
+    __syncthreads();
     const int NI = N - 1, QF = Q * F;
     const int p = blockIdx.z, iq = blockIdx.y;
     const int ifr = threadIdx.x;
@@ -587,7 +631,7 @@ returns_fused_kernel(const cd* __restrict__ planes, const cd* __restrict__ pre, 
                 }
                 cd hh, hv, c;
                 double ahh, ahv;
-                returns_point(m, e0, e1, gtm_phase, hh, hv, c, ahh, ahv);
+                if (TAMM_RARE(returns_point(m, e0, e1, gtm_phase, hh, hv, c, ahh, ahv))) s_bad = 1;
                 if (live) {
                     st_cd(E_HH + o, hh);
                     st_cd(E_HV + o, hv);
@@ -632,6 +676,10 @@ returns_fused_kernel(const cd* __restrict__ planes, const cd* __restrict__ pre, 
         // red / tot are rewritten by the next group only after its own barrier on red; tot is read above before the next
         // group's first barrier, and written after it -> no extra barrier needed
     }
+    __syncthreads();
+    if (TAMM_RARE(s_bad))
+        returns_tile_slow(planes, pre, N, Q, F, mode, chunk, nchunks, e0, e1, gtm_phase, E_HH, E_HV, c_HHVV, dP_HH, dP_HV, Pm_HH,
+                          Pm_HV, p, iq, (int)blockIdx.x * (TNF * TNG), ne, &red[0][0]);
 }
 
 // The same kernel fed by the TMA engine (F <= 256): the four plane rows of a depth (F x 16 B each, contiguous in the
@@ -652,6 +700,8 @@ returns_tma_kernel(const cd* __restrict__ planes, const cd* __restrict__ pre, in
     __shared__ alignas(8) uint64_t bar[NST];
     __shared__ double red[NW][2 * TNF];
     __shared__ double tot[2 * TNF];
+    __shared__ int s_bad;
+    if (threadIdx.x == 0) s_bad = 0;
     const int NI = N - 1, QF = Q * F;
     const int p = blockIdx.z, iq = blockIdx.y;
     const int ifr = threadIdx.x;
@@ -708,7 +758,7 @@ returns_tma_kernel(const cd* __restrict__ planes, const cd* __restrict__ pre, in
                 }
                 cd hh, hv, c;
                 double ahh, ahv;
-                returns_point(m, e0, e1, gtm_phase, hh, hv, c, ahh, ahv);
+                if (TAMM_RARE(returns_point(m, e0, e1, gtm_phase, hh, hv, c, ahh, ahv))) s_bad = 1;
                 if (live) {
                     st_cd(E_HH + o, hh);
                     st_cd(E_HV + o, hv);

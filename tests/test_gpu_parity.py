@@ -597,3 +597,39 @@ def test_near_degenerate_pair_crossing_on_device(eng):
                 got, want = np.sort_complex(qs[f, n, sl].astype(np.clongdouble)), np.sort_complex(qx[f, n, sl])
                 assert float(np.abs(got - want).max()) < 1e-15, (f, n, got, want)
     assert (np.abs(qs[0, 1:, 0] - qs[0, 1:, 1]) > 0.5 * split[1:]).all()
+
+
+def test_strongly_attenuating_deep_stack_both_returns_paths(eng):
+    """with sigma = 1e-2 S/m the two-way attenuation is ~9 dB per metre, so 400 m down the received field has
+    fallen from 1e-4 through 1e-154 (where |E|^2 underflows) to exactly 0.  The fused returns kernel (F >= 32) computes
+    |.| through rsqrt of squared moduli; points outside the range of that arithmetic make the CTA repeat its depth tile
+    with hypot / true division (returns_tile_slow), like the two-pass kernels (F < 32) and like numpy.abs in the
+    reference.  Both paths against the oracle: same non-finite pattern (dB of an exact 0 is -inf, 0/0 coherence is NaN),
+    powers to 1e-6 dB and coherence to 1e-7 wherever the oracle's field is above 1e-300, element-wise field errors 1e-9."""
+    import layerstack as ls
+    nlm, z = profiles.tilted(400, 400, seed=21)
+    alpha = np.deg2rad(10)
+    for F in (33, 9):                                                   # fused kernel / two-pass kernels
+        s = ls.LayerStack(nlm, z, N_frames=F, sigma=[1e-2], VERBOSE=0)
+        got = dict(zip(h.RET_NAMES, s.get_returns(1e3, f=179e6, alpha=alpha)))
+        want = dict(zip(h.RET_NAMES, orc.OracleStack(nlm, z, N_frames=F, sigma=[1e-2]).get_returns(1e3, f=179e6, alpha=alpha)))
+        amp = np.abs(want['E_HH'])
+        assert amp.max() > 1e-6 and (amp[amp > 0].min() < 1e-200) and (amp == 0).any()      # spans the whole range
+        ok = (np.abs(want['E_HH']) > 1e-300) & (np.abs(want['E_HV']) > 1e-300)
+        # non-finite patterns: identical wherever the field is resolved (cross-polar nulls included) and in the depths where it
+        # has vanished completely (ten rows past the first all-zero row; the denormal transition zone in between is rounding)
+        zero_rows = np.nonzero(((want['E_HH'] == 0) & (want['E_HV'] == 0)).all(axis=1))[0]
+        dead = np.zeros(amp.shape[0], dtype=bool)
+        dead[zero_rows[0] + 10:] = True
+        sel = ok.all(axis=1) | dead
+        assert ok.all(axis=1).sum() > 100 and dead.sum() > 20
+        for n in h.RET_NAMES:
+            h.assert_same_nonfinite(got[n][sel], want[n][sel], '%s F=%d' % (n, F))
+        for n in ('E_HH', 'E_HV'):
+            assert (np.abs(got[n] - want[n])[ok] / np.abs(want[n])[ok]).max() < 1e-9, (n, F)
+        assert np.abs(got['c_HHVV'] - want['c_HHVV'])[ok].max() < C_HHVV_ATOL, F
+        rows = ok.all(axis=1)                                           # depths where every azimuth is resolved
+        for n in ('Pm_HH', 'Pm_HV'):
+            assert np.abs(got[n] - want[n])[rows].max() < h.ATOL_DB, (n, F)
+        for n in ('dP_HH', 'dP_HV'):
+            assert np.abs(got[n] - want[n])[rows].max() < h.ATOL_DB, (n, F)
