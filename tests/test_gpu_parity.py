@@ -623,11 +623,16 @@ def test_strongly_attenuating_deep_stack_both_returns_paths(eng):
         dead[zero_rows[0] + 10:] = True
         sel = ok.all(axis=1) | dead
         assert ok.all(axis=1).sum() > 100 and dead.sum() > 20
+        # the coherence is a ratio of PRODUCTS of two reflection coefficients (layerstack.py:271-273): its own underflow zone
+        # starts where |URD_hh| |URD_vv| ~ 1e-308, i.e. at field amplitudes ~1e-140 -- resolved rows for it are those above
+        okc = (np.abs(want['E_HH']) > 1e-140) & (np.abs(want['E_HV']) > 1e-140)
+        selc = okc.all(axis=1) | dead
         for n in h.RET_NAMES:
-            h.assert_same_nonfinite(got[n][sel], want[n][sel], '%s F=%d' % (n, F))
+            rows_n = selc if n == 'c_HHVV' else sel
+            h.assert_same_nonfinite(got[n][rows_n], want[n][rows_n], '%s F=%d' % (n, F))
         for n in ('E_HH', 'E_HV'):
             assert (np.abs(got[n] - want[n])[ok] / np.abs(want[n])[ok]).max() < 1e-9, (n, F)
-        assert np.abs(got['c_HHVV'] - want['c_HHVV'])[ok].max() < C_HHVV_ATOL, F
+        assert np.abs(got['c_HHVV'] - want['c_HHVV'])[okc].max() < C_HHVV_ATOL, F
         rows = ok.all(axis=1)                                           # depths where every azimuth is resolved
         for n in ('Pm_HH', 'Pm_HV'):
             assert np.abs(got[n] - want[n])[rows].max() < h.ATOL_DB, (n, F)
