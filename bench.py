@@ -383,15 +383,31 @@ def hbm_peak():
         return 6550.4, 'fallback: the copy bandwidth MEASURED_PEAKS.json held when the kernels were profiled'
 
 
+def stack_sass_md5(lib_path):
+    """md5 of the disassembly of the stack kernel (URD, 384 x 1, mu = 1) in the loaded library: identifies the device code the
+    committed ncu capture was taken on, independent of host-side or other-kernel changes (same recipe as tools/sass_md5.sh)."""
+    import hashlib
+    cu = '/usr/local/cuda/bin/cuobjdump'
+    names = subprocess.run([cu, '-sass', lib_path], capture_output=True, text=True, timeout=120).stdout
+    fn = [l.split()[-1] for l in names.splitlines() if 'Function :' in l and 'stack_kernelILi0ELi384ELi1ELb1' in l]
+    body = subprocess.run([cu, '-sass', '-fun', fn[0], lib_path], capture_output=True, text=True, timeout=120).stdout
+    body = '\n'.join(l for l in body.splitlines() if '/*' in l)      # instruction lines only
+    return hashlib.md5(body.encode()).hexdigest()
+
+
 def stack_traffic(c, evals_per_launch):
     """DRAM bytes of one stack-kernel launch from the committed `ncu --set full` capture -- only when that capture was
-    taken on the very library file this run loaded (md5); otherwise null: a stale figure must not outlive a kernel change."""
+    taken on the very device code this run loaded (md5 of the kernel's SASS); otherwise null: a stale figure must not
+    outlive a kernel change."""
     try:
         tj = json.load(open(os.path.join(ROOT, 'profiles', 'r02_stack_traffic.json')))
-        if tj.get('library_md5') != c.lib_md5:
-            return None, 'none: profiles/r02_stack_traffic.json was captured on another build (md5 %s)' % tj.get('library_md5')
-        return tj['dram_bytes_per_eval'] * evals_per_launch, ('committed ncu capture of this same library build: '
-                                                               'profiles/r02_stack_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum per eval x evals per launch)')
+        have = stack_sass_md5(c.lib_path)
+        if tj.get('stack_sass_md5') != have:
+            return None, 'none: profiles/r02_stack_traffic.json was captured on other device code (SASS md5 %s, loaded %s)' % (
+                tj.get('stack_sass_md5'), have)
+        return tj['dram_bytes_per_eval'] * evals_per_launch, ('committed ncu capture of this same device code (SASS md5 %s): '
+                                                               'profiles/r02_stack_traffic.json, dram__bytes_read.sum + dram__bytes_write.sum '
+                                                               'per eval x evals per launch' % have)
     except Exception as e:
         return None, 'none: %s' % repr(e)[:80]
 

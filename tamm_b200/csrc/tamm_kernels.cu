@@ -524,7 +524,18 @@ __device__ __forceinline__ bool returns_point(const cd m[4], cd e0, cd e1, int g
     // all three within 2^-980 ... 2^+980 (normal, with room to spare, not inf / NaN; prod = 0 when a modulus is 0): the high
     // words of non-negative doubles order like the values, so this is two 3-way integer min/max and two compares
     const unsigned hp = (unsigned)__double2hiint(prod), hh_ = (unsigned)__double2hiint(shh), hv_ = (unsigned)__double2hiint(shv);
-    const bool bad = min(hp, min(hh_, hv_)) < 0x02B00000u || max(hp, max(hh_, hv_)) > 0x7D300000u;
+    bool bad = false;
+    if (TAMM_RARE(min(hp, min(hh_, hv_)) < 0x02B00000u || max(hp, max(hh_, hv_)) > 0x7D300000u)) {
+        // EXACT zeros are fine for the fast arithmetic (|0| = 0, 0/0 = NaN like the reference) and common: the cross-polar
+        // return vanishes identically on the symmetry azimuths at normal incidence.  Only a square that underflowed from a
+        // non-zero value, or an overflow / inf / NaN, needs the slow repeat.
+        auto is_zero = [](cd z) {
+            return ((((unsigned)__double2hiint(z.re) | (unsigned)__double2hiint(z.im)) & 0x7fffffffu) |
+                    (unsigned)__double2loint(z.re) | (unsigned)__double2loint(z.im)) == 0u;
+        };
+        bad = max(hp, max(hh_, hv_)) > 0x7D300000u || (hp < 0x02B00000u && !(is_zero(m[0]) || is_zero(m[3]))) ||
+              (hh_ < 0x02B00000u && !is_zero(hh)) || (hv_ < 0x02B00000u && !is_zero(hv));
+    }
     const cd num = cmul_(m[0], conj(m[3]));    // c_HHVV (layerstack.py:271-278): num / (|m0| |m3|)
     const double iden = tamm::frsqrt(prod);
     c = cd{num.re * iden, num.im * iden};

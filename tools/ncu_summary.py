@@ -114,7 +114,7 @@ def main():
     print()
     if a.traffic_json and rd is not None:
         json.dump(dict(kernel=name[:120], source='ncu --set full, %s' % a.report, evals_per_launch=a.evals, dram_bytes_read=rd,
-                       dram_bytes_write=wr, dram_bytes_per_eval=(rd + wr) / a.evals, library_md5=a.md5), open(a.traffic_json, 'w'), indent=1)
+                       dram_bytes_write=wr, dram_bytes_per_eval=(rd + wr) / a.evals, stack_sass_md5=a.md5), open(a.traffic_json, 'w'), indent=1)
 
 
 if __name__ == '__main__':
