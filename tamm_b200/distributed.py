@@ -195,7 +195,6 @@ class PeerGather:
             self._dst_base = [int(p) + off for p in self._hdl.buffer_ptrs]
         else:
             self._peers = [self._hdl.get_buffer(r, shape, torch.float64) for r in range(self.ws)]
-        lo, hi = torch.cuda.Stream.priority_range() if hasattr(torch.cuda.Stream, 'priority_range') else (0, -1)
         nstreams = self.ws if mode == 'ce' else 1
         self._streams = [torch.cuda.Stream(device, priority=-1) for _ in range(nstreams)]
         self._lib, self._ctypes, self._torch = _lib.load(), ctypes, torch
