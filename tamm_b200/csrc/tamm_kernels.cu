@@ -1126,7 +1126,7 @@ bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
 extern "C" {
 
-int tamm_version(void) { return 100; }
+int tamm_version(void) { return 200; }   // 2xx: round-2 ABI (returns_partial / _finish, layer_modes, peer_push; status zeroed by the library)
 const char* tamm_last_error(void) { return g_err; }
 
 int tamm_check_device(int device) {
