@@ -159,7 +159,10 @@ class PeerGather:
             millisecond per block, against the ~32 SMs an NCCL all-gather kernel holds for the whole transfer;
       'uc'  the same kernel with one store per destination rank (no multicast support);
       'ce'  copy engines: one cudaMemcpyAsync per destination rank on per-peer streams (no SM at all, ~450 GB/s).
-    mode='auto' picks 'mc' when the symmetric allocation has a multicast mapping, else 'uc'."""
+    mode='auto' picks 'mc' when the symmetric allocation has a multicast mapping, else 'uc'.
+    Reuse: `full` is written by the OTHER ranks; after `wait()` it is complete and stable until any rank submits again, so a
+    job that gathers repeatedly must finish reading `full` on every rank (e.g. a `dist.barrier()` or the next `wait()` of a
+    second PeerGather used alternately) before the next round of submits."""
 
     def __init__(self, P_total, B, tail_shape, dtype, device, group=None, mode='auto', ctas=8):
         import ctypes
@@ -216,6 +219,7 @@ class PeerGather:
                 st.wait_event(ready)
                 with torch.cuda.stream(st):
                     self._peers[r][first:first + self.sizes[b]].copy_(x, non_blocking=True)
+                x.record_stream(st)
             return
         st = self._streams[0]
         st.wait_event(ready)
