@@ -443,6 +443,24 @@ struct LayerDiag {   // optional diagnostics backing the `Layer` attributes of t
     int status;      // bit0: transmitted/reflected partition was not 2+2
 };
 
+// a < b / a <= b for NON-NEGATIVE doubles decided by their high words only (one integer compare instead of an FP64 compare,
+// which costs 2.18 issue slots on this chip): exact except when a and b agree in their leading 32 bits (relative distance
+// below 2^-20), where lt_hi says "not less" and le_hi says "less or equal"; NaN compares false like the FP64 test.  For
+// heuristic thresholds only (step selection, convergence test), where a decision that close to the threshold is arbitrary.
+TAMM_HD bool lt_hi(double a, double b) { return (unsigned)dbl_hi(a) < (unsigned)dbl_hi(b); }
+TAMM_HD bool le_hi(double a, double b) { return (unsigned)dbl_hi(a) <= (unsigned)dbl_hi(b); }
+// (Ex, Ey) == (0, 0) exactly, on the integer pipe (sign bits ignored): the OR of all words
+TAMM_HD bool both_zero(cd a, cd b) {
+    const unsigned hi = (unsigned)(dbl_hi(a.re) | dbl_hi(a.im) | dbl_hi(b.re) | dbl_hi(b.im)) & 0x7fffffffu;
+    const unsigned lo = (unsigned)(dbl_lo(a.re) | dbl_lo(a.im) | dbl_lo(b.re) | dbl_lo(b.im));
+    return (hi | lo) == 0u;
+}
+// |x| < ZERO_THR for either component, decided on the integer pipe from the high words (rare: q ~ 1.77 - 3e-4 i in ice);
+// inclusive of the threshold's own high word, so the exact test below still sees every candidate
+TAMM_HD bool maybe_tiny(cd q) {
+    const unsigned a = (unsigned)dbl_hi(q.re) & 0x7fffffffu, b = (unsigned)dbl_hi(q.im) & 0x7fffffffu;
+    return (a < b ? a : b) <= 0x3DDB7CDFu;          // high word of 1e-10
+}
 TAMM_HD cd clean_q(cd q) {  // layer_PPJ.py:199-203
     // (|x| == 0 needs no test of its own: zeroing a zero changes nothing that is observed later)
     return cd{fabs(q.re) < ZERO_THR ? 0.0 : q.re, fabs(q.im) < ZERO_THR ? 0.0 : q.im};
@@ -914,7 +932,7 @@ TAMM_HD void refine_root(const WaveCoef& w, cd& x, double sep2, double isep2, do
         cd h = -cmul_(f, crecip_s(tr));        // Newton step
         double hh = abs2(h);
         // Newton only when the error is well below the separation AND the step it proposes is small against it
-        if (TAMM_USUAL((err2 < sep2_400) && (hh <= sep2_16))) {
+        if (TAMM_USUAL(lt_hi(err2, sep2_400) && le_hi(hh, sep2_16))) {
             TAMM_STAT(newton);
             x = x + h;
             err2 = hh * hh * inewt;
@@ -925,7 +943,7 @@ TAMM_HD void refine_root(const WaveCoef& w, cd& x, double sep2, double isep2, do
             hh = abs2(h);
             err2 = hh * hh * ix2;
         }
-        if (err2 <= tol2) break;                  // conservative error bound below 3e-16 |x|
+        if (le_hi(err2, tol2)) break;             // conservative error bound below 3e-16 |x|
     }
 }
 
@@ -1364,13 +1382,16 @@ TAMM_HD int layer_modes(const LayerParams& lp, const LaneParams& ln, double zeta
 #pragma unroll
 #endif
     for (int k = 0; k < 4; ++k) {
-        const cd q = clean_q(sc.rv(k, 0));
-        sc.set_rv(k, 0, q);
+        cd q = sc.rv(k, 0);
+        if (TAMM_RARE(maybe_tiny(q))) {
+            q = clean_q(q);
+            sc.set_rv(k, 0, q);
+        }
         has_im = has_im || (q.im != 0.0);
         im_mask |= (q.im >= 0.0 ? 1 : 0) << k;
         re_mask |= (q.re > 0.0 ? 1 : 0) << k;
         cd Ex = sc.rv(k, 1), Ey = sc.rv(k, 2);
-        if (abs2(Ex) + abs2(Ey) == 0.0) { Ex = mk(1.0); Ey = mk(0.0); }
+        if (TAMM_RARE(both_zero(Ex, Ey))) { Ex = mk(1.0); Ey = mk(0.0); }
         cd t = cmul_(q - D00, Ex);
         cfma(t, -D02, Ey);
         cd Hy = cmul_(t, iD01);
