@@ -641,3 +641,30 @@ def test_strongly_attenuating_deep_stack_both_returns_paths(eng):
             assert np.abs(got[n] - want[n])[rows].max() < h.ATOL_DB, (n, F)
         for n in ('dP_HH', 'dP_HV'):
             assert np.abs(got[n] - want[n])[rows].max() < h.ATOL_DB, (n, F)
+
+
+def test_peer_push_kernels_on_one_device(eng):
+    """tamm_peer_push (the final all-gather as stores into peer memory, include/tamm_b200.h) with both destinations on THIS
+    device: the unicast kernel in its 16-byte and 8-byte variants (a float64 array cut at an odd row is only 8-byte aligned),
+    ragged sizes around the 8-loads-in-flight main loop, and the argument checks.  The multicast variant needs a multicast
+    mapping and runs in tests/test_gpu_sharded.py on two GPUs."""
+    import torch
+    lib = eng.lib
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for n, off in ((8 * 1024 * 8 * 3 + 10, 0), (4099, 1), (2, 0), (3, 1), (1 << 20, 0)):        # doubles, source offset in doubles
+        src = torch.randn(n + off, dtype=torch.float64, device=eng.device)[off:]
+        d0 = torch.zeros(n + 3, dtype=torch.float64, device=eng.device)
+        d1 = torch.zeros(n + 3, dtype=torch.float64, device=eng.device)
+        for doff in (0, 1):
+            d0.zero_(); d1.zero_()
+            dst = (ctypes.c_ulonglong * 2)(d0.data_ptr() + 8 * doff, d1.data_ptr() + 8 * doff)
+            rc = lib.tamm_peer_push(src.data_ptr(), n * 8, dst, 2, 0, 4, st)
+            assert rc == 0, lib.tamm_last_error()
+            torch.cuda.synchronize()
+            for d in (d0, d1):
+                assert torch.equal(d[doff:doff + n], src) and d[:doff].abs().sum() == 0 and d[doff + n:].abs().sum() == 0
+    dst = (ctypes.c_ulonglong * 1)(d0.data_ptr() + 4)
+    assert lib.tamm_peer_push(src.data_ptr(), 16, dst, 1, 0, 4, st) != 0 and b'8 bytes' in lib.tamm_last_error()
+    assert lib.tamm_peer_push(src.data_ptr(), 16, dst, 0, 0, 4, st) != 0
+    dst = (ctypes.c_ulonglong * 1)(0)
+    assert lib.tamm_peer_push(src.data_ptr(), 16, dst, 1, 0, 4, st) != 0 and b'null' in lib.tamm_last_error()
