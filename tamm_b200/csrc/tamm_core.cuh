@@ -1673,6 +1673,55 @@ TAMM_HD void mul22(const cd a[4], const cd b[4], cd o[4]) {
 }
 
 // =================================================================================================
+// Returns tail, one (depth, azimuth) point (layerstack.py:249-278): received fields for the transmitted polarisation,
+// HH-VV coherence phase, field amplitudes.
+// =================================================================================================
+// Reference-like arithmetic (hypot like numpy.abs, true division): the two-pass kernels and the slow repeat of a tile.
+TAMM_HD void returns_point_ref(const cd m[4], cd e0, cd e1, int gtm_phase, cd& hh, cd& hv, cd& c, double& ahh, double& ahv) {
+    hh = dot2(m[0], e0, m[1], e1);             // get_Rx_all (layerstack.py:298)
+    hv = dot2(m[2], e0, m[3], e1);
+    const cd num = m[0] * conj(m[3]);          // c_HHVV (layerstack.py:271-273)
+    const double den = cabs_(m[0]) * cabs_(m[3]);
+    c = cd{num.re / den, num.im / den};
+    if (gtm_phase) c = cd{-c.re, c.im};        // -|c| exp(-i angle c) = -conj(c)   (layerstack.py:276-278)
+    ahh = cabs_(hh);
+    ahv = cabs_(hv);
+}
+TAMM_HD bool cd_is_zero(cd z) {                // exactly (+-0, +-0), on the integer pipe
+    return ((((unsigned)dbl_hi(z.re) | (unsigned)dbl_hi(z.im)) & 0x7fffffffu) | (unsigned)dbl_lo(z.re) | (unsigned)dbl_lo(z.im)) == 0u;
+}
+// Fast arithmetic of the fused kernel: |.| through rsqrt of the squared modulus, the coherence normaliser as ONE rsqrt of
+// |m0|^2 |m3|^2.  That product / those squares leave the normal range once a modulus is below ~1e-75 / ~1e-148 (strongly
+// attenuating deep stacks) or a value is inf or NaN.  The point then only raises `bad` (return value); the CTA repeats its
+// whole depth tile afterwards with returns_point_ref, so the result does not depend on which returns kernel F selects
+// and is finite exactly where the reference's is -- and the hot loop carries no call and no extra live state.
+TAMM_HD bool returns_point(const cd m[4], cd e0, cd e1, int gtm_phase, cd& hh, cd& hv, cd& c, double& ahh, double& ahv) {
+    hh = dot2(m[0], e0, m[1], e1);             // get_Rx_all (layerstack.py:298)
+    hv = dot2(m[2], e0, m[3], e1);
+    const double prod = abs2(m[0]) * abs2(m[3]), shh = abs2(hh), shv = abs2(hv);
+    // all three within 2^-980 ... 2^+980 (normal, with room to spare, not inf / NaN; prod = 0 when a modulus is 0): the high
+    // words of non-negative doubles order like the values, so this is two 3-way integer min/max and two compares
+    const unsigned hp = (unsigned)dbl_hi(prod), hh_ = (unsigned)dbl_hi(shh), hv_ = (unsigned)dbl_hi(shv);
+    const unsigned lo3 = hp < hh_ ? (hp < hv_ ? hp : hv_) : (hh_ < hv_ ? hh_ : hv_);
+    const unsigned hi3 = hp > hh_ ? (hp > hv_ ? hp : hv_) : (hh_ > hv_ ? hh_ : hv_);
+    bool bad = false;
+    if (TAMM_RARE(lo3 < 0x02B00000u || hi3 > 0x7D300000u)) {
+        // EXACT zeros are fine for the fast arithmetic (|0| = 0, 0/0 = NaN like the reference) and common: the cross-polar
+        // return vanishes identically on the symmetry azimuths at normal incidence.  Only a square that underflowed from a
+        // non-zero value, or an overflow / inf / NaN, needs the slow repeat.
+        bad = hi3 > 0x7D300000u || (hp < 0x02B00000u && !(cd_is_zero(m[0]) || cd_is_zero(m[3]))) ||
+              (hh_ < 0x02B00000u && !cd_is_zero(hh)) || (hv_ < 0x02B00000u && !cd_is_zero(hv));
+    }
+    const cd num = cmul_(m[0], conj(m[3]));    // c_HHVV (layerstack.py:271-278): num / (|m0| |m3|)
+    const double iden = frsqrt(prod);
+    c = cd{num.re * iden, num.im * iden};
+    if (gtm_phase) c = cd{-c.re, c.im};
+    ahh = fsqrt(shh);
+    ahv = fsqrt(shv);
+    return bad;
+}
+
+// =================================================================================================
 // Fujita--Paren model (modeltype='FP'): layer.py:100-128, layerstack.py:158-181.
 // Per layer the host supplies the horizontal eigenvalues ai_horiz and the eigen-angle of <c^2> in the fabric frame
 // (layer.py:77-79, computed with the reference's own numpy.linalg.eig so ordering and signs are its own).

@@ -509,41 +509,8 @@ __device__ __forceinline__ double warp_sum8(const double v[8], int lane) {
     return r;
 }
 
-// One (depth, azimuth) point of the returns tail (layerstack.py:249-278): received fields for the transmitted
-// polarisation, HH-VV coherence phase, field amplitudes.  Fast arithmetic: |.| through rsqrt of the squared modulus, the
-// coherence normaliser as ONE rsqrt of |m0|^2 |m3|^2.  That product / those squares leave the normal range once a modulus
-// is below ~1e-75 / ~1e-148 (strongly attenuating deep stacks) or a value is zero, inf or NaN.  The point then only
-// raises `bad`; the CTA repeats its whole depth tile afterwards with the arithmetic of the two-pass kernels (hypot like
-// numpy.abs, true division: returns_tile_slow), so the result does not depend on which returns kernel F selects and
-// is finite exactly where the reference's is -- and the hot loop carries no call and no extra live state.
-__device__ __forceinline__ bool returns_point(const cd m[4], cd e0, cd e1, int gtm_phase, cd& hh, cd& hv, cd& c, double& ahh,
-                                              double& ahv) {
-    hh = dot2(m[0], e0, m[1], e1);             // get_Rx_all (layerstack.py:298)
-    hv = dot2(m[2], e0, m[3], e1);
-    const double prod = abs2(m[0]) * abs2(m[3]), shh = abs2(hh), shv = abs2(hv);
-    // all three within 2^-980 ... 2^+980 (normal, with room to spare, not inf / NaN; prod = 0 when a modulus is 0): the high
-    // words of non-negative doubles order like the values, so this is two 3-way integer min/max and two compares
-    const unsigned hp = (unsigned)__double2hiint(prod), hh_ = (unsigned)__double2hiint(shh), hv_ = (unsigned)__double2hiint(shv);
-    bool bad = false;
-    if (TAMM_RARE(min(hp, min(hh_, hv_)) < 0x02B00000u || max(hp, max(hh_, hv_)) > 0x7D300000u)) {
-        // EXACT zeros are fine for the fast arithmetic (|0| = 0, 0/0 = NaN like the reference) and common: the cross-polar
-        // return vanishes identically on the symmetry azimuths at normal incidence.  Only a square that underflowed from a
-        // non-zero value, or an overflow / inf / NaN, needs the slow repeat.
-        auto is_zero = [](cd z) {
-            return ((((unsigned)__double2hiint(z.re) | (unsigned)__double2hiint(z.im)) & 0x7fffffffu) |
-                    (unsigned)__double2loint(z.re) | (unsigned)__double2loint(z.im)) == 0u;
-        };
-        bad = max(hp, max(hh_, hv_)) > 0x7D300000u || (hp < 0x02B00000u && !(is_zero(m[0]) || is_zero(m[3]))) ||
-              (hh_ < 0x02B00000u && !is_zero(hh)) || (hv_ < 0x02B00000u && !is_zero(hv));
-    }
-    const cd num = cmul_(m[0], conj(m[3]));    // c_HHVV (layerstack.py:271-278): num / (|m0| |m3|)
-    const double iden = tamm::frsqrt(prod);
-    c = cd{num.re * iden, num.im * iden};
-    if (gtm_phase) c = cd{-c.re, c.im};        // -|c| exp(-i angle c) = -conj(c)   (layerstack.py:276-278)
-    ahh = tamm::fsqrt(shh);
-    ahv = tamm::fsqrt(shv);
-    return bad;
-}
+// returns_point / returns_point_ref: the per-(depth, azimuth) arithmetic of the returns tail lives in tamm_core.cuh (shared with
+// the host simulator).
 
 // Cold repeat of one CTA's depth tile [nbeg, ne) of (profile p, frequency iq) with the reference-like arithmetic of
 // returns_kernel + the azimuth sums + the dB step; thread = azimuth, called by ALL threads of the CTA (it synchronises).
@@ -565,12 +532,10 @@ __device__ __noinline__ void returns_tile_slow(const cd* __restrict__ planes, co
             if (mode == TAMM_MODE_URD) { mm22(m, Dp, t); mm22(Up, t, m); }
             else { mm22(Up, m, t); m[0] = t[0]; m[1] = t[1]; m[2] = t[2]; m[3] = t[3]; }
         }
-        const cd hh = dot2(m[0], e0, m[1], e1), hv = dot2(m[2], e0, m[3], e1);
-        const cd num = m[0] * conj(m[3]);
-        const double den = cabs_(m[0]) * cabs_(m[3]);
-        cd c = cd{num.re / den, num.im / den};
-        if (gtm_phase) c = cd{-c.re, c.im};
-        const double ahh = live ? cabs_(hh) : 0.0, ahv = live ? cabs_(hv) : 0.0;
+        cd hh, hv, c;
+        double ahh, ahv;
+        returns_point_ref(m, e0, e1, gtm_phase, hh, hv, c, ahh, ahv);
+        if (!live) { ahh = 0.0; ahv = 0.0; }
         const size_t o = (((size_t)p * Q + iq) * NI + n) * F + (live ? ifr : F - 1);
         if (live) { st_cd(E_HH + o, hh); st_cd(E_HV + o, hv); st_cd(c_HHVV + o, c); }
         double sh = ahh, sv = ahv;

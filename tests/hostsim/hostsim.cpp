@@ -312,4 +312,17 @@ int hostsim_modes(const double* layers, const double* lanes, int N, int F, doubl
     return 0;
 }
 
+// The per-point arithmetic of the returns tail: fast path of the fused kernel (out[0..7] = hh, hv, c, |hh|, |hv|; returns the
+// `bad` flag) and the reference-like path (out[8..15]).  m: 4 complex, e: 2 complex.
+int hostsim_returns_point(const double* m, const double* e, int gtm_phase, double* out) {
+    cd mm[4]; for (int k = 0; k < 4; ++k) mm[k] = cd{m[2 * k], m[2 * k + 1]};
+    const cd e0{e[0], e[1]}, e1{e[2], e[3]};
+    cd hh, hv, c; double ahh, ahv;
+    const bool bad = returns_point(mm, e0, e1, gtm_phase, hh, hv, c, ahh, ahv);
+    put(out, hh); put(out + 2, hv); put(out + 4, c); out[6] = ahh; out[7] = ahv;
+    returns_point_ref(mm, e0, e1, gtm_phase, hh, hv, c, ahh, ahv);
+    put(out + 8, hh); put(out + 10, hv); put(out + 12, c); out[14] = ahh; out[15] = ahv;
+    return bad ? 1 : 0;
+}
+
 }  // extern "C"

@@ -378,3 +378,54 @@ def test_near_degenerate_pair_crossing_at_oblique_incidence(sim):
         assert abs(qs[0, n, 0] - qs[0, n, 1]) > 0.5 * split[n]
     # only pairs whose two refinements actually met go to the cold solver; there the deflation step finds the partner
     assert 0 < st['collapsed'] <= M and st['fallback'] == st['collapsed'] and st['recentre'] > 0
+
+
+def test_returns_point_fast_and_reference_arithmetic(sim):
+    """The per-point arithmetic of the returns kernels (tamm_core.cuh: returns_point = fused kernel, returns_point_ref =
+    two-pass kernels and the slow tile repeat) against numpy (layerstack.py:249-278): ordinary values agree to rounding and
+    are not flagged; exact zeros (cross-polar nulls) stay on the fast path with the reference's results (|0| = 0, 0/0 = NaN);
+    squares that underflow from non-zero values, overflow, inf and NaN are flagged for the slow repeat, whose arithmetic is
+    numpy's."""
+    rng = np.random.default_rng(5)
+    e = np.array([1e3, 0.0, 0.0, 0.0])
+    out = np.zeros(16)
+
+    def run(m, gtm=1):
+        m = np.ascontiguousarray(np.asarray(m, dtype=np.complex128))
+        bad = sim.hostsim_returns_point(_P(m.view(np.float64)), _P(e), gtm, _P(out))
+        return bad, out.copy()
+
+    def want(m, gtm=1):
+        m = np.asarray(m, dtype=np.complex128)
+        hh, hv = m[0] * 1e3, m[2] * 1e3
+        with np.errstate(all='ignore'):
+            c = (m[0] * np.conj(m[3])) / (np.abs(m[0]) * np.abs(m[3]))
+            if gtm:
+                c = -np.abs(c) * np.exp(-1j * np.angle(c))
+        return hh, hv, c, np.abs(hh), np.abs(hv)
+
+    for scale in (1.0, 1e-7, 1e-60, 1e60):
+        for _ in range(50):
+            m = scale * (rng.normal(size=4) + 1j * rng.normal(size=4))
+            bad, o = run(m)
+            hh, hv, c, ahh, ahv = want(m)
+            assert bad == 0
+            for base in (0, 8):
+                assert abs(complex(o[base], o[base + 1]) - hh) <= 4e-16 * abs(hh) and abs(complex(o[base + 2], o[base + 3]) - hv) <= 4e-16 * abs(hv)
+                assert abs(complex(o[base + 4], o[base + 5]) - c) < 1e-15
+                assert abs(o[base + 6] - ahh) <= 4e-16 * ahh and abs(o[base + 7] - ahv) <= 4e-16 * ahv
+    # exact zeros: not flagged; fast results equal numpy's special values
+    bad, o = run([1 + 1j, 0.5, 0.0, 2 - 1j])              # E_HV == 0 exactly
+    assert bad == 0 and o[7] == 0.0 and o[6] > 0 and abs(complex(o[4], o[5])) == pytest.approx(1.0, abs=1e-15)
+    bad, o = run([0.0, 0.5, 0.3j, 2 - 1j])                # URD_hh == 0 exactly -> 0/0 coherence
+    assert bad == 0 and np.isnan(o[4]) and np.isnan(o[12]) and o[6] == 0.0
+    # underflow from non-zero values, overflow, inf, NaN: flagged, and the reference path is numpy's arithmetic
+    for m in ([1e-160 + 1e-161j, 0, 3e-170, 2e-158], [1e-80, 0, 1e-3, 1e-80j], [1e170, 0, 1.0, 1.0], [np.inf, 0, 1.0, 1.0],
+              [np.nan, 0, 1.0, 1.0], [1.0, 0, 1e-160, 1.0]):
+        bad, o = run(m)
+        assert bad == 1, m
+        hh, hv, c, ahh, ahv = want(m)
+        for got, w in ((o[14], ahh), (o[15], ahv)):
+            assert (np.isnan(w) and np.isnan(got)) or got == w or abs(got - w) <= 4e-16 * abs(w), (m, got, w)
+        if np.isfinite(c):
+            assert abs(complex(o[12], o[13]) - c) < 1e-15, m
