@@ -385,7 +385,7 @@ def hbm_peak():
 
 def stack_sass_md5(lib_path):
     """md5 of the disassembly of the stack kernel (URD, 384 x 1, mu = 1) in the loaded library: identifies the device code the
-    committed ncu capture was taken on, independent of host-side or other-kernel changes (same recipe as tools/sass_md5.sh)."""
+    committed ncu capture was taken on, independent of host-side or other-kernel changes (`python tools/sass_md5.py` prints it)."""
     import hashlib
     cu = '/usr/local/cuda/bin/cuobjdump'
     names = subprocess.run([cu, '-sass', lib_path], capture_output=True, text=True, timeout=120).stdout

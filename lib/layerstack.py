@@ -234,7 +234,7 @@ class LayerStack:
     def _solve_returns(self, E0, f, alpha, pols, URD, shard=None):
         """Device part of get_returns / get_returns_polarimetric: ONE pass over the stack, one returns pass per transmit
         polarisation in `pols`, one device->host copy per polarisation, one synchronisation.
-        -> (list of dict name -> host array (Q, N-1, F) / (Q, N-1), zeta).
+        -> list (one entry per polarisation) of dict name -> host array (Q, N-1, F) / (Q, N-1).
         shard: tamm_b200.distributed.AxisShard or None -- split the azimuth grid or the frequency vector over the ranks of
         a process group."""
         self.epsiso = (2 * self.epsa[0] + self.epsc[0]) / 3                       # layerstack.py:236
