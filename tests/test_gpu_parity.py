@@ -668,3 +668,28 @@ def test_peer_push_kernels_on_one_device(eng):
     assert lib.tamm_peer_push(src.data_ptr(), 16, dst, 0, 0, 4, st) != 0
     dst = (ctypes.c_ulonglong * 1)(0)
     assert lib.tamm_peer_push(src.data_ptr(), 16, dst, 1, 0, 4, st) != 0 and b'null' in lib.tamm_last_error()
+
+
+def test_config4_unchunked_bench_launch(eng):
+    """The launch shape bench.py uses on one GPU since round 2: 313 profiles x 5000 layers x 181 azimuths = exactly one wave of
+    384-lane CTAs, every thread walking the WHOLE depth (no chunks, no scan, no prefix fix-up in the returns kernel).  The
+    first 313 profiles of the bench ensemble through the batched public API in one block; three of them against the oracle on
+    12 azimuths x all 4,999 interfaces, and the power identities for those."""
+    from tamm_b200 import EnsembleStack
+    B, N, F = 313, 5000, 181
+    assert eng.suggest_chunk(B, N, F) == N - 1                       # the heuristic really leaves this launch uncut
+    nlm, z = profiles.ensemble(B, N)
+    alpha = np.deg2rad(10.0)
+    ens = EnsembleStack(nlm, z, N_frames=F)
+    got = ens.get_returns(1e3, f=179e6, alpha=alpha, batch=B, outputs=('E_HH', 'E_HV', 'c_HHVV', 'Pm_HH', 'dP_HV'))
+    assert got['E_HH'].shape == (B, N - 1, F)
+    idx = np.linspace(0, F - 1, 12).round().astype(int)
+    for p in (0, 157, 312):
+        want = orc.returns_from_URD(h.oracle_urd_parallel(nlm[p], z, F, 179e6, alpha, sel=idx), 1e3)
+        for name, k in (('E_HH', 5), ('E_HV', 6)):
+            assert h.peak_rel_err(got[name][p][:, idx], want[k], axis=0) < h.RTOL_COMPLEX, (name, p)
+        assert np.abs(got['c_HHVV'][p][:, idx] - want[4]).max() < 10 * C_HHVV_ATOL, p
+        amp_hh, amp_hv = np.abs(got['E_HH'][p]), np.abs(got['E_HV'][p])
+        assert np.abs(got['Pm_HH'][p] - 20 * np.log10(amp_hh.mean(axis=1))).max() < h.ATOL_DB
+        pm_hv = 20 * np.log10(amp_hv.mean(axis=1))
+        assert np.abs(got['dP_HV'][p] - (20 * np.log10(amp_hv) - pm_hv[:, None])).max() < h.ATOL_DB
