@@ -686,9 +686,16 @@ def test_config4_unchunked_bench_launch(eng):
     idx = np.linspace(0, F - 1, 12).round().astype(int)
     for p in (0, 157, 312):
         want = orc.returns_from_URD(h.oracle_urd_parallel(nlm[p], z, F, 179e6, alpha, sel=idx), 1e3)
+        exact = orc.returns_from_URD(h.oracle_urd_parallel(nlm[p], z, F, 179e6, alpha, sel=idx, eig='factored',
+                                                          precision='extended').astype(np.complex128), 1e3)
+        sc = h.field_scale(dict(E_HH=want[5], E_HV=want[6]))
+        rep = {}
         for name, k in (('E_HH', 5), ('E_HV', 6)):
-            assert h.peak_rel_err(got[name][p][:, idx], want[k], axis=0) < h.RTOL_COMPLEX, (name, p)
-        assert np.abs(got['c_HHVV'][p][:, idx] - want[4]).max() < 10 * C_HHVV_ATOL, p
+            rep[name] = _arbiter_rule(got[name][p][:, idx], want[k], exact[k], h.RTOL_COMPLEX * sc, name)
+        # unit-modulus coherence = element-wise relative accuracy of URD_hh, URD_vv down to returns 1e2 below the peak: judged
+        # against the extended-precision answer (arbiter rule), not by a blanket constant
+        rep['c_HHVV'] = _arbiter_rule(got['c_HHVV'][p][:, idx], want[4], exact[4], np.full(want[4].shape, C_HHVV_ATOL), 'c_HHVV')
+        h.record('configs[4] unchunked 313-profile launch, profile %d: (dev-ref, dev-exact, ref-exact) / tol' % p, {k: list(v) for k, v in rep.items()})
         amp_hh, amp_hv = np.abs(got['E_HH'][p]), np.abs(got['E_HV'][p])
         assert np.abs(got['Pm_HH'][p] - 20 * np.log10(amp_hh.mean(axis=1))).max() < h.ATOL_DB
         pm_hv = 20 * np.log10(amp_hv.mean(axis=1))
