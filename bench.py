@@ -412,15 +412,21 @@ def stack_traffic(c, evals_per_launch):
         return None, 'none: %s' % repr(e)[:80]
 
 
-def stack_roofline(c, stack_ms, stack_evals, launches, step_ms_total, evals_per_launch, kernel):
+def stack_roofline(c, stack_ms, stack_evals, launches, step_ms_total, evals_per_launch, kernel, flop_per_eval=F_ALG_STACK,
+                   capture='stack_kernel'):
+    """flop_per_eval: 3960 for stack_kernel (stages A-G), 4000 for stack_returns_kernel (it also runs stage H, the returns
+    tail).  capture: which kernel the committed ncu traffic capture describes (None: no capture of this kernel exists)."""
     peak, src = fp64_peak(c)
     rate = stack_evals / (stack_ms * 1e-3)
-    achieved = rate * F_ALG_STACK / 1e12
-    traffic, tsrc = stack_traffic(c, evals_per_launch)
+    achieved = rate * flop_per_eval / 1e12
+    if capture is None:
+        traffic, tsrc = None, 'none: no ncu capture of this kernel (its stores are the 64 B/eval of results, as stack_kernel\'s planes)'
+    else:
+        traffic, tsrc = stack_traffic(c, evals_per_launch)
     return dict(bound='fp64', kernel=kernel, achieved=achieved, peak=peak, unit='TFLOP/s', frac=achieved / peak,
                 frac_of_nominal=achieved / FP64_NOMINAL, nominal_peak=FP64_NOMINAL,
                 nominal_peak_source='148 SMs x 64 DFMA/clk/SM x 2 flop x 1.965 GHz', traffic=traffic, traffic_source=tsrc,
-                peak_source=src, flop_per_eval=F_ALG_STACK, evals_per_launch=evals_per_launch,
+                peak_source=src, flop_per_eval=flop_per_eval, evals_per_launch=evals_per_launch,
                 avg_launch_ms=stack_ms / max(1, launches), share_of_step=(stack_ms / step_ms_total) if c.world == 1 else None,
                 hbm_alg_bytes_per_eval=64.5, hbm_achieved_gbs=rate * 64.5 / 1e9)
 
@@ -595,6 +601,7 @@ def bench_single(c, args, w, emit):
 def bench_ensemble(c, args, w, emit):
     torch, dist, tdist, eng, dev = c.torch, c.dist, c.tdist, c.eng, c.dev
     from tamm_b200 import EnsembleStack, packing, profiles, shard_range
+    from tamm_b200 import engine as tengine
     from tamm_b200.engine import MODE_URD
     rank, world = c.rank, c.world
     P, N, F = w['profiles'], w['layers'], w['frames']
@@ -617,6 +624,12 @@ def bench_ensemble(c, args, w, emit):
     planes = eng.empty((B, NI, 4, F), cdt)
     status = eng.empty((Pl,), torch.int32)
     stack_events, returns_events = [], []
+    direct_cache = {}
+
+    def is_direct(nprof):
+        if nprof not in direct_cache:
+            direct_cache[nprof] = bool(tengine.DIRECT_RETURNS and eng.fills_device(nprof, N, F))
+        return direct_cache[nprof]
 
     def step(record=False, blk=B, pl=None, after_block=None):
         """One pass over the shard in launches of `blk` profiles (an int, or the list of block sizes of a gather schedule)."""
@@ -630,16 +643,27 @@ def bench_ensemble(c, args, w, emit):
             if record:
                 e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
                 e0.record()
-            res = eng.stack(layers_d[b0:b1], lanes_d, b1 - b0, N, 1, F, zeta, 1.0, MODE_URD, planes=pl[: b1 - b0],
-                            status=status[b0:b1])
+            o = {k: v[b0:b1] for k, v in out.items()}
+            direct = is_direct(b1 - b0)
+            if direct:
+                # a launch that fills the device with whole-depth lanes: the returns tail runs inside the stack kernel
+                # (tamm_stack_returns, no planes); its two kernels are issued separately only to time them
+                eng.stack_returns(layers_d[b0:b1], lanes_d, b1 - b0, N, 1, F, zeta, etx, 1.0, True, out=o, status=status[b0:b1],
+                                  finish=False)
+            else:
+                res = eng.stack(layers_d[b0:b1], lanes_d, b1 - b0, N, 1, F, zeta, 1.0, MODE_URD, planes=pl[: b1 - b0],
+                                status=status[b0:b1])
             if record:
                 e1.record()
-                stack_events.append((e0, e1, (b1 - b0)))
-            eng.returns(res, etx, True, out={k: v[b0:b1] for k, v in out.items()})
+                stack_events.append((e0, e1, (b1 - b0), direct))
+            if direct:
+                eng.power_inplace(o)
+            else:
+                eng.returns(res, etx, True, out=o)
             if record:
                 e2 = torch.cuda.Event(enable_timing=True)
                 e2.record()
-                returns_events.append((e1, e2, (b1 - b0)))
+                returns_events.append((e1, e2, (b1 - b0), direct))
             if after_block is not None:
                 after_block(bi, b0, b1)
 
@@ -664,19 +688,38 @@ def bench_ensemble(c, args, w, emit):
     evals_job = w['evals']
     value = evals_job / (ms_per_step * 1e-3)
 
-    stack_ms = sum(a.elapsed_time(b) for a, b, _ in stack_events)
-    stack_evals = sum(n for _, _, n in stack_events) * float(N) * F
-    line = base_line(c, args, w, value, ms_per_step, launches, dict(profiles_per_launch=B))
-    line['roofline'] = stack_roofline(c, stack_ms, stack_evals, len(stack_events), ms_local, float(B) * N * F,
-                                      'stack_kernel<URD> (+ chunk_scan_kernel)')
-    try:   # second kernel of the step (HBM-bound): fused returns, 64 B/eval of planes in + 64 B/eval of returns out
-        ret_ms = sum(a.elapsed_time(b) for a, b, _ in returns_events)
-        ret_evals = sum(n for _, _, n in returns_events) * float(NI) * F
+    # the roofline describes the DOMINANT kernel of the step: the launches that fill the device (stack_returns_kernel when the
+    # direct path is on), or all stack launches otherwise
+    n_direct = sum(1 for e in stack_events if e[3])
+    sel = (lambda e: e[3]) if n_direct else (lambda e: True)
+    st_ev = [e for e in stack_events if sel(e)]
+    stack_ms = sum(a.elapsed_time(b) for a, b, _, _ in st_ev)
+    stack_evals = sum(n for _, _, n, _ in st_ev) * float(N) * F
+    line = base_line(c, args, w, value, ms_per_step, launches, dict(
+        profiles_per_launch=B, direct_returns=bool(n_direct),
+        launches_per_step=dict(whole_depth=n_direct // max(1, args.steps), chunked=(len(stack_events) - n_direct) // max(1, args.steps))))
+    if n_direct:
+        line['roofline'] = stack_roofline(c, stack_ms, stack_evals, len(st_ev), ms_local, float(B) * N * F,
+                                          'stack_returns_kernel (whole-depth lanes; returns tail applied in place, no planes)',
+                                          flop_per_eval=F_ALG, capture=None)
+        line['roofline']['note'] = ('%d of %d stack launches per step are whole-depth launches and timed here; the rest (a shard '
+                                    'remainder too small to fill the device) run stack_kernel + chunk_scan_kernel + '
+                                    'returns_fused_kernel' % (n_direct // max(1, args.steps), len(stack_events) // max(1, args.steps)))
+        line['roofline']['share_of_step'] = (stack_ms / ms_local) if world == 1 else None
+    else:
+        line['roofline'] = stack_roofline(c, stack_ms, stack_evals, len(st_ev), ms_local, float(B) * N * F,
+                                          'stack_kernel<URD> (+ chunk_scan_kernel)')
+    try:   # second kernel of the step (HBM-bound)
+        rt_ev = [e for e in returns_events if sel(e)]
+        ret_ms = sum(a.elapsed_time(b) for a, b, _, _ in rt_ev)
+        ret_evals = sum(n for _, _, n, _ in rt_ev) * float(NI) * F
         hp, hsrc = hbm_peak()
-        ret_gbs = ret_evals * 128.0 / (ret_ms * 1e-3) / 1e9
-        line['roofline_returns'] = dict(bound='hbm', kernel='returns_fused_kernel', achieved=ret_gbs, peak=hp, unit='GB/s',
-                                        frac=ret_gbs / hp, alg_bytes_per_eval=128.0, peak_source=hsrc,
-                                        avg_launch_ms=ret_ms / max(1, len(returns_events)),
+        # fused returns: 64 B/eval of planes in + 64 B/eval of returns out; in-place power pass: 16 B/eval of |E| in, 16 out
+        bpe, kname = (32.0, 'power_inplace_kernel') if n_direct else (128.0, 'returns_fused_kernel')
+        ret_gbs = ret_evals * bpe / (ret_ms * 1e-3) / 1e9
+        line['roofline_returns'] = dict(bound='hbm', kernel=kname, achieved=ret_gbs, peak=hp, unit='GB/s',
+                                        frac=ret_gbs / hp, alg_bytes_per_eval=bpe, peak_source=hsrc,
+                                        avg_launch_ms=ret_ms / max(1, len(rt_ev)),
                                         share_of_step=ret_ms / ms_local if world == 1 else None)
     except Exception as e:
         line['roofline_returns'] = dict(error=repr(e)[:200])

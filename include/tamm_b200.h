@@ -127,6 +127,27 @@ int tamm_returns(const void* planes, const void* workspace, int P, int N, int Q,
                  double* dP_HV, double* Pm_HH, double* Pm_HV, void* stream);
 
 /*
+ * Stack and returns in ONE call for a batch that fills the device with whole-depth lanes (P * Q * F of the order of
+ * SMs x 384 or more, e.g. 313 profiles x 181 azimuths on a B200): every thread walks all N layers of its lane, so the Jones
+ * matrix URD_n of an interface is final when it is formed and the kernel applies get_Rx_all (layerstack.py:291-301) and the
+ * per-point part of the returns tail (249-278) on the spot.  Nothing intermediate goes to HBM -- no planes, no workspace,
+ * no prefix fix-up: 64 B/eval written by the stack kernel, then one in-place pass over |E| (16 B/eval read, 16 written) for the
+ * azimuth mean and the dB step (257-267).  Same outputs, layouts and arithmetic per point as tamm_stack_urd(mode = URD)
+ * followed by tamm_returns; Pm may differ in the last bits (summation order over azimuth).  Correct for any batch size, but
+ * a small batch leaves most SMs idle -- use tamm_stack_urd's chunked launch there (tamm_suggest_chunk < N - 1).
+ * status as in tamm_stack_urd.  GTM only.
+ */
+int tamm_stack_returns(const double* layers, const double* lanes, int P, int N, int Q, int F, double zeta, double mu,
+                       const double* etx, int gtm_phase, int finish, void* E_HH, void* E_HV, void* c_HHVV, double* dP_HH,
+                       double* dP_HV, double* Pm_HH, double* Pm_HV, int* status, void* stream);
+/*
+ * The in-place pass on its own: amp_HH, amp_HV (double [P][Q][N-1][F]) hold |E| on entry and the anomalies dP on exit,
+ * Pm_* (double [P][Q][N-1]) receive the azimuth means in dB.  tamm_stack_returns(finish = 0) stops before this pass (|E| left
+ * in dP_*, Pm_* untouched and allowed to be NULL), e.g. to time the two kernels separately; finish != 0 runs it.
+ */
+int tamm_power_inplace(double* amp_HH, double* amp_HV, int P, int N, int Q, int F, double* Pm_HH, double* Pm_HV, void* stream);
+
+/*
  * The same returns with the azimuth mean split open, for a stack whose AZIMUTHS are sharded over several GPUs
  * (the mean over azimuth in Pm / dP, layerstack.py:262,266, is the only cross-lane operation of the path).
  *   tamm_returns_partial : E_HH, E_HV, c_HHVV as tamm_returns for the F local azimuths; amp_HH, amp_HV = |E| (double

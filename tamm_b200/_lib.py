@@ -27,6 +27,8 @@ SIGNATURES = {
     'tamm_stack_urd_fp': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     'tamm_export_jones': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     'tamm_returns': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, ctypes.POINTER(_d), _i] + [_vp] * 7 + [_vp]),
+    'tamm_stack_returns': (_i, [_vp, _vp, _i, _i, _i, _i, _d, _d, ctypes.POINTER(_d), _i, _i] + [_vp] * 7 + [_vp, _vp]),
+    'tamm_power_inplace': (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     'tamm_returns_partial': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, ctypes.POINTER(_d), _i] + [_vp] * 7 + [_vp]),
     'tamm_returns_finish': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
 }

@@ -111,12 +111,42 @@ struct ScratchShared {
 };
 
 // ---- the hot kernel ------------------------------------------------------------------------------
+// Internal third mode (not part of the ABI's `mode` argument): URD with the returns tail applied in place.  In a launch
+// whose threads walk the WHOLE depth (one chunk) URD_n is final the moment it is formed, so the thread applies the transmit
+// polarisation, the coherence and |E| itself (tamm::returns_point) and stores the returns directly -- the planes, their
+// 64 B/eval round trip through HBM and the prefix fix-up do not exist.  Only the azimuth mean (cross-lane) is left to a
+// second pass over |E| (power_inplace_kernel).  Entry point: tamm_stack_returns.
+constexpr int MODE_RET = 2;
+struct RetArgs {
+    cd e0, e1;                    // E0 * Tx polarisation                       layerstack.py:252, 298
+    cd *E_HH, *E_HV, *c_HHVV;     // [P][Q][N-1][F]
+    double *aHH, *aHV;            // |E_HH|, |E_HV| in the same layout (the dP arrays: finished in place by the second pass)
+    int F, gtm_phase;
+};
+
+// Out-of-range point of the direct returns (tamm::returns_point said `bad`): the reference-like arithmetic, stored from here.
+__device__ __noinline__ void returns_point_store_cold(double m0r, double m0i, double m1r, double m1i, double m2r, double m2i,
+                                                      double m3r, double m3i, double e0r, double e0i, double e1r, double e1i,
+                                                      int gtm_phase, cd* E_HH, cd* E_HV, cd* c_HHVV, double* aHH, double* aHV,
+                                                      size_t o) {
+    const cd m[4] = {cd{m0r, m0i}, cd{m1r, m1i}, cd{m2r, m2i}, cd{m3r, m3i}};
+    cd hh, hv, c;
+    double ahh, ahv;
+    returns_point_ref(m, cd{e0r, e0i}, cd{e1r, e1i}, gtm_phase, hh, hv, c, ahh, ahv);
+    *reinterpret_cast<double2*>(E_HH + o) = make_double2(hh.re, hh.im);
+    *reinterpret_cast<double2*>(E_HV + o) = make_double2(hv.re, hv.im);
+    *reinterpret_cast<double2*>(c_HHVV + o) = make_double2(c.re, c.im);
+    aHH[o] = ahh;
+    aHV[o] = ahv;
+}
+
 // grid = (lane blocks, chunks); block = TB threads (multiple of 32).
 // MU1: specialisation for mu == 1 (every multiplication by mu or 1/mu folds away)
 template <int MODE, bool MU1, int CSTR>
 __device__ __forceinline__ void
 stack_body(const double* __restrict__ layers, const double* __restrict__ lanes, int P, int N, int QF, int flat, double zeta,
-             double mu_arg, int chunk, int nchunks, cd* __restrict__ planes, cd* __restrict__ agg, int* __restrict__ status) {
+             double mu_arg, int chunk, int nchunks, cd* __restrict__ planes, cd* __restrict__ agg, int* __restrict__ status,
+             const RetArgs& ra) {
     const double mu = MU1 ? 1.0 : mu_arg;
     __shared__ alignas(128) double sbuf[2][NPMAX][TL * LAYER_STRIDE];
     __shared__ alignas(8) uint64_t bar[2];
@@ -196,6 +226,11 @@ stack_body(const double* __restrict__ layers, const double* __restrict__ lanes, 
     }
     int st = 0;
     cd* out = planes + ((size_t)p * NI * 4) * QF + lc;
+    size_t obase = 0;             // MODE_RET: element (p, iq, 0, ifr) of the [P][Q][N-1][F] return arrays, lane = iq * F + ifr
+    if (MODE == MODE_RET) {
+        const int iq = lc / ra.F, ifr = lc - iq * ra.F;
+        obase = (((size_t)p * (QF / ra.F) + iq) * NI) * ra.F + ifr;
+    }
 
 #pragma unroll 1
     for (int t = 0; t < ntile; ++t) {
@@ -262,7 +297,7 @@ stack_body(const double* __restrict__ layers, const double* __restrict__ lanes, 
                 cd pYt[4], pYr[4], D[4], U[4], o[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) { pYt[k] = CS_LD(k); pYr[k] = CS_LD(4 + k); D[k] = CS_LD(8 + k); U[k] = CS_LD(12 + k); }
-                if (MODE == TAMM_MODE_URD) {
+                if (MODE != TAMM_MODE_U) {
                     interface_fb<true>(pYt, pYr, cur, D, U, o);
                 } else {
                     cd pEr[4] = {CS_LD(8), CS_LD(9), CS_LD(10), CS_LD(11)};
@@ -270,16 +305,39 @@ stack_body(const double* __restrict__ layers, const double* __restrict__ lanes, 
                     cd dummy[4];
                     interface_fb<false>(pYt, pYr, cur, D, U, dummy);
                 }
-                if (live) {
-                    cd* op = out + (size_t)n * 4 * QF;
-                    // streaming stores: the planes are read back by another kernel, keep them out of the small L1
-                    st_cd_stream(op, o[0]);
-                    st_cd_stream(op + QF, o[1]);
-                    st_cd_stream(op + 2 * (size_t)QF, o[2]);
-                    st_cd_stream(op + 3 * (size_t)QF, o[3]);
-                }
+                if (MODE == MODE_RET) {
+                    // one chunk: o = URD_n is final.  Carry first (frees D, U), then the returns tail of this point
 #pragma unroll
-                for (int k = 0; k < 4; ++k) { if (MODE == TAMM_MODE_URD) CS_ST(8 + k, D[k]); CS_ST(12 + k, U[k]); }
+                    for (int k = 0; k < 4; ++k) { CS_ST(8 + k, D[k]); CS_ST(12 + k, U[k]); }
+                    cd hh, hv, cc;
+                    double ahh, ahv;
+                    const bool bad = returns_point(o, ra.e0, ra.e1, ra.gtm_phase, hh, hv, cc, ahh, ahv);
+                    const size_t oi = obase + (size_t)n * ra.F;
+                    if (live) {
+                        if (TAMM_RARE(bad)) {
+                            returns_point_store_cold(o[0].re, o[0].im, o[1].re, o[1].im, o[2].re, o[2].im, o[3].re, o[3].im,
+                                                     ra.e0.re, ra.e0.im, ra.e1.re, ra.e1.im, ra.gtm_phase, ra.E_HH, ra.E_HV,
+                                                     ra.c_HHVV, ra.aHH, ra.aHV, oi);
+                        } else {
+                            st_cd_stream(ra.E_HH + oi, hh);
+                            st_cd_stream(ra.E_HV + oi, hv);
+                            st_cd_stream(ra.c_HHVV + oi, cc);
+                            __stcs(ra.aHH + oi, ahh);
+                            __stcs(ra.aHV + oi, ahv);
+                        }
+                    }
+                } else {
+                    if (live) {
+                        cd* op = out + (size_t)n * 4 * QF;
+                        // streaming stores: the planes are read back by another kernel, keep them out of the small L1
+                        st_cd_stream(op, o[0]);
+                        st_cd_stream(op + QF, o[1]);
+                        st_cd_stream(op + 2 * (size_t)QF, o[2]);
+                        st_cd_stream(op + 3 * (size_t)QF, o[3]);
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) { if (MODE == TAMM_MODE_URD) CS_ST(8 + k, D[k]); CS_ST(12 + k, U[k]); }
+                }
             }
 #pragma unroll
             for (int k = 0; k < 4; ++k) { CS_ST(k, cur.Yt[k]); CS_ST(4 + k, cur.Yr[k]); if (MODE == TAMM_MODE_U) CS_ST(8 + k, cur.Er[k]); }
@@ -290,7 +348,7 @@ stack_body(const double* __restrict__ layers, const double* __restrict__ lanes, 
             cd* a = agg + (((size_t)p * QF + l) * nchunks + c) * 8;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                st_cd(a + k, MODE == TAMM_MODE_URD ? CS_LD(8 + k) : mk((k == 0 || k == 3) ? 1.0 : 0.0));   // MODE_U carries no D'
+                st_cd(a + k, MODE != TAMM_MODE_U ? CS_LD(8 + k) : mk((k == 0 || k == 3) ? 1.0 : 0.0));   // MODE_U carries no D'
                 st_cd(a + 4 + k, CS_LD(12 + k));
             }
         }
@@ -304,7 +362,15 @@ stack_body(const double* __restrict__ layers, const double* __restrict__ lanes, 
 #define TAMM_STACK_PASS layers, lanes, P, N, QF, flat, zeta, mu, chunk, nchunks, planes, agg, status
 // MAXT / MINB: launch bounds (register budget): (256,1) -> 255 regs, (192,2) -> 168 regs, (256,2) -> 128 regs, ...
 template <int MODE, int MAXT, int MINB, bool MU1>
-__global__ void __launch_bounds__(MAXT, MINB) stack_kernel(TAMM_STACK_ARGS) { stack_body<MODE, MU1, MAXT>(TAMM_STACK_PASS); }
+__global__ void __launch_bounds__(MAXT, MINB) stack_kernel(TAMM_STACK_ARGS) {
+    const RetArgs none{};      // dead for the plane-writing modes
+    stack_body<MODE, MU1, MAXT>(TAMM_STACK_PASS, none);
+}
+// the same walk with the returns tail applied in place (MODE_RET): no planes, one chunk
+template <int MAXT, int MINB, bool MU1>
+__global__ void __launch_bounds__(MAXT, MINB) stack_returns_kernel(TAMM_STACK_ARGS, const RetArgs ra) {
+    stack_body<MODE_RET, MU1, MAXT>(TAMM_STACK_PASS, ra);
+}
 
 // ---- Fujita--Paren stack (modeltype 'FP'): thread = (profile, lane, chunk); same planes/aggregate layout as stack_kernel
 __global__ void __launch_bounds__(128)
@@ -832,6 +898,47 @@ power_finish_kernel(double* __restrict__ aHH, double* __restrict__ aHV, const do
     }
 }
 
+// Sum and finish in ONE pass for rows that fit the warp's registers (F <= 32 * KMAX): one warp per (p, iq, n) row reads the
+// row's |E_HH|, |E_HV| once, sums them over azimuth (per-lane partial sums in index order, then a butterfly: fixed order,
+// deterministic), and writes the anomalies over them -- 16 B/eval read, 16 B/eval written.  Second pass of
+// tamm_stack_returns, whose stack kernel leaves |E| in the dP arrays.
+template <int KMAX>
+__global__ void __launch_bounds__(256)
+power_inplace_kernel(double* __restrict__ aHH, double* __restrict__ aHV, double* __restrict__ Pm_HH,
+                     double* __restrict__ Pm_HV, long nrows, int F) {
+    const int lane = threadIdx.x & 31;
+    const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= nrows) return;          // whole warps leave together
+    double* hp = aHH + (size_t)row * F;
+    double* vp = aHV + (size_t)row * F;
+    double h[KMAX], v[KMAX];
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+        const int f = lane + 32 * k;
+        h[k] = f < F ? __ldcs(hp + f) : 0.0;
+        v[k] = f < F ? __ldcs(vp + f) : 0.0;
+    }
+    double sh = 0.0, sv = 0.0;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) { sh += h[k]; sv += v[k]; }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        sh += __shfl_xor_sync(0xffffffffu, sh, off);
+        sv += __shfl_xor_sync(0xffffffffu, sv, off);
+    }
+    const double pmh = 20.0 * log10(sh / (double)F);                      // layerstack.py:262
+    const double pmv = 20.0 * log10(sv / (double)F);
+    if (lane == 0) { Pm_HH[row] = pmh; Pm_HV[row] = pmv; }
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+        const int f = lane + 32 * k;
+        if (f < F) {
+            __stcs(hp + f, 20.0 * log10_dev(h[k]) - pmh);                 // layerstack.py:261-267
+            __stcs(vp + f, 20.0 * log10_dev(v[k]) - pmv);
+        }
+    }
+}
+
 // The same two steps with ONE THREAD per (p, iq, n) row, for F < 32 (wideband sweeps: many frequencies, one or a few
 // azimuths -- a warp per row would idle 31 lanes): do_sum forms the local sums, do_finish the dB step.
 __global__ void __launch_bounds__(256)
@@ -1087,6 +1194,26 @@ int peer_push_launch(const void* src, size_t bytes, const unsigned long long* ds
 
 bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
+// azimuth mean of |E| (the only cross-lane operation of the path), dB, anomalies -- in place over arrays holding |E|
+int power_inplace_launch(double* aHH, double* aHV, double* Pm_HH, double* Pm_HV, long nrows, int F, cudaStream_t s) {
+    if (F < 32) {              // one thread per row
+        power_rows_kernel<<<(int)((nrows + 255) / 256), 256, 0, s>>>(aHH, aHV, Pm_HH, Pm_HV, Pm_HH, Pm_HV, nrows, F, F, 1, 1);
+    } else if (F <= 256) {     // one warp per row, the row in registers
+        const int grid = (int)((nrows + 7) / 8);
+        if (F <= 64) power_inplace_kernel<2><<<grid, 256, 0, s>>>(aHH, aHV, Pm_HH, Pm_HV, nrows, F);
+        else if (F <= 128) power_inplace_kernel<4><<<grid, 256, 0, s>>>(aHH, aHV, Pm_HH, Pm_HV, nrows, F);
+        else if (F <= 192) power_inplace_kernel<6><<<grid, 256, 0, s>>>(aHH, aHV, Pm_HH, Pm_HV, nrows, F);
+        else power_inplace_kernel<8><<<grid, 256, 0, s>>>(aHH, aHV, Pm_HH, Pm_HV, nrows, F);
+    } else {                   // long rows: sums through the Pm arrays, finished in place
+        const int grid = (int)((nrows + 7) / 8);
+        azimuth_sum_kernel<<<grid, 256, 0, s>>>(aHH, aHV, Pm_HH, Pm_HV, nrows, F);
+        CUDA_OK(cudaGetLastError());
+        power_finish_kernel<<<grid, 256, 0, s>>>(aHH, aHV, Pm_HH, Pm_HV, Pm_HH, Pm_HV, nrows, F, F);
+    }
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -1260,6 +1387,53 @@ int tamm_stack_urd(const double* layers, const double* lanes, int P, int N, int 
         CUDA_OK(cudaGetLastError());
     }
     return 0;
+}
+
+int tamm_stack_returns(const double* layers, const double* lanes, int P, int N, int Q, int F, double zeta, double mu,
+                       const double* etx, int gtm_phase, int finish, void* E_HH, void* E_HV, void* c_HHVV, double* dP_HH,
+                       double* dP_HV, double* Pm_HH, double* Pm_HV, int* status, void* stream) {
+    if (!layers || !lanes || !etx || !E_HH || !E_HV || !c_HHVV || !dP_HH || !dP_HV || (finish && (!Pm_HH || !Pm_HV)))
+        return fail("tamm_stack_returns: null pointer%s", "");
+    if (P < 1 || Q < 1 || F < 1) return fail("tamm_stack_returns: empty batch%s", "");
+    if (N < 2) return fail("tamm_stack_returns: need at least 2 layers (N=%s%ld)", "", N);
+    if (!aligned16(layers) || !aligned16(lanes) || !aligned16(E_HH) || !aligned16(E_HV) || !aligned16(c_HHVV))
+        return fail("tamm_stack_returns: buffers must be 16-byte aligned%s", "");
+    if (!(mu != 0.0)) return fail("tamm_stack_returns: mu must be non-zero%s", "");
+    if (!lanes_fit(Q, F)) return fail("tamm_stack_returns: Q * F does not fit an int%s", "");
+    const int QF = Q * F, NI = N - 1;
+    // one 384-thread CTA per SM (the batch variant of stack_kernel); every thread walks all N layers (chunk = N - 1)
+    constexpr int MAXT = 384;
+    int tb, flat;
+    long gx;
+    stack_geometry(P, QF, MAXT, &tb, &flat, &gx);
+    if (gx > 2147483647L) return fail("tamm_stack_returns: grid too large%s", "");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (status) CUDA_OK(cudaMemsetAsync(status, 0, (size_t)P * sizeof(int), s));
+    RetArgs ra;
+    ra.e0 = cd{etx[0], etx[1]}; ra.e1 = cd{etx[2], etx[3]};
+    ra.E_HH = (cd*)E_HH; ra.E_HV = (cd*)E_HV; ra.c_HHVV = (cd*)c_HHVV;
+    ra.aHH = dP_HH; ra.aHV = dP_HV;
+    ra.F = F; ra.gtm_phase = gtm_phase ? 1 : 0;
+    const size_t dyn = (size_t)CARRY_SLOTS * sizeof(double2) * MAXT;
+    dim3 grid((unsigned)gx, 1, 1);
+    if (mu == 1.0) {
+        CUDA_OK(cudaFuncSetAttribute(stack_returns_kernel<MAXT, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+        stack_returns_kernel<MAXT, 1, true><<<grid, tb, dyn, s>>>(layers, lanes, P, N, QF, flat, zeta, mu, NI, 1, nullptr, nullptr,
+                                                                   status, ra);
+    } else {
+        CUDA_OK(cudaFuncSetAttribute(stack_returns_kernel<MAXT, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+        stack_returns_kernel<MAXT, 1, false><<<grid, tb, dyn, s>>>(layers, lanes, P, N, QF, flat, zeta, mu, NI, 1, nullptr, nullptr,
+                                                                    status, ra);
+    }
+    CUDA_OK(cudaGetLastError());
+    if (!finish) return 0;
+    return power_inplace_launch(dP_HH, dP_HV, Pm_HH, Pm_HV, (long)P * Q * NI, F, s);
+}
+
+int tamm_power_inplace(double* amp_HH, double* amp_HV, int P, int N, int Q, int F, double* Pm_HH, double* Pm_HV, void* stream) {
+    if (!amp_HH || !amp_HV || !Pm_HH || !Pm_HV) return fail("tamm_power_inplace: null pointer%s", "");
+    if (P < 1 || N < 2 || Q < 1 || F < 1) return fail("tamm_power_inplace: bad sizes%s", "");
+    return power_inplace_launch(amp_HH, amp_HV, Pm_HH, Pm_HV, (long)P * Q * (N - 1), F, (cudaStream_t)stream);
 }
 
 int tamm_stack_urd_fp(const double* layers_fp, const double* lanes, int P, int N, int Q, int F, int chunk, void* planes,

@@ -6,6 +6,7 @@ Reference entry points covered: LayerStack.get_layerstack + get_T_R + get_URD / 
 get_returns (lib/layerstack.py:65-66, 76-132, 135-225, 232-301).
 """
 import ctypes
+import os
 
 import numpy as np
 
@@ -13,6 +14,11 @@ from . import _lib, packing
 
 MODE_URD = 0
 MODE_U = 1
+
+# Launches that fill the device with whole-depth lanes (Engine.fills_device) can go through tamm_stack_returns -- the returns
+# tail applied inside the stack kernel, no planes round trip -- instead of tamm_stack_urd + tamm_returns.  The batched callers
+# (EnsembleStack, bench.py) consult this switch; TAMM_B200_DIRECT_RETURNS=0 / 1 overrides it.
+DIRECT_RETURNS = os.environ.get('TAMM_B200_DIRECT_RETURNS', '0') != '0'
 
 
 def _torch():
@@ -174,6 +180,56 @@ class Engine:
         _lib.check(rc, self.lib)
         self.launches += 1 if (N - 1 + chunk - 1) // chunk <= 1 else 2
         return StackResult(planes, workspace, P, N, Q, F, mode, chunk, status)
+
+    def fills_device(self, P, N, QF):
+        """True when a launch of P profiles x QF lanes fills the device with whole-depth lanes, i.e. the chunk heuristic
+        (tamm_suggest_chunk) would not cut the depth at all -- the launch shape `stack_returns` is meant for."""
+        return N >= 2 and self.suggest_chunk(P, N, QF) >= N - 1
+
+    def stack_returns(self, layers, lanes, P, N, Q, F, zeta, etx, mu=1.0, gtm_phase=True, out=None, status=None, finish=True):
+        """Stack and returns of one launch in a single call (tamm_stack_returns): every thread walks the whole depth of its
+        lane and stores the returns of each interface directly, then one in-place pass forms the azimuth mean and the dB
+        values (`finish=False` stops before that pass: |E| left in out['dP_*'], continue with `power_inplace`).  No planes, no
+        workspace.  -> (out, status): the dict `returns` gives, the status words `stack` gives.  GTM, mode URD, one transmit polarisation; meant
+        for launches with `fills_device(P, N, Q * F)` -- smaller ones are correct but leave SMs idle."""
+        torch = _torch()
+        if np.iscomplexobj(zeta) and np.imag(zeta) != 0:
+            raise NotImplementedError('complex zeta is not supported')
+        zeta = float(np.real(zeta)); mu = float(mu)
+        QF, NI = Q * F, N - 1
+        assert layers.dtype == torch.float64 and layers.is_contiguous() and layers.numel() == P * N * packing.LAYER_STRIDE
+        assert lanes.dtype == torch.float64 and lanes.is_contiguous() and lanes.numel() == QF * packing.LANE_STRIDE
+        if out is None:
+            layout, total = self.returns_layout(P, Q, NI, F)
+            out = self.returns_views(self.empty((total,), torch.float64), layout)
+        for n in self.RETURN_NAMES:
+            want = (P, Q, NI) if n.startswith('Pm') else (P, Q, NI, F)
+            assert tuple(out[n].shape) == want and out[n].is_contiguous(), (n, tuple(out[n].shape), want)
+        if status is None:
+            status = torch.empty((P,), dtype=torch.int32, device=self.device)
+        assert status.dtype == torch.int32 and status.numel() >= P
+        e = (ctypes.c_double * 4)(float(np.real(etx[0])), float(np.imag(etx[0])), float(np.real(etx[1])), float(np.imag(etx[1])))
+        rc = self.lib.tamm_stack_returns(layers.data_ptr(), lanes.data_ptr(), P, N, Q, F, zeta, mu, e, 1 if gtm_phase else 0,
+                                         1 if finish else 0, out['E_HH'].data_ptr(), out['E_HV'].data_ptr(), out['c_HHVV'].data_ptr(),
+                                         out['dP_HH'].data_ptr(), out['dP_HV'].data_ptr(), out['Pm_HH'].data_ptr(),
+                                         out['Pm_HV'].data_ptr(), status.data_ptr(), self._stream())
+        _lib.check(rc, self.lib)
+        self.launches += 1 + (self._power_launches(F) if finish else 0)
+        return out, status
+
+    @staticmethod
+    def _power_launches(F):
+        return 2 if F > 256 else 1                # rows longer than 256 azimuths: sums and dB step in two kernels
+
+    def power_inplace(self, out):
+        """The second pass of `stack_returns(finish=False)`: out['dP_*'] hold |E| on entry and the anomalies on exit,
+        out['Pm_*'] receive the azimuth means in dB (layerstack.py:257-267)."""
+        P, Q, NI, F = out['dP_HH'].shape
+        rc = self.lib.tamm_power_inplace(out['dP_HH'].data_ptr(), out['dP_HV'].data_ptr(), P, NI + 1, Q, F,
+                                         out['Pm_HH'].data_ptr(), out['Pm_HV'].data_ptr(), self._stream())
+        _lib.check(rc, self.lib)
+        self.launches += self._power_launches(F)
+        return out
 
     def stack_fp(self, layers_fp, lanes, P, N, Q, F, chunk=None, planes=None, workspace=None):
         """Fujita--Paren stack (modeltype 'FP').  layers_fp: packing.pack_layers_fp device tensor (P, N, 10)."""

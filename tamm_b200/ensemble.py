@@ -11,9 +11,11 @@ into pinned host arrays; profile batches are double-buffered so the D2H copy of 
 import numpy as np
 
 from . import packing
+from . import engine as _engine
 from .engine import MODE_U, MODE_URD, get_engine
 
 RETURN_NAMES = ('Pm_HH', 'Pm_HV', 'dP_HH', 'dP_HV', 'c_HHVV', 'E_HH', 'E_HV')
+
 
 
 def _pinned_empty(shape, dtype):
@@ -159,6 +161,8 @@ class EnsembleStack:
         lanes = eng.to_device(packing.pack_lanes(beta, fa))
         lay_all = self._packed_pinned(fp)
         compute, copy = eng.current_stream(), eng.new_stream()
+        # one transmit polarisation, GTM, URD, azimuth mean local: blocks that fill the device skip the planes (tamm_stack_returns)
+        direct = _engine.DIRECT_RETURNS and len(pols) == 1 and not fp and mode == MODE_URD and not split_mean
         dev = [[None] * len(pols), [None] * len(pols)]
         done = [None, None]
         planes = [None, None]
@@ -169,6 +173,21 @@ class EnsembleStack:
             if done[k] is not None:
                 compute.wait_event(done[k])       # the previous D2H from this buffer set must have finished
             lay = lay_all[b0:b1].to(eng.device, non_blocking=True)          # H2D of this block's inputs, every call
+            if direct and eng.fills_device(b1 - b0, N, Q * F):
+                # a block that fills the device with whole-depth lanes: stack and returns in one call, no planes at all
+                if dev[k][0] is not None and dev[k][0]['E_HH'].shape[0] != b1 - b0:
+                    dev[k] = [None]
+                dev[k][0], st = eng.stack_returns(lay, lanes, b1 - b0, N, Q, F, zeta, etx[0], self.mu, True, out=dev[k][0])
+                status.append((b0, st))
+                ready = eng.new_event()
+                ready.record(compute)
+                with eng.on_stream(copy):
+                    copy.wait_event(ready)
+                    for n in outputs:
+                        outs[0][n][b0:b1].copy_(dev[k][0][n], non_blocking=True)
+                    done[k] = eng.new_event()
+                    done[k].record(copy)
+                continue
             if planes[k] is None or planes[k].shape[0] != b1 - b0:
                 planes[k] = eng.empty((b1 - b0, NI, 4, Q * F), torch.complex128)
                 dev[k] = [None] * len(pols)

@@ -76,6 +76,17 @@ class HostSimEngine:
         self.blocks.append(P)
         return SimpleNamespace(urd=urd, P=P, Q=Q, F=F, N=N, mode=mode, status=torch.zeros(P, dtype=torch.int32))
 
+    whole_depth_profiles = None                # fills_device threshold (profiles per launch); None: never
+
+    def fills_device(self, P, N, QF):
+        return self.whole_depth_profiles is not None and P >= self.whole_depth_profiles
+
+    def stack_returns(self, layers, lanes, P, N, Q, F, zeta, etx, mu=1.0, gtm_phase=True, out=None, status=None):
+        """As Engine.stack_returns: the whole depth in one chunk, returns applied per point -> (out, status)."""
+        res = self.stack(layers, lanes, P, N, Q, F, zeta, mu, 0, chunk=N - 1)
+        self.direct = getattr(self, 'direct', 0) + 1
+        return self.returns(res, etx, gtm_phase, out=out), res.status
+
     def stack_fp(self, layers_fp, lanes, P, N, Q, F, chunk=None, planes=None, workspace=None):
         lay, lan = layers_fp.numpy().reshape(P, N, -1), lanes.numpy().reshape(Q * F, -1)
         urd = np.zeros((P, Q, F, N - 1, 2, 2), dtype=np.complex128)

@@ -114,3 +114,26 @@ def test_status_word_is_reported(host_engine, monkeypatch):
     with pytest.warns(UserWarning, match=r'local indices \[3\]'):
         ens.get_returns(1e3, f=179e6, alpha=0.1, batch=2)
     assert ens.last_status.tolist() == [0, 0, 0, 1]
+
+
+def test_blocks_that_fill_the_device_take_the_direct_path(host_engine, monkeypatch):
+    """Blocks for which Engine.fills_device holds go through stack_returns (tamm_stack_returns: no planes); a ragged last
+    block falls back to stack + returns with its own buffers; polarimetric calls and the switch being off never use it."""
+    from tamm_b200 import engine as eng_mod
+    P, N, F = 5, 24, 5
+    nlm, z = profiles.ensemble(P, N, H=11.5, first=2)
+    alpha = np.deg2rad(10)
+    ens = EnsembleStack(nlm, z, N_frames=F)
+    host_engine.whole_depth_profiles = 2
+    monkeypatch.setattr(eng_mod, 'DIRECT_RETURNS', True)
+    got = ens.get_returns(1e3, f=179e6, alpha=alpha, batch=2)                # blocks 2, 2 (direct) and 1 (planes)
+    assert host_engine.blocks == [2, 2, 1] and host_engine.direct == 2
+    for p in range(P):
+        h.assert_parity([got[n][p] for n in h.RET_NAMES], _want(nlm[p], z, F, 179e6, alpha), None, c_atol=1e-7)
+    assert ens.last_status.tolist() == [0] * P
+    ens.get_returns_polarimetric(1e3, f=179e6, alpha=alpha, batch=2)
+    assert host_engine.direct == 2
+    monkeypatch.setattr(eng_mod, 'DIRECT_RETURNS', False)
+    got0 = ens.get_returns(1e3, f=179e6, alpha=alpha, batch=2, outputs=('Pm_HH', 'E_HV'))
+    assert host_engine.direct == 2
+    assert np.abs(got0['E_HV'] - got['E_HV']).max() < 1e-12 * np.abs(got['E_HV']).max()     # other chunking: rounding only
