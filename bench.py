@@ -68,10 +68,11 @@ def parse():
                          'comma list of power, fields, jones')
     ap.add_argument('--gather-block', type=int, default=0, help='profiles per pipelined gather block (0: a quarter of the shard)')
     ap.add_argument('--gather-blocks', default='', help='explicit comma list of gather block sizes per rank (e.g. from tdist.gather_schedule)')
-    ap.add_argument('--gather-mode', default='peer', choices=['nccl', 'peer', 'mc', 'uc', 'ce', 'both'],
-                    help='transports of the pipelined gather timed besides NCCL collectives: peer = stores into symmetric memory '
-                         '(multicast if available, else unicast); mc / uc / ce = that one only (ce: copy engines); both = peer + ce; '
-                         'nccl = none')
+    ap.add_argument('--gather-mode', default='nccl', choices=['nccl', 'peer', 'mc', 'uc', 'ce', 'both'],
+                    help='transports of the pipelined gather timed besides NCCL collectives: nccl = none (default: after an 8-GPU '
+                         'run of this repository the pool operators reported NVLink faults, Xid 137 / 145, so the peer-store '
+                         'transports are opt-in); peer = stores into symmetric memory (multicast if available, else unicast); '
+                         'mc / uc / ce = that one only (ce: copy engines); both = peer + ce')
     ap.add_argument('--push-ctas', type=int, default=8, help='CTAs of the peer-push kernel (tamm_peer_push)')
     return ap.parse_args()
 

@@ -79,13 +79,17 @@ if backend == 'nccl':
     for dtype, src in ((torch.complex128, table), (torch.float64, table.real.copy())):
         loc = torch.from_numpy(src[mine]).cuda()
         makers = [('nccl', lambda: tdist.PipelinedGather(Pt, B, (3, 5), dtype, loc.device))]
-        for mode in ('auto', 'uc', 'ce'):       # peer stores (multicast if the allocation has it), unicast stores, copy engines
+        # peer stores (multicast if the allocation has it), unicast stores, copy engines: opt-in (TAMM_TEST_PEER_STORES=1) since
+        # the pool operators reported NVLink faults (Xid 137 / 145) after an 8-GPU run of this repository
+        peer_stores = os.environ.get('TAMM_TEST_PEER_STORES', '0') != '0'
+        for mode in (('auto', 'uc', 'ce') if peer_stores else ()):
             makers.append((mode, lambda mode=mode: tdist.PeerGather(Pt, B, (3, 5), dtype, loc.device, mode=mode, ctas=2)))
         sched = [1, 2, 1]                                              # non-uniform rounds (tdist.gather_schedule)
         mine_s = tdist.block_cyclic_profiles(Pt, sched, rank, ws)
         loc_s = torch.from_numpy(src[mine_s]).cuda()
         makers.append(('nccl-sched', lambda: tdist.PipelinedGather(Pt, sched, (3, 5), dtype, loc.device)))
-        makers.append(('peer-sched', lambda: tdist.PeerGather(Pt, sched, (3, 5), dtype, loc.device, ctas=2)))
+        if peer_stores:
+            makers.append(('peer-sched', lambda: tdist.PeerGather(Pt, sched, (3, 5), dtype, loc.device, ctas=2)))
         for label, make in makers:
             pg = make()
             for rep in range(2):                                      # reuse of the same gather object

@@ -12,7 +12,13 @@ import pytest
 import helpers as h
 from tamm_b200 import packing, profiles
 
-pytestmark = pytest.mark.gpu
+# STATUS: written after the pool operators closed GPU access for this repository (round 2), so none of these tests has run on
+# hardware yet; the path they cover is opt-in (TAMM_B200_DIRECT_RETURNS=1, tamm_b200/engine.py) and nothing else depends on it.
+# Until a first green run they are non-strict xfail -- the report then says XPASS or XFAIL for each of them without deciding
+# the outcome of the parity suite -- and the file sorts last so that a fault in the new kernel cannot disturb earlier tests.
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(strict=False, reason='tamm_stack_returns has not run on hardware yet (GPU access closed before '
+                                                     'its first run); opt-in path, XPASS = verified')]
 
 NAMES = ('E_HH', 'E_HV', 'c_HHVV', 'dP_HH', 'dP_HV', 'Pm_HH', 'Pm_HV')
 

@@ -1,12 +1,12 @@
 #!/bin/bash
 # One GPU call for the direct-returns path (tamm_stack_returns), sized for the last ~3 GPU-minutes of the round:
-#   1. tests/test_gpu_direct.py            direct path == two-call path on small shapes (all F regimes, cold path, ABI, ensemble)
+#   1. tests/test_zz_gpu_direct.py            direct path == two-call path on small shapes (all F regimes, cold path, ABI, ensemble)
 #   2. bench configs[4], direct on / off   10 timed steps each, no e2e, no CPU arm
 #   3. the full-size unchunked launch test with the direct path on (oracle + arbiter on three profiles)
 # Everything lands in gpurun_out/r02d_*; each step has its own timeout so a late step cannot lose the earlier results.
 mkdir -p gpurun_out
 T0=$SECONDS
-timeout 60 python -m pytest tests/test_gpu_direct.py -m gpu -x -q > gpurun_out/r02d_tests_direct.log 2>&1
+timeout 60 python -m pytest tests/test_zz_gpu_direct.py -m gpu -x -q --runxfail > gpurun_out/r02d_tests_direct.log 2>&1
 echo "rc=$? t=$((SECONDS-T0))s" >> gpurun_out/r02d_tests_direct.log
 tail -3 gpurun_out/r02d_tests_direct.log
 B="python bench.py --config 4 --steps 10 --warmup 3 --no-e2e --no-cpu"
