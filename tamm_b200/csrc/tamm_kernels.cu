@@ -17,7 +17,15 @@
 //   export_kernel       HBM bound.  Prefix fix-up + transpose into the reference's (F, N-1, 2, 2) layout.
 //   layer_diag_kernel   per-(lane, layer) matrices for the `Layer` attribute API and the parity tests.
 #include <atomic>
+#ifndef TAMM_EMULATE
 #include <cuda_runtime.h>
+// kernel<<<grid, block, dynamic shared bytes, stream>>> and the dynamic shared-memory array of a kernel, spelled as macros so
+// that the test-only host emulation of the CUDA execution model (tests/cuda_emu: this file compiled by g++ with a shim header
+// force-included, one OS thread per CUDA thread) can replace the two pieces of CUDA syntax a host compiler cannot parse.  For
+// nvcc they expand to exactly the CUDA spelling.
+#define TAMM_KERNEL(grid, block, dyn, stream, ...) __VA_ARGS__<<<(grid), (block), (dyn), (stream)>>>
+#define TAMM_DYN_SMEM(T, name) extern __shared__ T name[]
+#endif
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -57,6 +65,7 @@ constexpr int CARRY_SLOTS = 34;   // 16-byte shared-memory slots per thread of s
 constexpr int NPMAX = 4;   // a CTA's lanes may span at most this many profiles (flattened lane mapping)
 
 // ---- mbarrier / bulk-copy (TMA) primitives -----------------------------------------------------
+#ifndef TAMM_EMULATE   // (the host emulation supplies mbar_* / tma_bulk_g2s with the same semantics)
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -84,6 +93,7 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+#endif
 
 __device__ __forceinline__ void st_cd(cd* p, cd v) { *reinterpret_cast<double2*>(p) = make_double2(v.re, v.im); }
 __device__ __forceinline__ void st_cd_stream(cd* p, cd v) { __stcs(reinterpret_cast<double2*>(p), make_double2(v.re, v.im)); }
@@ -148,8 +158,8 @@ stack_body(const double* __restrict__ layers, const double* __restrict__ lanes, 
              double mu_arg, int chunk, int nchunks, cd* __restrict__ planes, cd* __restrict__ agg, int* __restrict__ status,
              const RetArgs& ra) {
     const double mu = MU1 ? 1.0 : mu_arg;
-    __shared__ alignas(128) double sbuf[2][NPMAX][TL * LAYER_STRIDE];
-    __shared__ alignas(8) uint64_t bar[2];
+    __shared__ __align__(128) double sbuf[2][NPMAX][TL * LAYER_STRIDE];
+    __shared__ __align__(8) uint64_t bar[2];
 
     // Lane mapping.  flat != 0: the (profile, lane) pairs of the batch are flattened, g = p*QF + l, and a CTA takes
     // blockDim.x consecutive g (full CTAs for any QF; spans <= NPMAX profiles).  flat == 0: one CTA = one lane tile
@@ -211,7 +221,7 @@ stack_body(const double* __restrict__ layers, const double* __restrict__ lanes, 
     // (MODE_U, which carries no D'), 12-15 = U' (field basis, see tamm_core.cuh: LayerF), 16-31 = scratch of the mode
     // solve (ScratchShared), 32-33 = (cos b, sin b), (cos 2b, sin 2b) of this lane.  Keeping all of it out of the register file and out of local memory matters twice: the
     // register-hungry layer solve stays (nearly) spill-free, and nothing competes for the small L1 that remains.
-    extern __shared__ double2 carry[];
+    TAMM_DYN_SMEM(double2, carry);
     double2* cs = carry + threadIdx.x;
     constexpr int cstr = CSTR;      // slot stride = maximum CTA size of this instantiation (>= blockDim.x)
 #define CS_LD(slot) ld_cd(reinterpret_cast<const cd*>(cs + (slot) * cstr))
@@ -738,8 +748,8 @@ returns_tma_kernel(const cd* __restrict__ planes, const cd* __restrict__ pre, in
     static_assert(TNF == 4, "warp_sum8 reduces 2 * TNF = 8 values");
     constexpr int NW = BLOCK / 32;
     constexpr int NST = 2 * TNF;                        // depth stages in the ring
-    extern __shared__ double2 ring[];                   // [NST][4][BLOCK] complex128
-    __shared__ alignas(8) uint64_t bar[NST];
+    TAMM_DYN_SMEM(double2, ring);                       // [NST][4][BLOCK] complex128
+    __shared__ __align__(8) uint64_t bar[NST];
     __shared__ double red[NW][2 * TNF];
     __shared__ double tot[2 * TNF];
     __shared__ int s_bad;
@@ -1061,6 +1071,7 @@ layer_modes_kernel(const double* __restrict__ layers, const double* __restrict__
 //   unicast  : one st.global per destination buffer (fallback without multicast support).
 // A handful of CTAs saturate the sender side (the block is 1/N of what each GPU receives), so the push is launched on a
 // high-priority side stream next to the stack kernel of the NEXT block and costs it a few SMs for about a millisecond.
+#ifndef TAMM_EMULATE   // (emulation: a plain store to the one "replica" there is)
 __device__ __forceinline__ void multimem_st(uint4* mc, uint4 v) {
     asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(__uint_as_float(v.x)),
                  "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w))
@@ -1070,6 +1081,7 @@ __device__ __forceinline__ void multimem_st(uint2* mc, uint2 v) {
     asm volatile("multimem.st.weak.global.v2.f32 [%0], {%1, %2};" ::"l"(mc), "f"(__uint_as_float(v.x)), "f"(__uint_as_float(v.y))
                  : "memory");
 }
+#endif
 template <class V>
 struct PeerPtrs {
     V* p[16];
@@ -1182,11 +1194,11 @@ template <class V>
 int peer_push_launch(const void* src, size_t bytes, const unsigned long long* dst, int ndst, int multicast, int ctas, cudaStream_t s) {
     const size_t n = bytes / sizeof(V);
     if (multicast) {
-        peer_push_mc_kernel<V><<<ctas, 1024, 0, s>>>((const V*)src, (V*)dst[0], n);
+        TAMM_KERNEL(ctas, 1024, 0, s, peer_push_mc_kernel<V>)((const V*)src, (V*)dst[0], n);
     } else {
         PeerPtrs<V> pp;
         for (int d = 0; d < 16; ++d) pp.p[d] = (V*)(d < ndst ? dst[d] : 0ull);
-        peer_push_uc_kernel<V><<<ctas, 1024, 0, s>>>((const V*)src, pp, ndst, n);
+        TAMM_KERNEL(ctas, 1024, 0, s, peer_push_uc_kernel<V>)((const V*)src, pp, ndst, n);
     }
     CUDA_OK(cudaGetLastError());
     return 0;
@@ -1197,18 +1209,18 @@ bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 // azimuth mean of |E| (the only cross-lane operation of the path), dB, anomalies -- in place over arrays holding |E|
 int power_inplace_launch(double* aHH, double* aHV, double* Pm_HH, double* Pm_HV, long nrows, int F, cudaStream_t s) {
     if (F < 32) {              // one thread per row
-        power_rows_kernel<<<(int)((nrows + 255) / 256), 256, 0, s>>>(aHH, aHV, Pm_HH, Pm_HV, Pm_HH, Pm_HV, nrows, F, F, 1, 1);
+        TAMM_KERNEL((int)((nrows + 255) / 256), 256, 0, s, power_rows_kernel)(aHH, aHV, Pm_HH, Pm_HV, Pm_HH, Pm_HV, nrows, F, F, 1, 1);
     } else if (F <= 256) {     // one warp per row, the row in registers
         const int grid = (int)((nrows + 7) / 8);
-        if (F <= 64) power_inplace_kernel<2><<<grid, 256, 0, s>>>(aHH, aHV, Pm_HH, Pm_HV, nrows, F);
-        else if (F <= 128) power_inplace_kernel<4><<<grid, 256, 0, s>>>(aHH, aHV, Pm_HH, Pm_HV, nrows, F);
-        else if (F <= 192) power_inplace_kernel<6><<<grid, 256, 0, s>>>(aHH, aHV, Pm_HH, Pm_HV, nrows, F);
-        else power_inplace_kernel<8><<<grid, 256, 0, s>>>(aHH, aHV, Pm_HH, Pm_HV, nrows, F);
+        if (F <= 64) TAMM_KERNEL(grid, 256, 0, s, power_inplace_kernel<2>)(aHH, aHV, Pm_HH, Pm_HV, nrows, F);
+        else if (F <= 128) TAMM_KERNEL(grid, 256, 0, s, power_inplace_kernel<4>)(aHH, aHV, Pm_HH, Pm_HV, nrows, F);
+        else if (F <= 192) TAMM_KERNEL(grid, 256, 0, s, power_inplace_kernel<6>)(aHH, aHV, Pm_HH, Pm_HV, nrows, F);
+        else TAMM_KERNEL(grid, 256, 0, s, power_inplace_kernel<8>)(aHH, aHV, Pm_HH, Pm_HV, nrows, F);
     } else {                   // long rows: sums through the Pm arrays, finished in place
         const int grid = (int)((nrows + 7) / 8);
-        azimuth_sum_kernel<<<grid, 256, 0, s>>>(aHH, aHV, Pm_HH, Pm_HV, nrows, F);
+        TAMM_KERNEL(grid, 256, 0, s, azimuth_sum_kernel)(aHH, aHV, Pm_HH, Pm_HV, nrows, F);
         CUDA_OK(cudaGetLastError());
-        power_finish_kernel<<<grid, 256, 0, s>>>(aHH, aHV, Pm_HH, Pm_HV, Pm_HH, Pm_HV, nrows, F, F);
+        TAMM_KERNEL(grid, 256, 0, s, power_finish_kernel)(aHH, aHV, Pm_HH, Pm_HV, Pm_HH, Pm_HV, nrows, F, F);
     }
     CUDA_OK(cudaGetLastError());
     return 0;
@@ -1218,7 +1230,7 @@ int power_inplace_launch(double* aHH, double* aHV, double* Pm_HH, double* Pm_HV,
 
 extern "C" {
 
-int tamm_version(void) { return 200; }   // 2xx: round-2 ABI (returns_partial / _finish, layer_modes, peer_push; status zeroed by the library)
+int tamm_version(void) { return 201; }   // 2xx: round-2 ABI (returns_partial / _finish, layer_modes, peer_push; status zeroed by the library); 201: + stack_returns, power_inplace
 const char* tamm_last_error(void) { return g_err; }
 
 int tamm_check_device(int device) {
@@ -1234,7 +1246,7 @@ int tamm_check_device(int device) {
 
 int tamm_fp64_probe(double* out, int blocks, int iters, void* stream) {
     if (!out || blocks < 1 || iters < 1) return fail("tamm_fp64_probe: bad arguments%s", "");
-    fp64_probe_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(out, iters, 0.999999, 1e-9);
+    TAMM_KERNEL(blocks, 256, 0, (cudaStream_t)stream, fp64_probe_kernel)(out, iters, 0.999999, 1e-9);
     CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -1246,7 +1258,7 @@ int tamm_layer_matrices(const double* layers, const double* lanes, int N, int QF
     if (N < 1 || QF < 1) return fail("tamm_layer_matrices: empty problem%s", "");
     long tot = (long)N * QF;
     int grid = (int)((tot + 127) / 128);
-    layer_diag_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(layers, lanes, N, QF, zeta, mu, (cd*)A, (cd*)Ainv, (cd*)Mfwd,
+    TAMM_KERNEL(grid, 128, 0, (cudaStream_t)stream, layer_diag_kernel)(layers, lanes, N, QF, zeta, mu, (cd*)A, (cd*)Ainv, (cd*)Mfwd,
                                                                (cd*)Mrev, (cd*)qs, (cd*)gamma, (cd*)eps, (cd*)Delta,
                                                                (cd*)Py, (cd*)Kd, status);
     CUDA_OK(cudaGetLastError());
@@ -1258,7 +1270,7 @@ int tamm_layer_modes(const double* layers, const double* lanes, int N, int QF, d
     if (!layers || !lanes || !qs) return fail("tamm_layer_modes: null pointer%s", "");
     if (N < 1 || QF < 1) return fail("tamm_layer_modes: empty problem%s", "");
     const long tot = (long)N * QF;
-    layer_modes_kernel<<<(int)((tot + 127) / 128), 128, 0, (cudaStream_t)stream>>>(layers, lanes, N, QF, zeta, mu, (cd*)qs, status);
+    TAMM_KERNEL((int)((tot + 127) / 128), 128, 0, (cudaStream_t)stream, layer_modes_kernel)(layers, lanes, N, QF, zeta, mu, (cd*)qs, status);
     CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -1358,13 +1370,13 @@ int tamm_stack_urd(const double* layers, const double* lanes, int P, int N, int 
             CUDA_OK(cudaFuncSetAttribute(stack_kernel<MODE, MAXT, MINB, true>,                                          \
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,                                   \
                                          CARRY_SLOTS * (int)sizeof(double2) * MAXT));                                   \
-            stack_kernel<MODE, MAXT, MINB, true><<<grid, tb, dyn, s>>>(layers, lanes, P, N, QF, flat, zeta, mu, chunk,  \
+            TAMM_KERNEL(grid, tb, dyn, s, stack_kernel<MODE, MAXT, MINB, true>)(layers, lanes, P, N, QF, flat, zeta, mu, chunk,  \
                                                                         nch, (cd*)planes, agg, status);                 \
         } else {                                                                                                        \
             CUDA_OK(cudaFuncSetAttribute(stack_kernel<MODE, MAXT, MINB, false>,                                         \
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,                                   \
                                          CARRY_SLOTS * (int)sizeof(double2) * MAXT));                                   \
-            stack_kernel<MODE, MAXT, MINB, false><<<grid, tb, dyn, s>>>(layers, lanes, P, N, QF, flat, zeta, mu, chunk, \
+            TAMM_KERNEL(grid, tb, dyn, s, stack_kernel<MODE, MAXT, MINB, false>)(layers, lanes, P, N, QF, flat, zeta, mu, chunk, \
                                                                          nch, (cd*)planes, agg, status);                \
         }                                                                                                               \
     } while (0)
@@ -1383,7 +1395,7 @@ int tamm_stack_urd(const double* layers, const double* lanes, int P, int N, int 
         long nseq = (long)P * QF;
         cd* pre = agg + (size_t)nseq * nch * 8;
         int grid2 = (int)((nseq + 3) / 4);
-        chunk_scan_kernel<<<grid2, 128, 0, s>>>(agg, pre, nseq, nch);
+        TAMM_KERNEL(grid2, 128, 0, s, chunk_scan_kernel)(agg, pre, nseq, nch);
         CUDA_OK(cudaGetLastError());
     }
     return 0;
@@ -1418,11 +1430,11 @@ int tamm_stack_returns(const double* layers, const double* lanes, int P, int N, 
     dim3 grid((unsigned)gx, 1, 1);
     if (mu == 1.0) {
         CUDA_OK(cudaFuncSetAttribute(stack_returns_kernel<MAXT, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-        stack_returns_kernel<MAXT, 1, true><<<grid, tb, dyn, s>>>(layers, lanes, P, N, QF, flat, zeta, mu, NI, 1, nullptr, nullptr,
+        TAMM_KERNEL(grid, tb, dyn, s, stack_returns_kernel<MAXT, 1, true>)(layers, lanes, P, N, QF, flat, zeta, mu, NI, 1, nullptr, nullptr,
                                                                    status, ra);
     } else {
         CUDA_OK(cudaFuncSetAttribute(stack_returns_kernel<MAXT, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-        stack_returns_kernel<MAXT, 1, false><<<grid, tb, dyn, s>>>(layers, lanes, P, N, QF, flat, zeta, mu, NI, 1, nullptr, nullptr,
+        TAMM_KERNEL(grid, tb, dyn, s, stack_returns_kernel<MAXT, 1, false>)(layers, lanes, P, N, QF, flat, zeta, mu, NI, 1, nullptr, nullptr,
                                                                     status, ra);
     }
     CUDA_OK(cudaGetLastError());
@@ -1451,11 +1463,11 @@ int tamm_stack_urd_fp(const double* layers_fp, const double* lanes, int P, int N
     dim3 grid((unsigned)((G + 127) / 128), nch, 1);
     cudaStream_t s = (cudaStream_t)stream;
     cd* agg = (cd*)workspace;
-    fp_stack_kernel<<<grid, 128, 0, s>>>(layers_fp, lanes, P, N, QF, chunk, nch, (cd*)planes, agg);
+    TAMM_KERNEL(grid, 128, 0, s, fp_stack_kernel)(layers_fp, lanes, P, N, QF, chunk, nch, (cd*)planes, agg);
     CUDA_OK(cudaGetLastError());
     if (nch > 1) {
         cd* pre = agg + (size_t)G * nch * 8;
-        chunk_scan_kernel<<<(int)((G + 3) / 4), 128, 0, s>>>(agg, pre, G, nch);
+        TAMM_KERNEL((int)((G + 3) / 4), 128, 0, s, chunk_scan_kernel)(agg, pre, G, nch);
         CUDA_OK(cudaGetLastError());
     }
     return 0;
@@ -1468,7 +1480,7 @@ int tamm_export_jones(const void* planes, const void* workspace, int P, int N, i
     const int QF = Q * F, NI = N - 1, nch = nchunks_of(N, chunk);
     const cd* pre = nch > 1 ? (const cd*)workspace + (size_t)P * QF * nch * 8 : nullptr;
     dim3 grid((QF + 127) / 128, (NI + TN - 1) / TN, P);
-    export_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>((const cd*)planes, pre, N, QF, mode, chunk, nch, (cd*)out);
+    TAMM_KERNEL(grid, 128, 0, (cudaStream_t)stream, export_kernel)((const cd*)planes, pre, N, QF, mode, chunk, nch, (cd*)out);
     CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -1487,7 +1499,7 @@ int tamm_returns(const void* planes, const void* workspace, int P, int N, int Q,
         dim3 grid((NI + TNF * TNG - 1) / (TNF * TNG), Q, P);
         const cd e0 = cd{etx[0], etx[1]}, e1 = cd{etx[2], etx[3]};
 #define TAMM_RF(BLK)                                                                                                     \
-    returns_fused_kernel<BLK><<<grid, BLK, 0, s>>>((const cd*)planes, pre, N, Q, F, mode, chunk, nch, e0, e1, gtm_phase, \
+    TAMM_KERNEL(grid, BLK, 0, s, returns_fused_kernel<BLK>)((const cd*)planes, pre, N, Q, F, mode, chunk, nch, e0, e1, gtm_phase, \
                                                    (cd*)E_HH, (cd*)E_HV, (cd*)c_HHVV, dP_HH, dP_HV, Pm_HH, Pm_HV)
         // TMA-fed variant (rows must be 16-byte multiples: always true for complex128); TAMM_RETURNS_TMA=0 disables it
         static std::atomic<int> use_tma_once{-1};
@@ -1501,7 +1513,7 @@ int tamm_returns(const void* planes, const void* workspace, int P, int N, int Q,
     do {                                                                                                                 \
         const int dyn = 2 * TNF * 4 * BLK * (int)sizeof(double2);                                                        \
         CUDA_OK(cudaFuncSetAttribute(returns_tma_kernel<BLK>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));        \
-        returns_tma_kernel<BLK><<<grid, BLK, dyn, s>>>((const cd*)planes, pre, N, Q, F, mode, chunk, nch, e0, e1,        \
+        TAMM_KERNEL(grid, BLK, dyn, s, returns_tma_kernel<BLK>)((const cd*)planes, pre, N, Q, F, mode, chunk, nch, e0, e1,        \
                                                        gtm_phase, (cd*)E_HH, (cd*)E_HV, (cd*)c_HHVV, dP_HH, dP_HV,      \
                                                        Pm_HH, Pm_HV);                                                    \
     } while (0)
@@ -1525,20 +1537,20 @@ int tamm_returns(const void* planes, const void* workspace, int P, int N, int Q,
         return 0;
     }
     dim3 grid((QF + 127) / 128, (NI + TN - 1) / TN, P);
-    returns_kernel<<<grid, 128, 0, s>>>((const cd*)planes, pre, N, Q, F, mode, chunk, nch, cd{etx[0], etx[1]},
+    TAMM_KERNEL(grid, 128, 0, s, returns_kernel)((const cd*)planes, pre, N, Q, F, mode, chunk, nch, cd{etx[0], etx[1]},
                                         cd{etx[2], etx[3]}, gtm_phase, (cd*)E_HH, (cd*)E_HV, (cd*)c_HHVV, dP_HH, dP_HV);
     CUDA_OK(cudaGetLastError());
     long nrows = (long)P * Q * NI;
     if (F < 32) {   // one thread per row: sums and dB step in one launch
-        power_rows_kernel<<<(int)((nrows + 255) / 256), 256, 0, s>>>(dP_HH, dP_HV, Pm_HH, Pm_HV, Pm_HH, Pm_HV, nrows, F, F, 1, 1);
+        TAMM_KERNEL((int)((nrows + 255) / 256), 256, 0, s, power_rows_kernel)(dP_HH, dP_HV, Pm_HH, Pm_HV, Pm_HH, Pm_HV, nrows, F, F, 1, 1);
         CUDA_OK(cudaGetLastError());
         return 0;
     }
     int grid2 = (int)((nrows + 7) / 8);
     // the sums go through the Pm arrays (finished in place)
-    azimuth_sum_kernel<<<grid2, 256, 0, s>>>(dP_HH, dP_HV, Pm_HH, Pm_HV, nrows, F);
+    TAMM_KERNEL(grid2, 256, 0, s, azimuth_sum_kernel)(dP_HH, dP_HV, Pm_HH, Pm_HV, nrows, F);
     CUDA_OK(cudaGetLastError());
-    power_finish_kernel<<<grid2, 256, 0, s>>>(dP_HH, dP_HV, Pm_HH, Pm_HV, Pm_HH, Pm_HV, nrows, F, F);
+    TAMM_KERNEL(grid2, 256, 0, s, power_finish_kernel)(dP_HH, dP_HV, Pm_HH, Pm_HV, Pm_HH, Pm_HV, nrows, F, F);
     CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -1554,14 +1566,14 @@ int tamm_returns_partial(const void* planes, const void* workspace, int P, int N
     const cd* pre = nch > 1 ? (const cd*)workspace + (size_t)P * QF * nch * 8 : nullptr;
     cudaStream_t s = (cudaStream_t)stream;
     dim3 grid((QF + 127) / 128, (NI + TN - 1) / TN, P);
-    returns_kernel<<<grid, 128, 0, s>>>((const cd*)planes, pre, N, Q, F, mode, chunk, nch, cd{etx[0], etx[1]},
+    TAMM_KERNEL(grid, 128, 0, s, returns_kernel)((const cd*)planes, pre, N, Q, F, mode, chunk, nch, cd{etx[0], etx[1]},
                                         cd{etx[2], etx[3]}, gtm_phase, (cd*)E_HH, (cd*)E_HV, (cd*)c_HHVV, amp_HH, amp_HV);
     CUDA_OK(cudaGetLastError());
     const long nrows = (long)P * Q * NI;
     if (F < 32)
-        power_rows_kernel<<<(int)((nrows + 255) / 256), 256, 0, s>>>(amp_HH, amp_HV, sum_HH, sum_HV, nullptr, nullptr, nrows, F, F, 1, 0);
+        TAMM_KERNEL((int)((nrows + 255) / 256), 256, 0, s, power_rows_kernel)(amp_HH, amp_HV, sum_HH, sum_HV, nullptr, nullptr, nrows, F, F, 1, 0);
     else
-        azimuth_sum_kernel<<<(int)((nrows + 7) / 8), 256, 0, s>>>(amp_HH, amp_HV, sum_HH, sum_HV, nrows, F);
+        TAMM_KERNEL((int)((nrows + 7) / 8), 256, 0, s, azimuth_sum_kernel)(amp_HH, amp_HV, sum_HH, sum_HV, nrows, F);
     CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -1572,10 +1584,10 @@ int tamm_returns_finish(double* amp_HH, double* amp_HV, const double* sum_HH, co
     if (P < 1 || N < 2 || Q < 1 || F < 1 || F_total < F) return fail("tamm_returns_finish: bad sizes%s", "");
     const long nrows = (long)P * Q * (N - 1);
     if (F < 32)
-        power_rows_kernel<<<(int)((nrows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        TAMM_KERNEL((int)((nrows + 255) / 256), 256, 0, (cudaStream_t)stream, power_rows_kernel)(
             amp_HH, amp_HV, const_cast<double*>(sum_HH), const_cast<double*>(sum_HV), Pm_HH, Pm_HV, nrows, F, F_total, 0, 1);
     else
-        power_finish_kernel<<<(int)((nrows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(amp_HH, amp_HV, sum_HH, sum_HV, Pm_HH,
+        TAMM_KERNEL((int)((nrows + 7) / 8), 256, 0, (cudaStream_t)stream, power_finish_kernel)(amp_HH, amp_HV, sum_HH, sum_HV, Pm_HH,
                                                                                       Pm_HV, nrows, F, F_total);
     CUDA_OK(cudaGetLastError());
     return 0;

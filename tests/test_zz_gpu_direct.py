@@ -29,6 +29,13 @@ def eng(built):
     return get_engine()
 
 
+def _sync(eng):
+    """Wait for the engine's device (nothing to wait for on the host emulation, tests/emu_engine.py)."""
+    if eng.device.type == 'cuda':
+        import torch
+        torch.cuda.synchronize()
+
+
 def _inputs(eng, P, N, F, freqs, seed, tilted=False, sigma=(1e-5,)):
     if tilted:
         one, z = profiles.tilted(N, float(N), seed=seed)
@@ -48,7 +55,7 @@ def _both(eng, layers, lanes, P, N, Q, F, zeta, etx, mu=1.0):
     two = eng.returns(res, etx, True)
     one, st = eng.stack_returns(layers, lanes, P, N, Q, F, zeta, etx, mu, True)
     import torch
-    torch.cuda.synchronize()
+    _sync(eng)
     assert torch.equal(st.cpu(), res.status.cpu())
     return {n: one[n].cpu().numpy() for n in NAMES}, {n: two[n].cpu().numpy() for n in NAMES}
 
@@ -98,11 +105,11 @@ def test_direct_returns_two_steps_equal_one_call(eng):
     etx = np.array([1e3, 0.0], dtype=np.complex128)
     one, _ = eng.stack_returns(layers, lanes, P, N, Q, F, 0.3, etx)
     part, _ = eng.stack_returns(layers, lanes, P, N, Q, F, 0.3, etx, finish=False)
-    torch.cuda.synchronize()
+    _sync(eng)
     amp, fld = part['dP_HV'].cpu().numpy(), np.abs(part['E_HV'].cpu().numpy())
     assert (np.abs(amp - fld) <= 4e-16 * fld).all()
     eng.power_inplace(part)
-    torch.cuda.synchronize()
+    _sync(eng)
     for n in NAMES:
         assert np.array_equal(one[n].cpu().numpy(), part[n].cpu().numpy(), equal_nan=True), n
 
@@ -138,7 +145,7 @@ def test_direct_returns_abi_errors(eng):
     layers, lanes = _inputs(eng, P, N, F, 179e6, seed=1)
     buf, v = eng.new_returns(P, Q, N - 1, F)
     e = (ctypes.c_double * 4)(1e3, 0.0, 0.0, 0.0)
-    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    st = eng._stream()
     ptr = [v[n].data_ptr() for n in NAMES]
 
     def call(lay=layers.data_ptr(), n=N, mu=1.0, finish=1, p=ptr):
@@ -150,7 +157,7 @@ def test_direct_returns_abi_errors(eng):
     assert call(p=ptr[:5] + [None, None]) != 0                       # finish needs the Pm arrays ...
     assert call(finish=0, p=ptr[:5] + [None, None]) == 0             # ... the first step alone does not
     assert lib.tamm_power_inplace(ptr[3], ptr[4], P, N, Q, F, None, ptr[6], st) != 0
-    torch.cuda.synchronize()
+    _sync(eng)
 
 
 def test_ensemble_blocks_that_fill_the_device_go_direct(eng, monkeypatch):
