@@ -13,8 +13,9 @@
 // What this checks that the arithmetic-only simulator (tests/hostsim) cannot: launch geometry, lane / profile / chunk
 // indexing, the staging protocol of the layer tiles, the scan, the reductions, every global-memory address the kernels
 // form (the arrays are ordinary host allocations: an out-of-range access is caught by the guard pages the tests put around
-// them or by AddressSanitizer) -- the role compute-sanitizer would play on the device.  What it cannot check: timing, the
-// memory model of a real GPU (races that sequential consistency on x86 hides), and nvcc's own code generation.
+// them or by AddressSanitizer; a shared-memory access that no barrier orders is a data race between two OS threads, which
+// ThreadSanitizer reports) -- the roles compute-sanitizer's memcheck and racecheck would play on the device.  What it cannot
+// check: timing, the weaker memory model of a real GPU, and nvcc's own code generation.
 // Nothing in the product (tamm_b200/, lib/) includes or loads this.
 #pragma once
 #include <algorithm>
@@ -92,7 +93,15 @@ struct Ctx {
     Warp* warp = nullptr;
     int lane = 0;
     unsigned shfl_count = 0;                   // shuffles this thread has executed (warp-uniform): selects the slot set
+    int sync_count = 0;                        // __syncthreads calls of this thread in this launch (fault injection below)
 };
+// Fault injection for the negative control of the race check (tests/test_cuda_emu.py): with CUDA_EMU_SKIP_SYNCTHREADS=k every
+// thread skips its k-th __syncthreads of every launch -- consistently, so nothing deadlocks, but the accesses that barrier
+// ordered now race, which ThreadSanitizer must report.
+inline int skip_sync() {
+    static const int k = [] { const char* e = std::getenv("CUDA_EMU_SKIP_SYNCTHREADS"); return e ? std::atoi(e) : 0; }();
+    return k;
+}
 inline thread_local Ctx ctx;
 
 inline void* dyn_smem() { return ctx.cta->dyn; }
@@ -128,7 +137,7 @@ struct Launch {
                             c.tid = dim3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
                             c.bid = dim3(bx, by, bz);
                             c.bdim = block; c.gdim = grid;
-                            c.cta = &cta; c.warp = cta.warps[t / 32].get(); c.lane = t % 32; c.shfl_count = 0;
+                            c.cta = &cta; c.warp = cta.warps[t / 32].get(); c.lane = t % 32; c.shfl_count = 0; c.sync_count = 0;
                             std::apply(kernel, args);
                             // a thread that has returned no longer takes part in barriers (CUDA semantics)
                             c.warp->bar.arrive_and_drop();
@@ -165,7 +174,11 @@ inline T shfl(T v, int src) {
 #define TAMM_DYN_SMEM(T, name) T* name = reinterpret_cast<T*>(cuda_emu::dyn_smem())
 
 // ---- synchronisation, shuffles, cache-hinted accesses, atomics ----------------------------------------------------------------
-inline void __syncthreads() { cuda_emu::ctx.cta->bar.arrive_and_wait(); }
+inline void __syncthreads() {
+    cuda_emu::Ctx& c = cuda_emu::ctx;
+    if (++c.sync_count == cuda_emu::skip_sync()) return;
+    c.cta->bar.arrive_and_wait();
+}
 inline void __syncwarp(unsigned = 0xffffffffu) { cuda_emu::ctx.warp->bar.arrive_and_wait(); }
 template <class T> inline T __shfl_xor_sync(unsigned, T v, int m) { return cuda_emu::shfl(v, cuda_emu::ctx.lane ^ m); }
 template <class T> inline T __shfl_up_sync(unsigned, T v, int d) { return cuda_emu::shfl(v, cuda_emu::ctx.lane >= d ? cuda_emu::ctx.lane - d : cuda_emu::ctx.lane); }

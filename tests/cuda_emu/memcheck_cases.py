@@ -2,7 +2,9 @@
 child process whose emulated library is the AddressSanitizer build (LD_PRELOAD=libasan.so, TAMM_EMU_LIB=_cuda_emu_asan.so).
 torch's CPU allocator goes through posix_memalign, so every tensor sits between ASan red zones: an out-of-range load or store
 of any kernel -- planes, workspace, aggregates, returns, layer tiles -- aborts the process with the kernel's source line.
-`python memcheck_cases.py overflow` is the negative control: a return array three doubles short, which ASan must report."""
+`python memcheck_cases.py overflow` is the negative control: a return array three doubles short, which ASan must report.
+`python memcheck_cases.py race` is the smaller set run under ThreadSanitizer (shared-memory protocols), `race returns-only` its
+negative control (with CUDA_EMU_SKIP_SYNCTHREADS=2 a barrier of the fused returns kernel is skipped)."""
 import os
 import sys
 
@@ -31,6 +33,24 @@ def main():
         return
     etx = np.array([700.0 + 5.0j, -200.0 + 60.0j])
     n = 0
+    if sys.argv[1:2] == ['race']:
+        # ThreadSanitizer pass (slow): one case per shared-memory protocol
+        P, N, F = 2, 40, 40
+        layers, lanes = td._inputs(eng, P, N, F, 179e6, seed=3)
+        if sys.argv[2:3] == ['returns-only']:
+            planes = torch.randn(P, N - 1, 4, F, dtype=torch.complex128)
+            from tamm_b200.engine import StackResult
+            eng.returns(StackResult(planes, torch.zeros(2, dtype=torch.float64), P, N, 1, F, MODE_URD, N - 1, None), etx, True)
+            print('returns-only done')
+            return
+        res = eng.stack(layers, lanes, P, N, 1, F, 0.31, 1.0, MODE_URD, chunk=7)      # tile staging, carry slots, scan
+        eng.returns(res, etx, True)                                                     # fused kernel: red / tot protocol
+        eng.export_jones(res)
+        eng.stack_returns(layers, lanes, P, N, 1, F, 0.31, etx)                         # direct path + in-place power pass
+        part = eng.returns_partial(eng.stack(layers, lanes, P, N, 1, F, 0.31, 1.0, MODE_U, chunk=13), etx, True)
+        eng.returns_finish(part, F)
+        print('race: 8 calls into the library clean')
+        return
     # (P, N, Q, F, chunk): lane grids that are flattened / tiled, ragged CTAs, CTAs spanning profiles, chunks around the 16-layer
     # TMA tile, single lanes, the 192 x 2 variant (P * Q * F <= 192), F in every regime of the returns kernels
     for P, N, Q, F, chunk, both_modes in [(1, 2, 1, 1, 1, True), (3, 19, 1, 181, 5, False), (5, 9, 1, 130, 3, False),

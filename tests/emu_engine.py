@@ -24,27 +24,28 @@ SOURCES = [os.path.join(ROOT, 'tamm_b200', 'csrc', 'tamm_kernels.cu'), os.path.j
            os.path.join(ROOT, 'include', 'tamm_b200.h'), os.path.join(EMU_DIR, 'cuda_emu.h')]
 
 
-ASAN_LIB = os.path.join(EMU_DIR, '_cuda_emu_asan.so')
+SANITIZED = {'address': os.path.join(EMU_DIR, '_cuda_emu_asan.so'), 'thread': os.path.join(EMU_DIR, '_cuda_emu_tsan.so')}
 
 
-def build(force=False, asan=False):
-    """g++ -> tests/cuda_emu/_cuda_emu.so, or with asan=True the AddressSanitizer build _cuda_emu_asan.so (both git-ignored),
-    rebuilt when a source is newer."""
-    out = ASAN_LIB if asan else EMU_LIB
+def build(force=False, sanitize=None):
+    """g++ -> tests/cuda_emu/_cuda_emu.so, or with sanitize='address' / 'thread' the AddressSanitizer / ThreadSanitizer build
+    (all git-ignored), rebuilt when a source is newer."""
+    out = SANITIZED[sanitize] if sanitize else EMU_LIB
     if not force and os.path.exists(out) and all(os.path.getmtime(s) <= os.path.getmtime(out) for s in SOURCES):
         return out
     cmd = ['g++', '-O1', '-std=c++20', '-pthread', '-DTAMM_EMULATE', '-Wno-unknown-pragmas', '-include', SOURCES[3]]
-    if asan:
-        cmd += ['-g', '-fsanitize=address', '-fno-omit-frame-pointer']
+    if sanitize:
+        cmd += ['-g', '-fsanitize=' + sanitize, '-fno-omit-frame-pointer']
     cmd += ['-x', 'c++', SOURCES[0], '-shared', '-fPIC', '-o', out]
     subprocess.run(cmd, check=True, cwd=ROOT)
     return out
 
 
-def asan_runtime():
-    """Path of libasan.so for LD_PRELOAD (the sanitizer runtime must be the first library of the process), or None."""
+def sanitizer_runtime(sanitize):
+    """Path of libasan.so / libtsan.so for LD_PRELOAD (the sanitizer runtime must be the first library of the process), or None."""
     try:
-        p = subprocess.run(['g++', '-print-file-name=libasan.so'], capture_output=True, text=True, check=True).stdout.strip()
+        name = {'address': 'libasan.so', 'thread': 'libtsan.so'}[sanitize]
+        p = subprocess.run(['g++', '-print-file-name=' + name], capture_output=True, text=True, check=True).stdout.strip()
         return os.path.realpath(p) if os.path.sep in p and os.path.exists(p) else None
     except Exception:
         return None

@@ -242,26 +242,45 @@ def test_ensemble_blocks_that_fill_the_device_go_direct(eng, monkeypatch):
     assert sorted(part) == ['c_HHVV', 'dP_HV'] and np.array_equal(part['dP_HV'], one['dP_HV'], equal_nan=True)
 
 
-# ---- memory safety: the kernels under AddressSanitizer (compute-sanitizer is closed on the GPU pool) ------------------------------
-def _asan_child(args):
+# ---- memory safety and shared-memory races: the kernels under Address- / ThreadSanitizer (compute-sanitizer is closed on the pool)
+def _sanitized_child(sanitize, args, extra_env=None):
     import emu_engine
-    rt = emu_engine.asan_runtime()
+    rt = emu_engine.sanitizer_runtime(sanitize)
     if rt is None:
-        pytest.skip('no libasan.so next to g++')
-    lib = emu_engine.build(asan=True)
-    env = dict(os.environ, LD_PRELOAD=rt, ASAN_OPTIONS='detect_leaks=0:abort_on_error=0', TAMM_EMU_LIB=lib, OMP_NUM_THREADS='1')
+        pytest.skip('no %s sanitizer runtime next to g++' % sanitize)
+    lib = emu_engine.build(sanitize=sanitize)
+    env = dict(os.environ, LD_PRELOAD=rt, TAMM_EMU_LIB=lib, OMP_NUM_THREADS='1', ASAN_OPTIONS='detect_leaks=0',
+               TSAN_OPTIONS='report_signal_unsafe=0 exitcode=66')
+    env.update(extra_env or {})
     return subprocess.run([sys.executable, os.path.join(ROOT, 'tests', 'cuda_emu', 'memcheck_cases.py')] + args, env=env,
                           capture_output=True, text=True, timeout=1500)
 
 
 def test_memcheck_every_kernel_under_address_sanitizer(built):
     """tests/cuda_emu/memcheck_cases.py: all kernels, all launch geometries, on exactly-sized buffers between ASan red zones."""
-    r = _asan_child([])
+    r = _sanitized_child('address', [])
     assert r.returncode == 0 and 'AddressSanitizer' not in r.stderr and 'clean' in r.stdout, (r.stdout[-500:], r.stderr[-3000:])
 
 
 def test_memcheck_negative_control(built):
     """The checker checks: a return array three doubles short is reported, with the kernel that read past it."""
-    r = _asan_child(['overflow'])
+    r = _sanitized_child('address', ['overflow'])
     assert r.returncode != 0 and 'heap-buffer-overflow' in r.stderr and 'power_inplace_kernel' in r.stderr, r.stderr[-2000:]
     assert 'NOT caught' not in r.stdout
+
+
+@pytest.mark.parametrize('tma', ['0', '1'])
+def test_racecheck_shared_memory_protocols_under_thread_sanitizer(built, tma):
+    """Every CUDA thread is an OS thread and __shared__ data is ordinary memory, so a shared-memory access that no barrier (or
+    mbarrier phase) orders is a data race ThreadSanitizer sees: the layer-tile double buffering of stack_kernel, the per-thread
+    carry slots, the CTA reduction of the fused returns kernel (red / tot reused from group to group without an extra
+    barrier), the TMA ring of returns_tma_kernel, the warp-shuffle scan."""
+    r = _sanitized_child('thread', ['race'], {'TAMM_RETURNS_TMA': tma})      # tma = 1: returns_tma_kernel instead of the fused one
+    assert r.returncode == 0 and 'ThreadSanitizer' not in r.stderr and 'clean' in r.stdout, (r.stdout[-500:], r.stderr[-3000:])
+
+
+def test_racecheck_negative_control(built):
+    """With the barrier between the per-warp partial sums and their reduction skipped (fault injection in cuda_emu.h), the
+    fused returns kernel races on `red` -- and ThreadSanitizer says so."""
+    r = _sanitized_child('thread', ['race', 'returns-only'], {'CUDA_EMU_SKIP_SYNCTHREADS': '2'})
+    assert 'ThreadSanitizer: data race' in r.stderr and 'returns_fused_kernel' in r.stderr, (r.stdout[-500:], r.stderr[-3000:])
