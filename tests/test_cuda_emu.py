@@ -181,6 +181,34 @@ def test_launch_geometries_against_whole_depth_walk(emu, P, N, Q, F, chunk):
     assert np.abs(rw['E_HH'].numpy() - np.moveaxis(e_hh, 2, 3)).max() <= 1e-12 * np.abs(e_hh).max()
 
 
+def test_random_launch_geometries(emu):
+    """A seeded random sweep over (profiles, layers, frequencies, azimuths, chunk, mode, mu, zeta) -- azimuth counts around
+    every block-size and warp boundary of the kernels: chunked launch = whole-depth launch = direct path."""
+    from tamm_b200.engine import MODE_URD
+    rng = np.random.default_rng(20260)
+    etx = np.array([600.0 + 10.0j, -300.0 + 90.0j])
+    done = 0
+    while done < 24:
+        P, N, Q = int(rng.integers(1, 8)), int(rng.integers(2, 30)), int(rng.integers(1, 4))
+        F = int(rng.choice([1, 2, 5, 31, 32, 33, 40, 63, 64, 65, 100, 128, 130, 181, 192, 193, 257]))
+        if P * Q * F > 800:
+            continue
+        chunk = int(rng.integers(1, N)) if N > 2 else 1
+        mode, mu, zeta = int(rng.integers(0, 2)), float(rng.choice([1.0, 1.0, 1.2])), float(rng.choice([0.0, 0.31, 0.9]))
+        tag = 'P%d N%d Q%d F%d chunk%d mode%d mu%g zeta%g' % (P, N, Q, F, chunk, mode, mu, zeta)
+        layers, lanes = td._inputs(emu, P, N, F, [179e6, 230e6, 310e6][:Q], seed=int(rng.integers(0, 50)))
+        whole = emu.stack(layers, lanes, P, N, Q, F, zeta, mu, mode, chunk=N - 1)
+        cut = emu.stack(layers, lanes, P, N, Q, F, zeta, mu, mode, chunk=chunk)
+        jw, jc = emu.export_jones(whole).numpy(), emu.export_jones(cut).numpy()
+        assert np.isfinite(jw).all(), tag
+        assert np.abs(jc - jw).max() <= 1e-11 * np.abs(jw).max(), tag
+        rw = {k: v.numpy() for k, v in emu.returns(whole, etx, True).items()}
+        td._compare({k: v.numpy() for k, v in emu.returns(cut, etx, True).items()}, rw, tag)
+        if mode == MODE_URD:
+            td._compare({k: v.numpy() for k, v in emu.stack_returns(layers, lanes, P, N, Q, F, zeta, etx, mu)[0].items()}, rw, tag)
+        done += 1
+
+
 # ---- the direct-returns path (tamm_stack_returns) ------------------------------------------------------------------------------
 @pytest.mark.parametrize('P,N,Q,F,alpha_deg,mu', [
     (3, 60, 1, 181, 10.0, 1.0), (2, 40, 3, 33, 10.0, 1.0), (5, 30, 1, 9, 25.0, 1.0), (1, 20, 1, 300, 10.0, 1.0),
