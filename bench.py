@@ -626,10 +626,17 @@ def bench_ensemble(c, args, w, emit):
     status = eng.empty((Pl,), torch.int32)
     stack_events, returns_events = [], []
     direct_cache = {}
+    # Which way do the launches that fill the device take?  TAMM_B200_DIRECT_RETURNS=1 / 0 forces tamm_stack_returns (returns
+    # tail inside the stack kernel, no planes) / tamm_stack_urd + tamm_returns; unset, the first such block is run both ways
+    # before the warm-up -- results compared, each timed -- and the faster one is used if the results agree (`autotune` below;
+    # the decision is the same on every rank).  Blocks that do not fill the device always take the chunked two-call path.
+    env_direct = os.environ.get('TAMM_B200_DIRECT_RETURNS')
+    use_direct = [env_direct == '1']
+    autotune = None
 
     def is_direct(nprof):
         if nprof not in direct_cache:
-            direct_cache[nprof] = bool(tengine.DIRECT_RETURNS and eng.fills_device(nprof, N, F))
+            direct_cache[nprof] = bool(use_direct[0] and eng.fills_device(nprof, N, F))
         return direct_cache[nprof]
 
     def step(record=False, blk=B, pl=None, after_block=None):
@@ -668,6 +675,62 @@ def bench_ensemble(c, args, w, emit):
             if after_block is not None:
                 after_block(bi, b0, b1)
 
+    if env_direct not in ('0', '1'):
+        autotune = dict(chosen='two calls')
+        want = False
+        try:
+            nb = min(B, Pl)
+            if eng.fills_device(nb, N, F):
+                o = {k: v[:nb] for k, v in out.items()}
+
+                def run_two():
+                    res = eng.stack(layers_d[:nb], lanes_d, nb, N, 1, F, zeta, 1.0, MODE_URD, planes=planes[:nb], status=status[:nb])
+                    eng.returns(res, etx, True, out=o)
+
+                def run_direct():
+                    eng.stack_returns(layers_d[:nb], lanes_d, nb, N, 1, F, zeta, etx, 1.0, True, out=o, status=status[:nb])
+
+                def timed(fn):
+                    fn()                                                     # untimed first run
+                    a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+                    a.record()
+                    fn(); fn()
+                    b.record()
+                    b.synchronize()
+                    return a.elapsed_time(b) / 2
+                t_two = timed(run_two)
+                ref = {k: o[k].clone() for k in ('E_HV', 'c_HHVV', 'dP_HH', 'Pm_HV')}
+                t_dir = timed(run_direct)
+                # same per-point code in both kernels: agreement to rounding, identical non-finite patterns
+                agree, worst = True, {}
+                for k in list(ref):
+                    r = ref.pop(k)
+                    g = o[k]
+                    gr, rr = (torch.view_as_real(g), torch.view_as_real(r)) if g.is_complex() else (g, r)
+                    fin = torch.isfinite(rr)
+                    agree = agree and bool(torch.equal(fin, torch.isfinite(gr)))
+                    diff = (gr - rr).abs_()
+                    diff[~fin] = 0.0
+                    rr = rr.abs()
+                    rr[~fin] = 0.0
+                    worst[k] = float(diff.max()) / max(float(rr.max()), 1e-300)
+                    agree = agree and worst[k] < (1e-9 if k in ('dP_HH', 'Pm_HV') else 1e-11)
+                    del r, g, gr, rr, fin, diff
+                want = bool(agree and t_dir < t_two)
+                autotune = dict(block_profiles=nb, two_calls_ms=t_two, direct_ms=t_dir, results_agree=agree, max_rel_diff=worst)
+            else:
+                autotune['note'] = 'no block of this shard fills the device with whole-depth lanes'
+        except Exception as e:
+            want = False
+            autotune = dict(error=repr(e)[:300])
+        if world > 1:          # one decision for the job (outside the try: every rank takes part, whatever happened above)
+            dec = torch.tensor([1.0 if want else 0.0], dtype=torch.float64, device=dev)
+            dist.all_reduce(dec, op=dist.ReduceOp.MIN)
+            want = bool(dec.item() == 1.0)
+        use_direct[0] = want
+        autotune['chosen'] = 'tamm_stack_returns' if want else 'two calls'
+        direct_cache.clear()
+        torch.cuda.empty_cache()
     for _ in range(max(3, args.warmup)):
         step()
     sync_all(c)
@@ -697,7 +760,7 @@ def bench_ensemble(c, args, w, emit):
     stack_ms = sum(a.elapsed_time(b) for a, b, _, _ in st_ev)
     stack_evals = sum(n for _, _, n, _ in st_ev) * float(N) * F
     line = base_line(c, args, w, value, ms_per_step, launches, dict(
-        profiles_per_launch=B, direct_returns=bool(n_direct),
+        profiles_per_launch=B, direct_returns=bool(n_direct), returns_path_autotune=autotune,
         launches_per_step=dict(whole_depth=n_direct // max(1, args.steps), chunked=(len(stack_events) - n_direct) // max(1, args.steps))))
     if n_direct:
         line['roofline'] = stack_roofline(c, stack_ms, stack_evals, len(st_ev), ms_local, float(B) * N * F,

@@ -188,7 +188,7 @@ def test_random_launch_geometries(emu):
     rng = np.random.default_rng(20260)
     etx = np.array([600.0 + 10.0j, -300.0 + 90.0j])
     done = 0
-    while done < 24:
+    while done < 16:
         P, N, Q = int(rng.integers(1, 8)), int(rng.integers(2, 30)), int(rng.integers(1, 4))
         F = int(rng.choice([1, 2, 5, 31, 32, 33, 40, 63, 64, 65, 100, 128, 130, 181, 192, 193, 257]))
         if P * Q * F > 800:
