@@ -95,7 +95,12 @@ def main():
         dst = (ctypes.c_ulonglong * 2)(d0.data_ptr(), d1.data_ptr())
         assert eng.lib.tamm_peer_push(src.data_ptr(), cnt * 8, dst, 2, 0, 2, None) == 0
         assert torch.equal(d0, src) and torch.equal(d1, src)
-        n += 1
+        # the multicast kernel's index arithmetic (its multimem.st is a plain store to the one "replica" of the emulation)
+        d2 = torch.zeros(cnt, dtype=torch.float64)
+        one = (ctypes.c_ulonglong * 1)(d2.data_ptr())
+        assert eng.lib.tamm_peer_push(src.data_ptr(), cnt * 8, one, 1, 1, 3, None) == 0
+        assert torch.equal(d2, src)
+        n += 2
     print('memcheck: %d calls into the library clean' % n)
 
 

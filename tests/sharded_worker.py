@@ -18,9 +18,24 @@ backend, outdir = sys.argv[1], sys.argv[2]
 from tamm_b200 import EnsembleStack, profiles                                   # noqa: E402
 from tamm_b200 import distributed as tdist                                       # noqa: E402
 rank, ws, local = tdist.world()
-torch.cuda.set_device(local if backend == 'nccl' else 0)
-tdist.init(backend)
+EMU = backend == 'emu'       # CPU tier: gloo ranks, the kernels on the host emulation of the CUDA execution model, toy sizes
+if EMU:
+    tdist.init('gloo')
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import layer                                                                 # noqa: E402
+    import layerstack                                                            # noqa: E402
+    from emu_engine import EmuEngine                                             # noqa: E402
+    from tamm_b200 import ensemble as ens_mod                                    # noqa: E402
+    _eng = EmuEngine()
+    layer._get_engine = layerstack._get_engine = ens_mod.get_engine = lambda: _eng
+    ens_mod._pinned_empty = lambda shape, dtype: torch.zeros(shape, dtype=dtype)
+    ens_mod._pinned_copy = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+else:
+    torch.cuda.set_device(local if backend == 'nccl' else 0)
+    tdist.init(backend)
 import layerstack as ls                                                          # noqa: E402
+N1, F1, N2, NB, NE = (61, 19, 40, 9, 30) if EMU else (3001, 181, 3000, 257, 400)  # layers / azimuths / bins of the three cases
 
 TOL = 1e-12
 
@@ -41,33 +56,33 @@ C_TOL = 1e-10
 
 names = ['Pm_HH', 'Pm_HV', 'dP_HH', 'dP_HV', 'c_HHVV', 'E_HH', 'E_HV']
 # configs[1]: 3001 layers x 181 azimuths, azimuths sharded; all-reduce of the |E| sums, all-gather along azimuth
-nlm, z = profiles.rathmann_transition(3001, 3000, fabric_type=2)
-st = ls.LayerStack(nlm, z, N_frames=181, VERBOSE=0)
+nlm, z = profiles.rathmann_transition(N1, 3000, fabric_type=2)
+st = ls.LayerStack(nlm, z, N_frames=F1, VERBOSE=0)
 for alpha in (0.0, np.deg2rad(10)):
     whole = st.get_returns(1e3, f=179e6, alpha=alpha)
     got = st.get_returns(1e3, f=179e6, alpha=alpha, shard=tdist.AxisShard('azimuth'))
     for n, a, b in zip(names, got, whole):
         assert a.shape == b.shape, n
         close(a, b, ('azimuth', alpha, n), C_TOL if n == 'c_HHVV' else TOL)
-    lo, hi = tdist.shard_range(181, rank, ws)
+    lo, hi = tdist.shard_range(F1, rank, ws)
     part = st.get_returns(1e3, f=179e6, alpha=alpha, shard=tdist.AxisShard('azimuth', gather=False))
-    assert part[5].shape == (3000, hi - lo)
+    assert part[5].shape == (N1 - 1, hi - lo)
     close(part[5], whole[5][:, lo:hi], 'local azimuths')
     close(part[0], whole[0], 'Pm is global on every rank')
 # configs[2]: frequency vector sharded (no exchange), both transmit polarisations from one pass
-nlm, z = profiles.rathmann_transition(3000, 3000, fabric_type=4)
+nlm, z = profiles.rathmann_transition(N2, 3000, fabric_type=4)
 st = ls.LayerStack(nlm, z, N_frames=3, VERBOSE=0)
-fs = np.linspace(150e6, 450e6, 257)
+fs = np.linspace(150e6, 450e6, NB)
 whole = st.get_returns_polarimetric(1e3, f=fs, alpha=np.deg2rad(10))
 got = st.get_returns_polarimetric(1e3, f=fs, alpha=np.deg2rad(10), shard=tdist.AxisShard('frequency'))
 for k in whole:
     assert got[k].shape == whole[k].shape, k
     close(got[k], whole[k], ('frequency', k), C_TOL if k == 'c_HHVV' else TOL)
 # batched API: all profiles everywhere, azimuths split
-nlm, z = profiles.ensemble(3, 400, 200)
-w = EnsembleStack(nlm, z, N_frames=181).get_returns(1e3, f=179e6, alpha=np.deg2rad(10))
-e = EnsembleStack(nlm, z, N_frames=181, shard=(rank, ws), shard_axis='azimuth').get_returns(1e3, f=179e6, alpha=np.deg2rad(10))
-lo, hi = tdist.shard_range(181, rank, ws)
+nlm, z = profiles.ensemble(3, NE, 200)
+w = EnsembleStack(nlm, z, N_frames=F1).get_returns(1e3, f=179e6, alpha=np.deg2rad(10))
+e = EnsembleStack(nlm, z, N_frames=F1, shard=(rank, ws), shard_axis='azimuth').get_returns(1e3, f=179e6, alpha=np.deg2rad(10))
+lo, hi = tdist.shard_range(F1, rank, ws)
 close(e['E_HV'], w['E_HV'][..., lo:hi], 'ensemble azimuth shard E_HV')
 close(e['dP_HH'], w['dP_HH'][..., lo:hi], 'ensemble azimuth shard dP_HH')
 close(e['Pm_HV'], w['Pm_HV'], 'ensemble azimuth shard Pm_HV')

@@ -270,6 +270,19 @@ def test_ensemble_blocks_that_fill_the_device_go_direct(eng, monkeypatch):
     assert sorted(part) == ['c_HHVV', 'dP_HV'] and np.array_equal(part['dP_HV'], one['dP_HV'], equal_nan=True)
 
 
+def test_sharded_solve_on_two_gloo_ranks(built, tmp_path):
+    """tests/sharded_worker.py (the worker of the two-rank GPU test) with the kernels on the emulation: azimuth-sharded and
+    frequency-sharded single stacks and the azimuth-sharded ensemble -- tamm_returns_partial, the all-reduce of the |E| sums,
+    tamm_returns_finish, the all-gathers -- against the unsharded solve."""
+    import socket
+    s = socket.socket(); s.bind(('127.0.0.1', 0)); port = s.getsockname()[1]; s.close()
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2', '--master-addr', '127.0.0.1',
+           '--master-port', str(port), os.path.join(ROOT, 'tests', 'sharded_worker.py'), 'emu', str(tmp_path)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(os.environ, OMP_NUM_THREADS='1', CUDA_VISIBLE_DEVICES=''))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert (tmp_path / 'rank0.ok').exists() and (tmp_path / 'rank1.ok').exists()
+
+
 # ---- memory safety and shared-memory races: the kernels under Address- / ThreadSanitizer (compute-sanitizer is closed on the pool)
 def _sanitized_child(sanitize, args, extra_env=None):
     import emu_engine
