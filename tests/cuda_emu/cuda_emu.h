@@ -26,6 +26,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <memory>
 #include <thread>
 #include <tuple>
@@ -106,6 +107,62 @@ inline thread_local Ctx ctx;
 
 inline void* dyn_smem() { return ctx.cta->dyn; }
 
+// Worker threads are kept from CTA to CTA and from launch to launch (creating 384 threads per CTA costs more than running a
+// small CTA): worker i sleeps on its own generation word and is woken only when a CTA has a thread i.
+class Pool {
+    struct Slot {
+        std::atomic<unsigned> go{0};
+        std::thread th;
+    };
+    std::vector<std::unique_ptr<Slot>> slots;
+    std::atomic<int> remaining{0};
+    const void* task = nullptr;
+    void (*call)(const void*, int) = nullptr;
+    std::atomic<bool> stop{false};
+
+    void worker(Slot* s, int id) {
+        unsigned seen = 0;
+        for (;;) {
+            s->go.wait(seen, std::memory_order_acquire);
+            seen = s->go.load(std::memory_order_acquire);
+            if (stop.load(std::memory_order_acquire)) return;
+            call(task, id);
+            if (remaining.fetch_sub(1, std::memory_order_acq_rel) == 1) remaining.notify_all();
+        }
+    }
+
+public:
+    template <class F>
+    void run(int nt, const F& f) {          // f(t) for t in [0, nt), each on its own thread, all alive at the same time
+        while ((int)slots.size() < nt) {
+            slots.emplace_back(new Slot);
+            Slot* s = slots.back().get();
+            const int id = (int)slots.size() - 1;
+            s->th = std::thread([this, s, id] { worker(s, id); });
+        }
+        task = &f;
+        call = [](const void* p, int t) { (*static_cast<const F*>(p))(t); };
+        remaining.store(nt, std::memory_order_release);
+        for (int t = 0; t < nt; ++t) {
+            slots[t]->go.fetch_add(1, std::memory_order_release);
+            slots[t]->go.notify_one();
+        }
+        for (int r; (r = remaining.load(std::memory_order_acquire)) != 0;) remaining.wait(r, std::memory_order_acquire);
+    }
+    ~Pool() {
+        stop.store(true, std::memory_order_release);
+        for (auto& s : slots) {
+            s->go.fetch_add(1, std::memory_order_release);
+            s->go.notify_one();
+            s->th.join();
+        }
+    }
+};
+inline Pool& pool() {
+    static Pool* p = new Pool;      // never destroyed: the workers may outlive static destruction order at process exit
+    return *p;
+}
+
 template <class... KArgs>
 struct Launch {
     void (*kernel)(KArgs...);
@@ -120,30 +177,26 @@ struct Launch {
                          nt, dyn, grid.x, grid.y, grid.z);
             std::abort();
         }
+        std::unique_ptr<unsigned char[]> mem(new unsigned char[dyn + 256]);
         for (unsigned bz = 0; bz < grid.z; ++bz)
             for (unsigned by = 0; by < grid.y; ++by)
                 for (unsigned bx = 0; bx < grid.x; ++bx) {
                     Cta cta(nt);
                     for (int w = 0; w < nt / 32; ++w) cta.warps.emplace_back(new Warp(32));
-                    // fresh, poisoned dynamic shared memory per CTA (the device's is uninitialised too)
-                    std::unique_ptr<unsigned char[]> mem(new unsigned char[dyn + 256]);
+                    // poisoned dynamic shared memory for every CTA (the device's is uninitialised too)
                     std::memset(mem.get(), 0xA5, dyn + 256);
                     cta.dyn = mem.get() + (128 - (reinterpret_cast<uintptr_t>(mem.get()) & 127)) % 128;
-                    std::vector<std::thread> th;
-                    th.reserve(nt);
-                    for (int t = 0; t < nt; ++t)
-                        th.emplace_back([&, t] {
-                            Ctx& c = ctx;
-                            c.tid = dim3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
-                            c.bid = dim3(bx, by, bz);
-                            c.bdim = block; c.gdim = grid;
-                            c.cta = &cta; c.warp = cta.warps[t / 32].get(); c.lane = t % 32; c.shfl_count = 0; c.sync_count = 0;
-                            std::apply(kernel, args);
-                            // a thread that has returned no longer takes part in barriers (CUDA semantics)
-                            c.warp->bar.arrive_and_drop();
-                            cta.bar.arrive_and_drop();
-                        });
-                    for (auto& x : th) x.join();
+                    pool().run(nt, [&](int t) {
+                        Ctx& c = ctx;
+                        c.tid = dim3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
+                        c.bid = dim3(bx, by, bz);
+                        c.bdim = block; c.gdim = grid;
+                        c.cta = &cta; c.warp = cta.warps[t / 32].get(); c.lane = t % 32; c.shfl_count = 0; c.sync_count = 0;
+                        std::apply(kernel, args);
+                        // a thread that has returned no longer takes part in barriers (CUDA semantics)
+                        c.warp->bar.arrive_and_drop();
+                        cta.bar.arrive_and_drop();
+                    });
                 }
     }
 };
