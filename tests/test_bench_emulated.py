@@ -68,6 +68,8 @@ def ctx(built, monkeypatch):
     monkeypatch.setattr(layer, '_get_engine', lambda: eng)
     monkeypatch.setattr(layerstack, '_get_engine', lambda: eng)
     monkeypatch.setattr(ensemble, 'get_engine', lambda: eng)
+    monkeypatch.setattr(ensemble, '_pinned_empty', lambda shape, dtype: torch.zeros(shape, dtype=dtype))
+    monkeypatch.setattr(ensemble, '_pinned_copy', lambda a: torch.from_numpy(np.ascontiguousarray(a)))
     c = bench.Ctx()
     import torch.distributed as dist
     from tamm_b200 import distributed as tdist
@@ -103,7 +105,15 @@ def test_ensemble_arm_on_the_emulated_device(ctx, monkeypatch, env):
         monkeypatch.delenv('TAMM_B200_DIRECT_RETURNS', raising=False)
     else:
         monkeypatch.setenv('TAMM_B200_DIRECT_RETURNS', env)
-    d = _run(bench.bench_ensemble, ctx, _args(profiles=17, layers=8, steps=1))     # launches of 8, 8 (whole depth) and 1 (chunked) profiles
+    # launches of 8, 8 (whole depth) and 1 (chunked) profiles; the end-to-end leg (host arrays -> EnsembleStack.get_returns ->
+    # host arrays, then the bare copies, then the power-only call) in the autotuned run only
+    d = _run(bench.bench_ensemble, ctx, _args(profiles=17, layers=8, steps=1, no_e2e=env is not None))
+    if env is None:
+        e = d['e2e']
+        assert 'error' not in e, e
+        assert e['value'] > 0 and e['steps'] == 1 and e['h2d_bytes_per_step'] == 17 * 8 * 80 + 181 * 64
+        assert e['d2h_bytes_per_step'] == 17 * 7 * 181 * 64 + 17 * 7 * 16 and 0 < e['frac_of_bare_d2h']
+        assert d['e2e_power']['d2h_bytes_per_step'] == 17 * 7 * 181 * 16 + 17 * 7 * 16
     for k in CONTRACT:
         assert k in d, k
     cfg = d['config']
