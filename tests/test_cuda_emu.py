@@ -225,6 +225,10 @@ def test_direct_returns_deep_stack(emu):
     td.test_direct_returns_strongly_attenuating_deep_stack(emu)
 
 
+def test_direct_returns_exact_zeros(emu):
+    td.test_direct_returns_exact_zeros(emu)
+
+
 def test_direct_returns_abi_errors(emu):
     td.test_direct_returns_abi_errors(emu)
 

@@ -138,6 +138,23 @@ def test_direct_returns_strongly_attenuating_deep_stack(eng):
         assert np.abs(one[n] - two[n])[rows].max() < 1e-9, n
 
 
+def test_direct_returns_exact_zeros(eng):
+    """The demo.ipynb fabric is symmetric about the x axis, so the cross-polar return vanishes IDENTICALLY on the symmetry
+    azimuths (0, 90 and 180 degrees): |E_HV| = 0, dP_HV = -inf there.  Exact zeros stay on the fast arithmetic (they are not
+    "out of range") and give the same non-finite pattern as the two-call path and as the reference."""
+    P, N, F = 2, 40, 33
+    nlm, z = profiles.demo(N, 1500)
+    zz = np.hstack(([np.abs(z[1] - z[0])], z))
+    dz = np.broadcast_to(np.abs(np.diff(zz)), (P, N))
+    one_ = np.ones((P, N))
+    layers = eng.to_device(packing.pack_layers(np.repeat(nlm[None, :, :6], P, axis=0), dz, (3.17 - 0.034) * one_, 3.17 * one_, 1e-5 * one_))
+    lanes = eng.to_device(packing.pack_lanes(np.linspace(0, np.pi, F), 179e6))
+    for zeta in (0.0, 0.3):
+        one, two = _both(eng, layers, lanes, P, N, 1, F, zeta, np.array([1e3, 0.0], dtype=np.complex128))
+        assert (two['E_HV'] == 0).sum() >= 2 * (N - 1) and np.isneginf(two['dP_HV']).sum() >= 2 * (N - 1)
+        _compare(one, two, 'demo zeta %g' % zeta)
+
+
 def test_direct_returns_abi_errors(eng):
     import torch
     lib = eng.lib
