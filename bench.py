@@ -926,6 +926,9 @@ def bench_ensemble(c, args, w, emit):
                     ok = ((got_s - sums).abs() <= 1e-12 * sums.abs()).all().to(torch.float64).reshape(1)
                     ok = ok * float(torch.equal(full0[rank * GB0: (rank + 1) * GB0], out[names[0]][:GB0]))
                     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+                    for pg in pgs.values():
+                        if hasattr(pg, 'close'):
+                            pg.close()            # symmetric memory: every rank done before any rank unmaps (tdist.PeerGather.close)
                     del pgs
                     torch.cuda.empty_cache()
                     return pm, ksteps, bool(ok.item() == 1.0)

@@ -237,6 +237,17 @@ class PeerGather:
         self._hdl.barrier()        # every rank's writes into THIS rank's array were enqueued before and are complete after
         return self.full
 
+    def close(self):
+        """Collective: call on every rank before dropping the object.  Freeing symmetric memory unmaps this rank's buffer from
+        its peers and from the multicast group, so no rank may still have a store to it in flight: finish this rank's own work,
+        then meet the others (host-side barrier), and only then release the views and the handle."""
+        import torch.distributed as dist
+        self._torch.cuda.synchronize()
+        dist.barrier(self.group)
+        self.full = self._flat = self._hdl = None
+        self._peers = None
+        self._dst_base = []
+
 
 def _via_host(t, group):
     """gloo moves host memory only: CUDA tensors are staged through the CPU for that backend (world-size-2 tests on ONE

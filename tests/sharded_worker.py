@@ -116,6 +116,8 @@ if backend == 'nccl':
                 full = pg.wait()
                 torch.cuda.synchronize()
                 assert np.array_equal(full.cpu().numpy(), src), (label, getattr(pg, 'mode', ''), str(dtype), rep)
+            if hasattr(pg, 'close'):
+                pg.close()
             del pg
 dist.barrier()
 dist.destroy_process_group()
