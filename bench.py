@@ -440,6 +440,13 @@ def base_line(c, args, w, value, ms_per_step, launches, extra_cfg=None):
 
 
 def finish(c, args, w, line, sampler, emit):
+    try:   # the whole step (every kernel of it) against the same FP64 peak: the job's 4000 algorithmic flop per eval x evals/s
+        r = line['roofline']
+        r['step_frac'] = line['fp64_tflops_alg'] / (c.world * r['peak'])
+        r['step_frac_note'] = ('value x 4000 flop/eval / (n_gpus x peak): what the step as a whole reaches, next to `frac` of its '
+                               'dominant kernel alone')
+    except Exception:
+        pass
     if c.rank == 0:
         line['clocks'] = sampler.summary()
         if c.world == 1 and not args.no_cpu:

@@ -138,6 +138,7 @@ def test_ensemble_arm_on_the_emulated_device(ctx, monkeypatch, env):
         assert d['roofline']['kernel'].startswith('stack_kernel') and d['roofline']['flop_per_eval'] == 3960.0
         assert d['roofline_returns']['kernel'] == 'returns_fused_kernel'
     assert 0 < d['roofline']['frac'] and d['roofline']['peak'] > 0
+    assert abs(d['roofline']['step_frac'] - d['value'] * 4000.0 / 1e12 / d['roofline']['peak']) < 1e-12
 
 
 @pytest.mark.parametrize('config,kw', [(0, dict(layers=30, frames=33)), (1, dict(layers=40, frames=40)),
