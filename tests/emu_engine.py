@@ -93,7 +93,12 @@ class EmuEngine(Engine):
     def empty(self, shape, dtype):
         # poisoned, not zeroed: an element a kernel fails to write shows up as NaN
         t = torch.empty(shape, dtype=dtype)
-        (torch.view_as_real(t) if t.is_complex() else t).fill_(float('nan')) if t.is_floating_point() or t.is_complex() else t.fill_(-1)
+        if t.is_complex():
+            torch.view_as_real(t).fill_(float('nan'))
+        elif t.is_floating_point():
+            t.fill_(float('nan'))
+        else:
+            t.fill_(-1)
         return t
 
     def stage_inputs(self, *arrays):
