@@ -68,10 +68,12 @@ def test_engine_refuses_to_run_without_cuda(built):
 
 
 def test_product_does_not_import_oracle():
-    """The product path (tamm_b200/, lib/) must never import, call or link the oracle."""
+    """The product path (tamm_b200/, lib/) must never import, call or link the oracle -- nor the other test-only checkers (the
+    arithmetic simulator tests/hostsim, the execution-model emulation tests/cuda_emu + tests/emu_engine.py)."""
     for sub in ('tamm_b200', 'lib'):
         for dirpath, _, files in os.walk(os.path.join(ROOT, sub)):
             for fn in files:
                 if fn.endswith(('.py', '.cu', '.cuh', '.h')):
                     txt = open(os.path.join(dirpath, fn)).read()
                     assert 'tamm_oracle' not in txt and 'hostsim' not in txt.replace('tests/hostsim', ''), (dirpath, fn)
+                    assert 'emu_engine' not in txt and 'cuda_emu' not in txt.replace('tests/cuda_emu', ''), (dirpath, fn)
