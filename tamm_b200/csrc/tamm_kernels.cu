@@ -590,6 +590,9 @@ __device__ __forceinline__ double warp_sum8(const double v[8], int lane) {
 
 // Cold repeat of one CTA's depth tile [nbeg, ne) of (profile p, frequency iq) with the reference-like arithmetic of
 // returns_kernel + the azimuth sums + the dB step; thread = azimuth, called by ALL threads of the CTA (it synchronises).
+// (WHO: one copy per calling kernel family -- 0 fused, 1 TMA-fed -- so that adding a caller with other launch bounds does not
+// re-allocate the registers of the copy the measured kernel calls)
+template <int WHO>
 __device__ __noinline__ void returns_tile_slow(const cd* __restrict__ planes, const cd* __restrict__ pre, int N, int Q, int F,
                                                int mode, int chunk, int nchunks, cd e0, cd e1, int gtm_phase, cd* E_HH, cd* E_HV,
                                                cd* c_HHVV, double* dP_HH, double* dP_HV, double* Pm_HH, double* Pm_HV, int p,
@@ -730,8 +733,8 @@ returns_fused_kernel(const cd* __restrict__ planes, const cd* __restrict__ pre, 
     }
     __syncthreads();
     if (TAMM_RARE(s_bad))
-        returns_tile_slow(planes, pre, N, Q, F, mode, chunk, nchunks, e0, e1, gtm_phase, E_HH, E_HV, c_HHVV, dP_HH, dP_HV, Pm_HH,
-                          Pm_HV, p, iq, (int)blockIdx.x * (TNF * TNG), ne, &red[0][0]);
+        returns_tile_slow<0>(planes, pre, N, Q, F, mode, chunk, nchunks, e0, e1, gtm_phase, E_HH, E_HV, c_HHVV, dP_HH, dP_HV, Pm_HH,
+                             Pm_HV, p, iq, (int)blockIdx.x * (TNF * TNG), ne, &red[0][0]);
 }
 
 // The same kernel fed by the TMA engine (F <= 256): the four plane rows of a depth (F x 16 B each, contiguous in the
@@ -864,6 +867,11 @@ returns_tma_kernel(const cd* __restrict__ planes, const cd* __restrict__ pre, in
             }
         }
     }
+    // as in returns_fused_kernel: a point outside the range of the fast arithmetic makes the CTA repeat its depth tile
+    __syncthreads();
+    if (TAMM_RARE(s_bad))
+        returns_tile_slow<1>(planes, pre, N, Q, F, mode, chunk, nchunks, e0, e1, gtm_phase, E_HH, E_HV, c_HHVV, dP_HH, dP_HV, Pm_HH,
+                             Pm_HV, p, iq, nbeg, ne, &red[0][0]);
 }
 
 // one warp per (p, iq, n): azimuth mean of |E|, dB, anomaly (layerstack.py:257-267).  a* hold |E| on entry, dP on exit.

@@ -126,23 +126,31 @@ def test_peer_push_kernels(eng, monkeypatch):
     tg.test_peer_push_kernels_on_one_device(eng)
 
 
-def test_returns_tma_variant(eng):
-    """returns_tma_kernel (mbarrier ring of bulk copies) against the fused kernel that loads through registers"""
-    P, N, F = 2, 50, 40
-    layers, lanes = td._inputs(eng, P, N, F, 179e6, seed=4)
+@pytest.mark.parametrize('deep', [False, True])
+def test_returns_tma_variant(eng, deep):
+    """returns_tma_kernel (mbarrier ring of bulk copies) against the fused kernel that loads through registers; `deep`: a
+    strongly attenuating stack, where both must repeat their depth tiles with the reference-like arithmetic (a g++ -Wall pass
+    over the emulation build found the TMA variant setting its out-of-range flag without ever reading it)."""
+    P, N, F = (2, 50, 40) if not deep else (1, 400, 33)
+    kw = "seed=4" if not deep else "seed=21, tilted=True, sigma=(1e-2,)"
+    layers, lanes = td._inputs(eng, P, N, F, 179e6, **eval('dict(%s)' % kw))
     etx = np.array([1e3, 0.0], dtype=np.complex128)
     res = eng.stack(layers, lanes, P, N, 1, F, 0.3, 1.0, chunk=9)
     a = eng.returns(res, etx, True)
+    if deep:
+        amp = a['E_HH'].abs().numpy()
+        assert amp[amp > 0].min() < 1e-200 and (amp == 0).any()
     # the TMA switch is read once per process: run the variant in a child with TAMM_RETURNS_TMA=1
     code = ('import sys; sys.path[:0] = [%r, %r, %r]\n'
             'import numpy as np, torch\n'
             'from emu_engine import EmuEngine\n'
             'import test_zz_gpu_direct as td\n'
             'eng = EmuEngine()\n'
-            'layers, lanes = td._inputs(eng, %d, %d, %d, 179e6, seed=4)\n'
+            'layers, lanes = td._inputs(eng, %d, %d, %d, 179e6, %s)\n'
             'res = eng.stack(layers, lanes, %d, %d, 1, %d, 0.3, 1.0, chunk=9)\n'
             'out = eng.returns(res, np.array([1e3, 0.0], dtype=np.complex128), True)\n'
-            'np.savez(sys.argv[1], **{k: v.numpy() for k, v in out.items()})\n') % (ROOT, os.path.join(ROOT, 'tests'), os.path.join(ROOT, 'oracle'), P, N, F, P, N, F)
+            'np.savez(sys.argv[1], **{k: v.numpy() for k, v in out.items()})\n') % (
+                ROOT, os.path.join(ROOT, 'tests'), os.path.join(ROOT, 'oracle'), P, N, F, kw, P, N, F)
     import tempfile
     with tempfile.TemporaryDirectory() as d:
         path = os.path.join(d, 'tma.npz')
