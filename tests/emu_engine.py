@@ -21,7 +21,7 @@ ROOT = os.path.dirname(HERE)
 EMU_DIR = os.path.join(HERE, 'cuda_emu')
 EMU_LIB = os.path.join(EMU_DIR, '_cuda_emu.so')
 SOURCES = [os.path.join(ROOT, 'tamm_b200', 'csrc', 'tamm_kernels.cu'), os.path.join(ROOT, 'tamm_b200', 'csrc', 'tamm_core.cuh'),
-           os.path.join(ROOT, 'include', 'tamm_b200.h'), os.path.join(EMU_DIR, 'cuda_emu.h')]
+           os.path.join(ROOT, 'include', 'tamm_b200.h'), os.path.join(EMU_DIR, 'cuda_emu.h'), os.path.abspath(__file__)]   # (this file: the flags)
 
 
 SANITIZED = {'address': os.path.join(EMU_DIR, '_cuda_emu_asan.so'), 'thread': os.path.join(EMU_DIR, '_cuda_emu_tsan.so')}
@@ -34,7 +34,9 @@ def build(force=False, sanitize=None):
     if not force and os.path.exists(out) and all(os.path.getmtime(s) <= os.path.getmtime(out) for s in SOURCES):
         return out
     cmd = ['g++', '-O1', '-std=c++20', '-pthread', '-DTAMM_EMULATE', '-Wno-unknown-pragmas', '-include', SOURCES[3]]
-    if sanitize:
+    if sanitize == 'address':      # memcheck: AddressSanitizer + UndefinedBehaviorSanitizer (overflow, shifts, alignment, bounds)
+        cmd += ['-g', '-fsanitize=address,undefined', '-fno-sanitize-recover=undefined', '-fno-omit-frame-pointer']
+    elif sanitize:
         cmd += ['-g', '-fsanitize=' + sanitize, '-fno-omit-frame-pointer']
     cmd += ['-x', 'c++', SOURCES[0], '-shared', '-fPIC', '-o', out]
     subprocess.run(cmd, check=True, cwd=ROOT)
@@ -42,11 +44,16 @@ def build(force=False, sanitize=None):
 
 
 def sanitizer_runtime(sanitize):
-    """Path of libasan.so / libtsan.so for LD_PRELOAD (the sanitizer runtime must be the first library of the process), or None."""
+    """LD_PRELOAD value for a sanitized build: libasan.so + libubsan.so, or libtsan.so (the sanitizer runtime must be the first
+    library of the process); None when a runtime is missing."""
     try:
-        name = {'address': 'libasan.so', 'thread': 'libtsan.so'}[sanitize]
-        p = subprocess.run(['g++', '-print-file-name=' + name], capture_output=True, text=True, check=True).stdout.strip()
-        return os.path.realpath(p) if os.path.sep in p and os.path.exists(p) else None
+        paths = []
+        for name in {'address': ('libasan.so', 'libubsan.so'), 'thread': ('libtsan.so',)}[sanitize]:
+            p = subprocess.run(['g++', '-print-file-name=' + name], capture_output=True, text=True, check=True).stdout.strip()
+            if not (os.path.sep in p and os.path.exists(p)):
+                return None
+            paths.append(os.path.realpath(p))
+        return ' '.join(paths)
     except Exception:
         return None
 

@@ -303,16 +303,18 @@ def _sanitized_child(sanitize, args, extra_env=None):
         pytest.skip('no %s sanitizer runtime next to g++' % sanitize)
     lib = emu_engine.build(sanitize=sanitize)
     env = dict(os.environ, LD_PRELOAD=rt, TAMM_EMU_LIB=lib, OMP_NUM_THREADS='1', ASAN_OPTIONS='detect_leaks=0',
-               TSAN_OPTIONS='report_signal_unsafe=0 exitcode=66')
+               UBSAN_OPTIONS='print_stacktrace=1', TSAN_OPTIONS='report_signal_unsafe=0 exitcode=66')
     env.update(extra_env or {})
     return subprocess.run([sys.executable, os.path.join(ROOT, 'tests', 'cuda_emu', 'memcheck_cases.py')] + args, env=env,
                           capture_output=True, text=True, timeout=1500)
 
 
 def test_memcheck_every_kernel_under_address_sanitizer(built):
-    """tests/cuda_emu/memcheck_cases.py: all kernels, all launch geometries, on exactly-sized buffers between ASan red zones."""
+    """tests/cuda_emu/memcheck_cases.py: all kernels, all launch geometries, on exactly-sized buffers between ASan red zones; the
+    same build carries UndefinedBehaviorSanitizer (integer overflow in index arithmetic, shifts, misaligned vector accesses)."""
     r = _sanitized_child('address', [])
-    assert r.returncode == 0 and 'AddressSanitizer' not in r.stderr and 'clean' in r.stdout, (r.stdout[-500:], r.stderr[-3000:])
+    assert r.returncode == 0 and 'AddressSanitizer' not in r.stderr and 'runtime error' not in r.stderr and 'clean' in r.stdout, (
+        r.stdout[-500:], r.stderr[-3000:])
 
 
 def test_memcheck_negative_control(built):
